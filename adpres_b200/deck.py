@@ -1,0 +1,501 @@
+"""Input-deck reader and node numbering for the test / bench harness.
+
+In a drop-in deployment the unchanged Fortran parser (``src/mod_io.f90``) fills the ``sdata``
+arrays and the patched ``mod_cmfd`` / ``mod_nodal`` bodies hand them to the C ABI
+(``include/adpres_b200.h``).  No Fortran compiler exists in this image, so the harness needs
+its own way to turn the reference's decks into exactly the arrays the Fortran side would
+pass.  This module restates only that data preparation (nothing of the hot path):
+
+* comment stripping / ``%CARD`` splitting        -- ``mod_io.f90:452-576``
+* ``%XSEC``                                       -- ``mod_io.f90:683-762``
+* ``%GEOM`` (sizes, divisions, planars, stagger)  -- ``mod_io.f90:809-1143``
+* node numbering, ``vdel``, default ``nupd``      -- ``mod_io.f90:1293-1365``
+* ``%ITER`` / ``%KERN`` / ``%THET`` / ``%ESRC`` / ``%ADF`` -- ``mod_io.f90:1522-1689,1369-1517,1732-2097``
+* ``base_updt`` + ``Dsigr_updt``                  -- ``mod_xsec.f90:172-226``
+
+All arrays are produced in Fortran (column-major) memory order with the reference's
+1-based node / mesh indices, i.e. bit-for-bit what ``sdata`` would hold.
+"""
+from __future__ import annotations
+
+import dataclasses
+import math
+import os
+from typing import Dict, List, Optional
+
+import numpy as np
+
+KERN_FDM, KERN_PNM, KERN_SANM = 0, 1, 2
+_KERN_CODE = {"FDM": KERN_FDM, "PNM": KERN_PNM, "SANM": KERN_SANM}
+
+
+# --------------------------------------------------------------------------- low-level text
+def _strip_comments(text: str) -> List[str]:
+    """``inp_comments`` (mod_io.f90:452-492): drop blank lines and everything after '!'."""
+    out = []
+    for raw in text.splitlines():
+        line = raw.strip()
+        pos = line.find("!")
+        if pos < 0:
+            if line:
+                out.append(line)
+        elif pos > 0:
+            line = line[:pos].rstrip()
+            if line:
+                out.append(line)
+    return out
+
+
+def _split_cards(lines: List[str], base_dir: str) -> Dict[str, List[str]]:
+    """``inp_rewrite`` (mod_io.f90:496-576): lines after ``%NAME`` belong to card NAME."""
+    cards: Dict[str, List[str]] = {}
+    cur: Optional[str] = None
+    for line in lines:
+        if "%" in line:
+            cur = line[line.index("%") + 1:].strip().upper()
+            cards.setdefault(cur, [])
+            continue
+        if cur is None:
+            continue
+        if "FILE" in line.upper().split()[:1]:
+            # ``FILE <path>`` indirection (mod_io.f90:519-535)
+            fname = line.split(None, 1)[1].strip()
+            if not os.path.isabs(fname) or not os.path.exists(fname):
+                fname = os.path.join(base_dir, os.path.basename(fname))
+            with open(fname) as fh:
+                cards[cur].extend(_strip_comments(fh.read()))
+            continue
+        cards[cur].append(line)
+    return cards
+
+
+def _tokens(line: str) -> List[str]:
+    """Fortran list-directed record: blanks/commas separate, ``n*v`` repeats."""
+    out: List[str] = []
+    for tok in line.replace(",", " ").split():
+        if "*" in tok:
+            rep, val = tok.split("*", 1)
+            out.extend([val] * int(rep))
+        else:
+            out.append(tok)
+    return out
+
+
+def _f(tok: str) -> float:
+    return float(tok.lower().replace("d", "e"))
+
+
+class _Reader:
+    """One READ per record, like the reference ('x' sentinel prevents record run-on)."""
+
+    def __init__(self, lines: List[str], card: str):
+        self.lines, self.pos, self.card = lines, 0, card
+
+    def more(self) -> bool:
+        return self.pos < len(self.lines)
+
+    def rec(self, n: Optional[int] = None) -> List[str]:
+        if self.pos >= len(self.lines):
+            raise ValueError(f"%{self.card}: unexpected end of card")
+        toks = _tokens(self.lines[self.pos])
+        self.pos += 1
+        if n is not None:
+            if len(toks) < n:
+                raise ValueError(f"%{self.card}: expected {n} values, got {toks}")
+            toks = toks[:n]
+        return toks
+
+    def ints(self, n: int) -> List[int]:
+        return [int(t) for t in self.rec(n)]
+
+    def floats(self, n: int) -> List[float]:
+        return [_f(t) for t in self.rec(n)]
+
+
+# --------------------------------------------------------------------------- the problem
+@dataclasses.dataclass
+class Problem:
+    """Everything ``sdata`` holds for the hot path, Fortran layout, 1-based indices."""
+    mode: str
+    ng: int
+    nmat: int
+    # assemblies
+    nx: int
+    ny: int
+    nz: int
+    xsize: np.ndarray
+    ysize: np.ndarray
+    zsize: np.ndarray
+    xdiv: np.ndarray
+    ydiv: np.ndarray
+    zdiv: np.ndarray
+    zpln: np.ndarray            # (nz) planar id, 1-based
+    planars: np.ndarray         # (npl, nx, ny) material per assembly, index [pl, i, j] 0-based
+    bc: np.ndarray              # xeast, xwest, ynorth, ysouth, zbott, ztop
+    # material-wise XS (nmat, ng[, ng]) Fortran order
+    xsigtr: np.ndarray
+    xsiga: np.ndarray
+    xnuf: np.ndarray
+    xsigf: np.ndarray
+    xsigs: np.ndarray
+    chi: np.ndarray
+    # iteration control
+    nout: int = 500
+    nin: int = 2
+    serc: float = 1.0e-5
+    ferc: float = 1.0e-5
+    nac: int = 5
+    nupd: int = 0
+    th_niter: int = 30
+    nth: int = 20
+    kern: int = KERN_SANM
+    biter: int = 0
+    sth: float = 1.0
+    bth: float = 0.0
+    mdc: Optional[np.ndarray] = None     # (nmat, ng, 6) ADF per material
+    adf_rot: Optional[list] = None       # [(rot, x1,x2,y1,y2,z1,z2), ...]
+    esrc: Optional[list] = None          # [(sden, spec[ng], [(zpos, [(xpos, ypos), ...]), ...]), ...]
+    cards: Optional[Dict[str, List[str]]] = None
+    # ---- node-wise (filled by build())
+    nxx: int = 0
+    nyy: int = 0
+    nzz: int = 0
+    nnod: int = 0
+    npl: int = 0                # nodes per z-plane (np in set_ind)
+    xdel: np.ndarray = None
+    ydel: np.ndarray = None
+    zdel: np.ndarray = None
+    ystag_smin: np.ndarray = None
+    ystag_smax: np.ndarray = None
+    xstag_smin: np.ndarray = None
+    xstag_smax: np.ndarray = None
+    ix: np.ndarray = None
+    iy: np.ndarray = None
+    iz: np.ndarray = None
+    mat: np.ndarray = None
+    vdel: np.ndarray = None
+    sigtr: np.ndarray = None
+    siga: np.ndarray = None
+    nuf: np.ndarray = None
+    sigf: np.ndarray = None
+    sigs: np.ndarray = None     # (nnod, ng, ng) F-order: sigs[n, g, h] = g -> h
+    D: np.ndarray = None
+    sigr: np.ndarray = None
+    dc: np.ndarray = None       # (nnod, ng, 6) F-order
+    exsrc: np.ndarray = None    # (nnod, ng) F-order
+
+    # ------------------------------------------------------------------ fixtures
+    _SPEC_FIELDS = ("mode", "ng", "nmat", "nx", "ny", "nz", "xsize", "ysize", "zsize", "xdiv", "ydiv",
+                    "zdiv", "zpln", "planars", "bc", "xsigtr", "xsiga", "xnuf", "xsigf", "xsigs", "chi",
+                    "nout", "nin", "serc", "ferc", "nac", "nupd", "th_niter", "nth", "kern", "biter",
+                    "sth", "bth", "mdc", "adf_rot", "esrc")
+
+    def to_spec(self) -> dict:
+        """JSON-able problem specification (what the deck says, before node expansion).
+        Used for the fixtures under tests/golden/ that travel to the GPU box, where
+        /root/reference (and so the decks themselves) does not exist."""
+        d = {}
+        for k in self._SPEC_FIELDS:
+            v = getattr(self, k)
+            if k == "nupd" and not self.biter:
+                v = 0
+            d[k] = v.tolist() if isinstance(v, np.ndarray) else v
+        return d
+
+    @staticmethod
+    def from_spec(d: dict) -> "Problem":
+        kw = dict(d)
+        for k in ("xsize", "ysize", "zsize"):
+            kw[k] = np.array(kw[k], dtype=np.float64)
+        for k in ("xdiv", "ydiv", "zdiv", "zpln", "planars", "bc"):
+            kw[k] = np.array(kw[k], dtype=np.int32)
+        for k in ("xsigtr", "xsiga", "xnuf", "xsigf", "xsigs", "chi"):
+            kw[k] = np.asfortranarray(np.array(kw[k], dtype=np.float64))
+        if kw.get("mdc") is not None:
+            kw["mdc"] = np.array(kw["mdc"], dtype=np.float64)
+        if kw.get("adf_rot") is not None:
+            kw["adf_rot"] = [tuple(r) for r in kw["adf_rot"]]
+        return Problem(**kw).build()
+
+    # ------------------------------------------------------------------ geometry
+    def refine(self, xdiv=None, ydiv=None, zdiv=None) -> "Problem":
+        """Return a copy with new assembly divisions (the synthetic refined meshes of
+        BASELINE.json configs 2-5 change only lines 3/5/7 of %GEOM)."""
+        p = dataclasses.replace(self)
+        if xdiv is not None:
+            p.xdiv = np.broadcast_to(np.asarray(xdiv, dtype=np.int32), (self.nx,)).copy()
+        if ydiv is not None:
+            p.ydiv = np.broadcast_to(np.asarray(ydiv, dtype=np.int32), (self.ny,)).copy()
+        if zdiv is not None:
+            p.zdiv = np.broadcast_to(np.asarray(zdiv, dtype=np.int32), (self.nz,)).copy()
+        if not p.biter:
+            p.nupd = 0
+        return p.build()
+
+    def build(self) -> "Problem":
+        """inp_geom1/2 + misc + XS_updt(base) -> node-wise arrays."""
+        nx, ny, nz = self.nx, self.ny, self.nz
+        self.nxx, self.nyy, self.nzz = int(self.xdiv.sum()), int(self.ydiv.sum()), int(self.zdiv.sum())
+        # node sizes: div = size / REAL(div)  (mod_io.f90:925-953)
+        self.xdel = np.repeat(self.xsize / self.xdiv.astype(np.float64), self.xdiv)
+        self.ydel = np.repeat(self.ysize / self.ydiv.astype(np.float64), self.ydiv)
+        self.zdel = np.repeat(self.zsize / self.zdiv.astype(np.float64), self.zdiv)
+        ia = np.repeat(np.arange(nx), self.xdiv)      # node -> assembly index
+        ja = np.repeat(np.arange(ny), self.ydiv)
+        ka = np.repeat(np.arange(nz), self.zdiv)
+        # mnum(i,j,1): staggering is taken from plane 1 only (mod_io.f90:1071-1110)
+        pl1 = self.planars[self.zpln[0] - 1]
+        m1 = pl1[np.ix_(ia, ja)]                       # (nxx, nyy)
+        nzmask = m1 != 0
+        if not nzmask.any(axis=0).all() or not nzmask.any(axis=1).all():
+            raise ValueError("empty row/column in planar 1 (unsupported by the reference too)")
+        i1 = np.arange(1, self.nxx + 1)
+        j1 = np.arange(1, self.nyy + 1)
+        self.ystag_smin = np.where(nzmask, i1[:, None], self.nxx + 1).min(axis=0).astype(np.int32)
+        self.ystag_smax = np.where(nzmask, i1[:, None], 0).max(axis=0).astype(np.int32)
+        self.xstag_smin = np.where(nzmask, j1[None, :], self.nyy + 1).min(axis=1).astype(np.int32)
+        self.xstag_smax = np.where(nzmask, j1[None, :], 0).max(axis=1).astype(np.int32)
+        # numbering k, j, i (mod_io.f90:1319-1330)
+        ii, jj = [], []
+        for j in range(self.nyy):
+            lo, hi = self.ystag_smin[j], self.ystag_smax[j]
+            ii.append(np.arange(lo, hi + 1, dtype=np.int32))
+            jj.append(np.full(hi - lo + 1, j + 1, dtype=np.int32))
+        ip, jp = np.concatenate(ii), np.concatenate(jj)
+        self.npl = int(ip.size)
+        self.nnod = self.npl * self.nzz
+        self.ix = np.tile(ip, self.nzz)
+        self.iy = np.tile(jp, self.nzz)
+        self.iz = np.repeat(np.arange(1, self.nzz + 1, dtype=np.int32), self.npl)
+        # material per node
+        matp = np.empty((self.nzz, self.npl), dtype=np.int32)
+        for k in range(self.nzz):
+            pl = self.planars[self.zpln[ka[k]] - 1]
+            matp[k] = pl[ia[ip - 1], ja[jp - 1]]
+        self.mat = matp.reshape(-1)
+        if (self.mat == 0).any():
+            raise ValueError("Zero material found inside core. Check material assignment")
+        if (self.mat > self.nmat).any():
+            raise ValueError("material id greater than number of materials")
+        self.vdel = self.xdel[self.ix - 1] * self.ydel[self.iy - 1] * self.zdel[self.iz - 1]
+        if self.nupd == 0:
+            # nupd = ceiling((nxx+nyy+nzz)/2.5), default REAL arithmetic (mod_io.f90:1363)
+            self.nupd = int(math.ceil(float(np.float32(self.nxx + self.nyy + self.nzz) / np.float32(2.5))))
+        self.update_xs()
+        self._build_adf()
+        self._build_esrc()
+        return self
+
+    def update_xs(self) -> None:
+        """base_updt + Dsigr_updt (mod_xsec.f90:172-226)."""
+        m = self.mat - 1
+        N, G = self.nnod, self.ng
+        self.sigtr = np.asfortranarray(self.xsigtr[m, :])
+        self.siga = np.asfortranarray(self.xsiga[m, :])
+        self.nuf = np.asfortranarray(self.xnuf[m, :])
+        self.sigf = np.asfortranarray(self.xsigf[m, :])
+        self.sigs = np.asfortranarray(self.xsigs[m, :, :])
+        self.finish_xs()
+
+    def finish_xs(self) -> None:
+        """Dsigr_updt: D = 1/(3 sigtr); sigr = siga + sum_{h != g} sigs(g -> h), h ascending."""
+        N, G = self.nnod, self.ng
+        if (self.sigtr < 1.0e-5).any():
+            raise ValueError("Negative diffusion coefficient encountered")
+        self.D = np.asfortranarray(1.0 / (3.0 * self.sigtr))
+        sigr = np.zeros((N, G), order="F")
+        for g in range(G):
+            dum = np.zeros(N)
+            for h in range(G):
+                if h != g:
+                    dum = dum + self.sigs[:, g, h]
+            sigr[:, g] = self.siga[:, g] + dum
+        self.sigr = sigr
+
+    # ------------------------------------------------------------------ ADF / ESRC
+    def _node_assembly_maps(self):
+        ia = np.repeat(np.arange(self.nx), self.xdiv)
+        ja = np.repeat(np.arange(self.ny), self.ydiv)
+        ka = np.repeat(np.arange(self.nz), self.zdiv)
+        return ia, ja, ka
+
+    def _build_adf(self) -> None:
+        N, G = self.nnod, self.ng
+        self.dc = np.ones((N, G, 6), order="F")
+        if self.mdc is None:
+            return
+        nx, ny, nz = self.nx, self.ny, self.nz
+        ia, ja, ka = self._node_assembly_maps()
+        # xdc(i,j,k,g) = mdc(asm material)   (mod_io.f90:1784-1792)
+        asm_mat = np.stack([self.planars[self.zpln[k] - 1] for k in range(nz)], axis=2)  # (nx,ny,nz)
+        xdc = np.zeros((nx, ny, nz, G, 6))
+        nzm = asm_mat != 0
+        xdc[nzm] = self.mdc[asm_mat[nzm] - 1]
+        for (rot, x1, x2, y1, y2, z1, z2) in (self.adf_rot or []):
+            blk = xdc[x1 - 1:x2, y1 - 1:y2, z1 - 1:z2]
+            a = blk[..., :4].copy()
+            if rot == 1:
+                blk[..., 0], blk[..., 1], blk[..., 2], blk[..., 3] = a[..., 3], a[..., 2], a[..., 0], a[..., 1]
+            elif rot == 2:
+                blk[..., 0], blk[..., 1], blk[..., 2], blk[..., 3] = a[..., 1], a[..., 0], a[..., 3], a[..., 2]
+            elif rot == 3:
+                blk[..., 0], blk[..., 1], blk[..., 2], blk[..., 3] = a[..., 2], a[..., 3], a[..., 1], a[..., 0]
+        tx = np.concatenate([[1], 1 + np.cumsum(self.xdiv)])
+        ty = np.concatenate([[1], 1 + np.cumsum(self.ydiv)])
+        tz = np.concatenate([[1], 1 + np.cumsum(self.zdiv)])
+        i, j, k = self.ix, self.iy, self.iz
+        ai, aj, ak = ia[i - 1], ja[j - 1], ka[k - 1]
+        src = xdc[ai, aj, ak]                       # (N, G, 6)
+        # only faces lying on an assembly boundary take the ADF (mod_io.f90:2071-2078);
+        # note faces 5/6: value 5 is applied at the assembly *bottom*, 6 at its top.
+        sel = [(i == tx[ai + 1] - 1), (i == tx[ai]), (j == ty[aj + 1] - 1), (j == ty[aj]),
+               (k == tz[ak]), (k == tz[ak + 1] - 1)]
+        for u in range(6):
+            self.dc[sel[u], :, u] = src[sel[u], :, u]
+
+    def _build_esrc(self) -> None:
+        N, G = self.nnod, self.ng
+        self.exsrc = np.zeros((N, G), order="F")
+        if not self.esrc or self.mode != "FIXEDSRC":
+            return
+        ia, ja, ka = self._node_assembly_maps()
+        ai, aj, ak = ia[self.ix - 1], ja[self.iy - 1], ka[self.iz - 1]
+        for sden, spec, zlist in self.esrc:
+            for zpos, xy in zlist:
+                for xpos, ypos in xy:
+                    sel = (ai == xpos - 1) & (aj == ypos - 1) & (ak == zpos - 1)
+                    for g in range(G):
+                        self.exsrc[sel, g] += sden * spec[g]
+
+    # ------------------------------------------------------------------ results
+    def asm_power(self, pow_n: np.ndarray) -> np.ndarray:
+        """AsmPow normalisation (mod_io.f90:3267-3363): axial average weighted by zdel,
+        area-weighted per assembly, scaled so the mean over assemblies with power>0 is 1.
+        Returns (nx, ny)."""
+        fx = np.zeros((self.nxx, self.nyy, self.nzz))
+        fx[self.ix - 1, self.iy - 1, self.iz - 1] = pow_n
+        fnode = (fx * self.zdel[None, None, :]).sum(axis=2) / self.zdel.sum()
+        ia, ja, _ = self._node_assembly_maps()
+        area = self.xdel[:, None] * self.ydel[None, :]
+        fasm = np.zeros((self.nx, self.ny))
+        for a in range(self.nx):
+            for b in range(self.ny):
+                sel = np.ix_(ia == a, ja == b)
+                fasm[a, b] = (fnode[sel] * area[sel]).sum() / area[sel].sum()
+        pos = fasm > 0
+        totp = fasm[pos].sum()
+        if totp > 0:
+            fasm = float(pos.sum()) / totp * fasm
+        return fasm
+
+
+# --------------------------------------------------------------------------- parsing
+def parse_deck(text: str, base_dir: str = ".") -> Problem:
+    cards = _split_cards(_strip_comments(text), base_dir)
+    if "MODE" not in cards:
+        raise ValueError("CARD %MODE DOES NOT PRESENT")
+    mode = cards["MODE"][0].split()[0].upper()
+    if "XSEC" not in cards:
+        raise ValueError("CARD %XSEC DOES NOT PRESENT (XTAB decks are out of scope)")
+    if "GEOM" not in cards:
+        raise ValueError("CARD %GEOM DOES NOT PRESENT")
+
+    # ---- %XSEC (mod_io.f90:683-762); xsigs(mat, g, h) = scattering g -> h
+    r = _Reader(cards["XSEC"], "XSEC")
+    ng, nmat = r.ints(2)
+    xsigtr = np.zeros((nmat, ng), order="F")
+    xsiga = np.zeros((nmat, ng), order="F")
+    xnuf = np.zeros((nmat, ng), order="F")
+    xsigf = np.zeros((nmat, ng), order="F")
+    chi = np.zeros((nmat, ng), order="F")
+    xsigs = np.zeros((nmat, ng, ng), order="F")
+    for i in range(nmat):
+        for g in range(ng):
+            v = r.floats(5 + ng)
+            xsigtr[i, g], xsiga[i, g], xnuf[i, g], xsigf[i, g], chi[i, g] = v[:5]
+            xsigs[i, g, :] = v[5:]
+            if xsigtr[i, g] <= 0.0:
+                raise ValueError("Transport cross section (sigtr) is zero or negative")
+
+    # ---- %GEOM part 1 (mod_io.f90:809-953)
+    r = _Reader(cards["GEOM"], "GEOM")
+    nx, ny, nz = r.ints(3)
+    xsize = np.array(r.floats(nx)); xdiv = np.array(r.ints(nx), dtype=np.int32)
+    ysize = np.array(r.floats(ny)); ydiv = np.array(r.ints(ny), dtype=np.int32)
+    zsize = np.array(r.floats(nz)); zdiv = np.array(r.ints(nz), dtype=np.int32)
+    # ---- %GEOM part 2 (mod_io.f90:958-1143): planars are listed north (j = ny) first
+    npl = r.ints(1)[0]
+    zpln = np.array(r.ints(nz), dtype=np.int32)
+    planars = np.zeros((npl, nx, ny), dtype=np.int32)
+    for k in range(npl):
+        for j in range(ny - 1, -1, -1):
+            planars[k, :, j] = r.ints(nx)
+    bc = np.array(r.ints(6), dtype=np.int32)
+    if (bc > 2).any() or (bc < 0).any():
+        raise ValueError("wrong boundary condition")
+
+    p = Problem(mode=mode, ng=ng, nmat=nmat, nx=nx, ny=ny, nz=nz, xsize=xsize, ysize=ysize,
+                zsize=zsize, xdiv=xdiv, ydiv=ydiv, zdiv=zdiv, zpln=zpln, planars=planars, bc=bc,
+                xsigtr=xsigtr, xsiga=xsiga, xnuf=xnuf, xsigf=xsigf, xsigs=xsigs, chi=chi,
+                cards=cards)
+
+    if "KERN" in cards:                 # mod_io.f90:1593-1621
+        name = cards["KERN"][0].split()[0].upper()
+        if name not in _KERN_CODE:
+            raise ValueError(f"COULD NOT RECOGNIZE NODAL KERNEL: {name}")
+        p.kern = _KERN_CODE[name]
+    if "ITER" in cards:                 # mod_io.f90:1522-1540
+        v = _tokens(cards["ITER"][0])
+        p.nout, p.nin = int(v[0]), int(v[1])
+        p.serc, p.ferc = _f(v[2]), _f(v[3])
+        p.nac, p.nupd, p.th_niter, p.nth = int(v[4]), int(v[5]), int(v[6]), int(v[7])
+        p.biter = 1
+    if "THET" in cards:                 # mod_io.f90:1650-1689
+        p.sth = _f(_tokens(cards["THET"][0])[0])
+        if p.sth < 0.001 or p.sth > 1.0:
+            raise ValueError("THETA VALUE out of range")
+        p.bth = (1.0 - p.sth) / p.sth
+    if "ADF" in cards:                  # mod_io.f90:1774-1831
+        r = _Reader(cards["ADF"], "ADF")
+        mdc = np.zeros((nmat, ng, 6))
+        for i in range(nmat):
+            for g in range(ng):
+                mdc[i, g, :] = r.floats(6)
+        rots = []
+        while r.more():
+            rot = r.ints(1)[0]
+            if rot < 1:
+                break
+            while True:
+                v = r.ints(6)
+                if min(v) < 1:
+                    break
+                rots.append((rot, *v))
+        p.mdc, p.adf_rot = mdc, rots
+    if "ESRC" in cards and mode == "FIXEDSRC":   # mod_io.f90:1369-1517
+        r = _Reader(cards["ESRC"], "ESRC")
+        nsrc = r.ints(1)[0]
+        srcs = []
+        for _ in range(nsrc):
+            sden = r.floats(1)[0]
+            spec = r.floats(ng)
+            zlist = []
+            while True:
+                zpos = r.ints(1)[0]
+                if zpos < 1:
+                    break
+                xy = []
+                while True:
+                    xpos, ypos = r.ints(2)
+                    if xpos < 1 or ypos < 1:
+                        break
+                    xy.append((xpos, ypos))
+                zlist.append((zpos, xy))
+            srcs.append((sden, spec, zlist))
+        p.esrc = srcs
+    return p.build()
+
+
+def read_deck(path: str) -> Problem:
+    with open(path) as fh:
+        return parse_deck(fh.read(), os.path.dirname(os.path.abspath(path)))
