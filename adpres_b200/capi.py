@@ -1,0 +1,290 @@
+"""ctypes binding of the C ABI (include/adpres_b200.h) -- the same entry points the Fortran
+ISO_C_BINDING shim binds (fortran/adpres_b200_bind.f90).  There is no CPU fallback: if the
+CUDA library is missing or no device is present, construction fails loudly.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libadpres_b200.so")
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+
+MODE_FORWARD, MODE_ADJOINT, MODE_FIXEDSRC, MODE_TRANSIENT = 0, 1, 2, 3
+STOP_MAXOUTER, STOP_LU_DIAG, STOP_NDMAX, STOP_ZERO_POWER = 1, 2, 3, 4
+
+TRACE_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int)
+
+# every symbol include/adpres_b200.h declares (checked by tests/test_abi.py)
+SYMBOLS = [
+    "adp_create", "adp_destroy", "adp_last_error", "adp_version", "adp_comm_unique_id", "adp_comm_init", "adp_slab",
+    "adp_set_geometry", "adp_set_xs", "adp_set_control", "adp_matrix_setup", "adp_init_flux", "adp_outer_begin",
+    "adp_outer_iter", "adp_nodal_upd", "adp_powdis", "adp_integrate", "adp_set_kinetics", "adp_set_transient",
+    "adp_get_exsrc", "adp_get_state", "adp_set_state", "adp_set_s0", "adp_get_nod", "adp_set_nod_dn", "adp_get_exsrc_arrays",
+    "adp_get_ndmax", "adp_set_trace", "adp_outer", "adp_outer_ad", "adp_outer_fs", "adp_outer_th", "adp_outer_tr",
+    "adp_sp_matvec", "adp_bicg", "adp_get_matrix", "adp_get_source", "adp_set_option", "adp_launch_count",
+    "adp_bench_kernel",
+]
+
+_lib = None
+
+
+class AdpresError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"adpres_b200 error {code}: {msg}")
+        self.code = code
+
+
+def load():
+    """Load libadpres_b200.so.  Raises if it has not been built -- never falls back."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} is missing: build it with `python -m adpres_b200.build` "
+                               "(there is no CPU fallback for the CUDA hot path)")
+        _lib = C.CDLL(LIB_PATH)
+        _lib.adp_last_error.restype = C.c_char_p
+        _lib.adp_last_error.argtypes = [C.c_void_p]
+        _lib.adp_version.restype = C.c_char_p
+    return _lib
+
+
+def _d(a):
+    if a is None:
+        return None
+    assert isinstance(a, np.ndarray) and a.dtype == np.float64 and (a.flags.f_contiguous or a.flags.c_contiguous), \
+        "expected a contiguous float64 array"
+    return a.ctypes.data_as(_dp)
+
+
+def _i(a):
+    if a is None:
+        return None
+    assert a.dtype == np.int32 and a.flags.c_contiguous
+    return a.ctypes.data_as(_ip)
+
+
+class Solver:
+    """One device context fed with the arrays of a ``deck.Problem`` (what ``sdata`` holds).
+    Method names are those of the reference procedures."""
+
+    def __init__(self, p, device=0, nranks=1, rank=0, uid=None, nupd=None, nout=None, nin=None, nac=None,
+                 serc=None, ferc=None, kern=None):
+        self.L = load()
+        self.p = p
+        self.N, self.G = p.nnod, p.ng
+        self.h = C.c_void_p()
+        rc = self.L.adp_create(C.byref(self.h), int(device))
+        if rc:
+            raise AdpresError(rc, self.L.adp_last_error(None).decode())
+        if nranks > 1:
+            self._chk(self.L.adp_comm_init(self.h, nranks, rank, uid))
+        self.nranks, self.rank = nranks, rank
+        self._chk(self.L.adp_set_geometry(self.h, p.nxx, p.nyy, p.nzz, p.nnod, p.ng, p.nmat, _i(p.ix), _i(p.iy),
+                                          _i(p.iz), _i(p.ystag_smin), _i(p.ystag_smax), _i(p.xstag_smin),
+                                          _i(p.xstag_smax), _d(p.xdel), _d(p.ydel), _d(p.zdel), _i(p.bc), _i(p.mat)))
+        k0, k1 = C.c_int(), C.c_int()
+        self.L.adp_slab(self.h, C.byref(k0), C.byref(k1))
+        self.k0, self.k1 = k0.value, k1.value
+        self.own = slice(self.k0 * p.npl, self.k1 * p.npl)      # node range this rank owns
+        self.set_xs()
+        self.set_control(nout=nout, nin=nin, nac=nac, nupd=nupd, serc=serc, ferc=ferc, kern=kern)
+        self._trace_cb = None
+        self.trace_rows, self.trace_nodal, self.trace_extrp = [], [], []
+
+    # ---- plumbing
+    def _chk(self, rc):
+        if rc < 0:
+            raise AdpresError(rc, self.L.adp_last_error(self.h).decode())
+        return rc
+
+    def close(self):
+        if getattr(self, "h", None) and self.h.value:
+            self.L.adp_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def last_error(self):
+        return self.L.adp_last_error(self.h).decode()
+
+    def set_option(self, name, value):
+        self._chk(self.L.adp_set_option(self.h, name.encode(), int(value)))
+
+    # ---- inputs
+    def set_xs(self, **kw):
+        p = self.p
+        keep = {}
+
+        def g(k):
+            if kw and k not in kw:
+                return None                      # partial update: NULL keeps the device copy
+            a = np.asfortranarray(kw.get(k, getattr(p, k)), dtype=np.float64)
+            keep[k] = a
+            return _d(a)
+        self._chk(self.L.adp_set_xs(self.h, g("D"), g("sigr"), g("nuf"), g("sigf"), g("sigs"), g("chi"), g("dc"),
+                                    g("exsrc")))
+
+    def set_control(self, nout=None, nin=None, nac=None, nupd=None, serc=None, ferc=None, kern=None):
+        p = self.p
+        v = lambda a, b: b if a is None else a
+        self.ctl = dict(nout=v(nout, p.nout), nin=v(nin, p.nin), nac=v(nac, p.nac), nupd=v(nupd, p.nupd),
+                        serc=v(serc, p.serc), ferc=v(ferc, p.ferc), kern=v(kern, p.kern))
+        c = self.ctl
+        self._chk(self.L.adp_set_control(self.h, c["nout"], c["nin"], c["nac"], c["nupd"], C.c_double(c["serc"]),
+                                         C.c_double(c["ferc"]), c["kern"]))
+
+    def set_state(self, f0=None, fs0=None, Ke=1.0):
+        f0 = None if f0 is None else np.asfortranarray(f0)
+        self._chk(self.L.adp_set_state(self.h, _d(f0), _d(fs0), C.c_double(Ke)))
+
+    def set_s0(self, s0, g):
+        self._chk(self.L.adp_set_s0(self.h, _d(np.asfortranarray(s0)), int(g)))
+
+    def set_kinetics(self, ibeta, lamb, velo, tbeta, sth, bth):
+        a = [np.ascontiguousarray(x, dtype=np.float64) for x in (ibeta, lamb, velo, tbeta)]
+        self._chk(self.L.adp_set_kinetics(self.h, _d(a[0]), _d(a[1]), _d(a[2]), _d(a[3]), C.c_double(sth), C.c_double(bth)))
+
+    def set_transient(self, c0=None, ft=None, fst=None, omeg=None, sigrp=None, L=None):
+        f = lambda a: None if a is None else np.asfortranarray(a, dtype=np.float64)
+        arrs = [f(x) for x in (c0, ft, fst, omeg, sigrp, L)]
+        self._chk(self.L.adp_set_transient(self.h, *[_d(a) for a in arrs]))
+
+    def set_nod_dn(self, dn):
+        self._chk(self.L.adp_set_nod_dn(self.h, _d(np.asfortranarray(dn))))
+
+    # ---- trace (what the reference prints)
+    def enable_trace(self):
+        self.trace_rows, self.trace_nodal, self.trace_extrp = [], [], []
+
+        def cb(user, event, p, a, b, c, i, j, k):
+            if event == 0:
+                self.trace_rows.append((p, a, b, c))
+            elif event == 1:
+                self.trace_extrp.append(p)
+            else:
+                self.trace_nodal.append((p, a, i, j, k))
+        self._trace_cb = TRACE_FN(cb)
+        self._chk(self.L.adp_set_trace(self.h, self._trace_cb, None))
+
+    # ---- hot path
+    def matrix_setup(self, opt):
+        return self._chk(self.L.adp_matrix_setup(self.h, opt))
+
+    def init_flux(self, adjoint=False):
+        return self._chk(self.L.adp_init_flux(self.h, int(adjoint)))
+
+    def outer_begin(self, mode=MODE_FORWARD):
+        return self._chk(self.L.adp_outer_begin(self.h, mode))
+
+    def outer_iter(self, mode, p):
+        ke, ser, fer = C.c_double(), C.c_double(), C.c_double()
+        self._chk(self.L.adp_outer_iter(self.h, mode, p, C.byref(ke), C.byref(ser), C.byref(fer)))
+        return ke.value, ser.value, fer.value
+
+    def nodal_upd(self, nmode):
+        nd, i, j, k = C.c_double(), C.c_int(), C.c_int(), C.c_int()
+        rc = self._chk(self.L.adp_nodal_upd(self.h, nmode, C.byref(nd), C.byref(i), C.byref(j), C.byref(k)))
+        return rc, nd.value, (i.value, j.value, k.value)
+
+    def _run(self, fn, *args):
+        n = C.c_int(0)
+        rc = self._chk(fn(self.h, *args, C.byref(n)))
+        return rc, n.value
+
+    def outer(self, popt=1):
+        return self._run(self.L.adp_outer, popt)
+
+    def outer_fs(self, popt=1):
+        return self._run(self.L.adp_outer_fs, popt)
+
+    def outer_ad(self, popt=1):
+        return self._run(self.L.adp_outer_ad, popt)
+
+    def outer_th(self, maxn):
+        return self._run(self.L.adp_outer_th, maxn)
+
+    def outer_tr(self, ht):
+        maxi, n = C.c_int(0), C.c_int(0)
+        rc = self._chk(self.L.adp_outer_tr(self.h, C.c_double(ht), C.byref(maxi), C.byref(n)))
+        return rc, bool(maxi.value), n.value
+
+    def get_exsrc(self, ht):
+        return self._chk(self.L.adp_get_exsrc(self.h, C.c_double(ht)))
+
+    def powdis(self, fixedsrc=False):
+        pw = np.zeros(self.N)
+        rc = self._chk(self.L.adp_powdis(self.h, _d(pw), int(fixedsrc)))
+        return rc, pw
+
+    def integrate(self, s):
+        r = C.c_double()
+        self._chk(self.L.adp_integrate(self.h, _d(np.ascontiguousarray(s, dtype=np.float64)), C.byref(r)))
+        return r.value
+
+    # ---- kernel level
+    def sp_matvec(self, g, x):
+        v = np.zeros(self.N)
+        self._chk(self.L.adp_sp_matvec(self.h, g, _d(np.ascontiguousarray(x)), _d(v)))
+        return v
+
+    def bicg(self, imax, g, b, x):
+        x = np.array(x, dtype=np.float64)
+        self._chk(self.L.adp_bicg(self.h, imax, g, _d(np.ascontiguousarray(b)), _d(x)))
+        return x
+
+    def matrix_dia(self):
+        a = np.zeros((7, self.N, self.G), order="F")
+        self._chk(self.L.adp_get_matrix(self.h, _d(a)))
+        return a
+
+    def get_source(self, cmode):
+        S = [np.zeros((self.N, self.G), order="F") for _ in range(3)]
+        self._chk(self.L.adp_get_source(self.h, cmode, _d(S[0]), _d(S[1]), _d(S[2])))
+        return S
+
+    # ---- outputs
+    def state(self):
+        f0 = np.zeros((self.N, self.G), order="F")
+        fs0 = np.zeros(self.N)
+        s0 = np.zeros((self.N, self.G), order="F")
+        ke = C.c_double()
+        self._chk(self.L.adp_get_state(self.h, _d(f0), _d(fs0), _d(s0), C.byref(ke)))
+        return dict(f0=f0, fs0=fs0, s0=s0, Ke=ke.value)
+
+    def nod(self):
+        df = np.zeros((6, self.N, self.G), order="F")
+        dn = np.zeros((6, self.N, self.G), order="F")
+        self._chk(self.L.adp_get_nod(self.h, _d(df), _d(dn)))
+        return df, dn
+
+    def exsrc_arrays(self):
+        ex = np.zeros((self.N, self.G), order="F")
+        dfis = np.zeros(self.N)
+        self._chk(self.L.adp_get_exsrc_arrays(self.h, _d(ex), _d(dfis)))
+        return ex, dfis
+
+    @property
+    def ndmax(self):
+        r = C.c_double()
+        self.L.adp_get_ndmax(self.h, C.byref(r))
+        return r.value
+
+    def launch_count(self):
+        n = C.c_longlong()
+        self.L.adp_launch_count(self.h, C.byref(n))
+        return n.value
+
+    def bench_kernel(self, what, reps):
+        ms = C.c_double()
+        self._chk(self.L.adp_bench_kernel(self.h, what, reps, C.byref(ms)))
+        return ms.value

@@ -1,0 +1,188 @@
+// adp_internal.cuh -- device data model shared by the kernels and the C ABI.
+//
+// Layout in HBM (all fp64 unless noted).  The core is numbered k-major with a constant
+// `np` nodes per z-plane (mod_io.f90:1319-1330, mod_cmfd.f90:174,208), so a z-slab is a
+// contiguous node range.  Every node array on the device covers the planes
+//      [-GH, nzl+GH)      GH = 2 ghost planes below and above the nzl owned planes
+// and is indexed  idx = (kl + GH) * np + r   (kl local plane, r position inside the plane).
+// Ghost planes hold the neighbouring slab's data (or zeros outside the core) so that the
+// z neighbours idx -+ np are always addressable: the stencil is branch free, a missing
+// neighbour simply has a zero coefficient.  x neighbours are idx -+ 1, y neighbours
+// idx -+ ypm[r] / ypp[r] (plane-invariant tables, the jagged core outline).
+//   vectors      f0[2][G] (ping-pong old/new), fs[2], r, rs, p, v, s, t           [NV]
+//   matrix       a[G][7][NV]  diagonals in set_ind order z-,y-,x-,diag,x+,y+,z+
+//   coupling     df[G][6][NV], dn[G][6][NV]   (reference AoS nod(n,g)%df(6),dn(6))
+//   XS           D,sigr,nuf,sigf,exsrc [G][NV]; sigs[G(to h)][G(from g)][NV]; dc[6][G][NV]
+//   nodal        S[3][G][NV]
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+#include <map>
+
+#include "../../include/adpres_b200.h"
+
+#define ADP_GH 2          // ghost planes on each side
+#define ADP_MAXG 16       // groups supported by the pointer tables in kernel params
+#define ADP_TILE 256      // threads per block = rows of one plane per tile
+#define ADP_NF 6          // delayed-neutron families (mod_data.f90:120)
+#define ADP_MAXPART 4096  // max blocks contributing partial sums
+
+// ---- device scalars (one array of doubles in HBM; slots) ---------------------------------
+enum {
+    S_KE = 0,     // k-eff
+    S_F,          // f  = Integrate(fs0)   (new)
+    S_FC,         // fc = previous f
+    S_E1,         // l2 norm of previous fission-source difference
+    S_EXC,        // extrapolation coefficient domiR / (1 - domiR)
+    // --- reduction results; contiguous groups are all-reduced together across ranks
+    S_RSV,        // (rs, v)
+    S_TT,         // (t, t)
+    S_TS,         // (t, s)
+    S_RHO0,       // rho ping
+    S_RHO1,       // rho pong
+    S_E2SQ,       // sum errn^2
+    S_FINT,       // sum vdel * fs
+    S_SER,        // max rel. fission source change
+    S_FER,        // max rel. flux change
+    S_NDMAX,      // max |delta dn|
+    S_POW,        // total power
+    S_TMP0, S_TMP1,
+    S_COUNT
+};
+
+struct Geo {
+    int np;        // nodes per plane
+    int nzl;       // owned planes
+    int nzz;       // global planes
+    int k0;        // global index (0-based) of owned plane 0
+    int tpp;       // tiles per plane = ceil(np / ADP_TILE)
+    int ntiles;    // tpp * nzl
+    long long NV;  // (nzl + 2 GH) * np
+    int bc[6];     // xeast, xwest, ynorth, ysouth, zbott, ztop
+    const int *ypm, *ypp;          // [np] offsets to the y-/y+ neighbour (0 = none)
+    const unsigned char *flag;     // [np] bit0 x- missing, bit1 x+ missing, bit2 y- missing, bit3 y+ missing
+    const double *hx, *hy;         // [np] node size in x, y at plane position r
+    const double *hz;              // [nzz + 2] node size in z, hz[1 + kg]; ends padded
+    const double *area;            // [np] xdel*ydel
+    const int *ixr, *iyr;          // [np] 1-based i, j of plane position r
+};
+
+#define FLAG_XM 1
+#define FLAG_XP 2
+#define FLAG_YM 4
+#define FLAG_YP 8
+
+struct adp_comm;  // comm.cu
+
+struct adp_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    // sizes
+    int nxx = 0, nyy = 0, nzz = 0, nnod = 0, ng = 0, nmat = 0, np = 0;
+    int k0 = 0, k1 = 0, nzl = 0;
+    long long NV = 0, NL = 0;
+    Geo geo{};
+    int bc[6] = {0, 0, 0, 0, 0, 0};
+    // host copies of small geometry
+    std::vector<int> h_ix, h_iy, h_iz;
+    // control
+    int nout = 500, nin = 2, nac = 5, nupd = 1000000, kern = ADP_KERN_SANM;
+    double serc = 1e-5, ferc = 1e-5;
+    double ndmax = 0.0;  // persists across outer*() calls, starts at 0 (mod_data.f90:199)
+    int im = 0, jm = 0, km = 0;
+    bool coup_first = true, have_flux = false, geometry_set = false, xs_set = false, matrix_ready = false;
+    bool outer_first = true, outer_ad_first = true;
+    // device arrays
+    int *d_ypm = nullptr, *d_ypp = nullptr, *d_ixr = nullptr, *d_iyr = nullptr, *d_mat = nullptr;
+    unsigned char *d_flag = nullptr;
+    double *d_hx = nullptr, *d_hy = nullptr, *d_hz = nullptr, *d_area = nullptr;
+    double *d_f0[2] = {nullptr, nullptr};  // [G][NV] each
+    double *d_fs[2] = {nullptr, nullptr};
+    int cur[ADP_MAXG] = {0};               // which of d_f0[.] holds the current flux of group g
+    int fcur = 0;
+    double *d_r = nullptr, *d_rs = nullptr, *d_p = nullptr, *d_v = nullptr, *d_s = nullptr, *d_t = nullptr;
+    double *d_s0 = nullptr;                // scattering source of the last group swept (s0 quirk)
+    int s0_group = 0;                      // 1-based group whose column of s0 is non-zero (0: none yet)
+    double *d_a = nullptr;                 // [G][7][NV]
+    double *d_df = nullptr, *d_dn = nullptr;  // [G][6][NV]
+    double *d_D = nullptr, *d_sigr = nullptr, *d_nuf = nullptr, *d_sigf = nullptr, *d_exsrc = nullptr;
+    double *d_sigs = nullptr;              // [h][g][NV]  = sigs(n,g,h)
+    double *d_dc = nullptr;                // [f][g][NV]
+    double *d_chi = nullptr;               // [g][nmat]
+    double *d_S = nullptr;                 // [3][G][NV]
+    // transient
+    double *d_c0 = nullptr, *d_ft = nullptr, *d_fst = nullptr, *d_omeg = nullptr, *d_sigrp = nullptr,
+           *d_L = nullptr, *d_dfis = nullptr, *d_tbeta = nullptr, *d_velo = nullptr;
+    double ibeta[ADP_NF] = {0}, lamb[ADP_NF] = {0};
+    double sth = 1.0, bth = 0.0;
+    bool kinetics_set = false;
+    // reductions
+    double *d_scal = nullptr;              // [S_COUNT]
+    double *d_part = nullptr;              // [4][ADP_MAXPART]
+    unsigned int *d_ticket = nullptr;
+    long long *d_argidx = nullptr;         // location of ndmax
+    int *d_errflag = nullptr;              // LU diagonal abort etc.
+    double *h_scal = nullptr;              // pinned mirror
+    int *h_flags = nullptr;                // pinned
+    double *d_stage = nullptr;             // staging for host<->device copies of node arrays
+    double *h_stage = nullptr;             // pinned staging [max(NL*?)]
+    size_t stage_elems = 0;
+    int grid_blocks = 0;                   // persistent grid size (multiple of the SM count)
+    int sm_count = 0;
+    // multi-rank
+    adp_comm *comm = nullptr;
+    int nranks = 1, rank = 0;
+    // CUDA graphs of one outer iteration, keyed by (mode, parity pattern, extrapolate)
+    std::map<unsigned long long, cudaGraphExec_t> graphs;
+    std::map<unsigned long long, long long> graph_launches;   // kernels inside each graph
+    bool use_graphs = true;
+    // bookkeeping
+    long long launches = 0;
+    adp_trace_fn trace = nullptr;
+    void *trace_user = nullptr;
+};
+
+#define CUDA_TRY(ctx, call)                                                                     \
+    do {                                                                                        \
+        cudaError_t e__ = (call);                                                               \
+        if (e__ != cudaSuccess) {                                                               \
+            (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e__) + " (" + __FILE__ + \
+                         ":" + std::to_string(__LINE__) + ")";                                  \
+            return ADP_ERR_CUDA;                                                                \
+        }                                                                                       \
+    } while (0)
+
+#define ADP_REQUIRE(ctx, cond, msg)                 \
+    do {                                            \
+        if (!(cond)) {                              \
+            (ctx)->err = (msg);                     \
+            return ADP_ERR_USAGE;                   \
+        }                                           \
+    } while (0)
+
+// ---- launch wrappers implemented in the kernel files ---------------------------------------
+// cmfd_kernels.cu
+int adp_k_coup_coef(adp_ctx *c);
+int adp_k_matrix_setup(adp_ctx *c);
+int adp_k_init_flux(adp_ctx *c, int adjoint);
+int adp_k_outer_begin(adp_ctx *c, int mode);
+int adp_k_bicg_group(adp_ctx *c, int mode, int g /*0-based*/, int nin, bool write_s0);
+int adp_k_bicg_raw(adp_ctx *c, int g, int imax, const double *d_b, double *d_x);
+int adp_k_spmv(adp_ctx *c, int g, const double *d_x, double *d_v);
+int adp_k_outer_tail(adp_ctx *c, int mode, bool extrapolate);
+int adp_k_powdis(adp_ctx *c, double *d_pow);
+int adp_k_get_exsrc(adp_ctx *c, double ht);
+int adp_k_integrate(adp_ctx *c, const double *d_vec, int slot);
+// nodal_kernels.cu
+int adp_k_nodal_source(adp_ctx *c, int cmode);
+int adp_k_nodal_update(adp_ctx *c, int cmode);
+// comm.cu
+int adp_comm_halo(adp_ctx *c, double *d_vec, int nplanes);            // exchange ghost planes of one vector
+int adp_comm_allreduce_sum(adp_ctx *c, double *d_scal, int count);
+int adp_comm_allreduce_max(adp_ctx *c, double *d_scal, int count);
+int adp_comm_allreduce_min_ll(adp_ctx *c, long long *d_val, int count);
+void adp_comm_destroy(adp_ctx *c);

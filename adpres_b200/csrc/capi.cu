@@ -1,0 +1,756 @@
+// capi.cu -- implementation of the C ABI declared in include/adpres_b200.h
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "adp_internal.cuh"
+
+int adp_k_scale_by_slot(adp_ctx *c, double *d_vec, int slot);
+
+static thread_local std::string g_create_err;
+
+extern "C" const char *adp_version(void) { return "adpres_b200 0.1 (sm_100a)"; }
+
+extern "C" const char *adp_last_error(const adp_ctx *c) { return c ? c->err.c_str() : g_create_err.c_str(); }
+
+template <typename T>
+static int dev_alloc(adp_ctx *c, T **p, size_t n, bool zero = true)
+{
+    if (*p) { cudaFree(*p); *p = nullptr; }
+    if (n == 0) n = 1;
+    CUDA_TRY(c, cudaMalloc((void **)p, n * sizeof(T)));
+    if (zero) CUDA_TRY(c, cudaMemsetAsync(*p, 0, n * sizeof(T), c->stream));
+    return ADP_OK;
+}
+#define TRY(x)              \
+    do {                    \
+        int rc__ = (x);     \
+        if (rc__) return rc__; \
+    } while (0)
+
+extern "C" int adp_create(adp_ctx **out, int device)
+{
+    if (!out) return ADP_ERR_USAGE;
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        g_create_err = std::string("adp_create: no CUDA device (") + cudaGetErrorString(e) + "); there is no CPU fallback";
+        return ADP_ERR_CUDA;
+    }
+    if (device < 0 || device >= ndev) { g_create_err = "adp_create: bad device index"; return ADP_ERR_USAGE; }
+    adp_ctx *c = new adp_ctx();
+    c->device = device;
+    if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+        g_create_err = std::string("adp_create: ") + cudaGetErrorString(e);
+        delete c;
+        return ADP_ERR_CUDA;
+    }
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, device);
+    c->sm_count = prop.multiProcessorCount;
+    // persistent grids: a multiple of the SM count (148 on B200) x resident CTAs per SM
+    c->grid_blocks = std::min(ADP_MAXPART, c->sm_count * 8);
+    if (dev_alloc(c, &c->d_scal, S_COUNT) || dev_alloc(c, &c->d_part, 4 * ADP_MAXPART) || dev_alloc(c, &c->d_ticket, 1) ||
+        dev_alloc(c, &c->d_argidx, 1) || dev_alloc(c, &c->d_errflag, 1) ||
+        cudaMallocHost((void **)&c->h_scal, (S_COUNT + 8) * sizeof(double)) != cudaSuccess ||
+        cudaMallocHost((void **)&c->h_flags, 8 * sizeof(long long)) != cudaSuccess) {
+        g_create_err = "adp_create: allocation failed: " + c->err;
+        delete c;
+        return ADP_ERR_CUDA;
+    }
+    *out = c;
+    return ADP_OK;
+}
+
+static void free_graphs(adp_ctx *c)
+{
+    for (auto &kv : c->graphs) cudaGraphExecDestroy(kv.second);
+    c->graphs.clear();
+}
+
+extern "C" int adp_destroy(adp_ctx *c)
+{
+    if (!c) return ADP_OK;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    free_graphs(c);
+    adp_comm_destroy(c);
+    void *ptrs[] = {c->d_ypm, c->d_ypp, c->d_ixr, c->d_iyr, c->d_mat, c->d_flag, c->d_hx, c->d_hy, c->d_hz, c->d_area,
+                    c->d_f0[0], c->d_f0[1], c->d_fs[0], c->d_fs[1], c->d_r, c->d_rs, c->d_p, c->d_v, c->d_s, c->d_t,
+                    c->d_s0, c->d_a, c->d_df, c->d_dn, c->d_D, c->d_sigr, c->d_nuf, c->d_sigf, c->d_exsrc, c->d_sigs,
+                    c->d_dc, c->d_chi, c->d_S, c->d_c0, c->d_ft, c->d_fst, c->d_omeg, c->d_sigrp, c->d_L, c->d_dfis,
+                    c->d_tbeta, c->d_velo, c->d_scal, c->d_part, c->d_ticket, c->d_argidx, c->d_errflag, c->d_stage};
+    for (void *p : ptrs) if (p) cudaFree(p);
+    if (c->h_scal) cudaFreeHost(c->h_scal);
+    if (c->h_flags) cudaFreeHost(c->h_flags);
+    if (c->h_stage) cudaFreeHost(c->h_stage);
+    cudaStreamDestroy(c->stream);
+    delete c;
+    return ADP_OK;
+}
+
+extern "C" int adp_slab(const adp_ctx *c, int *k0, int *k1)
+{
+    if (!c || !c->geometry_set) return ADP_ERR_USAGE;
+    if (k0) *k0 = c->k0;
+    if (k1) *k1 = c->k1;
+    return ADP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// host <-> device transfer of node arrays.  Host: Fortran (nnod, ncol) column-major, global.
+// Device: [col][NV] with ghost planes.  `ghost` selects whether the ghost planes inside the
+// core are filled from the (global) host array as well -- static data needs no communication
+// because every rank holds the global arrays.
+// ---------------------------------------------------------------------------------------------
+static int upload_nodes(adp_ctx *c, double *d, const double *h, int ncol, bool ghost)
+{
+    const int np = c->np;
+    const int ka = ghost ? std::max(0, c->k0 - ADP_GH) : c->k0;
+    const int kb = ghost ? std::min(c->nzz, c->k1 + ADP_GH) : c->k1;
+    const size_t cnt = (size_t)(kb - ka) * np;
+    for (int col = 0; col < ncol; ++col) {
+        const double *src = h + (size_t)col * c->nnod + (size_t)ka * np;
+        double *dst = d + (size_t)col * c->NV + (size_t)(ka - (c->k0 - ADP_GH)) * np;
+        CUDA_TRY(c, cudaMemcpyAsync(dst, src, cnt * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    }
+    return ADP_OK;
+}
+static int upload_nodes_int(adp_ctx *c, int *d, const int *h)
+{
+    const int np = c->np;
+    const int ka = std::max(0, c->k0 - ADP_GH), kb = std::min(c->nzz, c->k1 + ADP_GH);
+    CUDA_TRY(c, cudaMemcpyAsync(d + (size_t)(ka - (c->k0 - ADP_GH)) * np, h + (size_t)ka * np,
+                                (size_t)(kb - ka) * np * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    return ADP_OK;
+}
+// own planes of this rank -> the matching part of the global host array
+static int download_nodes(adp_ctx *c, double *h, const double *d, int ncol)
+{
+    const size_t cnt = (size_t)c->nzl * c->np;
+    for (int col = 0; col < ncol; ++col)
+        CUDA_TRY(c, cudaMemcpyAsync(h + (size_t)col * c->nnod + (size_t)c->k0 * c->np,
+                                    d + (size_t)col * c->NV + (size_t)ADP_GH * c->np, cnt * sizeof(double),
+                                    cudaMemcpyDeviceToHost, c->stream));
+    return ADP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+extern "C" int adp_set_geometry(adp_ctx *c, int nxx, int nyy, int nzz, int nnod, int ng, int nmat, const int *ix,
+                                const int *iy, const int *iz, const int *ysmin, const int *ysmax, const int *xsmin,
+                                const int *xsmax, const double *xdel, const double *ydel, const double *zdel,
+                                const int bc[6], const int *mat)
+{
+    if (!c) return ADP_ERR_USAGE;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    ADP_REQUIRE(c, ng >= 1 && ng <= ADP_MAXG, "adp_set_geometry: ng must be 1..16");
+    ADP_REQUIRE(c, nnod > 0 && nzz > 0 && nnod % nzz == 0, "adp_set_geometry: nnod must be np*nzz (plane-invariant core outline)");
+    free_graphs(c);
+    c->nxx = nxx; c->nyy = nyy; c->nzz = nzz; c->nnod = nnod; c->ng = ng; c->nmat = nmat;
+    const int np = nnod / nzz;
+    c->np = np;
+    for (int i = 0; i < 6; ++i) c->bc[i] = bc[i];
+    c->h_ix.assign(ix, ix + nnod); c->h_iy.assign(iy, iy + nnod); c->h_iz.assign(iz, iz + nnod);
+    // numbering must be the reference's: k-major, then j, then i = smin..smax (mod_io.f90:1319-1330)
+    {
+        int n = 0;
+        bool okn = true;
+        for (int j = 1; j <= nyy && okn; ++j)
+            for (int i = ysmin[j - 1]; i <= ysmax[j - 1]; ++i, ++n)
+                if (n >= np || ix[n] != i || iy[n] != j || iz[n] != 1) { okn = false; break; }
+        ADP_REQUIRE(c, okn && n == np, "adp_set_geometry: node numbering is not the reference's k,j,i order");
+        ADP_REQUIRE(c, iz[nnod - 1] == nzz && ix[nnod - 1] == ix[np - 1], "adp_set_geometry: planes differ");
+    }
+    // z-slab of this rank
+    {
+        const int base = nzz / c->nranks, rem = nzz % c->nranks;
+        c->k0 = c->rank * base + std::min(c->rank, rem);
+        c->k1 = c->k0 + base + (c->rank < rem ? 1 : 0);
+        c->nzl = c->k1 - c->k0;
+        ADP_REQUIRE(c, c->nzl >= ((c->nranks > 1) ? 2 : 1), "adp_set_geometry: fewer than 2 planes per rank");
+    }
+    c->NL = (long long)np * c->nzl;
+    c->NV = (long long)np * (c->nzl + 2 * ADP_GH);
+    // plane tables
+    std::vector<int> nodp((size_t)nxx * nyy, 0), ypm(np), ypp(np), ixr(np), iyr(np);
+    std::vector<unsigned char> flag(np);
+    std::vector<double> hx(np), hy(np), area(np), hz(nzz + 2, 0.0);
+    for (int r = 0; r < np; ++r) nodp[(size_t)(iy[r] - 1) * nxx + (ix[r] - 1)] = r + 1;
+    for (int r = 0; r < np; ++r) {
+        const int i = ix[r], j = iy[r];
+        unsigned f = 0;
+        if (i == ysmin[j - 1]) f |= FLAG_XM;
+        if (i == ysmax[j - 1]) f |= FLAG_XP;
+        if (j == xsmin[i - 1]) f |= FLAG_YM;
+        if (j == xsmax[i - 1]) f |= FLAG_YP;
+        flag[r] = (unsigned char)f;
+        // set_ind: n -+ (nodp(i,j) - nodp(i,j-+1))   (mod_cmfd.f90:180,202)
+        ypm[r] = (f & FLAG_YM) ? 0 : (r + 1) - nodp[(size_t)(j - 2) * nxx + (i - 1)];
+        ypp[r] = (f & FLAG_YP) ? 0 : nodp[(size_t)j * nxx + (i - 1)] - (r + 1);
+        ADP_REQUIRE(c, ypm[r] >= 0 && ypp[r] >= 0 && ((f & FLAG_YM) || ypm[r] > 0) && ((f & FLAG_YP) || ypp[r] > 0),
+                    "adp_set_geometry: inconsistent staggering (ystag/xstag)");
+        ixr[r] = i; iyr[r] = j;
+        hx[r] = xdel[i - 1]; hy[r] = ydel[j - 1];
+        area[r] = xdel[i - 1] * ydel[j - 1];
+    }
+    for (int k = 0; k < nzz; ++k) hz[1 + k] = zdel[k];
+    hz[0] = zdel[0]; hz[nzz + 1] = zdel[nzz - 1];
+    TRY(dev_alloc(c, &c->d_ypm, np)); TRY(dev_alloc(c, &c->d_ypp, np)); TRY(dev_alloc(c, &c->d_ixr, np));
+    TRY(dev_alloc(c, &c->d_iyr, np)); TRY(dev_alloc(c, &c->d_flag, np)); TRY(dev_alloc(c, &c->d_hx, np + 2));
+    TRY(dev_alloc(c, &c->d_hy, np)); TRY(dev_alloc(c, &c->d_area, np)); TRY(dev_alloc(c, &c->d_hz, nzz + 2));
+    CUDA_TRY(c, cudaMemcpyAsync(c->d_ypm, ypm.data(), np * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(c, cudaMemcpyAsync(c->d_ypp, ypp.data(), np * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(c, cudaMemcpyAsync(c->d_ixr, ixr.data(), np * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(c, cudaMemcpyAsync(c->d_iyr, iyr.data(), np * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(c, cudaMemcpyAsync(c->d_flag, flag.data(), np, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(c, cudaMemcpyAsync(c->d_hx + 1, hx.data(), np * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(c, cudaMemcpyAsync(c->d_hy, hy.data(), np * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(c, cudaMemcpyAsync(c->d_area, area.data(), np * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(c, cudaMemcpyAsync(c->d_hz, hz.data(), (nzz + 2) * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));   // the std::vectors die at return
+
+    Geo &G = c->geo;
+    G.np = np; G.nzl = c->nzl; G.nzz = nzz; G.k0 = c->k0;
+    G.tpp = (np + ADP_TILE - 1) / ADP_TILE;
+    G.ntiles = G.tpp * c->nzl;
+    G.NV = c->NV;
+    for (int i = 0; i < 6; ++i) G.bc[i] = bc[i];
+    G.ypm = c->d_ypm; G.ypp = c->d_ypp; G.flag = c->d_flag; G.hx = c->d_hx + 1; G.hy = c->d_hy; G.hz = c->d_hz;
+    G.area = c->d_area; G.ixr = c->d_ixr; G.iyr = c->d_iyr;
+
+    const size_t NV = (size_t)c->NV, Gn = (size_t)ng;
+    TRY(dev_alloc(c, &c->d_mat, NV));
+    {   // ghost planes outside the core keep material 1 so that table look-ups stay in range
+        std::vector<int> ones(NV, 1);
+        CUDA_TRY(c, cudaMemcpy(c->d_mat, ones.data(), NV * sizeof(int), cudaMemcpyHostToDevice));
+    }
+    TRY(upload_nodes_int(c, c->d_mat, mat));
+    for (int w = 0; w < 2; ++w) { TRY(dev_alloc(c, &c->d_f0[w], Gn * NV)); TRY(dev_alloc(c, &c->d_fs[w], NV)); }
+    TRY(dev_alloc(c, &c->d_r, NV)); TRY(dev_alloc(c, &c->d_rs, NV)); TRY(dev_alloc(c, &c->d_p, NV));
+    TRY(dev_alloc(c, &c->d_v, NV)); TRY(dev_alloc(c, &c->d_s, NV)); TRY(dev_alloc(c, &c->d_t, NV));
+    TRY(dev_alloc(c, &c->d_s0, NV));
+    TRY(dev_alloc(c, &c->d_a, Gn * 7 * NV));
+    TRY(dev_alloc(c, &c->d_df, Gn * 6 * NV)); TRY(dev_alloc(c, &c->d_dn, Gn * 6 * NV));
+    TRY(dev_alloc(c, &c->d_D, Gn * NV)); TRY(dev_alloc(c, &c->d_sigr, Gn * NV)); TRY(dev_alloc(c, &c->d_nuf, Gn * NV));
+    TRY(dev_alloc(c, &c->d_sigf, Gn * NV)); TRY(dev_alloc(c, &c->d_exsrc, Gn * NV));
+    TRY(dev_alloc(c, &c->d_sigs, Gn * Gn * NV)); TRY(dev_alloc(c, &c->d_dc, 6 * Gn * NV));
+    TRY(dev_alloc(c, &c->d_chi, Gn * nmat)); TRY(dev_alloc(c, &c->d_S, 3 * Gn * NV));
+    TRY(dev_alloc(c, &c->d_tbeta, nmat)); TRY(dev_alloc(c, &c->d_dfis, NV)); TRY(dev_alloc(c, &c->d_velo, ng));
+    TRY(dev_alloc(c, &c->d_stage, NV));
+    // D must stay non-zero on ghost planes outside the core (divisions in coup_coef never use
+    // them, but keep every table finite): initialise to 1
+    c->geometry_set = true;
+    c->xs_set = false; c->matrix_ready = false; c->have_flux = false; c->coup_first = true;
+    c->outer_first = c->outer_ad_first = true;
+    c->ndmax = 0.0; c->s0_group = 0;
+    for (int g = 0; g < ADP_MAXG; ++g) c->cur[g] = 0;
+    c->fcur = 0;
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return ADP_OK;
+}
+
+static int ensure_transient(adp_ctx *c)
+{
+    if (c->d_c0) return ADP_OK;
+    const size_t NV = (size_t)c->NV, Gn = (size_t)c->ng;
+    TRY(dev_alloc(c, &c->d_c0, ADP_NF * NV)); TRY(dev_alloc(c, &c->d_ft, Gn * NV)); TRY(dev_alloc(c, &c->d_fst, NV));
+    TRY(dev_alloc(c, &c->d_omeg, Gn * NV)); TRY(dev_alloc(c, &c->d_sigrp, Gn * NV)); TRY(dev_alloc(c, &c->d_L, Gn * NV));
+    return ADP_OK;
+}
+
+extern "C" int adp_set_xs(adp_ctx *c, const double *D, const double *sigr, const double *nuf, const double *sigf,
+                          const double *sigs, const double *chi, const double *dc, const double *exsrc)
+{
+    if (!c) return ADP_ERR_USAGE;
+    ADP_REQUIRE(c, c->geometry_set, "adp_set_xs: call adp_set_geometry first");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    const int G = c->ng;
+    if (D) TRY(upload_nodes(c, c->d_D, D, G, true));
+    if (sigr) TRY(upload_nodes(c, c->d_sigr, sigr, G, true));
+    if (nuf) TRY(upload_nodes(c, c->d_nuf, nuf, G, true));
+    if (sigf) TRY(upload_nodes(c, c->d_sigf, sigf, G, true));
+    if (sigs) TRY(upload_nodes(c, c->d_sigs, sigs, G * G, true));   // host (n,g,h): column g + G*h = device [h][g]
+    if (dc) {
+        // host dc(n,g,f): column g + G*f -> device [f][g]
+        TRY(upload_nodes(c, c->d_dc, dc, G * 6, true));
+    }
+    if (exsrc) TRY(upload_nodes(c, c->d_exsrc, exsrc, G, true));
+    if (chi) {
+        // host chi(nmat, ng) column-major = [g][nmat]
+        CUDA_TRY(c, cudaMemcpyAsync(c->d_chi, chi, (size_t)G * c->nmat * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    }
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    if (D && sigr && nuf && sigf && sigs && chi && dc && exsrc) c->xs_set = true;
+    return ADP_OK;
+}
+
+extern "C" int adp_set_control(adp_ctx *c, int nout, int nin, int nac, int nupd, double serc, double ferc, int kern)
+{
+    if (!c) return ADP_ERR_USAGE;
+    ADP_REQUIRE(c, nin >= 0 && nac >= 1 && nupd >= 1 && nout >= 1, "adp_set_control: bad iteration control");
+    ADP_REQUIRE(c, kern >= ADP_KERN_FDM && kern <= ADP_KERN_SANM, "adp_set_control: kern must be 0 FDM, 1 PNM, 2 SANM");
+    if (nin != c->nin) free_graphs(c);
+    c->nout = nout; c->nin = nin; c->nac = nac; c->nupd = nupd; c->serc = serc; c->ferc = ferc; c->kern = kern;
+    return ADP_OK;
+}
+
+extern "C" int adp_matrix_setup(adp_ctx *c, int opt)
+{
+    if (!c) return ADP_ERR_USAGE;
+    ADP_REQUIRE(c, c->xs_set, "adp_matrix_setup: cross sections not set");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    if (opt > 0) {
+        if (c->coup_first) {   // nod%dn = 0 on the first call (mod_cmfd.f90:25-33)
+            CUDA_TRY(c, cudaMemsetAsync(c->d_dn, 0, (size_t)c->ng * 6 * c->NV * sizeof(double), c->stream));
+            c->coup_first = false;
+        }
+        TRY(adp_k_coup_coef(c));
+    }
+    TRY(adp_k_matrix_setup(c));
+    c->matrix_ready = true;
+    return ADP_OK;
+}
+
+extern "C" int adp_init_flux(adp_ctx *c, int adjoint)
+{
+    if (!c) return ADP_ERR_USAGE;
+    ADP_REQUIRE(c, c->xs_set, "adp_init_flux: cross sections not set");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    return adp_k_init_flux(c, adjoint);
+}
+
+extern "C" int adp_outer_begin(adp_ctx *c, int mode)
+{
+    if (!c) return ADP_ERR_USAGE;
+    ADP_REQUIRE(c, c->have_flux && c->matrix_ready, "adp_outer_begin: needs adp_matrix_setup and a flux (adp_init_flux/adp_set_state)");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    return adp_k_outer_begin(c, mode);
+}
+
+// ---- one outer iteration -----------------------------------------------------------------
+static int issue_outer_iter(adp_ctx *c, int mode, bool extrap)
+{
+    const int G = c->ng;
+    if (mode == ADP_MODE_ADJOINT) {
+        for (int g = G - 1; g >= 0; --g) TRY(adp_k_bicg_group(c, mode, g, c->nin, g == 0));
+    } else {
+        for (int g = 0; g < G; ++g) TRY(adp_k_bicg_group(c, mode, g, c->nin, g == G - 1));
+    }
+    TRY(adp_k_outer_tail(c, mode, extrap));
+    CUDA_TRY(c, cudaMemcpyAsync(c->h_scal, c->d_scal, S_COUNT * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    return ADP_OK;
+}
+
+extern "C" int adp_outer_iter(adp_ctx *c, int mode, int p, double *Ke, double *ser, double *fer)
+{
+    if (!c) return ADP_ERR_USAGE;
+    ADP_REQUIRE(c, c->have_flux && c->matrix_ready, "adp_outer_iter: needs adp_matrix_setup and a flux");
+    ADP_REQUIRE(c, mode >= ADP_MODE_FORWARD && mode <= ADP_MODE_TRANSIENT, "adp_outer_iter: bad mode");
+    ADP_REQUIRE(c, mode != ADP_MODE_TRANSIENT || c->kinetics_set, "adp_outer_iter: transient mode needs adp_set_kinetics");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    const bool extrap = (p % c->nac) == 0;
+    bool use_graph = c->use_graphs && c->nranks == 1;
+    if (use_graph) {
+        unsigned long long key = (unsigned long long)mode | ((unsigned long long)(extrap ? 1 : 0) << 4) |
+                                 ((unsigned long long)c->fcur << 5);
+        for (int g = 0; g < c->ng; ++g) key |= (unsigned long long)c->cur[g] << (8 + g);
+        auto it = c->graphs.find(key);
+        if (it == c->graphs.end()) {
+            cudaGraph_t graph = nullptr;
+            const long long l0 = c->launches;
+            const int s0g = c->s0_group, fcur = c->fcur;
+            int cur[ADP_MAXG];
+            memcpy(cur, c->cur, sizeof(cur));
+            CUDA_TRY(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+            int rc = issue_outer_iter(c, mode, extrap);
+            cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
+            if (rc) return rc;
+            CUDA_TRY(c, e);
+            cudaGraphExec_t exec = nullptr;
+            CUDA_TRY(c, cudaGraphInstantiate(&exec, graph, 0));
+            cudaGraphDestroy(graph);
+            // capture advanced the host-side bookkeeping once; undo it, the launch below redoes it
+            c->graph_launches[key] = c->launches - l0;
+            c->launches = l0; c->s0_group = s0g; c->fcur = fcur;
+            memcpy(c->cur, cur, sizeof(cur));
+            it = c->graphs.emplace(key, exec).first;
+        }
+        CUDA_TRY(c, cudaGraphLaunch(it->second, c->stream));
+        // host bookkeeping of what the graph did
+        for (int g = 0; g < c->ng; ++g) c->cur[g] ^= 1;
+        c->fcur ^= 1;
+        c->s0_group = (mode == ADP_MODE_ADJOINT) ? 1 : c->ng;
+        c->launches += c->graph_launches[key];
+    } else {
+        TRY(issue_outer_iter(c, mode, extrap));
+    }
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    if (Ke) *Ke = c->h_scal[S_KE];
+    if (ser) *ser = c->h_scal[S_SER];
+    if (fer) *fer = c->h_scal[S_FER];
+    return ADP_OK;
+}
+
+extern "C" int adp_nodal_upd(adp_ctx *c, int nmode, double *ndmax, int *im, int *jm, int *km)
+{
+    if (!c) return ADP_ERR_USAGE;
+    ADP_REQUIRE(c, c->have_flux && c->matrix_ready, "adp_nodal_upd: needs adp_matrix_setup and a flux");
+    ADP_REQUIRE(c, c->kern != ADP_KERN_FDM, "adp_nodal_upd: kern is FDM");
+    ADP_REQUIRE(c, nmode != 2 || c->kinetics_set, "adp_nodal_upd: cmode 2 needs adp_set_kinetics");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    // ndmax = 0 (mod_cmfd.f90:358); the location keeps its previous value if nothing changes
+    CUDA_TRY(c, cudaMemsetAsync(c->d_scal + S_NDMAX, 0, sizeof(double), c->stream));
+    CUDA_TRY(c, cudaMemsetAsync(c->d_errflag, 0, sizeof(int), c->stream));
+    TRY(adp_k_nodal_update(c, nmode));
+    if (c->nranks > 1) {
+        // global maximum and, among the ranks holding it, the lowest node number
+        CUDA_TRY(c, cudaMemcpyAsync(c->d_scal + S_TMP0, c->d_scal + S_NDMAX, sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+        TRY(adp_comm_allreduce_max(c, c->d_scal + S_NDMAX, 1));
+        CUDA_TRY(c, cudaMemcpyAsync(c->h_scal, c->d_scal, S_COUNT * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+        if (c->h_scal[S_TMP0] != c->h_scal[S_NDMAX]) {
+            long long big = 0x7fffffffffffffffLL;
+            CUDA_TRY(c, cudaMemcpyAsync(c->d_argidx, &big, sizeof(big), cudaMemcpyHostToDevice, c->stream));
+        }
+        TRY(adp_comm_allreduce_min_ll(c, c->d_argidx, 1));
+        int flag = 0;
+        CUDA_TRY(c, cudaMemcpyAsync(&flag, c->d_errflag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+        double f = flag;
+        CUDA_TRY(c, cudaMemcpyAsync(c->d_scal + S_TMP1, &f, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        TRY(adp_comm_allreduce_max(c, c->d_scal + S_TMP1, 1));
+        CUDA_TRY(c, cudaMemcpyAsync(&f, c->d_scal + S_TMP1, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+        flag = (int)f;
+        CUDA_TRY(c, cudaMemcpyAsync(c->d_errflag, &flag, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    }
+    TRY(adp_k_matrix_setup(c));   // matrix_setup(0), mod_cmfd.f90:366
+    CUDA_TRY(c, cudaMemcpyAsync(c->h_scal, c->d_scal, S_COUNT * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaMemcpyAsync(c->h_flags, c->d_argidx, sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaMemcpyAsync(c->h_flags + 2, c->d_errflag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    c->ndmax = c->h_scal[S_NDMAX];
+    if (c->ndmax > 0.0) {
+        const long long loc = *(long long *)c->h_flags;
+        if (loc >= 0 && loc < c->nnod) { c->im = c->h_ix[loc]; c->jm = c->h_iy[loc]; c->km = c->h_iz[loc]; }
+    }
+    if (ndmax) *ndmax = c->ndmax;
+    if (im) *im = c->im;
+    if (jm) *jm = c->jm;
+    if (km) *km = c->km;
+    if (c->h_flags[2] != 0) { c->err = "ERROR IN MATRIX DECOMP: DIAGONAL ELEMENTS CLOSE TO ZERO"; return ADP_STOP_LU_DIAG; }
+    if (c->ndmax > 1.e3) { c->err = "Max. change in nodal coupling coefficient > 1e3: the two-node nonlinear iteration seems not stable"; return ADP_STOP_NDMAX; }
+    return ADP_OK;
+}
+
+extern "C" int adp_get_ndmax(adp_ctx *c, double *ndmax)
+{
+    if (!c || !ndmax) return ADP_ERR_USAGE;
+    *ndmax = c->ndmax;
+    return ADP_OK;
+}
+
+extern "C" int adp_powdis(adp_ctx *c, double *p, int fixedsrc_mode)
+{
+    if (!c || !p) return ADP_ERR_USAGE;
+    ADP_REQUIRE(c, c->have_flux, "adp_powdis: no flux");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    TRY(adp_k_powdis(c, c->d_stage));
+    CUDA_TRY(c, cudaMemcpyAsync(c->h_scal, c->d_scal, S_COUNT * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    if (c->h_scal[S_POW] <= 0.0 && !fixedsrc_mode) { c->err = "ERROR: TOTAL NODES POWER IS ZERO OR LESS"; return ADP_STOP_ZERO_POWER; }
+    TRY(adp_k_scale_by_slot(c, c->d_stage, S_POW));
+    TRY(download_nodes(c, p, c->d_stage, 1));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return ADP_OK;
+}
+
+extern "C" int adp_integrate(adp_ctx *c, const double *s, double *result)
+{
+    if (!c || !s || !result) return ADP_ERR_USAGE;
+    ADP_REQUIRE(c, c->geometry_set, "adp_integrate: geometry not set");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    TRY(upload_nodes(c, c->d_stage, s, 1, false));
+    TRY(adp_k_integrate(c, c->d_stage, S_TMP0));
+    CUDA_TRY(c, cudaMemcpyAsync(c->h_scal, c->d_scal, S_COUNT * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    *result = c->h_scal[S_TMP0];
+    return ADP_OK;
+}
+
+// ---- transient ------------------------------------------------------------------------------
+extern "C" int adp_set_kinetics(adp_ctx *c, const double *ibeta, const double *lamb, const double *velo,
+                                const double *tbeta, double sth, double bth)
+{
+    if (!c) return ADP_ERR_USAGE;
+    ADP_REQUIRE(c, c->geometry_set, "adp_set_kinetics: geometry not set");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    for (int i = 0; i < ADP_NF; ++i) { c->ibeta[i] = ibeta[i]; c->lamb[i] = lamb[i]; }
+    c->sth = sth; c->bth = bth;
+    CUDA_TRY(c, cudaMemcpyAsync(c->d_velo, velo, c->ng * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(c, cudaMemcpyAsync(c->d_tbeta, tbeta, c->nmat * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    TRY(ensure_transient(c));
+    c->kinetics_set = true;
+    return ADP_OK;
+}
+
+extern "C" int adp_set_transient(adp_ctx *c, const double *c0, const double *ft, const double *fst, const double *omeg,
+                                 const double *sigrp, const double *L)
+{
+    if (!c) return ADP_ERR_USAGE;
+    ADP_REQUIRE(c, c->geometry_set, "adp_set_transient: geometry not set");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    TRY(ensure_transient(c));
+    if (c0) TRY(upload_nodes(c, c->d_c0, c0, ADP_NF, false));
+    if (ft) TRY(upload_nodes(c, c->d_ft, ft, c->ng, false));
+    if (fst) TRY(upload_nodes(c, c->d_fst, fst, 1, false));
+    if (omeg) TRY(upload_nodes(c, c->d_omeg, omeg, c->ng, false));
+    if (sigrp) TRY(upload_nodes(c, c->d_sigrp, sigrp, c->ng, false));
+    if (L) TRY(upload_nodes(c, c->d_L, L, c->ng, false));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return ADP_OK;
+}
+
+extern "C" int adp_get_exsrc(adp_ctx *c, double ht)
+{
+    if (!c) return ADP_ERR_USAGE;
+    ADP_REQUIRE(c, c->kinetics_set, "adp_get_exsrc: needs adp_set_kinetics");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    return adp_k_get_exsrc(c, ht);
+}
+
+extern "C" int adp_get_exsrc_arrays(adp_ctx *c, double *exsrc, double *dfis)
+{
+    if (!c) return ADP_ERR_USAGE;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    if (exsrc) TRY(download_nodes(c, exsrc, c->d_exsrc, c->ng));
+    if (dfis) TRY(download_nodes(c, dfis, c->d_dfis, 1));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return ADP_OK;
+}
+
+// ---- state ------------------------------------------------------------------------------------
+extern "C" int adp_get_state(adp_ctx *c, double *f0, double *fs0, double *s0, double *Ke)
+{
+    if (!c) return ADP_ERR_USAGE;
+    ADP_REQUIRE(c, c->have_flux, "adp_get_state: no flux yet");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    if (f0)
+        for (int g = 0; g < c->ng; ++g)
+            TRY(download_nodes(c, f0 + (size_t)g * c->nnod, c->d_f0[c->cur[g]] + (size_t)g * c->NV, 1));
+    if (fs0) TRY(download_nodes(c, fs0, c->d_fs[c->fcur], 1));
+    if (s0) {
+        // TSrc* zero all of s0 and fill only the column of the group being solved
+        // (mod_cmfd.f90:1022,1053,1084): after an outer iteration only the last group's column is non-zero
+        for (int g = 0; g < c->ng; ++g) {
+            double *dst = s0 + (size_t)g * c->nnod + (size_t)c->k0 * c->np;
+            if (g + 1 == c->s0_group) TRY(download_nodes(c, s0 + (size_t)g * c->nnod, c->d_s0, 1));
+            else memset(dst, 0, (size_t)c->nzl * c->np * sizeof(double));
+        }
+    }
+    CUDA_TRY(c, cudaMemcpyAsync(c->h_scal, c->d_scal, S_COUNT * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    if (Ke) *Ke = c->h_scal[S_KE];
+    return ADP_OK;
+}
+
+extern "C" int adp_set_state(adp_ctx *c, const double *f0, const double *fs0, double Ke)
+{
+    if (!c) return ADP_ERR_USAGE;
+    ADP_REQUIRE(c, c->geometry_set, "adp_set_state: geometry not set");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    if (f0)
+        for (int g = 0; g < c->ng; ++g)
+            TRY(upload_nodes(c, c->d_f0[c->cur[g]] + (size_t)g * c->NV, f0 + (size_t)g * c->nnod, 1, false));
+    if (fs0) TRY(upload_nodes(c, c->d_fs[c->fcur], fs0, 1, false));
+    CUDA_TRY(c, cudaMemcpyAsync(c->d_scal + S_KE, &Ke, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    if (f0 && fs0) c->have_flux = true;
+    c->outer_first = false;
+    return ADP_OK;
+}
+
+extern "C" int adp_set_s0(adp_ctx *c, const double *s0, int g)
+{
+    if (!c) return ADP_ERR_USAGE;
+    ADP_REQUIRE(c, c->geometry_set && g >= 0 && g <= c->ng, "adp_set_s0: geometry not set or bad group");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    if (g > 0) {
+        ADP_REQUIRE(c, s0 != nullptr, "adp_set_s0: s0 missing");
+        TRY(upload_nodes(c, c->d_s0, s0 + (size_t)(g - 1) * c->nnod, 1, false));
+        CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    }
+    c->s0_group = g;
+    return ADP_OK;
+}
+
+// device [g][6][NV]  <->  host df(6, nnod, ng) (face fastest) via the pinned staging buffer
+static int ensure_host_stage(adp_ctx *c, size_t elems)
+{
+    if (c->stage_elems >= elems) return ADP_OK;
+    if (c->h_stage) cudaFreeHost(c->h_stage);
+    c->h_stage = nullptr;
+    CUDA_TRY(c, cudaMallocHost((void **)&c->h_stage, elems * sizeof(double)));
+    c->stage_elems = elems;
+    return ADP_OK;
+}
+
+extern "C" int adp_get_nod(adp_ctx *c, double *df, double *dn)
+{
+    if (!c) return ADP_ERR_USAGE;
+    ADP_REQUIRE(c, c->matrix_ready, "adp_get_nod: call adp_matrix_setup first");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    const size_t NL = (size_t)c->NL, off = (size_t)c->k0 * c->np;
+    TRY(ensure_host_stage(c, NL));
+    for (int which = 0; which < 2; ++which) {
+        double *dst = which ? dn : df;
+        const double *src = which ? c->d_dn : c->d_df;
+        if (!dst) continue;
+        for (int g = 0; g < c->ng; ++g)
+            for (int f = 0; f < 6; ++f) {
+                CUDA_TRY(c, cudaMemcpyAsync(c->h_stage, src + ((size_t)g * 6 + f) * c->NV + (size_t)ADP_GH * c->np,
+                                            NL * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+                CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+                double *o = dst + ((size_t)g * c->nnod + off) * 6 + f;
+                for (size_t n = 0; n < NL; ++n) o[n * 6] = c->h_stage[n];
+            }
+    }
+    return ADP_OK;
+}
+
+extern "C" int adp_set_nod_dn(adp_ctx *c, const double *dn)
+{
+    if (!c || !dn) return ADP_ERR_USAGE;
+    ADP_REQUIRE(c, c->geometry_set, "adp_set_nod_dn: geometry not set");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    // include one ghost plane on interior slab boundaries
+    const int ka = std::max(0, c->k0 - 1), kb = std::min(c->nzz, c->k1 + 1);
+    const size_t cnt = (size_t)(kb - ka) * c->np, off = (size_t)ka * c->np;
+    TRY(ensure_host_stage(c, cnt));
+    for (int g = 0; g < c->ng; ++g)
+        for (int f = 0; f < 6; ++f) {
+            const double *in = dn + ((size_t)g * c->nnod + off) * 6 + f;
+            for (size_t n = 0; n < cnt; ++n) c->h_stage[n] = in[n * 6];
+            CUDA_TRY(c, cudaMemcpyAsync(c->d_dn + ((size_t)g * 6 + f) * c->NV + (size_t)(ka - (c->k0 - ADP_GH)) * c->np,
+                                        c->h_stage, cnt * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+            CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+        }
+    c->coup_first = false;
+    return ADP_OK;
+}
+
+// ---- kernel-level entry points --------------------------------------------------------------
+extern "C" int adp_sp_matvec(adp_ctx *c, int g, const double *x, double *v)
+{
+    if (!c || !x || !v) return ADP_ERR_USAGE;
+    ADP_REQUIRE(c, c->matrix_ready && g >= 1 && g <= c->ng, "adp_sp_matvec: matrix not set up or bad group");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    TRY(upload_nodes(c, c->d_p, x, 1, false));
+    TRY(adp_k_spmv(c, g - 1, c->d_p, c->d_v));
+    TRY(download_nodes(c, v, c->d_v, 1));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return ADP_OK;
+}
+
+extern "C" int adp_bicg(adp_ctx *c, int imax, int g, const double *b, double *x)
+{
+    if (!c || !b || !x) return ADP_ERR_USAGE;
+    ADP_REQUIRE(c, c->matrix_ready && g >= 1 && g <= c->ng, "adp_bicg: matrix not set up or bad group");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    TRY(upload_nodes(c, c->d_stage, b, 1, false));
+    // x lives in the spare flux buffer of group g
+    double *dx = c->d_f0[c->cur[g - 1] ^ 1] + (size_t)(g - 1) * c->NV;
+    TRY(upload_nodes(c, dx, x, 1, false));
+    TRY(adp_k_bicg_raw(c, g - 1, imax, c->d_stage, dx));
+    TRY(download_nodes(c, x, dx, 1));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return ADP_OK;
+}
+
+extern "C" int adp_get_matrix(adp_ctx *c, double *a)
+{
+    if (!c || !a) return ADP_ERR_USAGE;
+    ADP_REQUIRE(c, c->matrix_ready, "adp_get_matrix: matrix not set up");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    const size_t NL = (size_t)c->NL, off = (size_t)c->k0 * c->np;
+    TRY(ensure_host_stage(c, NL));
+    for (int g = 0; g < c->ng; ++g)
+        for (int d = 0; d < 7; ++d) {
+            CUDA_TRY(c, cudaMemcpyAsync(c->h_stage, c->d_a + ((size_t)g * 7 + d) * c->NV + (size_t)ADP_GH * c->np,
+                                        NL * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+            CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+            double *o = a + ((size_t)g * c->nnod + off) * 7 + d;
+            for (size_t n = 0; n < NL; ++n) o[n * 7] = c->h_stage[n];
+        }
+    return ADP_OK;
+}
+
+extern "C" int adp_get_source(adp_ctx *c, int cmode, double *S1, double *S2, double *S3)
+{
+    if (!c) return ADP_ERR_USAGE;
+    ADP_REQUIRE(c, c->have_flux && c->matrix_ready, "adp_get_source: needs matrix and flux");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    TRY(adp_k_nodal_source(c, cmode));
+    double *out[3] = {S1, S2, S3};
+    for (int u = 0; u < 3; ++u)
+        if (out[u]) TRY(download_nodes(c, out[u], c->d_S + (size_t)u * c->ng * c->NV, c->ng));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return ADP_OK;
+}
+
+extern "C" int adp_set_trace(adp_ctx *c, adp_trace_fn fn, void *user)
+{
+    if (!c) return ADP_ERR_USAGE;
+    c->trace = fn; c->trace_user = user;
+    return ADP_OK;
+}
+
+extern "C" int adp_launch_count(const adp_ctx *c, long long *launches)
+{
+    if (!c || !launches) return ADP_ERR_USAGE;
+    *launches = c->launches;
+    return ADP_OK;
+}
+
+extern "C" int adp_set_option(adp_ctx *c, const char *name, int value)
+{
+    if (!c || !name) return ADP_ERR_USAGE;
+    if (!strcmp(name, "graphs")) { c->use_graphs = value != 0; free_graphs(c); return ADP_OK; }
+    if (!strcmp(name, "grid_blocks")) {
+        ADP_REQUIRE(c, value >= 1 && value <= ADP_MAXPART, "grid_blocks out of range");
+        c->grid_blocks = value; free_graphs(c); return ADP_OK;
+    }
+    c->err = std::string("unknown option ") + name;
+    return ADP_ERR_USAGE;
+}
+
+// device-resident micro-benchmarks (no host copies inside the timed region) ------------------
+extern "C" int adp_bench_kernel(adp_ctx *c, int what, int reps, double *avg_ms)
+{
+    if (!c || !avg_ms || reps < 1) return ADP_ERR_USAGE;
+    ADP_REQUIRE(c, c->have_flux && c->matrix_ready, "adp_bench_kernel: needs matrix and flux");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    cudaEvent_t e0, e1;
+    CUDA_TRY(c, cudaEventCreate(&e0));
+    CUDA_TRY(c, cudaEventCreate(&e1));
+    int rc = ADP_OK;
+    auto body = [&](int i) -> int {
+        switch (what) {
+        case 0: return adp_k_spmv(c, i % c->ng, c->d_p, c->d_v);
+        case 2: return adp_k_bicg_raw(c, i % c->ng, c->nin, c->d_stage, c->d_s0);
+        default: return ADP_ERR_UNSUPPORTED;
+        }
+    };
+    for (int i = 0; i < 3 && !rc; ++i) rc = body(i);
+    CUDA_TRY(c, cudaEventRecord(e0, c->stream));
+    for (int i = 0; i < reps && !rc; ++i) rc = body(i);
+    CUDA_TRY(c, cudaEventRecord(e1, c->stream));
+    CUDA_TRY(c, cudaEventSynchronize(e1));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    *avg_ms = (double)ms / reps;
+    return rc;
+}

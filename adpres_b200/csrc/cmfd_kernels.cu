@@ -1,0 +1,808 @@
+// cmfd_kernels.cu -- hand-written sm_100a kernels for the CMFD part of the hot path
+// (reference: src/mod_cmfd.f90).  Everything here is HBM-bound fp64 stencil / vector work;
+// there is no dense contraction, so no tensor cores.  Compiled with -fmad=false: every
+// product and sum is rounded exactly as the reference's (gfortran -O4, no FMA contraction),
+// so the only arithmetic difference to the reference is the order of the global reductions.
+//
+// Kernel list (one BiCGSTAB iteration = B, C, D [+ A from the 2nd iteration on]):
+//   k_coup_coef      coup_coef                         mod_cmfd.f90:11-137
+//   k_matrix_setup   matrix_setup -> 7 diagonals       mod_cmfd.f90:217-304
+//   k_residual  (P)  TSrc*/bs, r = bs - A x, rs = r, p = r, rho = (rs,r)   :1006-1096,1223-1226
+//   k_update_p  (A)  p = r + beta (p - omega v)                            :1231-1232
+//   k_spmv_dot  (B)  v = A p, (rs,v)                                       :1233-1234
+//   k_st        (C)  s = r - alpha v (on the fly), t = A s, (t,t), (t,s)   :1235-1238
+//   k_update_xr (D)  x += alpha p + omega s, r = s - omega t, rho=(rs,r)   :1239-1240,1230
+//   k_fsrc_norms(F)  FSrc*, errn, l2norm, Integrate, RelE, RelEg           :479-487,956-1002,1100-1199
+//   k_extrap    (E)  fiss_extrp, Integrate, RelE                           :308-335
+//   k_scalar_*       the handful of scalar statements of the outer loop    :467-485
+#include "adp_internal.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------
+// deterministic grid-wide reductions: warp shuffle -> shared memory -> one partial per block
+// -> the last block to finish (atomic ticket) combines the partials in a fixed order.
+// NS sums followed by NM maxima; results go to scal[slot[i]].
+// ------------------------------------------------------------------------------------------
+struct RedOut {
+    double *scal;        // device scalar array
+    double *part;        // [4][ADP_MAXPART]
+    unsigned int *ticket;
+    int slot[4];
+};
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = v + __shfl_down_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_down_sync(0xffffffffu, v, o));
+    return v;
+}
+
+template <int NS, int NM>
+__device__ __forceinline__ void grid_reduce(double (&val)[NS + NM], const RedOut &ro)
+{
+    constexpr int NVAL = NS + NM;
+    __shared__ double sm[NVAL][ADP_TILE / 32];
+    __shared__ bool is_last;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < NVAL; ++i) {
+        double w = (i < NS) ? warp_sum(val[i]) : warp_max(val[i]);
+        if (lane == 0) sm[i][wid] = w;
+    }
+    __syncthreads();
+    if (wid == 0) {
+#pragma unroll
+        for (int i = 0; i < NVAL; ++i) {
+            double w = (lane < ADP_TILE / 32) ? sm[i][lane] : 0.0;
+            w = (i < NS) ? warp_sum(w) : warp_max(w);
+            if (lane == 0) ro.part[i * ADP_MAXPART + blockIdx.x] = w;
+        }
+    }
+    if (threadIdx.x == 0) {
+        __threadfence();
+        unsigned int t = atomicAdd(ro.ticket, 1u);
+        is_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    double acc[NVAL];
+#pragma unroll
+    for (int i = 0; i < NVAL; ++i) {
+        acc[i] = 0.0;
+        for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) {
+            double w = __ldcg(&ro.part[i * ADP_MAXPART + b]);
+            acc[i] = (i < NS) ? acc[i] + w : fmax(acc[i], w);
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < NVAL; ++i) {
+        double w = (i < NS) ? warp_sum(acc[i]) : warp_max(acc[i]);
+        if (lane == 0) sm[i][wid] = w;
+    }
+    __syncthreads();
+    if (wid == 0) {
+#pragma unroll
+        for (int i = 0; i < NVAL; ++i) {
+            double w = (lane < ADP_TILE / 32) ? sm[i][lane] : 0.0;
+            w = (i < NS) ? warp_sum(w) : warp_max(w);
+            if (lane == 0) ro.scal[ro.slot[i]] = w;
+        }
+        if (lane == 0) *ro.ticket = 0u;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// tile iteration: tile t -> (local plane kl, chunk) ; thread -> plane position r
+// ------------------------------------------------------------------------------------------
+#define FOR_EACH_ROW(G_, KLO, NPL)                                                                  \
+    for (int tile__ = blockIdx.x; tile__ < (G_).tpp * (NPL); tile__ += gridDim.x)                   \
+        for (int kl = (KLO) + tile__ / (G_).tpp, r = (tile__ % (G_).tpp) * ADP_TILE + threadIdx.x, \
+                 once__ = 1;                                                                        \
+             once__ && r < (G_).np; once__ = 0)
+
+__device__ __forceinline__ long long node_idx(const Geo &G, int kl, int r)
+{
+    return (long long)(kl + ADP_GH) * G.np + r;
+}
+
+// y = A_g x at row idx, terms added in set_ind order (z-,y-,x-,diag,x+,y+,z+) from 0,
+// exactly like sp_matvec (mod_cmfd.f90:1261-1266); absent neighbours have a == 0.
+__device__ __forceinline__ double stencil7(const double *__restrict__ a, long long NV, const double *__restrict__ x,
+                                           long long idx, int np, int ym, int yp)
+{
+    double v = 0.0;
+    v = v + a[idx] * x[idx - np];
+    v = v + a[NV + idx] * x[idx - ym];
+    v = v + a[2 * NV + idx] * x[idx - 1];
+    v = v + a[3 * NV + idx] * x[idx];
+    v = v + a[4 * NV + idx] * x[idx + 1];
+    v = v + a[5 * NV + idx] * x[idx + yp];
+    v = v + a[6 * NV + idx] * x[idx + np];
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------
+// coup_coef (mod_cmfd.f90:11-137): FDM coupling coefficients df(1..6) for group g.
+// Runs over planes [klo, klo+npl) which may include ghost plane -1 / nzl (multi-rank nodal).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ double df_boundary(int bc, double Dn, double h)
+{
+    const double alb = 1.e30;
+    if (bc == 0) return 2.0 * alb * Dn / (2.0 * Dn + alb * h);
+    if (bc == 1) return Dn / (2.0 * Dn + 0.5 * h);
+    return 0.0;
+}
+__device__ __forceinline__ double df_interior(double Dn, double Dnb, double hn, double hnb)
+{
+    return 2.0 * Dn * Dnb / (Dn * hnb + Dnb * hn);
+}
+
+__global__ void __launch_bounds__(ADP_TILE) k_coup_coef(Geo G, const double *__restrict__ D, double *__restrict__ df,
+                                                        int klo, int npl)
+{
+    FOR_EACH_ROW(G, klo, npl)
+    {
+        const long long idx = node_idx(G, kl, r), NV = G.NV;
+        const int kg = G.k0 + kl;
+        const unsigned f = G.flag[r];
+        const int ym = G.ypm[r], yp = G.ypp[r];
+        const double Dn = D[idx], hx = G.hx[r], hy = G.hy[r], hz = G.hz[1 + kg];
+        df[0 * NV + idx] = (f & FLAG_XP) ? df_boundary(G.bc[0], Dn, hx) : df_interior(Dn, D[idx + 1], hx, G.hx[r + 1]);
+        df[1 * NV + idx] = (f & FLAG_XM) ? df_boundary(G.bc[1], Dn, hx) : df_interior(Dn, D[idx - 1], hx, G.hx[r - 1]);
+        df[2 * NV + idx] = (f & FLAG_YP) ? df_boundary(G.bc[2], Dn, hy) : df_interior(Dn, D[idx + yp], hy, G.hy[r + yp]);
+        df[3 * NV + idx] = (f & FLAG_YM) ? df_boundary(G.bc[3], Dn, hy) : df_interior(Dn, D[idx - ym], hy, G.hy[r - ym]);
+        df[4 * NV + idx] = (kg == G.nzz - 1) ? df_boundary(G.bc[5], Dn, hz) : df_interior(Dn, D[idx + G.np], hz, G.hz[1 + kg + 1]);
+        df[5 * NV + idx] = (kg == 0) ? df_boundary(G.bc[4], Dn, hz) : df_interior(Dn, D[idx - G.np], hz, G.hz[1 + kg - 1]);
+    }
+}
+
+// matrix_setup (mod_cmfd.f90:247-302): rows of A_g from df, dn, sigr
+__global__ void __launch_bounds__(ADP_TILE) k_matrix_setup(Geo G, const double *__restrict__ df, const double *__restrict__ dn,
+                                                           const double *__restrict__ sigr, double *__restrict__ a)
+{
+    FOR_EACH_ROW(G, 0, G.nzl)
+    {
+        const long long idx = node_idx(G, kl, r), NV = G.NV;
+        const int kg = G.k0 + kl;
+        const unsigned f = G.flag[r];
+        const double hx = G.hx[r], hy = G.hy[r], hz = G.hz[1 + kg];
+        const double f1 = df[idx], f2 = df[NV + idx], f3 = df[2 * NV + idx], f4 = df[3 * NV + idx],
+                     f5 = df[4 * NV + idx], f6 = df[5 * NV + idx];
+        const double n1 = dn[idx], n2 = dn[NV + idx], n3 = dn[2 * NV + idx], n4 = dn[3 * NV + idx],
+                     n5 = dn[4 * NV + idx], n6 = dn[5 * NV + idx];
+        a[0 * NV + idx] = (kg != 0) ? -(f6 - n6) / hz : 0.0;
+        a[1 * NV + idx] = (f & FLAG_YM) ? 0.0 : -(f4 - n4) / hy;
+        a[2 * NV + idx] = (f & FLAG_XM) ? 0.0 : -(f2 - n2) / hx;
+        a[3 * NV + idx] = (f1 + f2 - n1 + n2) / hx + (f3 + f4 - n3 + n4) / hy + (f5 + f6 - n5 + n6) / hz + sigr[idx];
+        a[4 * NV + idx] = (f & FLAG_XP) ? 0.0 : -(f1 + n1) / hx;
+        a[5 * NV + idx] = (f & FLAG_YP) ? 0.0 : -(f3 + n3) / hy;
+        a[6 * NV + idx] = (kg != G.nzz - 1) ? -(f5 + n5) / hz : 0.0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// P: total source + residual.  bs as TSrc / TSrcAd / TSrcTr build it (never stored):
+//   fwd : bs = chi(mat,g)*fs/Ke + sum_{h/=g} sigs(n,h,g) f0(n,h) + exsrc(n,g)
+//   adj : bs = nuf(n,g)*fs/Ke   + sum_{h/=g} sigs(n,g,h) f0(n,h) + exsrc(n,g)
+//   tr  : bs = (1 - tbeta(mat) + dfis(n))*chi(mat,g)*fs + sum ... + exsrc(n,g)
+// then r = bs - A x ; rs = r ; p = r (the first "p = r + beta (p - omega v)" with p = v = 0)
+// and the partial sums of rho = (rs, r).
+// ------------------------------------------------------------------------------------------
+struct SrcArgs {
+    int mode, g, ng, nmat;
+    const double *f0[ADP_MAXG];    // current flux of every group
+    const double *sg[ADP_MAXG];    // scattering into g from h (fwd/tr: sigs(n,h,g); adj: sigs(n,g,h))
+    const double *fs, *exsrc, *nuf_g, *chi_g, *tbeta, *dfis;
+    const int *mat;
+    double *s0;                    // optional: scattering source column kept for get_exsrc
+    const double *b;               // raw mode: right-hand side given explicitly (adp_bicg)
+};
+
+__global__ void __launch_bounds__(ADP_TILE) k_residual(Geo G, SrcArgs A, const double *__restrict__ a,
+                                                        const double *__restrict__ x, double *__restrict__ rv,
+                                                        double *__restrict__ rs, double *__restrict__ pv, RedOut ro)
+{
+    double acc[1] = {0.0};
+    const double Ke = ro.scal[S_KE];
+    FOR_EACH_ROW(G, 0, G.nzl)
+    {
+        const long long idx = node_idx(G, kl, r);
+        double bs;
+        if (A.b) {
+            bs = A.b[idx];
+        } else {
+            double s0 = 0.0;
+            for (int h = 0; h < A.ng; ++h)
+                if (h != A.g) s0 = s0 + A.sg[h][idx] * A.f0[h][idx];
+            if (A.s0) A.s0[idx] = s0;
+            const int m = A.mat[idx] - 1;
+            if (A.mode == ADP_MODE_ADJOINT) bs = A.nuf_g[idx] * A.fs[idx] / Ke + s0 + A.exsrc[idx];
+            else if (A.mode == ADP_MODE_TRANSIENT)
+                bs = (1.0 - A.tbeta[m] + A.dfis[idx]) * A.chi_g[m] * A.fs[idx] + s0 + A.exsrc[idx];
+            else bs = A.chi_g[m] * A.fs[idx] / Ke + s0 + A.exsrc[idx];
+        }
+        const double ax = stencil7(a, G.NV, x, idx, G.np, G.ypm[r], G.ypp[r]);
+        const double res = bs - ax;
+        rv[idx] = res;
+        rs[idx] = res;
+        pv[idx] = res;
+        acc[0] = acc[0] + res * res;
+    }
+    grid_reduce<1, 0>(acc, ro);
+}
+
+// A: p = r + beta (p - omega v), beta = (rho/rho_prev)(alpha/omega)   (mod_cmfd.f90:1231-1232)
+__global__ void __launch_bounds__(ADP_TILE) k_update_p(Geo G, const double *__restrict__ scal, int slot_rho, int slot_rho_prev,
+                                                        const double *__restrict__ rv, const double *__restrict__ v,
+                                                        double *__restrict__ pv)
+{
+    const double rho = scal[slot_rho], rho_prev = scal[slot_rho_prev];
+    const double alpha = rho_prev / scal[S_RSV];
+    const double omega = scal[S_TS] / scal[S_TT];
+    const double beta = (rho / rho_prev) * (alpha / omega);
+    FOR_EACH_ROW(G, 0, G.nzl)
+    {
+        const long long idx = node_idx(G, kl, r);
+        pv[idx] = rv[idx] + beta * (pv[idx] - omega * v[idx]);
+    }
+}
+
+// B: v = A p and the partial sums of (rs, v)   (mod_cmfd.f90:1233-1234)
+__global__ void __launch_bounds__(ADP_TILE) k_spmv_dot(Geo G, const double *__restrict__ a, const double *__restrict__ pv,
+                                                        const double *__restrict__ rs, double *__restrict__ v, RedOut ro)
+{
+    double acc[1] = {0.0};
+    FOR_EACH_ROW(G, 0, G.nzl)
+    {
+        const long long idx = node_idx(G, kl, r);
+        const double y = stencil7(a, G.NV, pv, idx, G.np, G.ypm[r], G.ypp[r]);
+        v[idx] = y;
+        if (rs) acc[0] = acc[0] + rs[idx] * y;
+    }
+    if (rs) grid_reduce<1, 0>(acc, ro);
+}
+
+// C: s = r - alpha v evaluated on the fly at the 7 stencil points, t = A s, (t,t), (t,s)
+//    (mod_cmfd.f90:1234-1238).  s is stored for the own row only.
+__global__ void __launch_bounds__(ADP_TILE) k_st(Geo G, const double *__restrict__ a, int slot_rho,
+                                                  const double *__restrict__ rv, const double *__restrict__ v,
+                                                  double *__restrict__ s, double *__restrict__ t, RedOut ro)
+{
+    double acc[2] = {0.0, 0.0};
+    const double alpha = ro.scal[slot_rho] / ro.scal[S_RSV];
+    const long long NV = G.NV;
+    const int np = G.np;
+    FOR_EACH_ROW(G, 0, G.nzl)
+    {
+        const long long idx = node_idx(G, kl, r);
+        const int ym = G.ypm[r], yp = G.ypp[r];
+        const double sc = rv[idx] - alpha * v[idx];
+        double y = 0.0;
+        y = y + a[idx] * (rv[idx - np] - alpha * v[idx - np]);
+        y = y + a[NV + idx] * (rv[idx - ym] - alpha * v[idx - ym]);
+        y = y + a[2 * NV + idx] * (rv[idx - 1] - alpha * v[idx - 1]);
+        y = y + a[3 * NV + idx] * sc;
+        y = y + a[4 * NV + idx] * (rv[idx + 1] - alpha * v[idx + 1]);
+        y = y + a[5 * NV + idx] * (rv[idx + yp] - alpha * v[idx + yp]);
+        y = y + a[6 * NV + idx] * (rv[idx + np] - alpha * v[idx + np]);
+        s[idx] = sc;
+        t[idx] = y;
+        acc[0] = acc[0] + y * y;
+        acc[1] = acc[1] + y * sc;
+    }
+    grid_reduce<2, 0>(acc, ro);
+}
+
+// C for the multi-rank path: s has been materialised (and its ghost planes exchanged)
+__global__ void __launch_bounds__(ADP_TILE) k_s(Geo G, const double *__restrict__ scal, int slot_rho,
+                                                 const double *__restrict__ rv, const double *__restrict__ v,
+                                                 double *__restrict__ s)
+{
+    const double alpha = scal[slot_rho] / scal[S_RSV];
+    FOR_EACH_ROW(G, 0, G.nzl)
+    {
+        const long long idx = node_idx(G, kl, r);
+        s[idx] = rv[idx] - alpha * v[idx];
+    }
+}
+__global__ void __launch_bounds__(ADP_TILE) k_t(Geo G, const double *__restrict__ a, const double *__restrict__ s,
+                                                 double *__restrict__ t, RedOut ro)
+{
+    double acc[2] = {0.0, 0.0};
+    FOR_EACH_ROW(G, 0, G.nzl)
+    {
+        const long long idx = node_idx(G, kl, r);
+        const double y = stencil7(a, G.NV, s, idx, G.np, G.ypm[r], G.ypp[r]);
+        t[idx] = y;
+        acc[0] = acc[0] + y * y;
+        acc[1] = acc[1] + y * s[idx];
+    }
+    grid_reduce<2, 0>(acc, ro);
+}
+
+// D: x = x + alpha p + omega s ; r = s - omega t ; partial sums of the next rho = (rs, r)
+//    (mod_cmfd.f90:1239-1240, 1230).  x_in/x_out differ in the first iteration: the old flux
+//    buffer is kept untouched and doubles as f0c for RelEg (no copy kernel).
+__global__ void __launch_bounds__(ADP_TILE) k_update_xr(Geo G, int slot_rho, int last, const double *x_in,
+                                                         double *x_out, const double *__restrict__ pv,
+                                                         const double *__restrict__ s, const double *__restrict__ t,
+                                                         const double *__restrict__ rs, double *__restrict__ rv, RedOut ro)
+{
+    double acc[1] = {0.0};
+    const double alpha = ro.scal[slot_rho] / ro.scal[S_RSV];
+    const double omega = ro.scal[S_TS] / ro.scal[S_TT];
+    FOR_EACH_ROW(G, 0, G.nzl)
+    {
+        const long long idx = node_idx(G, kl, r);
+        const double sv = s[idx];
+        x_out[idx] = x_in[idx] + alpha * pv[idx] + omega * sv;
+        if (!last) {
+            const double rn = sv - omega * t[idx];
+            rv[idx] = rn;
+            acc[0] = acc[0] + rs[idx] * rn;
+        }
+    }
+    if (!last) grid_reduce<1, 0>(acc, ro);
+}
+
+// ------------------------------------------------------------------------------------------
+// F: fission source and the outer-iteration norms in one pass
+//   fs_new = sum_g f0_new(g) * nuf(g)     (adjoint: * chi(mat,g))     FSrc / FSrcAd
+//   errn = fs_new - fs_old ; e2^2 = sum errn^2 ; f = sum vdel fs_new ; ser ; fer
+// ------------------------------------------------------------------------------------------
+struct FsrcArgs {
+    int ng, nmat, adjoint;
+    const double *fnew[ADP_MAXG], *fold[ADP_MAXG], *w[ADP_MAXG];  // w = nuf(g) (fwd) ; chi column (adj)
+    const int *mat;
+    const double *fs_old;
+    double *fs_new;
+};
+
+__global__ void __launch_bounds__(ADP_TILE) k_fsrc_norms(Geo G, FsrcArgs A, int do_norms, RedOut ro)
+{
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    FOR_EACH_ROW(G, 0, G.nzl)
+    {
+        const long long idx = node_idx(G, kl, r);
+        const int m = A.adjoint ? A.mat[idx] - 1 : 0;
+        double fs = 0.0, fer = 0.0;
+        for (int g = 0; g < A.ng; ++g) {
+            const double fn = A.fnew[g][idx];
+            const double w = A.adjoint ? A.w[g][m] : A.w[g][idx];
+            fs = fs + fn * w;
+            if (do_norms && fabs(fn) > 1.e-10) {
+                const double e = fabs(fn - A.fold[g][idx]) / fabs(fn);
+                fer = fmax(fer, e);
+            }
+        }
+        A.fs_new[idx] = fs;
+        if (do_norms) {
+            const double errn = fs - A.fs_old[idx];
+            acc[0] = acc[0] + errn * errn;
+            acc[1] = acc[1] + (G.area[r] * G.hz[1 + G.k0 + kl]) * fs;
+            if (fabs(fs) > 1.e-10) acc[2] = fmax(acc[2], fabs(errn) / fabs(fs));
+            acc[3] = fmax(acc[3], fer);
+        }
+    }
+    if (do_norms) grid_reduce<2, 2>(acc, ro);
+}
+
+// E: fiss_extrp (mod_cmfd.f90:326-329): fs = fs + domiR/(1-domiR) * errn, then Integrate + RelE
+__global__ void __launch_bounds__(ADP_TILE) k_extrap(Geo G, const double *__restrict__ fs_old, double *__restrict__ fs_new, RedOut ro)
+{
+    double acc[2] = {0.0, 0.0};
+    const double c = ro.scal[S_EXC];
+    FOR_EACH_ROW(G, 0, G.nzl)
+    {
+        const long long idx = node_idx(G, kl, r);
+        const double fo = fs_old[idx];
+        const double errn = fs_new[idx] - fo;
+        const double fs = fs_new[idx] + c * errn;
+        fs_new[idx] = fs;
+        acc[0] = acc[0] + (G.area[r] * G.hz[1 + G.k0 + kl]) * fs;
+        if (fabs(fs) > 1.e-10) acc[1] = fmax(acc[1], fabs(fs - fo) / fabs(fs));
+    }
+    grid_reduce<1, 1>(acc, ro);
+}
+
+// weighted sum: Integrate(s) = sum vdel(n) s(n)   (mod_cmfd.f90:1120-1139); w==1: plain volume
+__global__ void __launch_bounds__(ADP_TILE) k_integrate(Geo G, const double *__restrict__ vec, RedOut ro)
+{
+    double acc[1] = {0.0};
+    FOR_EACH_ROW(G, 0, G.nzl)
+    {
+        const long long idx = node_idx(G, kl, r);
+        const double w = G.area[r] * G.hz[1 + G.k0 + kl];
+        acc[0] = acc[0] + w * (vec ? vec[idx] : 1.0);
+    }
+    grid_reduce<1, 0>(acc, ro);
+}
+
+__global__ void k_fill(Geo G, double *__restrict__ vec, double val)
+{
+    FOR_EACH_ROW(G, 0, G.nzl) vec[node_idx(G, kl, r)] = val;
+}
+
+// scalar statements of the outer loop ----------------------------------------------------
+//  what 0: (begin)   f = S_FINT ; e1 = S_TMP0 (Integrate(errn=1))                :457-459
+//  what 1: (extrap)  domiR = e2/e1 ; c = domiR/(1-domiR) ; e1 = e2              :326,483
+//  what 2: (finish)  [e1 = e2 unless extrapolated] fc = f ; f = S_FINT ; Ke = Ke*f/fc   :483-485
+__global__ void k_scalar(double *scal, int what, int update_ke, int extrapolated)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (what == 0) {
+        scal[S_F] = scal[S_FINT];
+        scal[S_E1] = scal[S_TMP0];
+    } else if (what == 1) {
+        const double e2 = sqrt(scal[S_E2SQ]);
+        const double domiR = e2 / scal[S_E1];
+        scal[S_EXC] = domiR / (1.0 - domiR);
+        scal[S_E1] = e2;
+    } else {
+        if (!extrapolated) scal[S_E1] = sqrt(scal[S_E2SQ]);
+        if (update_ke) {
+            const double fc = scal[S_F], f = scal[S_FINT];
+            scal[S_FC] = fc;
+            scal[S_F] = f;
+            scal[S_KE] = scal[S_KE] * f / fc;
+        }
+    }
+}
+
+// PowDis (mod_cmfd.f90:1307-1320): p(n) = sum_g max(0, f0*sigf*vdel), and its total
+struct PowArgs {
+    int ng;
+    const double *f0[ADP_MAXG], *sigf[ADP_MAXG];
+};
+__global__ void __launch_bounds__(ADP_TILE) k_powdis(Geo G, PowArgs A, double *__restrict__ pw, RedOut ro)
+{
+    double acc[1] = {0.0};
+    FOR_EACH_ROW(G, 0, G.nzl)
+    {
+        const long long idx = node_idx(G, kl, r);
+        const double vdel = G.area[r] * G.hz[1 + G.k0 + kl];
+        double p = 0.0;
+        for (int g = 0; g < A.ng; ++g) {
+            double q = A.f0[g][idx] * A.sigf[g][idx] * vdel;
+            if (q < 0.0) q = 0.0;
+            p = p + q;
+        }
+        pw[idx] = p;
+        acc[0] = acc[0] + p;
+    }
+    grid_reduce<1, 0>(acc, ro);
+}
+__global__ void k_scale(Geo G, double *__restrict__ vec, const double *__restrict__ scal, int slot)
+{
+    const double d = scal[slot];
+    FOR_EACH_ROW(G, 0, G.nzl)
+    {
+        const long long idx = node_idx(G, kl, r);
+        vec[idx] = vec[idx] / d;
+    }
+}
+
+// get_exsrc (mod_cmfd.f90:926-949, bxtab == 0)
+struct ExsrcArgs {
+    int ng, nmat;
+    double ht, sth, bth;
+    double lamb[ADP_NF], ibeta[ADP_NF];
+    const double *c0;   // [NF][NV]
+    const double *fst, *tbeta, *velo, *chi /*[g][nmat]*/;
+    const int *mat;
+    const double *L, *sigrp, *ft, *s0, *omeg;   // [G][NV]
+    int s0_group;       // 0-based group whose s0 column is non-zero (-1 none)
+    double *exsrc;      // [G][NV]
+    double *dfis;
+};
+__global__ void __launch_bounds__(ADP_TILE) k_get_exsrc(Geo G, ExsrcArgs A)
+{
+    const long long NV = G.NV;
+    FOR_EACH_ROW(G, 0, G.nzl)
+    {
+        const long long idx = node_idx(G, kl, r);
+        const int m = A.mat[idx] - 1;
+        double dt = 0.0, dtp = 0.0, dfis = 0.0;
+        const double fst = A.fst[idx];
+#pragma unroll
+        for (int i = 0; i < ADP_NF; ++i) {
+            const double pxe = exp(-A.lamb[i] * A.ht);
+            double a1 = (1.0 - pxe) / (A.lamb[i] * A.ht);
+            const double a2 = 1.0 - a1;
+            a1 = a1 - pxe;
+            const double c0 = A.c0[i * NV + idx];
+            dfis = dfis + A.ibeta[i] * a2;
+            dt = dt + A.lamb[i] * c0 * pxe + A.ibeta[i] * a1 * fst;
+            dtp = dtp + A.lamb[i] * c0;
+        }
+        A.dfis[idx] = dfis;
+        for (int g = 0; g < A.ng; ++g) {
+            const double chi = A.chi[g * A.nmat + m];
+            const double ft = A.ft[g * NV + idx];
+            const double s0 = (g == A.s0_group) ? A.s0[idx] : 0.0;
+            const double pthet = -A.L[g * NV + idx] - A.sigrp[g * NV + idx] * ft + s0 + (1.0 - A.tbeta[m]) * chi * fst + chi * dtp;
+            A.exsrc[g * NV + idx] = chi * dt + exp(A.omeg[g * NV + idx] * A.ht) * ft / (A.sth * A.velo[g] * A.ht) + A.bth * pthet;
+        }
+    }
+}
+
+}  // namespace
+
+// =========================================================================================
+// host-side launch wrappers
+// =========================================================================================
+static inline RedOut make_red(adp_ctx *c, int s0, int s1 = S_TMP1, int s2 = S_TMP1, int s3 = S_TMP1)
+{
+    RedOut ro;
+    ro.scal = c->d_scal; ro.part = c->d_part; ro.ticket = c->d_ticket;
+    ro.slot[0] = s0; ro.slot[1] = s1; ro.slot[2] = s2; ro.slot[3] = s3;
+    return ro;
+}
+static inline int grid_for(adp_ctx *c, int ntiles)
+{
+    int g = c->grid_blocks;
+    if (ntiles < g) g = ntiles;
+    return g < 1 ? 1 : g;
+}
+#define LAUNCH_CHECK(c)                                                                     \
+    do {                                                                                    \
+        (c)->launches++;                                                                    \
+        cudaError_t e__ = cudaPeekAtLastError();                                            \
+        if (e__ != cudaSuccess) {                                                           \
+            (c)->err = std::string("kernel launch: ") + cudaGetErrorString(e__) + " (" + __FILE__ + ":" + std::to_string(__LINE__) + ")"; \
+            return ADP_ERR_CUDA;                                                            \
+        }                                                                                   \
+    } while (0)
+
+static inline double *f0ptr(adp_ctx *c, int which, int g) { return c->d_f0[which] + (size_t)g * c->NV; }
+static inline const double *a_of(adp_ctx *c, int g) { return c->d_a + (size_t)g * 7 * c->NV; }
+
+int adp_k_coup_coef(adp_ctx *c)
+{
+    // own planes plus one ghost plane on interior slab boundaries (needed by the nodal z-surfaces)
+    int klo = (c->k0 > 0) ? -1 : 0;
+    int khi = (c->k1 < c->nzz) ? c->nzl + 1 : c->nzl;
+    int npl = khi - klo;
+    for (int g = 0; g < c->ng; ++g) {
+        k_coup_coef<<<grid_for(c, c->geo.tpp * npl), ADP_TILE, 0, c->stream>>>(
+            c->geo, c->d_D + (size_t)g * c->NV, c->d_df + (size_t)g * 6 * c->NV, klo, npl);
+        LAUNCH_CHECK(c);
+    }
+    return ADP_OK;
+}
+
+int adp_k_matrix_setup(adp_ctx *c)
+{
+    for (int g = 0; g < c->ng; ++g) {
+        k_matrix_setup<<<grid_for(c, c->geo.ntiles), ADP_TILE, 0, c->stream>>>(
+            c->geo, c->d_df + (size_t)g * 6 * c->NV, c->d_dn + (size_t)g * 6 * c->NV, c->d_sigr + (size_t)g * c->NV,
+            c->d_a + (size_t)g * 7 * c->NV);
+        LAUNCH_CHECK(c);
+    }
+    return ADP_OK;
+}
+
+static int launch_fsrc(adp_ctx *c, bool adjoint, bool do_norms, int fs_in, int fs_out, const int *cur_new, const int *cur_old)
+{
+    FsrcArgs A{};
+    A.ng = c->ng; A.nmat = c->nmat; A.adjoint = adjoint ? 1 : 0; A.mat = c->d_mat;
+    for (int g = 0; g < c->ng; ++g) {
+        A.fnew[g] = f0ptr(c, cur_new[g], g);
+        A.fold[g] = f0ptr(c, cur_old[g], g);
+        A.w[g] = adjoint ? c->d_chi + (size_t)g * c->nmat : c->d_nuf + (size_t)g * c->NV;
+    }
+    A.fs_old = c->d_fs[fs_in];
+    A.fs_new = c->d_fs[fs_out];
+    k_fsrc_norms<<<grid_for(c, c->geo.ntiles), ADP_TILE, 0, c->stream>>>(c->geo, A, do_norms ? 1 : 0,
+                                                                         make_red(c, S_E2SQ, S_FINT, S_SER, S_FER));
+    LAUNCH_CHECK(c);
+    return ADP_OK;
+}
+
+int adp_k_init_flux(adp_ctx *c, int adjoint)
+{
+    // Ke = 1 ; f0 = 1 ; fs0 = FSrc(f0)   (mod_cmfd.f90:448-454)
+    for (int g = 0; g < c->ng; ++g) {
+        c->cur[g] = 0;
+        k_fill<<<grid_for(c, c->geo.ntiles), ADP_TILE, 0, c->stream>>>(c->geo, f0ptr(c, 0, g), 1.0);
+        LAUNCH_CHECK(c);
+    }
+    c->fcur = 0;
+    double one = 1.0;
+    CUDA_TRY(c, cudaMemcpyAsync(c->d_scal + S_KE, &one, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    int rc = launch_fsrc(c, adjoint != 0, false, 0, 0, c->cur, c->cur);
+    if (rc) return rc;
+    c->s0_group = 0;
+    c->have_flux = true;
+    return ADP_OK;
+}
+
+int adp_k_integrate(adp_ctx *c, const double *d_vec, int slot)
+{
+    k_integrate<<<grid_for(c, c->geo.ntiles), ADP_TILE, 0, c->stream>>>(c->geo, d_vec, make_red(c, slot));
+    LAUNCH_CHECK(c);
+    if (c->nranks > 1) return adp_comm_allreduce_sum(c, c->d_scal + slot, 1);
+    return ADP_OK;
+}
+
+int adp_k_outer_begin(adp_ctx *c, int mode)
+{
+    // f = Integrate(fs0) ; errn = 1 ; e1 = Integrate(errn)   (mod_cmfd.f90:457-459)
+    int rc = adp_k_integrate(c, c->d_fs[c->fcur], S_FINT);
+    if (rc) return rc;
+    rc = adp_k_integrate(c, nullptr, S_TMP0);
+    if (rc) return rc;
+    k_scalar<<<1, 32, 0, c->stream>>>(c->d_scal, 0, 0, 0);
+    LAUNCH_CHECK(c);
+    (void)mode;
+    return ADP_OK;
+}
+
+// One bicg(nin, g, bs, f0(:,g)) including the source construction.  After the call the new
+// flux of group g lives in the other ping-pong buffer and c->cur[g] has been flipped.
+static int bicg_core(adp_ctx *c, const SrcArgs &src, const double *a, const double *x_in, double *x_out, int nin)
+{
+    const int grid = grid_for(c, c->geo.ntiles);
+    const bool multi = c->nranks > 1;
+    int rc;
+    if (multi && (rc = adp_comm_halo(c, const_cast<double *>(x_in), 1))) return rc;
+    // iteration i uses rho slot S_RHO0 + (i & 1); P produces the one of iteration 1
+    k_residual<<<grid, ADP_TILE, 0, c->stream>>>(c->geo, src, a, x_in, c->d_r, c->d_rs, c->d_p, make_red(c, S_RHO1));
+    LAUNCH_CHECK(c);
+    if (multi && (rc = adp_comm_allreduce_sum(c, c->d_scal + S_RHO1, 1))) return rc;
+    if (nin <= 0) {
+        if (x_in != x_out) CUDA_TRY(c, cudaMemcpyAsync(x_out, x_in, sizeof(double) * c->NV, cudaMemcpyDeviceToDevice, c->stream));
+        return ADP_OK;
+    }
+    for (int i = 1; i <= nin; ++i) {
+        const int slot = S_RHO0 + (i & 1), slot_prev = S_RHO0 + ((i - 1) & 1), slot_next = S_RHO0 + ((i + 1) & 1);
+        if (i > 1) {
+            k_update_p<<<grid, ADP_TILE, 0, c->stream>>>(c->geo, c->d_scal, slot, slot_prev, c->d_r, c->d_v, c->d_p);
+            LAUNCH_CHECK(c);
+        }
+        if (multi && (rc = adp_comm_halo(c, c->d_p, 1))) return rc;
+        k_spmv_dot<<<grid, ADP_TILE, 0, c->stream>>>(c->geo, a, c->d_p, c->d_rs, c->d_v, make_red(c, S_RSV));
+        LAUNCH_CHECK(c);
+        if (multi) {
+            if ((rc = adp_comm_allreduce_sum(c, c->d_scal + S_RSV, 1))) return rc;
+            k_s<<<grid, ADP_TILE, 0, c->stream>>>(c->geo, c->d_scal, slot, c->d_r, c->d_v, c->d_s);
+            LAUNCH_CHECK(c);
+            if ((rc = adp_comm_halo(c, c->d_s, 1))) return rc;
+            k_t<<<grid, ADP_TILE, 0, c->stream>>>(c->geo, a, c->d_s, c->d_t, make_red(c, S_TT, S_TS));
+            LAUNCH_CHECK(c);
+            if ((rc = adp_comm_allreduce_sum(c, c->d_scal + S_TT, 2))) return rc;
+        } else {
+            k_st<<<grid, ADP_TILE, 0, c->stream>>>(c->geo, a, slot, c->d_r, c->d_v, c->d_s, c->d_t, make_red(c, S_TT, S_TS));
+            LAUNCH_CHECK(c);
+        }
+        const int last = (i == nin) ? 1 : 0;
+        k_update_xr<<<grid, ADP_TILE, 0, c->stream>>>(c->geo, slot, last, (i == 1) ? x_in : x_out, x_out, c->d_p, c->d_s,
+                                                      c->d_t, c->d_rs, c->d_r, make_red(c, slot_next));
+        LAUNCH_CHECK(c);
+        if (!last && multi && (rc = adp_comm_allreduce_sum(c, c->d_scal + slot_next, 1))) return rc;
+    }
+    return ADP_OK;
+}
+
+int adp_k_bicg_group(adp_ctx *c, int mode, int g, int nin, bool write_s0)
+{
+    SrcArgs S{};
+    S.mode = mode; S.g = g; S.ng = c->ng; S.nmat = c->nmat;
+    for (int h = 0; h < c->ng; ++h) {
+        S.f0[h] = f0ptr(c, c->cur[h], h);
+        // fwd/tr: sigs(n,h,g) -> d_sigs[(g*G + h)] ; adj: sigs(n,g,h) -> d_sigs[(h*G + g)]
+        S.sg[h] = (mode == ADP_MODE_ADJOINT) ? c->d_sigs + ((size_t)h * c->ng + g) * c->NV
+                                             : c->d_sigs + ((size_t)g * c->ng + h) * c->NV;
+    }
+    S.fs = c->d_fs[c->fcur];
+    S.exsrc = c->d_exsrc + (size_t)g * c->NV;
+    S.nuf_g = c->d_nuf + (size_t)g * c->NV;
+    S.chi_g = c->d_chi + (size_t)g * c->nmat;
+    S.tbeta = c->d_tbeta; S.dfis = c->d_dfis; S.mat = c->d_mat;
+    S.s0 = write_s0 ? c->d_s0 : nullptr;
+    S.b = nullptr;
+    const double *x_in = f0ptr(c, c->cur[g], g);
+    double *x_out = f0ptr(c, c->cur[g] ^ 1, g);
+    int rc = bicg_core(c, S, a_of(c, g), x_in, x_out, nin);
+    if (rc) return rc;
+    c->cur[g] ^= 1;
+    if (write_s0) c->s0_group = g + 1;
+    return ADP_OK;
+}
+
+// bicg(imax, g, b, x) with an explicit right-hand side (kernel-level tests, adp_bicg)
+int adp_k_bicg_raw(adp_ctx *c, int g, int imax, const double *d_b, double *d_x)
+{
+    SrcArgs S{};
+    S.b = d_b;
+    // D's first iteration reads x_in and writes x_out; in-place is fine (same element)
+    return bicg_core(c, S, a_of(c, g), d_x, d_x, imax);
+}
+
+int adp_k_spmv(adp_ctx *c, int g, const double *d_x, double *d_v)
+{
+    int rc;
+    if (c->nranks > 1 && (rc = adp_comm_halo(c, const_cast<double *>(d_x), 1))) return rc;
+    k_spmv_dot<<<grid_for(c, c->geo.ntiles), ADP_TILE, 0, c->stream>>>(c->geo, a_of(c, g), d_x, nullptr, d_v, make_red(c, S_TMP1));
+    LAUNCH_CHECK(c);
+    return ADP_OK;
+}
+
+// FSrc* ... RelEg of one outer iteration (mod_cmfd.f90:479-487).  cur_old[g] is the flux
+// buffer that held f0c (the flux before this outer iteration).
+int adp_k_outer_tail(adp_ctx *c, int mode, bool extrapolate)
+{
+    int cur_old[ADP_MAXG];
+    for (int g = 0; g < c->ng; ++g) cur_old[g] = c->cur[g] ^ 1;
+    const int fs_in = c->fcur, fs_out = c->fcur ^ 1;
+    const bool multi = c->nranks > 1;
+    const int update_ke = (mode == ADP_MODE_FORWARD || mode == ADP_MODE_ADJOINT) ? 1 : 0;
+    int rc = launch_fsrc(c, mode == ADP_MODE_ADJOINT, true, fs_in, fs_out, c->cur, cur_old);
+    if (rc) return rc;
+    if (multi) {
+        if ((rc = adp_comm_allreduce_sum(c, c->d_scal + S_E2SQ, 2))) return rc;
+        if ((rc = adp_comm_allreduce_max(c, c->d_scal + S_SER, 2))) return rc;
+    }
+    if (extrapolate) {
+        k_scalar<<<1, 32, 0, c->stream>>>(c->d_scal, 1, 0, 0);
+        LAUNCH_CHECK(c);
+        k_extrap<<<grid_for(c, c->geo.ntiles), ADP_TILE, 0, c->stream>>>(c->geo, c->d_fs[fs_in], c->d_fs[fs_out],
+                                                                         make_red(c, S_FINT, S_SER));
+        LAUNCH_CHECK(c);
+        if (multi) {
+            if ((rc = adp_comm_allreduce_sum(c, c->d_scal + S_FINT, 1))) return rc;
+            if ((rc = adp_comm_allreduce_max(c, c->d_scal + S_SER, 1))) return rc;
+        }
+    }
+    k_scalar<<<1, 32, 0, c->stream>>>(c->d_scal, 2, update_ke, extrapolate ? 1 : 0);
+    LAUNCH_CHECK(c);
+    c->fcur = fs_out;
+    return ADP_OK;
+}
+
+int adp_k_powdis(adp_ctx *c, double *d_pow)
+{
+    PowArgs A{};
+    A.ng = c->ng;
+    for (int g = 0; g < c->ng; ++g) {
+        A.f0[g] = f0ptr(c, c->cur[g], g);
+        A.sigf[g] = c->d_sigf + (size_t)g * c->NV;
+    }
+    k_powdis<<<grid_for(c, c->geo.ntiles), ADP_TILE, 0, c->stream>>>(c->geo, A, d_pow, make_red(c, S_POW));
+    LAUNCH_CHECK(c);
+    if (c->nranks > 1) {
+        int rc = adp_comm_allreduce_sum(c, c->d_scal + S_POW, 1);
+        if (rc) return rc;
+    }
+    return ADP_OK;
+}
+
+int adp_k_scale_by_slot(adp_ctx *c, double *d_vec, int slot)
+{
+    k_scale<<<grid_for(c, c->geo.ntiles), ADP_TILE, 0, c->stream>>>(c->geo, d_vec, c->d_scal, slot);
+    LAUNCH_CHECK(c);
+    return ADP_OK;
+}
+
+int adp_k_get_exsrc(adp_ctx *c, double ht)
+{
+    ExsrcArgs A{};
+    A.ng = c->ng; A.nmat = c->nmat; A.ht = ht; A.sth = c->sth; A.bth = c->bth;
+    for (int i = 0; i < ADP_NF; ++i) { A.lamb[i] = c->lamb[i]; A.ibeta[i] = c->ibeta[i]; }
+    A.c0 = c->d_c0; A.fst = c->d_fst; A.tbeta = c->d_tbeta; A.velo = c->d_velo; A.chi = c->d_chi; A.mat = c->d_mat;
+    A.L = c->d_L; A.sigrp = c->d_sigrp; A.ft = c->d_ft; A.s0 = c->d_s0; A.omeg = c->d_omeg;
+    A.s0_group = c->s0_group - 1;
+    A.exsrc = c->d_exsrc; A.dfis = c->d_dfis;
+    k_get_exsrc<<<grid_for(c, c->geo.ntiles), ADP_TILE, 0, c->stream>>>(c->geo, A);
+    LAUNCH_CHECK(c);
+    return ADP_OK;
+}

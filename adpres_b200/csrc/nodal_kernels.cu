@@ -1,0 +1,628 @@
+// nodal_kernels.cu -- the two-node nonlinear nodal update (reference: src/mod_nodal.f90).
+//
+// The reference walks every line of nodes sequentially and carries a2p, a4p, Lp1, Bcp,
+// Ap..Hp from one interface to the next (mod_nodal.f90:53-125).  Every carried quantity is a
+// pure function of one node and one direction, and the transverse-leakage sources S1..S3 are
+// frozen by get_source before any dn is overwritten (mod_nodal.f90:49), so all surfaces are
+// independent.  Here:
+//   k_nodal_source    one thread per node: Lxyz -> S1,S2,S3              mod_nodal.f90:901-1043
+//   k_nodal_surfaces  one thread per (node, direction): the surface on the node's "+" side
+//                     (two-node 2Gx2G problem, or the one-node boundary problem), plus the
+//                     "-" boundary surface if the node is the first of its line.  The
+//                     4th-order expansion coefficients live in registers.      :282-897,1047-1451
+// Each surface is evaluated with the reference's operation order (same Doolittle LU without
+// pivoting, same accumulation order), so results differ from the sweep only through the libm
+// (sinh/cosh) and not at all for PNM.
+#include "adp_internal.cuh"
+
+namespace {
+
+#define FOR_EACH_ROW(G_, KLO, NPL)                                                                  \
+    for (int tile__ = blockIdx.x; tile__ < (G_).tpp * (NPL); tile__ += gridDim.x)                   \
+        for (int kl = (KLO) + tile__ / (G_).tpp, r = (tile__ % (G_).tpp) * ADP_TILE + threadIdx.x, \
+                 once__ = 1;                                                                        \
+             once__ && r < (G_).np; once__ = 0)
+
+__device__ __forceinline__ long long node_idx(const Geo &G, int kl, int r)
+{
+    return (long long)(kl + ADP_GH) * G.np + r;
+}
+
+struct NodalArgs {
+    int ng, nmat, cmode, kern;
+    long long nnod_total;
+    const double *f0[ADP_MAXG];          // current flux per group
+    const double *D, *sigr, *nuf, *exsrc; // [G][NV]
+    const double *sigs;                  // [h][g][NV] = sigs(n,g,h)
+    const double *chi;                   // [g][nmat]
+    const double *dc;                    // [f][g][NV]
+    const int *mat;
+    const double *tbeta, *dfis;
+    const double *df;                    // [g][6][NV]
+    double *dn;                          // [g][6][NV]
+    double *S;                           // [3][G][NV]
+    const double *scal;
+    int *errflag;
+};
+
+// ---------------------------------------------------------------------------------------
+// Lxyz + get_source (mod_nodal.f90:901-1043)
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(ADP_TILE) k_nodal_source(Geo G, NodalArgs A)
+{
+    const long long NV = G.NV;
+    const int np = G.np;
+    FOR_EACH_ROW(G, 0, G.nzl)
+    {
+        const long long idx = node_idx(G, kl, r);
+        const int kg = G.k0 + kl;
+        const unsigned fl = G.flag[r];
+        const int ym = G.ypm[r], yp = G.ypp[r];
+        const double hx = G.hx[r], hy = G.hy[r], hz = G.hz[1 + kg];
+        for (int g = 0; g < A.ng; ++g) {
+            const double *f0 = A.f0[g];
+            const double *df = A.df + (size_t)g * 6 * NV, *dn = A.dn + (size_t)g * 6 * NV;
+            const double fn = f0[idx];
+            double jp, jm;
+            // x
+            if (fl & FLAG_XP) jp = (G.bc[0] == 2) ? 0.0 : df[idx] * fn - dn[idx] * fn;
+            else { const double fp = f0[idx + 1]; jp = -df[idx] * (fp - fn) - dn[idx] * (fp + fn); }
+            if (fl & FLAG_XM) jm = (G.bc[1] == 2) ? 0.0 : -df[NV + idx] * fn - dn[NV + idx] * fn;
+            else { const double fm = f0[idx - 1]; jm = -df[NV + idx] * (fn - fm) - dn[NV + idx] * (fn + fm); }
+            const double L1 = (jp - jm) / hx;
+            // y
+            if (fl & FLAG_YP) jp = (G.bc[2] == 2) ? 0.0 : df[2 * NV + idx] * fn - dn[2 * NV + idx] * fn;
+            else { const double fp = f0[idx + yp]; jp = -df[2 * NV + idx] * (fp - fn) - dn[2 * NV + idx] * (fp + fn); }
+            if (fl & FLAG_YM) jm = (G.bc[3] == 2) ? 0.0 : -df[3 * NV + idx] * fn - dn[3 * NV + idx] * fn;
+            else { const double fm = f0[idx - ym]; jm = -df[3 * NV + idx] * (fn - fm) - dn[3 * NV + idx] * (fn + fm); }
+            const double L2 = (jp - jm) / hy;
+            // z
+            if (kg == G.nzz - 1) jp = (G.bc[5] == 2) ? 0.0 : df[4 * NV + idx] * fn - dn[4 * NV + idx] * fn;
+            else { const double fp = f0[idx + np]; jp = -df[4 * NV + idx] * (fp - fn) - dn[4 * NV + idx] * (fp + fn); }
+            if (kg == 0) jm = (G.bc[4] == 2) ? 0.0 : -df[5 * NV + idx] * fn - dn[5 * NV + idx] * fn;
+            else { const double fm = f0[idx - np]; jm = -df[5 * NV + idx] * (fn - fm) - dn[5 * NV + idx] * (fn + fm); }
+            const double L3 = (jp - jm) / hz;
+            double *S1 = A.S + ((size_t)0 * A.ng + g) * NV, *S2 = A.S + ((size_t)1 * A.ng + g) * NV,
+                   *S3 = A.S + ((size_t)2 * A.ng + g) * NV;
+            if (A.cmode == 2) {
+                const double ex = A.exsrc[(size_t)g * NV + idx];
+                S1[idx] = L2 + L3 - ex; S2[idx] = L1 + L3 - ex; S3[idx] = L1 + L2 - ex;
+            } else {
+                S1[idx] = L2 + L3; S2[idx] = L1 + L3; S3[idx] = L1 + L2;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// geometry of the line through a node in direction u
+// ---------------------------------------------------------------------------------------
+struct Line {
+    bool has_m, has_p;
+    long long off_m, off_p;  // index distance to the m / p neighbour
+    double h, hm, hp;        // node size and the neighbours' sizes in direction u
+    int bcm, bcp;            // boundary codes at the line's ends
+};
+
+__device__ __forceinline__ Line line_of(const Geo &G, int u, int kl, int r)
+{
+    Line q;
+    if (u == 0) {
+        const unsigned f = G.flag[r];
+        q.has_m = !(f & FLAG_XM); q.has_p = !(f & FLAG_XP);
+        q.off_m = 1; q.off_p = 1;
+        q.h = G.hx[r]; q.hm = q.has_m ? G.hx[r - 1] : 0.0; q.hp = q.has_p ? G.hx[r + 1] : 0.0;
+        q.bcm = G.bc[1]; q.bcp = G.bc[0];
+    } else if (u == 1) {
+        const unsigned f = G.flag[r];
+        q.has_m = !(f & FLAG_YM); q.has_p = !(f & FLAG_YP);
+        q.off_m = G.ypm[r]; q.off_p = G.ypp[r];
+        q.h = G.hy[r]; q.hm = q.has_m ? G.hy[r - q.off_m] : 0.0; q.hp = q.has_p ? G.hy[r + q.off_p] : 0.0;
+        q.bcm = G.bc[3]; q.bcp = G.bc[2];
+    } else {
+        const int kg = G.k0 + kl;
+        q.has_m = kg > 0; q.has_p = kg < G.nzz - 1;
+        q.off_m = G.np; q.off_p = G.np;
+        q.h = G.hz[1 + kg]; q.hm = G.hz[kg]; q.hp = G.hz[2 + kg];
+        q.bcm = G.bc[4]; q.bcp = G.bc[5];
+    }
+    return q;
+}
+
+// LU_solve (mod_nodal.f90:829-897): Doolittle without pivoting, operation order kept.
+// Returns false if |mat(i,i)| < 1e-4 for an original diagonal element.
+template <int M>
+__device__ __forceinline__ bool lu_solve(double (&U)[M][M], const double (&b)[M], double (&x)[M])
+{
+    bool ok = true;
+#pragma unroll
+    for (int i = 0; i < M; ++i) ok = ok && !(fabs(U[i][i]) < (double)10e-5f);
+    // decomposition; multipliers are kept in the (otherwise zeroed) lower triangle
+#pragma unroll
+    for (int i = 0; i < M; ++i) {
+#pragma unroll
+        for (int j = i + 1; j < M; ++j) {
+            const double piv = U[j][i] / U[i][i];
+#pragma unroll
+            for (int k = i + 1; k < M; ++k) U[j][k] = U[j][k] - piv * U[i][k];
+            U[j][i] = piv;
+        }
+    }
+    double y[M];
+    y[0] = b[0];
+#pragma unroll
+    for (int i = 1; i < M; ++i) {
+        double isum = 0.0;
+#pragma unroll
+        for (int k = 0; k < i; ++k) isum = isum + U[i][k] * y[k];
+        y[i] = b[i] - isum;
+    }
+    x[M - 1] = y[M - 1] / U[M - 1][M - 1];
+#pragma unroll
+    for (int i = M - 2; i >= 0; --i) {
+        double isum = 0.0;
+#pragma unroll
+        for (int k = i + 1; k < M; ++k) isum = isum + U[i][k] * x[k];
+        x[i] = (y[i] - isum) / U[i][i];
+    }
+    return ok;
+}
+
+// everything the sweep carries for one (node, direction)
+template <int NG>
+struct NodeDir {
+    double Bc[NG][NG];
+    double A[NG], B[NG], E[NG], F[NG], Gc[NG], H[NG];
+    double a2[NG], a4[NG], L1[NG];
+    double f0[NG], D[NG];
+};
+
+// get_B + get_ABEFGH + TLUpd1/2 + get_a2matvec + LU + get_a4 for node idx, direction u
+// (mod_nodal.f90:1345-1451, 1047-1341, 769-825, 740-765)
+template <int NG, int KERN>
+__device__ __forceinline__ bool node_dir(const Geo &G, const NodalArgs &A, int u, long long idx, const Line &q,
+                                         NodeDir<NG> &nd)
+{
+    const long long NV = G.NV;
+    const int m = A.mat[idx] - 1;
+    const double Ke = A.scal[S_KE];
+    const double hh = q.h * q.h;
+    double nuf[NG], chi[NG], sigr[NG];
+#pragma unroll
+    for (int g = 0; g < NG; ++g) {
+        nd.f0[g] = A.f0[g][idx];
+        nd.D[g] = A.D[(size_t)g * NV + idx];
+        nuf[g] = A.nuf[(size_t)g * NV + idx];
+        sigr[g] = A.sigr[(size_t)g * NV + idx];
+        chi[g] = A.chi[g * A.nmat + m];
+    }
+    double tfac = 0.0;
+    if (A.cmode == 2) tfac = 1.0 - A.tbeta[m] + A.dfis[idx];
+    // ---- get_B
+#pragma unroll
+    for (int g = 0; g < NG; ++g) {
+#pragma unroll
+        for (int h = 0; h < NG; ++h) {
+            double dum;
+            if (A.cmode == 1) {
+                if (g == h) dum = sigr[g] - chi[g] * nuf[h] / Ke;
+                else dum = -A.sigs[((size_t)g * NG + h) * NV + idx] - chi[g] * nuf[h] / Ke;   // sigs(n,h,g)
+            } else if (A.cmode == 2) {
+                if (g == h) dum = sigr[g] - tfac * chi[g] * chi[g] * nuf[h];                    // sic, :1383-1384
+                else dum = -A.sigs[((size_t)g * NG + h) * NV + idx] - tfac * chi[g] * nuf[h];
+            } else {
+                if (g == h) dum = sigr[g] - chi[g] * nuf[h] / Ke;
+                else dum = -A.sigs[((size_t)h * NG + g) * NV + idx] - chi[h] * nuf[g] / Ke;   // sigs(n,g,h)
+            }
+            nd.Bc[g][h] = 0.25 * hh / nd.D[g] * dum;
+        }
+    }
+    // ---- get_ABEFGH (SANM) or the PNM constants (mod_nodal.f90:180-182)
+#pragma unroll
+    for (int g = 0; g < NG; ++g) {
+        if (KERN == ADP_KERN_SANM) {
+            const double alp = 0.5 * sqrt(sigr[g] / nd.D[g]) * q.h;
+            const double alp2 = alp * alp;
+            const double sh = sinh(alp), ch = cosh(alp);
+            const double m0c = sh / alp;
+            const double m1s = 3.0 * (ch / alp - sh / alp2);
+            const double m2c = 5.0 * (sh / alp - 3.0 * ch / alp2 + 3.0 * sh / (alp * alp * alp));
+            nd.A[g] = (sh - m1s) / (alp2 * m1s);
+            nd.B[g] = (ch - m0c - m2c) / (alp2 * m2c);
+            nd.E[g] = (m0c / m2c - 3.0 / alp2);
+            nd.F[g] = (alp * ch - m1s) / (alp2 * m1s);
+            nd.Gc[g] = (alp * sh - 3.0 * m2c) / (ch - m0c - m2c);
+            nd.H[g] = (alp * ch - m1s) / (sh - m1s);
+        } else {
+            nd.A[g] = 1.0 / 15.0; nd.B[g] = 1.0 / 35.0; nd.E[g] = 2.0 / 7.0;
+            nd.F[g] = 2.0 / 5.0; nd.Gc[g] = 10.0; nd.H[g] = 6.0;
+        }
+    }
+    // ---- transverse leakage moments (TLUpd1 / TLUpd2) and the a2 system
+    double M2[NG][NG], b[NG], Lm2[NG];
+    const double *Su = A.S + (size_t)u * NG * NV;
+#pragma unroll
+    for (int g = 0; g < NG; ++g) {
+        const double Sn = Su[(size_t)g * NV + idx];
+        const double Sp = q.has_p ? Su[(size_t)g * NV + idx + q.off_p] : 0.0;
+        const double Sm = q.has_m ? Su[(size_t)g * NV + idx - q.off_m] : 0.0;
+        double l1, l2, tm, tp, p1m, p2m, p1p, p2p, hp;
+        if (!q.has_m) {
+            if (q.bcm == 2) {
+                tm = 1.0; tp = q.hp / q.h;
+                p1m = tm + 1.0; p2m = 2.0 * tm + 1.0; p1p = tp + 1.0;
+                hp = 2.0 * p1m * p1p * (tm + tp + 1.0);
+                l1 = (p1m * p2m * (Sp - Sn)) / hp;
+                l2 = (p1m * (Sp - Sn)) / hp;
+            } else {
+                tp = q.hp / q.h; p1p = tp + 1.0;
+                l1 = (Sp - Sn) / p1p;
+                l2 = 0.0;
+            }
+        } else if (!q.has_p) {
+            if (q.bcp == 2) {
+                tm = q.hm / q.h; tp = 1.0;
+                p1m = tm + 1.0; p1p = tp + 1.0; p2p = 2.0 * tp + 1.0;
+                hp = 2.0 * p1m * p1p * (tm + tp + 1.0);
+                l1 = (p1p * p2p * (Sn - Sm)) / hp;
+                l2 = (p1p * (Sm - Sn)) / hp;
+            } else {
+                tm = q.hm / q.h; p1m = tm + 1.0;
+                l1 = (Sn - Sm) / p1m;
+                l2 = 0.0;
+            }
+        } else {
+            tm = q.hm / q.h; tp = q.hp / q.h;
+            p1m = tm + 1.0; p2m = 2.0 * tm + 1.0; p1p = tp + 1.0; p2p = 2.0 * tp + 1.0;
+            hp = 2.0 * p1m * p1p * (tm + tp + 1.0);
+            l1 = (p1m * p2m * (Sp - Sn) + p1p * p2p * (Sn - Sm)) / hp;
+            l2 = (p1m * (Sp - Sn) + p1p * (Sm - Sn)) / hp;
+        }
+        nd.L1[g] = 0.25 * hh / nd.D[g] * l1;
+        Lm2[g] = 0.25 * hh / nd.D[g] * l2;
+        // get_a2matvec
+        double S;
+        if (A.cmode == 2) S = 0.25 * hh / nd.D[g] * Sn;
+        else S = 0.25 * hh / nd.D[g] * (Sn - A.exsrc[(size_t)g * NV + idx]);
+        double Bf = 0.0;
+#pragma unroll
+        for (int h = 0; h < NG; ++h) {
+            M2[g][h] = (h == g) ? nd.Bc[g][h] * nd.E[g] + 3.0 : nd.Bc[g][h] * nd.E[g];
+            Bf = Bf + nd.Bc[g][h] * nd.f0[h];
+        }
+        b[g] = Bf - nd.E[g] * Lm2[g] + S;
+    }
+    const bool ok = lu_solve<NG>(M2, b, nd.a2);
+    // get_a4
+#pragma unroll
+    for (int g = 0; g < NG; ++g) {
+        double Bf = 0.0;
+#pragma unroll
+        for (int h = 0; h < NG; ++h) Bf = Bf + nd.Bc[g][h] * nd.a2[h];
+        nd.a4[g] = nd.B[g] * (Bf + Lm2[g]);
+    }
+    return ok;
+}
+
+// get_a3 (mod_nodal.f90:702-736)
+template <int NG>
+__device__ __forceinline__ void get_a3(const NodeDir<NG> &nd, const double (&a1)[NG], double (&a3)[NG])
+{
+#pragma unroll
+    for (int g = 0; g < NG; ++g) {
+        double Bf = 0.0;
+#pragma unroll
+        for (int h = 0; h < NG; ++h) Bf = Bf + nd.Bc[g][h] * a1[h];
+        a3[g] = nd.A[g] * (Bf + nd.L1[g]);
+    }
+}
+
+struct ArgMax {
+    double *scal;
+    double *part;              // [ADP_MAXPART]
+    long long *part_loc;       // [ADP_MAXPART]
+    unsigned int *ticket;
+    long long *loc_out;
+};
+
+__device__ __forceinline__ void argmax_combine(double &v, long long &l, double v2, long long l2)
+{
+    if (v2 > v || (v2 == v && l2 < l)) { v = v2; l = l2; }
+}
+
+__device__ __forceinline__ void grid_argmax(double v, long long l, const ArgMax &ro)
+{
+    __shared__ double smv[ADP_TILE / 32];
+    __shared__ long long sml[ADP_TILE / 32];
+    __shared__ bool is_last;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double v2 = __shfl_down_sync(0xffffffffu, v, o);
+        const long long l2 = __shfl_down_sync(0xffffffffu, l, o);
+        argmax_combine(v, l, v2, l2);
+    }
+    if (lane == 0) { smv[wid] = v; sml[wid] = l; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < ADP_TILE / 32; ++w) argmax_combine(v, l, smv[w], sml[w]);
+        ro.part[blockIdx.x] = v;
+        ro.part_loc[blockIdx.x] = l;
+        __threadfence();
+        const unsigned int t = atomicAdd(ro.ticket, 1u);
+        is_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    double bv = -1.0;
+    long long bl = 0x7fffffffffffffffLL;
+    for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x)
+        argmax_combine(bv, bl, __ldcg(&ro.part[b]), __ldcg(&ro.part_loc[b]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double v2 = __shfl_down_sync(0xffffffffu, bv, o);
+        const long long l2 = __shfl_down_sync(0xffffffffu, bl, o);
+        argmax_combine(bv, bl, v2, l2);
+    }
+    __syncthreads();
+    if (lane == 0) { smv[wid] = bv; sml[wid] = bl; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < ADP_TILE / 32; ++w) argmax_combine(bv, bl, smv[w], sml[w]);
+        // strict ">" against the running maximum of the directions already swept
+        // (x before y before z, as in the reference's sweep order)
+        if (bv > ro.scal[S_NDMAX]) { ro.scal[S_NDMAX] = bv; *ro.loc_out = bl; }
+        *ro.ticket = 0u;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// one thread per (node, direction u): surface on the "+" side (+ the "-" boundary surface
+// of the first node of a line).  get_coefs / get_coefs_first / get_coefs_last +
+// nodal_coup_upd (mod_nodal.f90:282-698).
+// ---------------------------------------------------------------------------------------
+template <int NG, int KERN>
+__global__ void __launch_bounds__(ADP_TILE) k_nodal_surfaces(Geo G, NodalArgs A, int u, int klo, int npl, ArgMax am)
+{
+    const long long NV = G.NV;
+    double best = -1.0;
+    long long best_loc = 0x7fffffffffffffffLL;
+    bool ok = true;
+    FOR_EACH_ROW(G, klo, npl)
+    {
+        const long long idx = node_idx(G, kl, r);
+        const bool owned = (kl >= 0 && kl < G.nzl);
+        const long long gnode = (long long)(G.k0 + kl) * G.np + r;   // global node number - 1
+        const Line qn = line_of(G, u, kl, r);
+        const int sf = 2 * u;                                         // 0-based "+" face; "-" face = sf + 1
+        NodeDir<NG> n;
+        ok = node_dir<NG, KERN>(G, A, u, idx, qn, n) && ok;
+        double a1[NG], a3[NG];
+
+        if (!qn.has_m && owned) {
+            // ---- first node of the line: one-node problem on its "-" face (get_a1matvec_first)
+            double M1[NG][NG], b[NG];
+#pragma unroll
+            for (int g = 0; g < NG; ++g) {
+                const double Pp = 2.0 * n.D[g] / qn.h;
+                const double dcp = A.dc[((size_t)(sf + 1) * NG + g) * NV + idx];
+                if (qn.bcm == 2) {
+#pragma unroll
+                    for (int h = 0; h < NG; ++h)
+                        M1[g][h] = (h == g) ? Pp * (n.Bc[g][h] * n.F[g] + 1.0) : Pp * n.Bc[g][h] * n.F[g];
+                    b[g] = Pp * (3.0 * n.a2[g] + n.Gc[g] * n.a4[g] - n.F[g] * n.L1[g]);
+                } else if (qn.bcm == 1) {
+#pragma unroll
+                    for (int h = 0; h < NG; ++h)
+                        M1[g][h] = (h == g) ? -dcp * (1.0 + n.A[g] * n.Bc[g][h]) - 2.0 * Pp * (n.A[g] * n.Bc[g][h] * n.H[g] + 1.0)
+                                            : -dcp * n.A[g] * n.Bc[g][h] - 2.0 * Pp * n.A[g] * n.Bc[g][h] * n.H[g];
+                    b[g] = 2.0 * Pp * (n.A[g] * n.H[g] * n.L1[g] - 3.0 * n.a2[g] - n.Gc[g] * n.a4[g]) -
+                           dcp * (n.a2[g] + n.a4[g] + n.f0[g] - n.A[g] * n.L1[g]);
+                } else {
+#pragma unroll
+                    for (int h = 0; h < NG; ++h)
+                        M1[g][h] = (h == g) ? dcp * (1.0 + n.A[g] * n.Bc[g][h]) : dcp * n.A[g] * n.Bc[g][h];
+                    b[g] = dcp * (n.a2[g] + n.a4[g] + n.f0[g] - n.A[g] * n.L1[g]);
+                }
+            }
+            ok = lu_solve<NG>(M1, b, a1) && ok;
+            get_a3<NG>(n, a1, a3);
+#pragma unroll
+            for (int g = 0; g < NG; ++g) {
+                const double jp = -2.0 * n.D[g] / qn.h * (a1[g] - 3.0 * n.a2[g] + n.H[g] * a3[g] - n.Gc[g] * n.a4[g]);
+                double *dn = A.dn + ((size_t)g * 6 + sf + 1) * NV;
+                const double dfm = A.df[((size_t)g * 6 + sf + 1) * NV + idx];
+                const double ndpr = dn[idx];
+                const double nw = -(jp / n.f0[g] + dfm);
+                dn[idx] = nw;
+                const double nder = fabs(nw - ndpr);
+                if (nder > best || (nder == best && gnode < best_loc)) { best = nder; best_loc = gnode; }
+            }
+        }
+
+        if (qn.has_p) {
+            // ---- interior surface between n = this node and p = its "+" neighbour (get_coefs)
+            const long long idp = idx + qn.off_p;
+            const int klp = (u == 2) ? kl + 1 : kl;
+            const int rp = (u == 0) ? r + 1 : (u == 1) ? r + (int)qn.off_p : r;
+            const Line qp = line_of(G, u, klp, rp);
+            NodeDir<NG> p;
+            ok = node_dir<NG, KERN>(G, A, u, idp, qp, p) && ok;
+            double R[2 * NG][2 * NG], s[2 * NG], sx[2 * NG];
+#pragma unroll
+            for (int g = 0; g < NG; ++g) {
+                const double Pn = 2.0 * n.D[g] / qn.h, Pp = 2.0 * p.D[g] / qp.h;
+#pragma unroll
+                for (int h = 0; h < NG; ++h) {
+                    if (h == g) {
+                        R[g][g] = -Pn * (n.Bc[g][h] * n.F[g] + 1.0);
+                        R[g][g + NG] = Pp * (p.Bc[g][h] * p.F[g] + 1.0);
+                    } else {
+                        R[g][h] = -Pn * n.Bc[g][h] * n.F[g];
+                        R[g][h + NG] = Pp * p.Bc[g][h] * p.F[g];
+                    }
+                }
+                s[g] = Pn * (3.0 * n.a2[g] + n.Gc[g] * n.a4[g] + n.F[g] * n.L1[g]) +
+                       Pp * (3.0 * p.a2[g] + p.Gc[g] * p.a4[g] - p.F[g] * p.L1[g]);
+            }
+#pragma unroll
+            for (int g = 0; g < NG; ++g) {
+                const double dcn = A.dc[((size_t)sf * NG + g) * NV + idx];
+                const double dcp = A.dc[((size_t)(sf + 1) * NG + g) * NV + idp];
+#pragma unroll
+                for (int h = 0; h < NG; ++h) {
+                    if (h == g) {
+                        R[g + NG][g] = dcn * (n.Bc[g][h] * n.A[g] + 1.0);
+                        R[g + NG][g + NG] = dcp * (p.Bc[g][h] * p.A[g] + 1.0);
+                    } else {
+                        R[g + NG][h] = dcn * n.Bc[g][h] * n.A[g];
+                        R[g + NG][h + NG] = dcp * p.Bc[g][h] * p.A[g];
+                    }
+                }
+                // ADF cross terms exactly as mod_nodal.f90:693-694 (An*Ln1 with dc_p, Ap*Lp1 with dc_n)
+                s[g + NG] = dcp * (p.a2[g] + p.a4[g] + p.f0[g] - n.A[g] * n.L1[g]) -
+                            dcn * (n.a2[g] + n.a4[g] + n.f0[g] + p.A[g] * p.L1[g]);
+            }
+            ok = lu_solve<2 * NG>(R, s, sx) && ok;
+#pragma unroll
+            for (int g = 0; g < NG; ++g) a1[g] = sx[g];
+            get_a3<NG>(n, a1, a3);
+#pragma unroll
+            for (int g = 0; g < NG; ++g) {
+                const double jp = -2.0 * n.D[g] / qn.h * (a1[g] + 3.0 * n.a2[g] + n.H[g] * a3[g] + n.Gc[g] * n.a4[g]);
+                double *dn = A.dn + ((size_t)g * 6 + sf) * NV;
+                const double dfp = A.df[((size_t)g * 6 + sf) * NV + idx];
+                const double ndpr = dn[idx];
+                const double nw = (dfp * (n.f0[g] - p.f0[g]) - jp) / (n.f0[g] + p.f0[g]);
+                dn[idx] = nw;
+                A.dn[((size_t)g * 6 + sf + 1) * NV + idp] = nw;
+                if (owned) {
+                    const double nder = fabs(nw - ndpr);
+                    if (nder > best || (nder == best && gnode < best_loc)) { best = nder; best_loc = gnode; }
+                }
+            }
+        } else if (owned) {
+            // ---- last node of the line: one-node problem on its "+" face (get_a1matvec_last)
+            double M1[NG][NG], b[NG];
+#pragma unroll
+            for (int g = 0; g < NG; ++g) {
+                const double Pn = 2.0 * n.D[g] / qn.h;
+                const double dcn = A.dc[((size_t)sf * NG + g) * NV + idx];
+                if (qn.bcp == 2) {
+#pragma unroll
+                    for (int h = 0; h < NG; ++h)
+                        M1[g][h] = (h == g) ? -Pn * (n.Bc[g][h] * n.F[g] + 1.0) : -Pn * n.Bc[g][h] * n.F[g];
+                    b[g] = Pn * (3.0 * n.a2[g] + n.Gc[g] * n.a4[g] + n.F[g] * n.L1[g]);
+                } else if (qn.bcp == 1) {
+#pragma unroll
+                    for (int h = 0; h < NG; ++h)
+                        M1[g][h] = (h == g) ? dcn * (1.0 + n.A[g] * n.Bc[g][h]) + 2.0 * Pn * (n.A[g] * n.Bc[g][h] * n.H[g] + 1.0)
+                                            : dcn * n.A[g] * n.Bc[g][h] + 2.0 * Pn * n.A[g] * n.Bc[g][h] * n.H[g];
+                    b[g] = -2.0 * Pn * (n.A[g] * n.H[g] * n.L1[g] + 3.0 * n.a2[g] + n.Gc[g] * n.a4[g]) -
+                           dcn * (n.a2[g] + n.a4[g] + n.f0[g] + n.A[g] * n.L1[g]);
+                } else {
+#pragma unroll
+                    for (int h = 0; h < NG; ++h)
+                        M1[g][h] = (h == g) ? dcn * (1.0 + n.A[g] * n.Bc[g][h]) : dcn * n.A[g] * n.Bc[g][h];
+                    b[g] = -dcn * (n.a2[g] + n.a4[g] + n.f0[g] + n.A[g] * n.L1[g]);
+                }
+            }
+            ok = lu_solve<NG>(M1, b, a1) && ok;
+            get_a3<NG>(n, a1, a3);
+#pragma unroll
+            for (int g = 0; g < NG; ++g) {
+                const double jp = -2.0 * n.D[g] / qn.h * (a1[g] + 3.0 * n.a2[g] + n.H[g] * a3[g] + n.Gc[g] * n.a4[g]);
+                double *dn = A.dn + ((size_t)g * 6 + sf) * NV;
+                const double dfp = A.df[((size_t)g * 6 + sf) * NV + idx];
+                const double ndpr = dn[idx];
+                const double nw = -(jp / n.f0[g] - dfp);
+                dn[idx] = nw;
+                const double nder = fabs(nw - ndpr);
+                if (nder > best || (nder == best && gnode < best_loc)) { best = nder; best_loc = gnode; }
+            }
+        }
+    }
+    if (!ok) atomicExch(A.errflag, ADP_STOP_LU_DIAG);
+    grid_argmax(best, best_loc, am);
+}
+
+template <int NG>
+void launch_surfaces(adp_ctx *c, const NodalArgs &A, int u, int klo, int npl, int grid, const ArgMax &am)
+{
+    if (A.kern == ADP_KERN_SANM)
+        k_nodal_surfaces<NG, ADP_KERN_SANM><<<grid, ADP_TILE, 0, c->stream>>>(c->geo, A, u, klo, npl, am);
+    else
+        k_nodal_surfaces<NG, ADP_KERN_PNM><<<grid, ADP_TILE, 0, c->stream>>>(c->geo, A, u, klo, npl, am);
+}
+
+}  // namespace
+
+static NodalArgs make_args(adp_ctx *c, int cmode)
+{
+    NodalArgs A{};
+    A.ng = c->ng; A.nmat = c->nmat; A.cmode = cmode; A.kern = c->kern;
+    A.nnod_total = c->nnod;
+    for (int g = 0; g < c->ng; ++g) A.f0[g] = c->d_f0[c->cur[g]] + (size_t)g * c->NV;
+    A.D = c->d_D; A.sigr = c->d_sigr; A.nuf = c->d_nuf; A.exsrc = c->d_exsrc; A.sigs = c->d_sigs;
+    A.chi = c->d_chi; A.dc = c->d_dc; A.mat = c->d_mat; A.tbeta = c->d_tbeta; A.dfis = c->d_dfis;
+    A.df = c->d_df; A.dn = c->d_dn; A.S = c->d_S; A.scal = c->d_scal; A.errflag = c->d_errflag;
+    return A;
+}
+
+static inline int grid_for(adp_ctx *c, int ntiles)
+{
+    int g = c->grid_blocks;
+    if (ntiles < g) g = ntiles;
+    return g < 1 ? 1 : g;
+}
+
+int adp_k_nodal_source(adp_ctx *c, int cmode)
+{
+    NodalArgs A = make_args(c, cmode);
+    int rc;
+    if (c->nranks > 1)
+        for (int g = 0; g < c->ng; ++g)
+            if ((rc = adp_comm_halo(c, c->d_f0[c->cur[g]] + (size_t)g * c->NV, 1))) return rc;
+    k_nodal_source<<<grid_for(c, c->geo.ntiles), ADP_TILE, 0, c->stream>>>(c->geo, A);
+    c->launches++;
+    if (cudaPeekAtLastError() != cudaSuccess) { c->err = "k_nodal_source launch failed"; return ADP_ERR_CUDA; }
+    return ADP_OK;
+}
+
+int adp_k_nodal_update(adp_ctx *c, int cmode)
+{
+    int rc = adp_k_nodal_source(c, cmode);
+    if (rc) return rc;
+    NodalArgs A = make_args(c, cmode);
+    if (c->nranks > 1) {
+        // S3 is needed two planes deep across a slab boundary (quadratic transverse-leakage fit)
+        for (int g = 0; g < c->ng; ++g)
+            if ((rc = adp_comm_halo(c, c->d_S + ((size_t)2 * c->ng + g) * c->NV, 2))) return rc;
+    }
+    ArgMax am;
+    am.scal = c->d_scal; am.part = c->d_part; am.part_loc = (long long *)(c->d_part + ADP_MAXPART);
+    am.ticket = c->d_ticket; am.loc_out = c->d_argidx;
+    for (int u = 0; u < 3; ++u) {
+        int klo = 0, npl = c->nzl;
+        if (u == 2 && c->k0 > 0) { klo = -1; npl = c->nzl + 1; }   // the surface shared with the slab below
+        const int grid = grid_for(c, c->geo.tpp * npl);
+        switch (c->ng) {
+        case 1: launch_surfaces<1>(c, A, u, klo, npl, grid, am); break;
+        case 2: launch_surfaces<2>(c, A, u, klo, npl, grid, am); break;
+        case 3: launch_surfaces<3>(c, A, u, klo, npl, grid, am); break;
+        case 4: launch_surfaces<4>(c, A, u, klo, npl, grid, am); break;
+        case 5: launch_surfaces<5>(c, A, u, klo, npl, grid, am); break;
+        case 6: launch_surfaces<6>(c, A, u, klo, npl, grid, am); break;
+        case 7: launch_surfaces<7>(c, A, u, klo, npl, grid, am); break;
+        case 8: launch_surfaces<8>(c, A, u, klo, npl, grid, am); break;
+        default: c->err = "nodal update supports 1..8 energy groups"; return ADP_ERR_UNSUPPORTED;
+        }
+        c->launches++;
+        if (cudaPeekAtLastError() != cudaSuccess) {
+            c->err = std::string("k_nodal_surfaces launch failed: ") + cudaGetErrorString(cudaGetLastError());
+            return ADP_ERR_CUDA;
+        }
+    }
+    return ADP_OK;
+}

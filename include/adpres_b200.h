@@ -1,0 +1,198 @@
+/*
+ * adpres_b200.h -- C ABI of the B200-native ADPRES eigenvalue hot path.
+ *
+ * What it replaces.  ADPRES (Fortran 90) has no plugin / FFI interface: its modules USE
+ * each other and share state through the global module `sdata` (src/mod_data.f90).  The
+ * boundary therefore consists of the *bodies* of the hot-path procedures of
+ *     src/mod_cmfd.f90   (outer, outer_ad, outer_fs, outer_th, outer_tr, PowDis, ...)
+ *     src/mod_nodal.f90  (nodal_update, nodal_update_pnm, Lxyz)
+ * The Fortran procedure names and argument lists stay; their bodies pack the `sdata`
+ * arrays and call the functions below through ISO_C_BINDING (fortran/adpres_b200_bind.f90,
+ * INTEGRATION.md).  Each entry point cites the reference code it stands for.
+ *
+ * Conventions
+ *  - plain C: pointers + sizes only; every pointer is HOST memory owned by the caller.
+ *  - arrays are Fortran column-major exactly as `sdata` stores them, node index fastest:
+ *      f0(nnod,ng), sigs(nnod,ng,ng) [from g to h], dc(nnod,ng,6), chi(nmat,ng) ...
+ *    node / mesh / material indices are 1-based as in the Fortran.
+ *  - face index: 1=x+ (east) 2=x- 3=y+ (north) 4=y- 5=z+ (top) 6=z-  (mod_data.f90:59-60)
+ *  - boundary codes: 0 zero flux, 1 zero incoming current, 2 reflective.
+ *  - all arithmetic is fp64 (dp = selected_real_kind(10,15), mod_data.f90:5).
+ *  - return value: 0 ok; >0 one of the reference's STOP conditions (ADP_STOP_*);
+ *    <0 a CUDA / NCCL / usage error (adp_last_error() has the text).
+ *  - one context per process and GPU; calls are synchronous and not re-entrant, like the
+ *    SAVE'd single-threaded reference.  With adp_comm_init() the core is split in z-slabs
+ *    over the ranks (one process per GPU); every rank passes the same GLOBAL arrays.
+ *  - there is NO CPU fallback: without a CUDA device adp_create() fails.
+ */
+#ifndef ADPRES_B200_H
+#define ADPRES_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct adp_ctx adp_ctx;
+
+/* ---- status codes ------------------------------------------------------------------- */
+enum {
+    ADP_OK = 0,
+    ADP_STOP_MAXOUTER = 1,   /* "MAXIMUM NUMBER OF OUTER ITERATION IS REACHED" mod_cmfd.f90:498-505,589-596,688-695 */
+    ADP_STOP_LU_DIAG = 2,    /* "ERROR IN MATRIX DECOMP: DIAGONAL ELEMENTS CLOSE TO ZERO" mod_nodal.f90:856-862 */
+    ADP_STOP_NDMAX = 3,      /* "Max. change in nodal coupling coefficient" > 1e3, mod_nodal.f90:131-142 */
+    ADP_STOP_ZERO_POWER = 4, /* "TOTAL NODES POWER IS ZERO OR LESS" mod_cmfd.f90:1322-1326 */
+    ADP_ERR_CUDA = -1,
+    ADP_ERR_USAGE = -2,
+    ADP_ERR_NCCL = -3,
+    ADP_ERR_UNSUPPORTED = -4
+};
+
+/* kern: the %KERN card (mod_io.f90:1593-1621) */
+enum { ADP_KERN_FDM = 0, ADP_KERN_PNM = 1, ADP_KERN_SANM = 2 };
+
+/* which outer iteration: selects TSrc/FSrc flavour, group sweep order and k-eff update */
+enum {
+    ADP_MODE_FORWARD = 0,  /* outer     mod_cmfd.f90:415-509  TSrc  + FSrc,   g = 1..G, Ke update   */
+    ADP_MODE_ADJOINT = 1,  /* outer_ad  mod_cmfd.f90:602-699  TSrcAd+ FSrcAd, g = G..1, Ke update   */
+    ADP_MODE_FIXEDSRC = 2, /* outer_fs  mod_cmfd.f90:513-598  TSrc  + FSrc,   no Ke update          */
+    ADP_MODE_TRANSIENT = 3 /* outer_tr  mod_cmfd.f90:800-868  TSrcTr+ FSrc,   no Ke update          */
+};
+
+/* ---- lifecycle ---------------------------------------------------------------------- */
+int adp_create(adp_ctx **ctx, int device);
+int adp_destroy(adp_ctx *ctx);
+const char *adp_last_error(const adp_ctx *ctx);
+const char *adp_version(void);
+
+/* z-slab decomposition over ranks (one process per GPU).  The 128-byte NCCL unique id is
+ * produced on rank 0 by adp_comm_unique_id() and distributed by the launcher (torchrun /
+ * MPI / a file).  Must be called before adp_set_geometry().  Not calling it = 1 rank. */
+int adp_comm_unique_id(void *uid128);
+int adp_comm_init(adp_ctx *ctx, int nranks, int rank, const void *uid128);
+/* planes [k0, k1) (0-based) owned by this rank, valid after adp_set_geometry() */
+int adp_slab(const adp_ctx *ctx, int *k0, int *k1);
+
+/* ---- problem definition (what inp_geom1/2 + misc leave in sdata, mod_io.f90:809-1365) -- */
+int adp_set_geometry(adp_ctx *ctx, int nxx, int nyy, int nzz, int nnod, int ng, int nmat,
+                     const int *ix, const int *iy, const int *iz,          /* (nnod) */
+                     const int *ystag_smin, const int *ystag_smax,        /* (nyy) ystag(j)%smin/smax */
+                     const int *xstag_smin, const int *xstag_smax,        /* (nxx) xstag(i)%smin/smax */
+                     const double *xdel, const double *ydel, const double *zdel,
+                     const int bc[6] /* xeast, xwest, ynorth, ysouth, zbott, ztop */,
+                     const int *mat /* (nnod) */);
+
+/* node-wise cross sections as XS_updt leaves them (mod_xsec.f90:11-46).  A NULL pointer
+ * keeps the values already on the device (e.g. only sigr changes in trans_calc,
+ * mod_trans.f90:398-412). */
+int adp_set_xs(adp_ctx *ctx, const double *D, const double *sigr, const double *nuf,
+               const double *sigf, const double *sigs /* (nnod,ng,ng) */,
+               const double *chi /* (nmat,ng) */, const double *dc /* (nnod,ng,6) */,
+               const double *exsrc /* (nnod,ng) */);
+
+/* %ITER and %KERN values (mod_io.f90:1522-1540; defaults mod_data.f90:78-86) */
+int adp_set_control(adp_ctx *ctx, int nout, int nin, int nac, int nupd, double serc, double ferc,
+                    int kern);
+
+/* ---- the hot path, fine grained ------------------------------------------------------- */
+/* matrix_setup(opt): opt > 0 recomputes the FDM coupling coefficients (coup_coef) first.
+ * mod_cmfd.f90:217-304, 11-137.  The first call with opt > 0 zeroes nod%dn (:25-33). */
+int adp_matrix_setup(adp_ctx *ctx, int opt);
+
+/* first-call initialisation of outer*: Ke = 1, f0 = 1, fs0 = FSrc / FSrcAd.
+ * mod_cmfd.f90:448-454, 635-641 */
+int adp_init_flux(adp_ctx *ctx, int adjoint);
+
+/* the statements before the `do p` loop: f = Integrate(fs0); errn = 1; e1 = Integrate(errn)
+ * mod_cmfd.f90:457-459 (and 553-554, 644-646).  Call once per outer*() after matrix_setup. */
+int adp_outer_begin(adp_ctx *ctx, int mode);
+
+/* one pass of the `do p = 1, nout` loop body up to and including RelE/RelEg
+ * (mod_cmfd.f90:467-487; 562-578; 654-674; 838-854): G x (TSrc* + bicg), FSrc*, errn, l2norm,
+ * fission-source extrapolation when mod(p,nac)==0, Integrate, k-eff update, RelE, RelEg.
+ * Returns the scalars the Fortran loop prints and tests. */
+int adp_outer_iter(adp_ctx *ctx, int mode, int p, double *Ke, double *ser, double *fer);
+
+/* nodal_upd(popt, nmode): ndmax = 0; nodal_update | nodal_update_pnm (cmode = nmode:
+ * 0 adjoint, 1 forward, 2 transient); matrix_setup(0).  mod_cmfd.f90:339-383,
+ * mod_nodal.f90:18-278.  im/jm/km = location of the maximum (ties: lowest node number). */
+int adp_nodal_upd(adp_ctx *ctx, int nmode, double *ndmax, int *im, int *jm, int *km);
+
+/* PowDis(p): nodal power, normalised to sum 1 (mod_cmfd.f90:1290-1333).  p(nnod). */
+int adp_powdis(adp_ctx *ctx, double *p, int fixedsrc_mode);
+
+/* Integrate(s) = sum vdel*s (mod_cmfd.f90:1120-1139); s(nnod) host array */
+int adp_integrate(adp_ctx *ctx, const double *s, double *result);
+
+/* ---- transient terms (outer_tr / get_exsrc, mod_cmfd.f90:800-952) ---------------------- */
+/* kinetics data: iBeta(6), lamb(6), velo(ng), tbeta(nmat), sth, bth (mod_data.f90:120-127) */
+int adp_set_kinetics(adp_ctx *ctx, const double *ibeta, const double *lamb, const double *velo,
+                     const double *tbeta, double sth, double bth);
+/* state of the previous time level saved by trans_calc (mod_trans.f90:398-416) and the
+ * precursors / frequencies / leakage: c0(nnod,6), ft(nnod,ng), fst(nnod), omeg(nnod,ng),
+ * sigrp(nnod,ng), L(nnod,ng).  NULL keeps the device copy. */
+int adp_set_transient(adp_ctx *ctx, const double *c0, const double *ft, const double *fst,
+                      const double *omeg, const double *sigrp, const double *L);
+/* get_exsrc(ht, exsrc): fills exsrc and dfis on the device (mod_cmfd.f90:872-952, bxtab=0) */
+int adp_get_exsrc(adp_ctx *ctx, double ht);
+
+/* ---- state exchange with the Fortran side ----------------------------------------------- */
+/* f0(nnod,ng), fs0(nnod), s0(nnod,ng); NULL = skip.  (drivers read them after outer*) */
+int adp_get_state(adp_ctx *ctx, double *f0, double *fs0, double *s0, double *Ke);
+/* restart / KNE1 paths: load flux, fission source and k-eff (NULL keeps) */
+int adp_set_state(adp_ctx *ctx, const double *f0, const double *fs0, double Ke);
+/* restart path for s0(nnod,ng): column g (1-based) is loaded, the others are zero, which is the
+ * only shape TSrc* ever leave behind (mod_cmfd.f90:1022); g = 0 clears s0 */
+int adp_set_s0(adp_ctx *ctx, const double *s0, int g);
+/* nod(n,g)%df / %dn as df(6,nnod,ng), dn(6,nnod,ng) (Lxyz in reactivity, mod_trans.f90:677) */
+int adp_get_nod(adp_ctx *ctx, double *df, double *dn);
+int adp_set_nod_dn(adp_ctx *ctx, const double *dn);
+/* exsrc(nnod,ng), dfis(nnod) after adp_get_exsrc */
+int adp_get_exsrc_arrays(adp_ctx *ctx, double *exsrc, double *dfis);
+/* ndmax persists across outer*() calls and starts at 0 (mod_data.f90:199) */
+int adp_get_ndmax(adp_ctx *ctx, double *ndmax);
+
+/* ---- whole procedures (host loop in C++, adpres_b200/csrc/host_cmfd.cpp) ---------------- */
+/* Trace callback: called once per outer iteration with what the reference prints
+ * (mod_cmfd.f90:491-494); event: 0 iteration line, 1 "FISSION SOURCE EXTRAPOLATED",
+ * 2 "NODAL COUPLING UPDATED" (then a = ndmax, i,j,k = location). */
+typedef void (*adp_trace_fn)(void *user, int event, int p, double a, double b, double c, int i,
+                             int j, int k);
+int adp_set_trace(adp_ctx *ctx, adp_trace_fn fn, void *user);
+
+/* outer(popt) / outer_ad(popt) / outer_fs(popt): mod_cmfd.f90:415-509 / 602-699 / 513-598.
+ * niter receives the number of outer iterations done. */
+int adp_outer(adp_ctx *ctx, int popt, int *niter);
+int adp_outer_ad(adp_ctx *ctx, int popt, int *niter);
+int adp_outer_fs(adp_ctx *ctx, int popt, int *niter);
+/* outer_th(maxn): mod_cmfd.f90:703-796 (at most maxn iterations, no STOP) */
+int adp_outer_th(adp_ctx *ctx, int maxn, int *niter);
+/* outer_tr(ht, maxi): mod_cmfd.f90:800-868 */
+int adp_outer_tr(adp_ctx *ctx, double ht, int *maxi, int *niter);
+
+/* ---- kernel-level entry points (used by the parity tests and the micro-benchmarks) ------ */
+/* v = A_g x  (sp_matvec, mod_cmfd.f90:1247-1268); g 1-based; x, v host (nnod) */
+int adp_sp_matvec(adp_ctx *ctx, int g, const double *x, double *v);
+/* bicg(imax, g, b, x): mod_cmfd.f90:1203-1243; x in/out host (nnod) */
+int adp_bicg(adp_ctx *ctx, int imax, int g, const double *b, double *x);
+/* the assembled matrix as a(7,nnod,ng): z-,y-,x-,diag,x+,y+,z+ (set_ind order) */
+int adp_get_matrix(adp_ctx *ctx, double *a);
+/* get_source (mod_nodal.f90:1009-1043): S1,S2,S3 (nnod,ng) for cmode */
+int adp_get_source(adp_ctx *ctx, int cmode, double *S1, double *S2, double *S3);
+
+/* runtime options: "graphs" 0/1 (CUDA-graph replay of an outer iteration, default 1),
+ * "grid_blocks" n (persistent grid size, default 8 x SM count) */
+int adp_set_option(adp_ctx *ctx, const char *name, int value);
+
+/* ---- measurement ------------------------------------------------------------------------ */
+/* number of kernel launches issued by this context so far (graph launches count the kernels
+ * inside) and device time accumulated per class, in ms, measured with CUDA events */
+int adp_launch_count(const adp_ctx *ctx, long long *launches);
+/* device-resident micro-benchmark of one kernel class on the current problem, no host copies:
+ * what: 0 SpMV (v=A p + (rs,v)), 1 fused s/t kernel, 2 whole bicg (nin iterations),
+ * 3 whole outer iteration, 4 nodal update.  Runs `reps` launches, returns average ms. */
+int adp_bench_kernel(adp_ctx *ctx, int what, int reps, double *avg_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ADPRES_B200_H */

@@ -1,0 +1,51 @@
+"""CPU-only: the C-ABI shared library loads and exports every symbol include/adpres_b200.h
+declares; without a GPU the product fails loudly instead of falling back to the CPU."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from conftest import ROOT
+from adpres_b200 import capi
+
+HEADER = os.path.join(ROOT, "include", "adpres_b200.h")
+
+
+def _declared():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(adp_[a-z0-9_]+)\s*\(", text)) - {"adp_trace_fn"})
+
+
+def test_library_exports_every_declared_symbol():
+    lib = capi.load()
+    names = _declared()
+    assert len(names) >= 35
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/adpres_b200.h but not exported"
+    assert sorted(capi.SYMBOLS) == names
+
+
+def test_version_string():
+    assert b"sm_100a" in capi.load().adp_version()
+
+
+def test_no_cpu_fallback_without_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    h = ctypes.c_void_p()
+    rc = capi.load().adp_create(ctypes.byref(h), 0)
+    assert rc < 0 and not h.value
+    assert b"no CPU fallback" in capi.load().adp_last_error(None)
+
+
+def test_product_does_not_import_oracle():
+    """The product path must never route through oracle/ (only tests, smoke and the bench baseline may)."""
+    pkg = os.path.join(ROOT, "adpres_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src and "liboracle" not in src, f

@@ -1,0 +1,262 @@
+"""GPU parity tests: the CUDA hot path, called through the C ABI, against the CPU oracle on
+the same inputs.  Bars (BASELINE.json north_star): k-eff within 1 pcm, nodal / assembly
+power within 1e-5 relative; fp64 throughout, differences come only from reduction order
+(and the device libm's sinh/cosh in the SANM constants).  Kernels without a global reduction
+are held to bit-exactness (the library is built with -fmad=false).
+"""
+import numpy as np
+import pytest
+
+from conftest import load_problem
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def mods():
+    from adpres_b200 import capi
+    from oracle import Oracle
+    return capi, Oracle
+
+
+def _pair(mods, name, **kw):
+    capi, Oracle = mods
+    p = load_problem(name)
+    return p, capi.Solver(p, **kw), Oracle(p, **kw)
+
+
+def _rel(a, b):
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+# ------------------------------------------------------------------ kernel level, bit exact
+@pytest.mark.parametrize("deck", ["IAEA3Ds", "KOEBERG", "DVP"])
+def test_coup_coef_and_matrix_bit_exact(mods, deck):
+    p, s, o = _pair(mods, deck)
+    s.matrix_setup(1)
+    o.matrix_setup(1)
+    df_g, dn_g = s.nod()
+    df_o, dn_o = o.nod()
+    assert np.array_equal(df_g, df_o)
+    assert np.array_equal(dn_g, dn_o) and not dn_g.any()
+    assert np.array_equal(s.matrix_dia(), o.matrix_dia())
+
+
+@pytest.mark.parametrize("deck", ["IAEA3Ds", "KOEBERG"])
+def test_sp_matvec_bit_exact(mods, deck):
+    p, s, o = _pair(mods, deck)
+    s.matrix_setup(1)
+    o.matrix_setup(1)
+    rng = np.random.default_rng(7)
+    for g in range(1, p.ng + 1):
+        x = rng.standard_normal(p.nnod)
+        assert np.array_equal(s.sp_matvec(g, x), o.sp_matvec(g, x))
+
+
+def test_bicg_matches_to_reduction_order(mods):
+    p, s, o = _pair(mods, "IAEA3Ds")
+    s.matrix_setup(1)
+    o.matrix_setup(1)
+    rng = np.random.default_rng(11)
+    for g in (1, 2):
+        for imax in (1, 2, 5):
+            b = rng.random(p.nnod)
+            x0 = rng.random(p.nnod)
+            xg = s.bicg(imax, g, b, x0)
+            xo = o.bicg(imax, g, b, x0)
+            assert _rel(xg, xo) < 1e-11, (g, imax, _rel(xg, xo))
+
+
+def test_first_outer_iteration_is_deterministic(mods, golden_trace):
+    """Iteration 1 starts from f0 = 1, Ke = 1: checks coup_coef + matrix_setup + TSrc + bicg +
+    FSrc + RelE/RelEg against the docs trace line `1  0.981424  5.47871E-01  8.55259E+03`."""
+    p, s, o = _pair(mods, "IAEA3Ds")
+    s.matrix_setup(1)
+    s.init_flux()
+    s.outer_begin()
+    ke, ser, fer = s.outer_iter(0, 1)
+    row = golden_trace["rows"][0]
+    assert ("%.6f" % ke, "%.5E" % ser, "%.5E" % fer) == (row[1], row[2], row[3])
+
+
+def test_nodal_source_bit_exact(mods):
+    p, s, o = _pair(mods, "IAEA3Ds", nupd=5)
+    for x in (s, o):
+        x.set_control(nout=7, nupd=5)
+    o.outer(0)
+    # same state into both: take the oracle's flux and coupling coefficients
+    st = o.state()
+    df, dn = o.nod()
+    s.matrix_setup(1)
+    s.set_state(st["f0"], st["fs0"], st["Ke"])
+    s.set_nod_dn(dn)
+    So = o.get_source(1)
+    Sg = s.get_source(1)
+    for u in range(3):
+        assert np.array_equal(Sg[u], So[u]), u
+
+
+@pytest.mark.parametrize("deck,kern,tol", [("IAEA3Ds", 2, 1e-9), ("IAEA3Ds", 1, 1e-13), ("DVP", 2, 1e-9), ("KOEBERG", 2, 1e-9)])
+def test_nodal_update_from_identical_state(mods, deck, kern, tol):
+    """One nodal update (SANM / PNM) from an identical flux / dn state: new dn and ndmax."""
+    p, s, o = _pair(mods, deck, kern=kern)
+    for x in (s, o):
+        x.set_control(nout=6, nupd=1000, kern=kern)
+    o.outer(0)
+    st = o.state()
+    s.matrix_setup(1)
+    s.set_state(st["f0"], st["fs0"], st["Ke"])
+    rc_o = o.nodal_upd(1)
+    rc_s, ndmax, loc = s.nodal_upd(1)
+    assert rc_o == 0 and rc_s == 0
+    _, dn_o = o.nod()
+    _, dn_s = s.nod()
+    assert np.abs(dn_s - dn_o).max() <= tol * max(1.0, np.abs(dn_o).max()), np.abs(dn_s - dn_o).max()
+    assert abs(ndmax - o.ndmax) <= tol * max(1.0, o.ndmax)
+    assert np.allclose(s.matrix_dia(), o.matrix_dia(), rtol=1e-8, atol=1e-12)
+
+
+# ------------------------------------------------------------------ whole procedures
+def _compare_run(s, o, rc_s, n_s, rc_o, n_o, p, pcm=1.0, ptol=1e-5):
+    assert rc_s == rc_o == 0
+    ks, ko = s.state()["Ke"], o.state()["Ke"]
+    assert abs(ks - ko) * 1e5 < pcm, (ks, ko)
+    assert abs(n_s - n_o) <= 1, (n_s, n_o)
+    rc, pw_s = s.powdis(p.mode == "FIXEDSRC")
+    rc2, pw_o = o.powdis()
+    nz = pw_o > 1e-12
+    assert np.abs(pw_s[nz] / pw_o[nz] - 1.0).max() < ptol
+    a_s, a_o = p.asm_power(pw_s), p.asm_power(pw_o)
+    nz = a_o > 0
+    assert np.abs(a_s[nz] / a_o[nz] - 1.0).max() < ptol
+
+
+def test_iaea3ds_forward_trace_and_keff(mods, golden_trace):
+    p, s, o = _pair(mods, "IAEA3Ds")
+    s.enable_trace()
+    rc_s, n_s = s.outer(1)
+    rc_o, n_o = o.outer(1)
+    _compare_run(s, o, rc_s, n_s, rc_o, n_o, p)
+    assert n_s == golden_trace["outers"]
+    assert "%.6f" % s.state()["Ke"] == golden_trace["keff"]
+    rows = {r[0]: r for r in s.trace_rows}
+    for pnum, gk, gs, gf in golden_trace["rows"]:
+        _, ke, ser, fer = rows[pnum]
+        assert abs(ke - float(gk)) < 2e-6
+        assert abs(ser / float(gs) - 1) < 1e-4 and abs(fer / float(gf) - 1) < 1e-4, (pnum, ser, gs, fer, gf)
+    assert [u[0] for u in s.trace_nodal] == [22, 44, 66, 88, 110]
+    assert "%.5E" % s.trace_nodal[0][1] == golden_trace["nodal_update"]["ndmax"]
+    assert s.trace_extrp[:4] == [5, 10, 15, 20]
+
+
+@pytest.mark.parametrize("deck", ["IAEA2D", "BIBLIS", "KOEBERG", "DVP", "PNM", "FDM"])
+def test_static_decks_forward(mods, deck):
+    p, s, o = _pair(mods, deck)
+    rc_s, n_s = s.outer(0)
+    rc_o, n_o = o.outer(0)
+    _compare_run(s, o, rc_s, n_s, rc_o, n_o, p)
+
+
+def test_adjoint_deck(mods):
+    p, s, o = _pair(mods, "adjoint")
+    rc_s, n_s = s.outer_ad(1)
+    rc_o, n_o = o.outer_ad(1)
+    assert rc_s == rc_o == 0 and abs(n_s - n_o) <= 1
+    assert abs(s.state()["Ke"] - o.state()["Ke"]) * 1e5 < 1.0
+    assert _rel(s.state()["f0"], o.state()["f0"]) < 1e-5
+
+
+def test_fixed_source_deck(mods):
+    p, s, o = _pair(mods, "fixed_source")
+    rc_s, n_s = s.outer_fs(1)
+    rc_o, n_o = o.outer_fs(1)
+    assert rc_s == rc_o == 0 and abs(n_s - n_o) <= 1
+    fs, fo = s.state()["f0"], o.state()["f0"]
+    assert _rel(fs, fo) < 1e-5
+    # s0 quirk: only the column of the last group swept is non-zero (mod_cmfd.f90:1022)
+    s0s, s0o = s.state()["s0"], o.state()["s0"]
+    assert not s0s[:, 0].any() and not s0o[:, 0].any()
+    assert _rel(s0s[:, 1], s0o[:, 1]) < 1e-5
+
+
+def test_graph_replay_equals_direct_launches(mods):
+    capi, _ = mods
+    p = load_problem("IAEA3Ds")
+    res = []
+    for graphs in (1, 0):
+        s = capi.Solver(p)
+        s.set_option("graphs", graphs)
+        s.set_control(nout=30)
+        s.matrix_setup(1)
+        s.init_flux()
+        s.outer_begin()
+        out = [s.outer_iter(0, q) for q in range(1, 13)]
+        res.append((out, s.state()["f0"].copy()))
+    assert res[0][0] == res[1][0]
+    assert np.array_equal(res[0][1], res[1][1])
+
+
+def test_max_outer_stop_code(mods):
+    capi, _ = mods
+    p = load_problem("IAEA3Ds")
+    s = capi.Solver(p, nout=25)
+    rc, n = s.outer(0)
+    assert rc == capi.STOP_MAXOUTER and n == 25
+    assert "MAXIMUM NUMBER OF OUTER ITERATION" in s.last_error()
+
+
+def test_transient_outer_tr_synthetic_state(mods):
+    """outer_tr + get_exsrc (theta method, theta = 0.5) for one time step from a critical
+    steady state with a 0.1 % thermal-absorption perturbation (power rises ~13.6 %).
+    The reference pins nothing for transients: GPU-vs-oracle only ("parity unpinned")."""
+    p, s, o = _pair(mods, "IAEA3Ds")
+    o.outer(0)
+    st = o.state()
+    ke = st["Ke"]
+    # make the problem critical the way KNE1 does (mod_trans.f90:483-518): nuf /= Ke
+    nuf = np.asfortranarray(p.nuf / ke)
+    ibeta = np.array([0.000247, 0.0013845, 0.001222, 0.0026455, 0.000832, 0.000169])
+    lamb = np.array([0.0127, 0.0317, 0.115, 0.311, 1.40, 3.87])
+    velo = np.array([1.25e7, 2.5e5])
+    tbeta = np.full(p.nmat, ibeta.sum())
+    sth, ht = 0.5, 0.05
+    bth = (1 - sth) / sth
+    f0, fs0 = st["f0"], st["fs0"] / ke
+    c0 = np.asfortranarray((ibeta / lamb)[None, :] * fs0[:, None])      # iPden
+    omeg = np.zeros((p.nnod, p.ng), order="F")
+    sigrp = np.asfortranarray(p.sigr.copy())
+    sigr = p.sigr.copy()
+    sigr[:, 1] *= 0.999
+    for g in range(p.ng):
+        sigr[:, g] += 1.0 / (sth * velo[g] * ht)                        # mod_trans.f90:398-412
+    sigr = np.asfortranarray(sigr)
+    df, dn = o.nod()
+    # L(n,g) as reactivity() leaves it before the first step (mod_trans.f90:95, 677-678)
+    o.set_xs(nuf=nuf)
+    o.set_state(f0, fs0, 1.0)
+    rho0 = o.reactivity(f0, sigrp)
+    assert abs(rho0) < 1e-5
+    L = o.transient()["L"]
+    for x in (s, o):
+        x.set_control(nout=300, nupd=20)
+        x.set_xs(nuf=nuf, sigr=sigr)
+        x.set_kinetics(ibeta, lamb, velo, tbeta, sth, bth)
+        x.set_transient(c0=c0, ft=f0, fst=fs0, omeg=omeg, sigrp=sigrp, L=L)
+    s.matrix_setup(1)
+    s.set_state(f0, fs0, 1.0)
+    s.set_nod_dn(dn)
+    s.set_s0(st["s0"], p.ng)
+    o.set_state(f0, fs0, 1.0)
+    pw0 = o.powtot(f0)
+    rc_o, maxi_o, n_o = o.outer_tr(ht)
+    rc_s, maxi_s, n_s = s.outer_tr(ht)
+    assert rc_o == rc_s == 0 and not maxi_o and not maxi_s and abs(n_s - n_o) <= 1
+    ex_s, dfis_s = s.exsrc_arrays()
+    tr = o.transient()
+    assert _rel(ex_s, tr["exsrc"]) < 1e-12 and _rel(dfis_s, tr["dfis"]) < 1e-14
+    # transient power within 1e-4 relative (north_star)
+    assert _rel(s.state()["f0"], o.state()["f0"]) < 1e-4
+    pw_s = o.powtot(s.state()["f0"]) / pw0
+    pw_o = o.powtot(o.state()["f0"]) / pw0
+    assert 1.05 < pw_o < 1.25
+    assert abs(pw_s / pw_o - 1) < 1e-4
