@@ -28,7 +28,7 @@ SYMBOLS = [
     "adp_get_exsrc", "adp_get_state", "adp_set_state", "adp_set_s0", "adp_get_nod", "adp_set_nod_dn", "adp_get_exsrc_arrays",
     "adp_get_ndmax", "adp_set_trace", "adp_outer", "adp_outer_ad", "adp_outer_fs", "adp_outer_th", "adp_outer_tr",
     "adp_sp_matvec", "adp_bicg", "adp_get_matrix", "adp_get_source", "adp_set_option", "adp_launch_count",
-    "adp_bench_kernel",
+    "adp_bench_kernel", "adp_outer_steps", "adp_timer_start", "adp_timer_stop",
 ]
 
 _lib = None
@@ -287,4 +287,17 @@ class Solver:
     def bench_kernel(self, what, reps):
         ms = C.c_double()
         self._chk(self.L.adp_bench_kernel(self.h, what, reps, C.byref(ms)))
+        return ms.value
+
+    def outer_steps(self, mode, p_first, nsteps):
+        ke, ser, fer = C.c_double(), C.c_double(), C.c_double()
+        rc = self._chk(self.L.adp_outer_steps(self.h, mode, p_first, nsteps, C.byref(ke), C.byref(ser), C.byref(fer)))
+        return rc, ke.value, ser.value, fer.value
+
+    def timer_start(self):
+        self._chk(self.L.adp_timer_start(self.h))
+
+    def timer_stop(self):
+        ms = C.c_double()
+        self._chk(self.L.adp_timer_stop(self.h, C.byref(ms)))
         return ms.value

@@ -131,7 +131,8 @@ struct adp_ctx {
     double *d_stage = nullptr;             // staging for host<->device copies of node arrays
     double *h_stage = nullptr;             // pinned staging [max(NL*?)]
     size_t stage_elems = 0;
-    int grid_blocks = 0;                   // persistent grid size (multiple of the SM count)
+    int grid_blocks = 0;                   // persistent grid size override (option "grid_blocks")
+    bool grid_override = false;
     int sm_count = 0;
     // multi-rank
     adp_comm *comm = nullptr;
@@ -140,8 +141,11 @@ struct adp_ctx {
     std::map<unsigned long long, cudaGraphExec_t> graphs;
     std::map<unsigned long long, long long> graph_launches;   // kernels inside each graph
     bool use_graphs = true;
+    int bench_warmup = 3;
+    bool fuse_st = true;                   // C kernel: s on the fly inside t = A s (false: k_s then k_t)
     // bookkeeping
     long long launches = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     adp_trace_fn trace = nullptr;
     void *trace_user = nullptr;
 };
@@ -163,6 +167,29 @@ struct adp_ctx {
             return ADP_ERR_USAGE;                   \
         }                                           \
     } while (0)
+
+// Persistent grids: one wave of exactly (SMs x resident CTAs per SM of THIS kernel) CTAs, each
+// looping over tiles.  Sizing every kernel with one fixed multiple of the SM count leaves a
+// ragged second wave whenever a kernel's registers allow fewer CTAs per SM (ncu: k_st at 40
+// registers ran at 54 % achieved occupancy with a 8-per-SM grid).
+template <typename K>
+static inline int adp_grid(adp_ctx *c, K kernel, int ntiles)
+{
+    static std::map<const void *, int> cache;
+    const void *key = (const void *)kernel;
+    auto it = cache.find(key);
+    int per_sm;
+    if (it == cache.end()) {
+        per_sm = 1;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, ADP_TILE, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+        cache[key] = per_sm;
+    } else per_sm = it->second;
+    long long g = (long long)c->sm_count * per_sm;
+    if (c->grid_blocks > 0 && c->grid_override) g = c->grid_blocks;
+    if (g > ADP_MAXPART) g = ADP_MAXPART;
+    if (ntiles < g) g = ntiles;
+    return g < 1 ? 1 : (int)g;
+}
 
 // ---- launch wrappers implemented in the kernel files ---------------------------------------
 // cmfd_kernels.cu

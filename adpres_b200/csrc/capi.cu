@@ -6,6 +6,8 @@
 #include "adp_internal.cuh"
 
 int adp_k_scale_by_slot(adp_ctx *c, double *d_vec, int slot);
+void adp_k_preload_cmfd(adp_ctx *c);
+void adp_k_preload_nodal(adp_ctx *c);
 
 static thread_local std::string g_create_err;
 
@@ -50,7 +52,7 @@ extern "C" int adp_create(adp_ctx **out, int device)
     cudaGetDeviceProperties(&prop, device);
     c->sm_count = prop.multiProcessorCount;
     // persistent grids: a multiple of the SM count (148 on B200) x resident CTAs per SM
-    c->grid_blocks = std::min(ADP_MAXPART, c->sm_count * 8);
+    c->grid_blocks = 0;
     if (dev_alloc(c, &c->d_scal, S_COUNT) || dev_alloc(c, &c->d_part, 4 * ADP_MAXPART) || dev_alloc(c, &c->d_ticket, 1) ||
         dev_alloc(c, &c->d_argidx, 1) || dev_alloc(c, &c->d_errflag, 1) ||
         cudaMallocHost((void **)&c->h_scal, (S_COUNT + 8) * sizeof(double)) != cudaSuccess ||
@@ -292,6 +294,11 @@ extern "C" int adp_set_control(adp_ctx *c, int nout, int nin, int nac, int nupd,
     ADP_REQUIRE(c, kern >= ADP_KERN_FDM && kern <= ADP_KERN_SANM, "adp_set_control: kern must be 0 FDM, 1 PNM, 2 SANM");
     if (nin != c->nin) free_graphs(c);
     c->nout = nout; c->nin = nin; c->nac = nac; c->nupd = nupd; c->serc = serc; c->ferc = ferc; c->kern = kern;
+    if (c->geometry_set) {
+        cudaSetDevice(c->device);
+        adp_k_preload_cmfd(c);
+        if (kern != ADP_KERN_FDM) adp_k_preload_nodal(c);
+    }
     return ADP_OK;
 }
 
@@ -329,7 +336,7 @@ extern "C" int adp_outer_begin(adp_ctx *c, int mode)
 }
 
 // ---- one outer iteration -----------------------------------------------------------------
-static int issue_outer_iter(adp_ctx *c, int mode, bool extrap)
+static int issue_outer_iter(adp_ctx *c, int mode, bool extrap, bool readback = true)
 {
     const int G = c->ng;
     if (mode == ADP_MODE_ADJOINT) {
@@ -338,7 +345,7 @@ static int issue_outer_iter(adp_ctx *c, int mode, bool extrap)
         for (int g = 0; g < G; ++g) TRY(adp_k_bicg_group(c, mode, g, c->nin, g == G - 1));
     }
     TRY(adp_k_outer_tail(c, mode, extrap));
-    CUDA_TRY(c, cudaMemcpyAsync(c->h_scal, c->d_scal, S_COUNT * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (readback) CUDA_TRY(c, cudaMemcpyAsync(c->h_scal, c->d_scal, S_COUNT * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     return ADP_OK;
 }
 
@@ -718,15 +725,81 @@ extern "C" int adp_set_option(adp_ctx *c, const char *name, int value)
 {
     if (!c || !name) return ADP_ERR_USAGE;
     if (!strcmp(name, "graphs")) { c->use_graphs = value != 0; free_graphs(c); return ADP_OK; }
+    if (!strcmp(name, "bench_warmup")) { c->bench_warmup = value; return ADP_OK; }
+    if (!strcmp(name, "fuse_st")) { c->fuse_st = value != 0; free_graphs(c); return ADP_OK; }
     if (!strcmp(name, "grid_blocks")) {
         ADP_REQUIRE(c, value >= 1 && value <= ADP_MAXPART, "grid_blocks out of range");
-        c->grid_blocks = value; free_graphs(c); return ADP_OK;
+        c->grid_blocks = value; c->grid_override = true; free_graphs(c); return ADP_OK;
     }
     c->err = std::string("unknown option ") + name;
     return ADP_ERR_USAGE;
 }
 
-// device-resident micro-benchmarks (no host copies inside the timed region) ------------------
+// ---- nodal update without host round trip (used by adp_outer_steps) -------------------------
+static int enqueue_nodal_upd(adp_ctx *c, int nmode)
+{
+    CUDA_TRY(c, cudaMemsetAsync(c->d_scal + S_NDMAX, 0, sizeof(double), c->stream));
+    TRY(adp_k_nodal_update(c, nmode));
+    if (c->nranks > 1) TRY(adp_comm_allreduce_max(c, c->d_scal + S_NDMAX, 1));
+    TRY(adp_k_matrix_setup(c));
+    return ADP_OK;
+}
+
+// Enqueue `nsteps` consecutive passes of the outer loop body (p = p_first ...), including the
+// nodal update + matrix_setup(0) whenever mod(p, nupd) == 0, WITHOUT the per-iteration host
+// read-back and exit test; one synchronisation at the end.  This is the device-resident
+// throughput path (bench `value`); adp_outer() with its per-iteration test is the product path.
+extern "C" int adp_outer_steps(adp_ctx *c, int mode, int p_first, int nsteps, double *Ke, double *ser, double *fer)
+{
+    if (!c) return ADP_ERR_USAGE;
+    ADP_REQUIRE(c, c->have_flux && c->matrix_ready, "adp_outer_steps: needs adp_matrix_setup and a flux");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    CUDA_TRY(c, cudaMemsetAsync(c->d_errflag, 0, sizeof(int), c->stream));
+    for (int p = p_first; p < p_first + nsteps; ++p) {
+        const bool extrap = (p % c->nac) == 0;
+        TRY(issue_outer_iter(c, mode, extrap, false));
+        if (p % c->nupd == 0 && c->kern != ADP_KERN_FDM) {
+            const int nmode = (mode == ADP_MODE_ADJOINT) ? 0 : (mode == ADP_MODE_TRANSIENT) ? 2 : 1;
+            TRY(enqueue_nodal_upd(c, nmode));
+        }
+    }
+    CUDA_TRY(c, cudaMemcpyAsync(c->h_scal, c->d_scal, S_COUNT * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaMemcpyAsync(c->h_flags + 2, c->d_errflag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    if (Ke) *Ke = c->h_scal[S_KE];
+    if (ser) *ser = c->h_scal[S_SER];
+    if (fer) *fer = c->h_scal[S_FER];
+    if (c->h_flags[2] != 0) { c->err = "ERROR IN MATRIX DECOMP: DIAGONAL ELEMENTS CLOSE TO ZERO"; return ADP_STOP_LU_DIAG; }
+    return ADP_OK;
+}
+
+// CUDA-event timer on the library's stream (torch.cuda.Event only sees torch's stream)
+extern "C" int adp_timer_start(adp_ctx *c)
+{
+    if (!c) return ADP_ERR_USAGE;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    if (!c->ev0) { CUDA_TRY(c, cudaEventCreate(&c->ev0)); CUDA_TRY(c, cudaEventCreate(&c->ev1)); }
+    CUDA_TRY(c, cudaEventRecord(c->ev0, c->stream));
+    return ADP_OK;
+}
+extern "C" int adp_timer_stop(adp_ctx *c, double *ms)
+{
+    if (!c || !ms || !c->ev0) return ADP_ERR_USAGE;
+    CUDA_TRY(c, cudaEventRecord(c->ev1, c->stream));
+    CUDA_TRY(c, cudaEventSynchronize(c->ev1));
+    float f = 0.f;
+    CUDA_TRY(c, cudaEventElapsedTime(&f, c->ev0, c->ev1));
+    *ms = f;
+    return ADP_OK;
+}
+
+int adp_k_bench_one(adp_ctx *c, int what, int g);
+
+// device-resident micro-benchmarks of one kernel class on the current problem (no host copies
+// in the timed region).  what: 0 B SpMV+dot, 1 C fused s/t, 2 D, 3 A, 4 P, 5 F, 8 plain SpMV,
+// 6 nodal source, 7 whole nodal update (source + 3 surface launches), 9 matrix_setup(0).
+// Launches alternate over the energy groups so that consecutive launches stream different
+// matrices (working set >> L2).  Returns the average device time per launch in ms.
 extern "C" int adp_bench_kernel(adp_ctx *c, int what, int reps, double *avg_ms)
 {
     if (!c || !avg_ms || reps < 1) return ADP_ERR_USAGE;
@@ -738,12 +811,13 @@ extern "C" int adp_bench_kernel(adp_ctx *c, int what, int reps, double *avg_ms)
     int rc = ADP_OK;
     auto body = [&](int i) -> int {
         switch (what) {
-        case 0: return adp_k_spmv(c, i % c->ng, c->d_p, c->d_v);
-        case 2: return adp_k_bicg_raw(c, i % c->ng, c->nin, c->d_stage, c->d_s0);
-        default: return ADP_ERR_UNSUPPORTED;
+        case 6: return adp_k_nodal_source(c, 1);
+        case 7: return adp_k_nodal_update(c, 1);
+        case 9: return adp_k_matrix_setup(c);
+        default: return adp_k_bench_one(c, what, i % c->ng);
         }
     };
-    for (int i = 0; i < 3 && !rc; ++i) rc = body(i);
+    for (int i = 0; i < c->bench_warmup && !rc; ++i) rc = body(i);
     CUDA_TRY(c, cudaEventRecord(e0, c->stream));
     for (int i = 0; i < reps && !rc; ++i) rc = body(i);
     CUDA_TRY(c, cudaEventRecord(e1, c->stream));

@@ -194,8 +194,11 @@ __global__ void __launch_bounds__(ADP_TILE) k_matrix_setup(Geo G, const double *
 //   fwd : bs = chi(mat,g)*fs/Ke + sum_{h/=g} sigs(n,h,g) f0(n,h) + exsrc(n,g)
 //   adj : bs = nuf(n,g)*fs/Ke   + sum_{h/=g} sigs(n,g,h) f0(n,h) + exsrc(n,g)
 //   tr  : bs = (1 - tbeta(mat) + dfis(n))*chi(mat,g)*fs + sum ... + exsrc(n,g)
-// then r = bs - A x ; rs = r ; p = r (the first "p = r + beta (p - omega v)" with p = v = 0)
-// and the partial sums of rho = (rs, r).
+// then r = bs - A x and the partial sums of rho = (rs, r).  The reference stores r, rs = r and
+// (first loop pass, p = v = 0, so p = r + beta*0) p = r as three vectors; here the ONE vector rs
+// plays all three roles during the first BiCGSTAB iteration: B and D read it as p, C reads it
+// as r, D writes the new r into the separate r buffer, and the second iteration's A reads the
+// old p from rs.  Same values, 16 B/row less traffic.
 // ------------------------------------------------------------------------------------------
 struct SrcArgs {
     int mode, g, ng, nmat;
@@ -208,8 +211,7 @@ struct SrcArgs {
 };
 
 __global__ void __launch_bounds__(ADP_TILE) k_residual(Geo G, SrcArgs A, const double *__restrict__ a,
-                                                        const double *__restrict__ x, double *__restrict__ rv,
-                                                        double *__restrict__ rs, double *__restrict__ pv, RedOut ro)
+                                                        const double *__restrict__ x, double *__restrict__ rs, RedOut ro)
 {
     double acc[1] = {0.0};
     const double Ke = ro.scal[S_KE];
@@ -232,9 +234,7 @@ __global__ void __launch_bounds__(ADP_TILE) k_residual(Geo G, SrcArgs A, const d
         }
         const double ax = stencil7(a, G.NV, x, idx, G.np, G.ypm[r], G.ypp[r]);
         const double res = bs - ax;
-        rv[idx] = res;
-        rs[idx] = res;
-        pv[idx] = res;
+        rs[idx] = res;      // r0 = rs = p1: one store serves all three (see bicg_core)
         acc[0] = acc[0] + res * res;
     }
     grid_reduce<1, 0>(acc, ro);
@@ -243,7 +243,7 @@ __global__ void __launch_bounds__(ADP_TILE) k_residual(Geo G, SrcArgs A, const d
 // A: p = r + beta (p - omega v), beta = (rho/rho_prev)(alpha/omega)   (mod_cmfd.f90:1231-1232)
 __global__ void __launch_bounds__(ADP_TILE) k_update_p(Geo G, const double *__restrict__ scal, int slot_rho, int slot_rho_prev,
                                                         const double *__restrict__ rv, const double *__restrict__ v,
-                                                        double *__restrict__ pv)
+                                                        const double *p_in, double *p_out)
 {
     const double rho = scal[slot_rho], rho_prev = scal[slot_rho_prev];
     const double alpha = rho_prev / scal[S_RSV];
@@ -252,7 +252,7 @@ __global__ void __launch_bounds__(ADP_TILE) k_update_p(Geo G, const double *__re
     FOR_EACH_ROW(G, 0, G.nzl)
     {
         const long long idx = node_idx(G, kl, r);
-        pv[idx] = rv[idx] + beta * (pv[idx] - omega * v[idx]);
+        p_out[idx] = rv[idx] + beta * (p_in[idx] - omega * v[idx]);
     }
 }
 
@@ -573,7 +573,7 @@ int adp_k_coup_coef(adp_ctx *c)
     int khi = (c->k1 < c->nzz) ? c->nzl + 1 : c->nzl;
     int npl = khi - klo;
     for (int g = 0; g < c->ng; ++g) {
-        k_coup_coef<<<grid_for(c, c->geo.tpp * npl), ADP_TILE, 0, c->stream>>>(
+        k_coup_coef<<<adp_grid(c, k_coup_coef, c->geo.tpp * npl), ADP_TILE, 0, c->stream>>>(
             c->geo, c->d_D + (size_t)g * c->NV, c->d_df + (size_t)g * 6 * c->NV, klo, npl);
         LAUNCH_CHECK(c);
     }
@@ -583,7 +583,7 @@ int adp_k_coup_coef(adp_ctx *c)
 int adp_k_matrix_setup(adp_ctx *c)
 {
     for (int g = 0; g < c->ng; ++g) {
-        k_matrix_setup<<<grid_for(c, c->geo.ntiles), ADP_TILE, 0, c->stream>>>(
+        k_matrix_setup<<<adp_grid(c, k_matrix_setup, c->geo.ntiles), ADP_TILE, 0, c->stream>>>(
             c->geo, c->d_df + (size_t)g * 6 * c->NV, c->d_dn + (size_t)g * 6 * c->NV, c->d_sigr + (size_t)g * c->NV,
             c->d_a + (size_t)g * 7 * c->NV);
         LAUNCH_CHECK(c);
@@ -602,7 +602,7 @@ static int launch_fsrc(adp_ctx *c, bool adjoint, bool do_norms, int fs_in, int f
     }
     A.fs_old = c->d_fs[fs_in];
     A.fs_new = c->d_fs[fs_out];
-    k_fsrc_norms<<<grid_for(c, c->geo.ntiles), ADP_TILE, 0, c->stream>>>(c->geo, A, do_norms ? 1 : 0,
+    k_fsrc_norms<<<adp_grid(c, k_fsrc_norms, c->geo.ntiles), ADP_TILE, 0, c->stream>>>(c->geo, A, do_norms ? 1 : 0,
                                                                          make_red(c, S_E2SQ, S_FINT, S_SER, S_FER));
     LAUNCH_CHECK(c);
     return ADP_OK;
@@ -613,7 +613,7 @@ int adp_k_init_flux(adp_ctx *c, int adjoint)
     // Ke = 1 ; f0 = 1 ; fs0 = FSrc(f0)   (mod_cmfd.f90:448-454)
     for (int g = 0; g < c->ng; ++g) {
         c->cur[g] = 0;
-        k_fill<<<grid_for(c, c->geo.ntiles), ADP_TILE, 0, c->stream>>>(c->geo, f0ptr(c, 0, g), 1.0);
+        k_fill<<<adp_grid(c, k_fill, c->geo.ntiles), ADP_TILE, 0, c->stream>>>(c->geo, f0ptr(c, 0, g), 1.0);
         LAUNCH_CHECK(c);
     }
     c->fcur = 0;
@@ -628,7 +628,7 @@ int adp_k_init_flux(adp_ctx *c, int adjoint)
 
 int adp_k_integrate(adp_ctx *c, const double *d_vec, int slot)
 {
-    k_integrate<<<grid_for(c, c->geo.ntiles), ADP_TILE, 0, c->stream>>>(c->geo, d_vec, make_red(c, slot));
+    k_integrate<<<adp_grid(c, k_integrate, c->geo.ntiles), ADP_TILE, 0, c->stream>>>(c->geo, d_vec, make_red(c, slot));
     LAUNCH_CHECK(c);
     if (c->nranks > 1) return adp_comm_allreduce_sum(c, c->d_scal + slot, 1);
     return ADP_OK;
@@ -651,12 +651,12 @@ int adp_k_outer_begin(adp_ctx *c, int mode)
 // flux of group g lives in the other ping-pong buffer and c->cur[g] has been flipped.
 static int bicg_core(adp_ctx *c, const SrcArgs &src, const double *a, const double *x_in, double *x_out, int nin)
 {
-    const int grid = grid_for(c, c->geo.ntiles);
+    const int nt = c->geo.ntiles;
     const bool multi = c->nranks > 1;
     int rc;
     if (multi && (rc = adp_comm_halo(c, const_cast<double *>(x_in), 1))) return rc;
     // iteration i uses rho slot S_RHO0 + (i & 1); P produces the one of iteration 1
-    k_residual<<<grid, ADP_TILE, 0, c->stream>>>(c->geo, src, a, x_in, c->d_r, c->d_rs, c->d_p, make_red(c, S_RHO1));
+    k_residual<<<adp_grid(c, k_residual, nt), ADP_TILE, 0, c->stream>>>(c->geo, src, a, x_in, c->d_rs, make_red(c, S_RHO1));
     LAUNCH_CHECK(c);
     if (multi && (rc = adp_comm_allreduce_sum(c, c->d_scal + S_RHO1, 1))) return rc;
     if (nin <= 0) {
@@ -665,28 +665,32 @@ static int bicg_core(adp_ctx *c, const SrcArgs &src, const double *a, const doub
     }
     for (int i = 1; i <= nin; ++i) {
         const int slot = S_RHO0 + (i & 1), slot_prev = S_RHO0 + ((i - 1) & 1), slot_next = S_RHO0 + ((i + 1) & 1);
+        // first iteration: r = p = rs (one vector); afterwards the separate r and p buffers
+        const double *r_cur = (i == 1) ? c->d_rs : c->d_r;
+        double *p_cur = (i == 1) ? c->d_rs : c->d_p;
         if (i > 1) {
-            k_update_p<<<grid, ADP_TILE, 0, c->stream>>>(c->geo, c->d_scal, slot, slot_prev, c->d_r, c->d_v, c->d_p);
+            k_update_p<<<adp_grid(c, k_update_p, nt), ADP_TILE, 0, c->stream>>>(c->geo, c->d_scal, slot, slot_prev, c->d_r, c->d_v,
+                                                                              (i == 2) ? c->d_rs : c->d_p, c->d_p);
             LAUNCH_CHECK(c);
         }
-        if (multi && (rc = adp_comm_halo(c, c->d_p, 1))) return rc;
-        k_spmv_dot<<<grid, ADP_TILE, 0, c->stream>>>(c->geo, a, c->d_p, c->d_rs, c->d_v, make_red(c, S_RSV));
+        if (multi && (rc = adp_comm_halo(c, p_cur, 1))) return rc;
+        k_spmv_dot<<<adp_grid(c, k_spmv_dot, nt), ADP_TILE, 0, c->stream>>>(c->geo, a, p_cur, c->d_rs, c->d_v, make_red(c, S_RSV));
         LAUNCH_CHECK(c);
-        if (multi) {
-            if ((rc = adp_comm_allreduce_sum(c, c->d_scal + S_RSV, 1))) return rc;
-            k_s<<<grid, ADP_TILE, 0, c->stream>>>(c->geo, c->d_scal, slot, c->d_r, c->d_v, c->d_s);
+        if (multi || !c->fuse_st) {
+            if (multi && (rc = adp_comm_allreduce_sum(c, c->d_scal + S_RSV, 1))) return rc;
+            k_s<<<adp_grid(c, k_s, nt), ADP_TILE, 0, c->stream>>>(c->geo, c->d_scal, slot, r_cur, c->d_v, c->d_s);
             LAUNCH_CHECK(c);
-            if ((rc = adp_comm_halo(c, c->d_s, 1))) return rc;
-            k_t<<<grid, ADP_TILE, 0, c->stream>>>(c->geo, a, c->d_s, c->d_t, make_red(c, S_TT, S_TS));
+            if (multi && (rc = adp_comm_halo(c, c->d_s, 1))) return rc;
+            k_t<<<adp_grid(c, k_t, nt), ADP_TILE, 0, c->stream>>>(c->geo, a, c->d_s, c->d_t, make_red(c, S_TT, S_TS));
             LAUNCH_CHECK(c);
-            if ((rc = adp_comm_allreduce_sum(c, c->d_scal + S_TT, 2))) return rc;
+            if (multi && (rc = adp_comm_allreduce_sum(c, c->d_scal + S_TT, 2))) return rc;
         } else {
-            k_st<<<grid, ADP_TILE, 0, c->stream>>>(c->geo, a, slot, c->d_r, c->d_v, c->d_s, c->d_t, make_red(c, S_TT, S_TS));
+            k_st<<<adp_grid(c, k_st, nt), ADP_TILE, 0, c->stream>>>(c->geo, a, slot, r_cur, c->d_v, c->d_s, c->d_t, make_red(c, S_TT, S_TS));
             LAUNCH_CHECK(c);
         }
         const int last = (i == nin) ? 1 : 0;
-        k_update_xr<<<grid, ADP_TILE, 0, c->stream>>>(c->geo, slot, last, (i == 1) ? x_in : x_out, x_out, c->d_p, c->d_s,
-                                                      c->d_t, c->d_rs, c->d_r, make_red(c, slot_next));
+        k_update_xr<<<adp_grid(c, k_update_xr, nt), ADP_TILE, 0, c->stream>>>(c->geo, slot, last, (i == 1) ? x_in : x_out, x_out, p_cur, c->d_s,
+                                                                            c->d_t, c->d_rs, c->d_r, make_red(c, slot_next));
         LAUNCH_CHECK(c);
         if (!last && multi && (rc = adp_comm_allreduce_sum(c, c->d_scal + slot_next, 1))) return rc;
     }
@@ -732,7 +736,7 @@ int adp_k_spmv(adp_ctx *c, int g, const double *d_x, double *d_v)
 {
     int rc;
     if (c->nranks > 1 && (rc = adp_comm_halo(c, const_cast<double *>(d_x), 1))) return rc;
-    k_spmv_dot<<<grid_for(c, c->geo.ntiles), ADP_TILE, 0, c->stream>>>(c->geo, a_of(c, g), d_x, nullptr, d_v, make_red(c, S_TMP1));
+    k_spmv_dot<<<adp_grid(c, k_spmv_dot, c->geo.ntiles), ADP_TILE, 0, c->stream>>>(c->geo, a_of(c, g), d_x, nullptr, d_v, make_red(c, S_TMP1));
     LAUNCH_CHECK(c);
     return ADP_OK;
 }
@@ -755,7 +759,7 @@ int adp_k_outer_tail(adp_ctx *c, int mode, bool extrapolate)
     if (extrapolate) {
         k_scalar<<<1, 32, 0, c->stream>>>(c->d_scal, 1, 0, 0);
         LAUNCH_CHECK(c);
-        k_extrap<<<grid_for(c, c->geo.ntiles), ADP_TILE, 0, c->stream>>>(c->geo, c->d_fs[fs_in], c->d_fs[fs_out],
+        k_extrap<<<adp_grid(c, k_extrap, c->geo.ntiles), ADP_TILE, 0, c->stream>>>(c->geo, c->d_fs[fs_in], c->d_fs[fs_out],
                                                                          make_red(c, S_FINT, S_SER));
         LAUNCH_CHECK(c);
         if (multi) {
@@ -777,7 +781,7 @@ int adp_k_powdis(adp_ctx *c, double *d_pow)
         A.f0[g] = f0ptr(c, c->cur[g], g);
         A.sigf[g] = c->d_sigf + (size_t)g * c->NV;
     }
-    k_powdis<<<grid_for(c, c->geo.ntiles), ADP_TILE, 0, c->stream>>>(c->geo, A, d_pow, make_red(c, S_POW));
+    k_powdis<<<adp_grid(c, k_powdis, c->geo.ntiles), ADP_TILE, 0, c->stream>>>(c->geo, A, d_pow, make_red(c, S_POW));
     LAUNCH_CHECK(c);
     if (c->nranks > 1) {
         int rc = adp_comm_allreduce_sum(c, c->d_scal + S_POW, 1);
@@ -788,7 +792,7 @@ int adp_k_powdis(adp_ctx *c, double *d_pow)
 
 int adp_k_scale_by_slot(adp_ctx *c, double *d_vec, int slot)
 {
-    k_scale<<<grid_for(c, c->geo.ntiles), ADP_TILE, 0, c->stream>>>(c->geo, d_vec, c->d_scal, slot);
+    k_scale<<<adp_grid(c, k_scale, c->geo.ntiles), ADP_TILE, 0, c->stream>>>(c->geo, d_vec, c->d_scal, slot);
     LAUNCH_CHECK(c);
     return ADP_OK;
 }
@@ -802,7 +806,80 @@ int adp_k_get_exsrc(adp_ctx *c, double ht)
     A.L = c->d_L; A.sigrp = c->d_sigrp; A.ft = c->d_ft; A.s0 = c->d_s0; A.omeg = c->d_omeg;
     A.s0_group = c->s0_group - 1;
     A.exsrc = c->d_exsrc; A.dfis = c->d_dfis;
-    k_get_exsrc<<<grid_for(c, c->geo.ntiles), ADP_TILE, 0, c->stream>>>(c->geo, A);
+    k_get_exsrc<<<adp_grid(c, k_get_exsrc, c->geo.ntiles), ADP_TILE, 0, c->stream>>>(c->geo, A);
+    LAUNCH_CHECK(c);
+    if (c->nranks > 1) {
+        // the two-node problem across a slab boundary reads dfis (cmode 2) of the neighbour's plane
+        int rc = adp_comm_halo(c, c->d_dfis, 1);
+        if (rc) return rc;
+        for (int g = 0; g < c->ng; ++g)
+            if ((rc = adp_comm_halo(c, c->d_exsrc + (size_t)g * c->NV, 1))) return rc;
+    }
+    return ADP_OK;
+}
+
+// ---- single launches of each kernel class on the current device state (micro-benchmarks) ----
+// what: 0 B (v=Ap + (rs,v))   1 C (s,t fused)   2 D (x,r update)   3 A (p update)
+//       4 P (source + residual)   5 F (fission source + norms)   8 plain SpMV (no dot product)
+int adp_k_bench_one(adp_ctx *c, int what, int g)
+{
+    const int nt = c->geo.ntiles;
+    const double *a = a_of(c, g);
+    switch (what) {
+    case 0:
+        k_spmv_dot<<<adp_grid(c, k_spmv_dot, nt), ADP_TILE, 0, c->stream>>>(c->geo, a, c->d_p, c->d_rs, c->d_v, make_red(c, S_TMP1));
+        break;
+    case 8:
+        k_spmv_dot<<<adp_grid(c, k_spmv_dot, nt), ADP_TILE, 0, c->stream>>>(c->geo, a, c->d_p, nullptr, c->d_v, make_red(c, S_TMP1));
+        break;
+    case 1:
+        k_st<<<adp_grid(c, k_st, nt), ADP_TILE, 0, c->stream>>>(c->geo, a, S_RHO1, c->d_r, c->d_v, c->d_s, c->d_t, make_red(c, S_TMP0, S_TMP1));
+        break;
+    case 2:
+        k_update_xr<<<adp_grid(c, k_update_xr, nt), ADP_TILE, 0, c->stream>>>(c->geo, S_RHO1, 0, c->d_stage, c->d_stage, c->d_p, c->d_s, c->d_t, c->d_rs,
+                                                      c->d_S, make_red(c, S_TMP1));
+        break;
+    case 3:
+        k_update_p<<<adp_grid(c, k_update_p, nt), ADP_TILE, 0, c->stream>>>(c->geo, c->d_scal, S_RHO0, S_RHO1, c->d_r, c->d_v, c->d_p, c->d_S);
+        break;
+    case 4: {
+        SrcArgs S{};
+        S.mode = ADP_MODE_FORWARD; S.g = g; S.ng = c->ng; S.nmat = c->nmat;
+        for (int h = 0; h < c->ng; ++h) {
+            S.f0[h] = f0ptr(c, c->cur[h], h);
+            S.sg[h] = c->d_sigs + ((size_t)g * c->ng + h) * c->NV;
+        }
+        S.fs = c->d_fs[c->fcur]; S.exsrc = c->d_exsrc + (size_t)g * c->NV; S.nuf_g = c->d_nuf + (size_t)g * c->NV;
+        S.chi_g = c->d_chi + (size_t)g * c->nmat; S.tbeta = c->d_tbeta; S.dfis = c->d_dfis; S.mat = c->d_mat;
+        S.s0 = nullptr; S.b = nullptr;
+        k_residual<<<adp_grid(c, k_residual, nt), ADP_TILE, 0, c->stream>>>(c->geo, S, a, f0ptr(c, c->cur[g], g), c->d_S, make_red(c, S_TMP1));
+        break;
+    }
+    case 5: {
+        int cur_old[ADP_MAXG];
+        for (int h = 0; h < c->ng; ++h) cur_old[h] = c->cur[h] ^ 1;
+        FsrcArgs A{};
+        A.ng = c->ng; A.nmat = c->nmat; A.adjoint = 0; A.mat = c->d_mat;
+        for (int h = 0; h < c->ng; ++h) {
+            A.fnew[h] = f0ptr(c, c->cur[h], h); A.fold[h] = f0ptr(c, cur_old[h], h); A.w[h] = c->d_nuf + (size_t)h * c->NV;
+        }
+        A.fs_old = c->d_fs[c->fcur]; A.fs_new = c->d_stage;
+        k_fsrc_norms<<<adp_grid(c, k_fsrc_norms, nt), ADP_TILE, 0, c->stream>>>(c->geo, A, 1, make_red(c, S_TMP0, S_TMP1, S_TMP0, S_TMP1));
+        break;
+    }
+    default:
+        return ADP_ERR_UNSUPPORTED;
+    }
     LAUNCH_CHECK(c);
     return ADP_OK;
+}
+
+// Resolve (and thereby load) every kernel of this file once, so that CUDA's lazy module loading
+// never falls inside a timed region or the first time step.
+void adp_k_preload_cmfd(adp_ctx *c)
+{
+    adp_grid(c, k_coup_coef, 1); adp_grid(c, k_matrix_setup, 1); adp_grid(c, k_residual, 1); adp_grid(c, k_update_p, 1);
+    adp_grid(c, k_spmv_dot, 1); adp_grid(c, k_st, 1); adp_grid(c, k_s, 1); adp_grid(c, k_t, 1); adp_grid(c, k_update_xr, 1);
+    adp_grid(c, k_fsrc_norms, 1); adp_grid(c, k_extrap, 1); adp_grid(c, k_integrate, 1); adp_grid(c, k_fill, 1);
+    adp_grid(c, k_scalar, 1); adp_grid(c, k_powdis, 1); adp_grid(c, k_scale, 1); adp_grid(c, k_get_exsrc, 1);
 }

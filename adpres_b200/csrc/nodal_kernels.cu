@@ -48,7 +48,7 @@ struct NodalArgs {
 // ---------------------------------------------------------------------------------------
 // Lxyz + get_source (mod_nodal.f90:901-1043)
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(ADP_TILE) k_nodal_source(Geo G, NodalArgs A)
+__global__ void __launch_bounds__(ADP_TILE, 4) k_nodal_source(Geo G, NodalArgs A)
 {
     const long long NV = G.NV;
     const int np = G.np;
@@ -383,7 +383,7 @@ __device__ __forceinline__ void grid_argmax(double v, long long l, const ArgMax 
 // nodal_coup_upd (mod_nodal.f90:282-698).
 // ---------------------------------------------------------------------------------------
 template <int NG, int KERN>
-__global__ void __launch_bounds__(ADP_TILE) k_nodal_surfaces(Geo G, NodalArgs A, int u, int klo, int npl, ArgMax am)
+__global__ void __launch_bounds__(ADP_TILE, (NG <= 2) ? 2 : 1) k_nodal_surfaces(Geo G, NodalArgs A, int u, int klo, int npl, ArgMax am)
 {
     const long long NV = G.NV;
     double best = -1.0;
@@ -548,12 +548,12 @@ __global__ void __launch_bounds__(ADP_TILE) k_nodal_surfaces(Geo G, NodalArgs A,
 }
 
 template <int NG>
-void launch_surfaces(adp_ctx *c, const NodalArgs &A, int u, int klo, int npl, int grid, const ArgMax &am)
+void launch_surfaces(adp_ctx *c, const NodalArgs &A, int u, int klo, int npl, int ntiles, const ArgMax &am)
 {
     if (A.kern == ADP_KERN_SANM)
-        k_nodal_surfaces<NG, ADP_KERN_SANM><<<grid, ADP_TILE, 0, c->stream>>>(c->geo, A, u, klo, npl, am);
+        k_nodal_surfaces<NG, ADP_KERN_SANM><<<adp_grid(c, k_nodal_surfaces<NG, ADP_KERN_SANM>, ntiles), ADP_TILE, 0, c->stream>>>(c->geo, A, u, klo, npl, am);
     else
-        k_nodal_surfaces<NG, ADP_KERN_PNM><<<grid, ADP_TILE, 0, c->stream>>>(c->geo, A, u, klo, npl, am);
+        k_nodal_surfaces<NG, ADP_KERN_PNM><<<adp_grid(c, k_nodal_surfaces<NG, ADP_KERN_PNM>, ntiles), ADP_TILE, 0, c->stream>>>(c->geo, A, u, klo, npl, am);
 }
 
 }  // namespace
@@ -584,7 +584,7 @@ int adp_k_nodal_source(adp_ctx *c, int cmode)
     if (c->nranks > 1)
         for (int g = 0; g < c->ng; ++g)
             if ((rc = adp_comm_halo(c, c->d_f0[c->cur[g]] + (size_t)g * c->NV, 1))) return rc;
-    k_nodal_source<<<grid_for(c, c->geo.ntiles), ADP_TILE, 0, c->stream>>>(c->geo, A);
+    k_nodal_source<<<adp_grid(c, k_nodal_source, c->geo.ntiles), ADP_TILE, 0, c->stream>>>(c->geo, A);
     c->launches++;
     if (cudaPeekAtLastError() != cudaSuccess) { c->err = "k_nodal_source launch failed"; return ADP_ERR_CUDA; }
     return ADP_OK;
@@ -606,7 +606,7 @@ int adp_k_nodal_update(adp_ctx *c, int cmode)
     for (int u = 0; u < 3; ++u) {
         int klo = 0, npl = c->nzl;
         if (u == 2 && c->k0 > 0) { klo = -1; npl = c->nzl + 1; }   // the surface shared with the slab below
-        const int grid = grid_for(c, c->geo.tpp * npl);
+        const int grid = c->geo.tpp * npl;
         switch (c->ng) {
         case 1: launch_surfaces<1>(c, A, u, klo, npl, grid, am); break;
         case 2: launch_surfaces<2>(c, A, u, klo, npl, grid, am); break;
@@ -625,4 +625,14 @@ int adp_k_nodal_update(adp_ctx *c, int cmode)
         }
     }
     return ADP_OK;
+}
+
+void adp_k_preload_nodal(adp_ctx *c)
+{
+    adp_grid(c, k_nodal_source, 1);
+    const bool sanm = c->kern != ADP_KERN_PNM;
+#define PRE(NG_) \
+    case NG_: if (sanm) adp_grid(c, k_nodal_surfaces<NG_, ADP_KERN_SANM>, 1); else adp_grid(c, k_nodal_surfaces<NG_, ADP_KERN_PNM>, 1); break;
+    switch (c->ng) { PRE(1) PRE(2) PRE(3) PRE(4) PRE(5) PRE(6) PRE(7) PRE(8) default: break; }
+#undef PRE
 }

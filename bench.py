@@ -1,0 +1,357 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the ADPRES eigenvalue hot path on B200.
+
+Metric (BASELINE.json): node-group unknowns per second per outer iteration, on the
+configuration the metric is quoted on: IAEA-3D refined to 1 cm x 1 cm x 2 cm nodes
+(170 x 170 x 190 mesh, 4 579 000 nodes, 2 groups = 9.158 M node-groups, SANM kernel),
+iteration control `%ITER . 2 1e-5 1e-5 5 50` (nin = 2, nac = 5, nupd = 50).
+
+A "step" is one pass of the reference's `do p = 1, nout` loop body (mod_cmfd.f90:465-496):
+G x (TSrc + bicg(nin)), FSrc, l2norm, [fiss_extrp], Integrate, k-eff, RelE, RelEg and, whenever
+mod(p, nupd) == 0, the SANM nodal update + matrix_setup(0).
+
+  value   device-resident: K steps enqueued back to back (adp_outer_steps), CUDA events on the
+          library's stream, max over ranks.
+  e2e     the same K steps through the drop-in boundary the Fortran driver uses, with HOST
+          (pinned) buffers: one outer() call = adp_set_xs (all cross sections H2D) +
+          adp_set_state + adp_matrix_setup(1) + K x adp_outer_iter (scalars D2H, exit test on
+          the host) + nodal updates + adp_get_state (flux, fission source D2H) + adp_powdis.
+          h2d/d2h bytes are the totals of that call divided by K.
+  roofline  the dominant kernel (BiCGSTAB SpMV + dot, k_spmv_dot) timed alone with CUDA events,
+          algorithmic 72 B/row against the measured HBM peak.
+  cpu_baseline  the C oracle (oracle/, a line-by-line port of the Fortran; no Fortran compiler
+          exists in the image, so oracle/_ref cannot be built) on 1 host core -- the reference
+          is serial -- on a bounded sample (same radial mesh, 19 of the 190 planes).
+
+N > 1 (torchrun): z-slab decomposition, one rank per GPU, weak scaling (190 planes per rank:
+the axial mesh is refined to 190*N planes); halo planes + scalar all-reduces over NCCL.
+
+`--impl reference` times the reference algorithm on the host CPU (oracle port, 1 thread).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "node_group_unknowns_per_s_per_outer_iteration"
+UNIT = "unknowns/s"
+CTL = dict(nin=2, nac=5, nupd=50, nout=1000000, serc=1e-5, ferc=1e-5)
+SPMV_BYTES_PER_ROW = 72.0   # 7 coefficients + x + y, fp64
+
+
+def load_c2(planes_factor=1, sample_planes=None):
+    """IAEA-3D (smpl/static/IAEA3Ds) with %GEOM lines 3/5/7 changed to `10 8*20`, `8*20 10`,
+    `19*10`  (BASELINE.json configs[1]); planes_factor multiplies the axial refinement (weak
+    scaling); sample_planes = 19 coarsens the axial mesh to one plane per assembly (CPU sample)."""
+    from adpres_b200.deck import Problem
+    with open(os.path.join(ROOT, "tests", "golden", "IAEA3Ds.spec.json")) as fh:
+        p = Problem.from_spec(json.load(fh))
+    zdiv = [10 * planes_factor] * 19 if sample_planes is None else [sample_planes // 19] * 19
+    return p.refine(xdiv=[10] + [20] * 8, ydiv=[20] * 8 + [10], zdiv=zdiv)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device, self.proc, self.lines = device, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)), "power_w_max": float(max(power)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def cpu_model():
+    try:
+        for ln in open("/proc/cpuinfo"):
+            if ln.startswith("model name"):
+                return ln.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
+def run_oracle_sample(steps, warmup, sample_planes=19):
+    """The reference algorithm (oracle port) on one host core: `warmup + steps` passes of the
+    outer loop body on the bounded sample.  Returns (unknowns/s/iter, seconds, description)."""
+    from oracle import Oracle
+    p = load_c2(sample_planes=sample_planes)
+    o = Oracle(p, nout=CTL["nout"], nin=CTL["nin"], nac=CTL["nac"], nupd=CTL["nupd"], serc=0.0, ferc=0.0)
+    o.matrix_setup(1)
+    o.init_flux()
+    # drive the oracle's own outer() for warmup+steps iterations: serc = ferc = 0 never exits
+    o.set_control(nout=warmup, nin=CTL["nin"], nac=CTL["nac"], nupd=CTL["nupd"], serc=0.0, ferc=0.0)
+    if warmup > 0:
+        o.outer(0)
+    o.set_control(nout=steps, nin=CTL["nin"], nac=CTL["nac"], nupd=CTL["nupd"], serc=0.0, ferc=0.0)
+    o.reset_times()
+    t0 = time.perf_counter()
+    o.outer(0)
+    dt = time.perf_counter() - t0
+    fdm, nod = o.times()
+    units = p.nnod * p.ng * steps
+    desc = (f"IAEA-3D 1 cm radial mesh, axial mesh coarsened to {p.nzz} planes ({p.nnod} nodes x {p.ng} groups), "
+            f"{steps} outer iterations after {warmup} warm-up, nin={CTL['nin']} nac={CTL['nac']} nupd={CTL['nupd']}, "
+            f"CMFD {fdm:.2f} s + nodal {nod:.2f} s, {cpu_model()}")
+    return units / dt, dt, desc
+
+
+def reference_arm(args, rank):
+    """--impl reference: the reference's CPU implementation of the path (oracle port of the
+    Fortran; oracle/_ref cannot be built without a Fortran compiler), all the threads it can
+    use = 1 (the reference is serial)."""
+    if rank != 0:
+        return
+    val, dt, desc = run_oracle_sample(args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "IAEA-3D refined 1cm x 1cm x 2cm (170x170x190, 4.579M nodes, 2 groups), SANM; "
+                               "CPU arm runs a bounded sample of it", "nin": CTL["nin"], "nac": CTL["nac"], "nupd": CTL["nupd"]},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": "port", "sample": desc},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def pinned(a):
+    import torch
+    t = torch.from_numpy(np.ascontiguousarray(a.ravel(order="K"))).pin_memory()
+    return t, t.numpy().reshape(a.shape, order="F" if a.flags.f_contiguous else "C")
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        reference_arm(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from adpres_b200 import capi
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the hot path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    uid = None
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        buf = (capi.C.c_ubyte * 128)()
+        if rank == 0:
+            assert capi.load().adp_comm_unique_id(buf) == 0
+        t = torch.tensor(list(bytes(buf)), dtype=torch.uint8, device="cuda")
+        dist.broadcast(t, 0)
+        uid = bytes(t.cpu().tolist())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------------------------------------------------------- problem
+    p = load_c2(planes_factor=world)
+    s = capi.Solver(p, device=local_rank, nranks=world, rank=rank, uid=uid, **CTL)
+    units_per_step = p.nnod * p.ng
+    N_own = (s.k1 - s.k0) * p.npl
+    s.matrix_setup(1)
+    s.init_flux()
+    s.outer_begin(capi.MODE_FORWARD)
+    W, K = args.warmup, args.steps
+
+    # ---------------------------------------------------------------- value (device resident)
+    s.outer_steps(capi.MODE_FORWARD, 1, W)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    l0 = s.launch_count()
+    s.timer_start()
+    rc, ke, ser, fer = s.outer_steps(capi.MODE_FORWARD, W + 1, K)
+    ms = s.timer_stop()
+    barrier()
+    launches = s.launch_count() - l0
+    clocks = sampler.stop()
+    assert rc == 0 and np.isfinite(ke), (rc, ke)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = units_per_step * K / (ms * 1e-3)
+
+    # ---------------------------------------------------------------- e2e (public API, host buffers)
+    e2e = None
+    if not args.no_e2e:
+        keep, hx = [], {}
+        for k in ("D", "sigr", "nuf", "sigf", "sigs", "chi", "dc", "exsrc"):
+            t, hx[k] = pinned(getattr(p, k))
+            keep.append(t)
+        st0 = s.state()
+        t1, f0_h = pinned(st0["f0"]); t2, fs0_h = pinned(st0["fs0"])
+        t3, f0_out = pinned(np.zeros((p.nnod, p.ng), order="F")); t4, fs0_out = pinned(np.zeros(p.nnod))
+        t5, pw_out = pinned(np.zeros(p.nnod))
+        L = s.L
+        d = capi._d
+
+        def one_call(nsteps, p_first):
+            # what the patched Fortran outer() does: hand over sdata, iterate, take the results back
+            s._chk(L.adp_set_xs(s.h, d(hx["D"]), d(hx["sigr"]), d(hx["nuf"]), d(hx["sigf"]), d(hx["sigs"]), d(hx["chi"]),
+                                d(hx["dc"]), d(hx["exsrc"])))
+            s._chk(L.adp_set_state(s.h, d(f0_h), d(fs0_h), capi.C.c_double(st0["Ke"])))
+            s.matrix_setup(1)
+            s.outer_begin(capi.MODE_FORWARD)
+            for q in range(p_first, p_first + nsteps):
+                s.outer_iter(capi.MODE_FORWARD, q)
+                if q % CTL["nupd"] == 0:
+                    s.nodal_upd(1)
+            ke_ = capi.C.c_double()
+            s._chk(L.adp_get_state(s.h, d(f0_out), d(fs0_out), None, capi.C.byref(ke_)))
+            s._chk(L.adp_powdis(s.h, d(pw_out), 0))
+            return ke_.value
+
+        one_call(W, 1)
+        barrier()
+        t0 = time.perf_counter()
+        s.timer_start()
+        ke_e2e = one_call(K, W + 1)
+        ms_e2e_dev = s.timer_stop()
+        barrier()
+        wall = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([wall], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            wall = float(t.item())
+        nd, G = N_own, p.ng
+        h2d = 8 * (nd * (4 * G + G * G + 6 * G + G) + p.nmat * G) + 8 * nd * (G + 1)   # XS + dc + exsrc + chi ; f0, fs0
+        d2h = 8 * nd * (G + 1) + 8 * nd + 8 * 18 * K                                     # f0, fs0 ; power ; scalars per step
+        e2e = {"value": units_per_step * K / wall, "unit": UNIT, "h2d_bytes_per_step": int(h2d * world / K),
+               "d2h_bytes_per_step": int(d2h * world / K), "ms_per_step": 1e3 * wall / K,
+               "device_ms_per_step": ms_e2e_dev / K, "keff_after": ke_e2e,
+               "what": "one outer() call through the C ABI with pinned host buffers: adp_set_xs + adp_set_state + "
+                       "adp_matrix_setup + K x adp_outer_iter (+ adp_nodal_upd every nupd) + adp_get_state + adp_powdis"}
+
+    # ---------------------------------------------------------------- roofline of the dominant kernel
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
+    else:
+        peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+    kern = {}
+    rows = N_own
+    for name, what, bytes_per_row in (("k_spmv_dot (B: v=Ap,(rs,v))", 0, 72.0), ("k_spmv (plain v=Ap)", 8, 72.0),
+                                      ("k_st (C: s,t fused)", 1, 88.0), ("k_update_xr (D)", 2, 56.0),
+                                      ("k_update_p (A)", 3, 32.0), ("k_residual (P)", 4, 8.0 * (7 + 1 + 1 + 2 * (p.ng - 1) + 1 + 3) + 4.0),
+                                      ("k_fsrc_norms (F)", 5, 8.0 * (3 * p.ng + 2))):
+        kms = s.bench_kernel(what, 20)
+        kern[name] = {"ms": kms, "alg_bytes_per_row": bytes_per_row, "GBps": rows * bytes_per_row / (kms * 1e-3) / 1e9}
+    nodal_ms = s.bench_kernel(7, 3)
+    kern["nodal update (source + 3 surface sweeps)"] = {
+        "ms": nodal_ms, "alg_bytes_per_node": 8.0 * (41 * p.ng + p.ng ** 2),
+        "GBps": rows * 8.0 * (41 * p.ng + p.ng ** 2) / (nodal_ms * 1e-3) / 1e9}
+    dom = kern["k_spmv_dot (B: v=Ap,(rs,v))"]
+    roofline = {"bound": "hbm", "kernel": "k_spmv_dot", "achieved": dom["GBps"], "peak": peak, "unit": "GB/s",
+                "frac": dom["GBps"] / peak, "traffic": None, "peak_source": peak_src,
+                "alg_bytes_per_launch": rows * SPMV_BYTES_PER_ROW, "ms_per_launch": dom["ms"],
+                "kernels": kern}
+    # whole outer iteration: SURVEY.md 8(d): bicg 8(8+32 nin) + TSrc 8(2(G-1)+4) + tail 8(3G+4)/G per node-group row
+    row_bytes = 8.0 * (8 + 32 * CTL["nin"]) + 8.0 * (2 * (p.ng - 1) + 4) + 8.0 * (3 * p.ng + 4) / p.ng
+    step_gbps = (units_per_step / world) * row_bytes / (ms * 1e-3 / K) / 1e9
+    roofline["outer_iteration"] = {"alg_bytes_per_row": row_bytes, "GBps_per_gpu": step_gbps, "frac": step_gbps / peak,
+                                   "note": "includes the nodal updates that fall inside the timed steps"}
+
+    # ---------------------------------------------------------------- CPU baseline (rank 0, N = 1)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, dt, desc = run_oracle_sample(steps=50, warmup=2)
+        cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port", "sample": desc, "seconds": dt,
+               "host_cores_available": host_cores()}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": f"IAEA-3D refined 1cm x 1cm x {2.0 / world:g}cm ({p.nxx}x{p.nyy}x{p.nzz} mesh, "
+                                   f"{p.nnod} nodes, {p.ng} groups = {units_per_step} node-groups), SANM kernel; "
+                                   f"{s.k1 - s.k0} planes per GPU",
+                       "nin": CTL["nin"], "nac": CTL["nac"], "nupd": CTL["nupd"], "parallelism": f"z-slab x{world}",
+                       "l2": "inputs larger than L2 (each kernel streams >= 290 MB per launch; 126 MB L2)",
+                       "keff_after_steps": ke},
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

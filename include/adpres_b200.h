@@ -188,9 +188,17 @@ int adp_set_option(adp_ctx *ctx, const char *name, int value);
  * inside) and device time accumulated per class, in ms, measured with CUDA events */
 int adp_launch_count(const adp_ctx *ctx, long long *launches);
 /* device-resident micro-benchmark of one kernel class on the current problem, no host copies:
- * what: 0 SpMV (v=A p + (rs,v)), 1 fused s/t kernel, 2 whole bicg (nin iterations),
- * 3 whole outer iteration, 4 nodal update.  Runs `reps` launches, returns average ms. */
+ * what: 0 B SpMV + (rs,v); 1 C fused s/t; 2 D x,r update; 3 A p update; 4 P source+residual;
+ * 5 F fission source + norms; 6 nodal source; 7 whole nodal update; 8 plain SpMV; 9 matrix_setup(0).
+ * Runs `reps` launches (alternating over groups), returns the average device ms per launch. */
 int adp_bench_kernel(adp_ctx *ctx, int what, int reps, double *avg_ms);
+/* `nsteps` passes of the outer loop body starting at p_first, nodal update + matrix_setup(0)
+ * whenever mod(p,nupd)==0, enqueued back to back with ONE synchronisation at the end (no
+ * per-iteration exit test): the device-resident throughput path. */
+int adp_outer_steps(adp_ctx *ctx, int mode, int p_first, int nsteps, double *Ke, double *ser, double *fer);
+/* CUDA-event stopwatch on the library's stream */
+int adp_timer_start(adp_ctx *ctx);
+int adp_timer_stop(adp_ctx *ctx, double *ms);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,84 @@
+"""Worker for the multi-GPU z-slab tests (launched by torchrun, one rank per GPU).
+Every rank holds the global problem (as N copies of the Fortran driver would), owns a z-slab,
+and checks its own slab against the single-process CPU oracle."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    from conftest import load_problem
+    from adpres_b200 import capi
+    from oracle import Oracle
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    buf = (capi.C.c_ubyte * 128)()
+    if rank == 0:
+        assert capi.load().adp_comm_unique_id(buf) == 0
+    t = torch.tensor(list(bytes(buf)), dtype=torch.uint8, device="cuda")
+    dist.broadcast(t, 0)
+    uid = bytes(t.cpu().tolist())
+
+    deck = sys.argv[1] if len(sys.argv) > 1 else "IAEA3Ds"
+    p = load_problem(deck)
+    if deck == "IAEA2D":                      # only 2 planes: refine axially so that every rank gets >= 2
+        p = p.refine(zdiv=[4, 4])
+    s = capi.Solver(p, device=local, nranks=world, rank=rank, uid=uid)
+    o = Oracle(p)
+    own = s.own
+    rel = lambda a, b: np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+    # 1. matrix + SpMV on the owned rows: bit exact
+    s.matrix_setup(1); o.matrix_setup(1)
+    assert np.array_equal(s.matrix_dia()[:, own, :], o.matrix_dia()[:, own, :])
+    x = np.random.default_rng(3).standard_normal(p.nnod)
+    for g in range(1, p.ng + 1):
+        assert np.array_equal(s.sp_matvec(g, x)[own], o.sp_matvec(g, x)[own]), "spmv halo"
+    # 2. BiCGSTAB with halo exchange + all-reduced dot products
+    b = np.random.default_rng(4).random(p.nnod); x0 = np.random.default_rng(5).random(p.nnod)
+    assert rel(s.bicg(3, 1, b, x0)[own], o.bicg(3, 1, b, x0)[own]) < 1e-11
+    # 3. one nodal update from an identical state (interface surfaces computed redundantly)
+    o.set_control(nout=6, nupd=1000); o.outer(0)
+    st = o.state()
+    s.set_state(st["f0"], st["fs0"], st["Ke"])
+    rc_o = o.nodal_upd(1)
+    rc_s, ndmax, loc = s.nodal_upd(1)
+    assert rc_o == 0 and rc_s == 0
+    dn_s, dn_o = s.nod()[1], o.nod()[1]
+    assert np.abs(dn_s[:, own, :] - dn_o[:, own, :]).max() < 1e-9, np.abs(dn_s[:, own, :] - dn_o[:, own, :]).max()
+    assert abs(ndmax - o.ndmax) < 1e-9 * max(1.0, o.ndmax), (ndmax, o.ndmax)
+    # 4. the whole eigenvalue solve
+    s2 = capi.Solver(p, device=local, nranks=world, rank=rank, uid=None) if False else None
+    del s
+    dist.barrier()
+    buf2 = (capi.C.c_ubyte * 128)()
+    if rank == 0:
+        assert capi.load().adp_comm_unique_id(buf2) == 0
+    t = torch.tensor(list(bytes(buf2)), dtype=torch.uint8, device="cuda")
+    dist.broadcast(t, 0)
+    s = capi.Solver(p, device=local, nranks=world, rank=rank, uid=bytes(t.cpu().tolist()))
+    o = Oracle(p)
+    rc_s, n_s = s.outer(0)
+    rc_o, n_o = o.outer(0)
+    assert rc_s == rc_o == 0 and abs(n_s - n_o) <= 1, (rc_s, rc_o, n_s, n_o)
+    ks, ko = s.state()["Ke"], o.state()["Ke"]
+    assert abs(ks - ko) * 1e5 < 1.0, (ks, ko)
+    _, pw_s = s.powdis()
+    _, pw_o = o.powdis()
+    nz = pw_o[own] > 1e-12
+    assert np.abs(pw_s[own][nz] / pw_o[own][nz] - 1).max() < 1e-5
+    print(f"RANK {rank}/{world} OK deck={deck} planes=[{s.k0},{s.k1}) keff={ks:.6f} outers={n_s}", flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
