@@ -2,6 +2,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <cstdlib>
 
 #include "adp_internal.cuh"
 
@@ -40,7 +41,12 @@ extern "C" int adp_create(adp_ctx **out, int device)
         g_create_err = std::string("adp_create: no CUDA device (") + cudaGetErrorString(e) + "); there is no CPU fallback";
         return ADP_ERR_CUDA;
     }
-    if (device < 0 || device >= ndev) { g_create_err = "adp_create: bad device index"; return ADP_ERR_USAGE; }
+    if (device < 0) {   // -1: take the device from the launcher's environment (one process per GPU)
+        const char *v = getenv("ADP_LOCAL_RANK");
+        if (!v) v = getenv("LOCAL_RANK");
+        device = v ? atoi(v) % ndev : 0;
+    }
+    if (device >= ndev) { g_create_err = "adp_create: bad device index"; return ADP_ERR_USAGE; }
     adp_ctx *c = new adp_ctx();
     c->device = device;
     if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) {

@@ -4,6 +4,9 @@
 // NCCL is resolved at run time (dlopen) so that the single-GPU library has no link-time
 // dependency on it; whichever libnccl.so.2 the process already has loaded (e.g. torch's) wins.
 #include <dlfcn.h>
+#include <time.h>
+#include <cstdlib>
+#include <cstring>
 
 #include "adp_internal.cuh"
 
@@ -87,6 +90,44 @@ extern "C" int adp_comm_init(adp_ctx *c, int nranks, int rank, const void *uid12
     NCCL_TRY(c, g_nccl.CommInitRank(&c->comm->comm, nranks, id, rank));
     c->nranks = nranks; c->rank = rank;
     return ADP_OK;
+}
+
+// Launcher-free bootstrap for the Fortran driver started N times (mpirun / a shell loop / torchrun):
+// ADP_NRANKS (or WORLD_SIZE), ADP_RANK (or RANK), ADP_UID_FILE (default /tmp/adpres_b200.uid).
+// Rank 0 writes the NCCL unique id to the file (atomically, via rename), the others wait for it.
+extern "C" int adp_comm_init_env(adp_ctx *c)
+{
+    if (!c) return ADP_ERR_USAGE;
+    auto env_int = [](const char *a, const char *b, int dflt) {
+        const char *v = getenv(a);
+        if (!v) v = getenv(b);
+        return v ? atoi(v) : dflt;
+    };
+    const int nranks = env_int("ADP_NRANKS", "WORLD_SIZE", 1), rank = env_int("ADP_RANK", "RANK", 0);
+    if (nranks <= 1) return adp_comm_init(c, 1, 0, nullptr);
+    const char *path = getenv("ADP_UID_FILE");
+    std::string file = path ? path : "/tmp/adpres_b200.uid";
+    char uid[128];
+    if (rank == 0) {
+        int rc = adp_comm_unique_id(uid);
+        if (rc) { c->err = "adp_comm_init_env: cannot create the NCCL unique id"; return rc; }
+        std::string tmp = file + ".tmp";
+        FILE *f = fopen(tmp.c_str(), "wb");
+        if (!f || fwrite(uid, 1, 128, f) != 128) { c->err = "adp_comm_init_env: cannot write " + tmp; if (f) fclose(f); return ADP_ERR_USAGE; }
+        fclose(f);
+        if (rename(tmp.c_str(), file.c_str()) != 0) { c->err = "adp_comm_init_env: rename failed"; return ADP_ERR_USAGE; }
+    } else {
+        bool ok = false;
+        for (int tries = 0; tries < 6000 && !ok; ++tries) {
+            FILE *f = fopen(file.c_str(), "rb");
+            if (f) { ok = fread(uid, 1, 128, f) == 128; fclose(f); }
+            if (!ok) { struct timespec ts = {0, 10000000}; nanosleep(&ts, nullptr); }
+        }
+        if (!ok) { c->err = "adp_comm_init_env: timed out waiting for " + file; return ADP_ERR_NCCL; }
+    }
+    int rc = adp_comm_init(c, nranks, rank, uid);
+    if (rank == 0 && rc == ADP_OK) remove(file.c_str());   // every rank has joined once CommInitRank returns
+    return rc;
 }
 
 void adp_comm_destroy(adp_ctx *c)

@@ -152,7 +152,7 @@ def run_oracle_sample(steps, warmup, sample_planes=19):
     return units / dt, dt, desc
 
 
-def reference_arm(args, rank):
+def reference_arm(args, rank, emit):
     """--impl reference: the reference's CPU implementation of the path (oracle port of the
     Fortran; oracle/_ref cannot be built without a Fortran compiler), all the threads it can
     use = 1 (the reference is serial)."""
@@ -169,7 +169,7 @@ def reference_arm(args, rank):
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def pinned(a):
@@ -179,6 +179,12 @@ def pinned(a):
 
 
 def main():
+    # Only the JSON line may reach stdout: NCCL / torchrun banners go to stderr.
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)
@@ -193,7 +199,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
-        reference_arm(args, rank)
+        reference_arm(args, rank, emit)
         return
 
     import torch
@@ -347,7 +353,7 @@ def main():
                        "keff_after_steps": ke},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -1,0 +1,160 @@
+!> ISO_C_BINDING interface to libadpres_b200.so (include/adpres_b200.h).
+!!
+!! This module and fortran/mod_cmfd_b200.f90 are what a maintainer adds to ADPRES 1.2 to run
+!! the CMFD/BiCGSTAB + SANM/PNM hot path on a B200:  src/mod_cmfd.f90 is replaced by
+!! fortran/mod_cmfd_b200.f90 (same module name `cmfd`, same public procedures and argument
+!! lists), every other source file -- ADPRES.f90, mod_io.f90 (deck parser), mod_data.f90,
+!! mod_xsec.f90, mod_nodal.f90 (Lxyz is still used on the host by `reactivity`), mod_th.f90,
+!! mod_trans.f90, mod_control.f90 -- stays byte-for-byte as it is.
+!!
+!! NOTE: no Fortran compiler exists in the image this was developed in (gfortran, flang, ifx,
+!! nvfortran all absent), so these two files are delivered as source and are exercised only
+!! indirectly: the C ABI they bind is driven by the identical call sequence from
+!! adpres_b200/csrc/host_cmfd.cpp and from the Python ctypes binding in the tests.
+module adpres_b200
+  use iso_c_binding
+  implicit none
+
+  integer(c_int), parameter :: ADP_MODE_FORWARD = 0, ADP_MODE_ADJOINT = 1, &
+                               ADP_MODE_FIXEDSRC = 2, ADP_MODE_TRANSIENT = 3
+  integer(c_int), parameter :: ADP_KERN_FDM = 0, ADP_KERN_PNM = 1, ADP_KERN_SANM = 2
+
+  type(c_ptr), save :: ctx = c_null_ptr      ! one device context per process (the reference is SAVE'd and serial)
+
+  interface
+    integer(c_int) function adp_create(ctx, device) bind(C, name="adp_create")
+      import; type(c_ptr), intent(out) :: ctx; integer(c_int), value :: device
+    end function
+    integer(c_int) function adp_destroy(ctx) bind(C, name="adp_destroy")
+      import; type(c_ptr), value :: ctx
+    end function
+    !> multi-GPU (one process per GPU): reads ADP_NRANKS / ADP_RANK / ADP_UID_FILE from the environment
+    integer(c_int) function adp_comm_init_env(ctx) bind(C, name="adp_comm_init_env")
+      import; type(c_ptr), value :: ctx
+    end function
+    integer(c_int) function adp_set_geometry(ctx, nxx, nyy, nzz, nnod, ng, nmat, ix, iy, iz, ysmin, ysmax, &
+                                             xsmin, xsmax, xdel, ydel, zdel, bc, mat) bind(C, name="adp_set_geometry")
+      import; type(c_ptr), value :: ctx
+      integer(c_int), value :: nxx, nyy, nzz, nnod, ng, nmat
+      integer(c_int), intent(in) :: ix(*), iy(*), iz(*), ysmin(*), ysmax(*), xsmin(*), xsmax(*), bc(6), mat(*)
+      real(c_double), intent(in) :: xdel(*), ydel(*), zdel(*)
+    end function
+    integer(c_int) function adp_set_xs(ctx, D, sigr, nuf, sigf, sigs, chi, dc, exsrc) bind(C, name="adp_set_xs")
+      import; type(c_ptr), value :: ctx
+      real(c_double), intent(in) :: D(*), sigr(*), nuf(*), sigf(*), sigs(*), chi(*), dc(*), exsrc(*)
+    end function
+    integer(c_int) function adp_set_control(ctx, nout, nin, nac, nupd, serc, ferc, kern) bind(C, name="adp_set_control")
+      import; type(c_ptr), value :: ctx
+      integer(c_int), value :: nout, nin, nac, nupd, kern
+      real(c_double), value :: serc, ferc
+    end function
+    integer(c_int) function adp_matrix_setup(ctx, opt) bind(C, name="adp_matrix_setup")
+      import; type(c_ptr), value :: ctx; integer(c_int), value :: opt
+    end function
+    integer(c_int) function adp_init_flux(ctx, adjoint) bind(C, name="adp_init_flux")
+      import; type(c_ptr), value :: ctx; integer(c_int), value :: adjoint
+    end function
+    integer(c_int) function adp_outer_begin(ctx, mode) bind(C, name="adp_outer_begin")
+      import; type(c_ptr), value :: ctx; integer(c_int), value :: mode
+    end function
+    integer(c_int) function adp_outer_iter(ctx, mode, p, Ke, ser, fer) bind(C, name="adp_outer_iter")
+      import; type(c_ptr), value :: ctx; integer(c_int), value :: mode, p
+      real(c_double), intent(out) :: Ke, ser, fer
+    end function
+    integer(c_int) function adp_nodal_upd(ctx, nmode, ndmax, im, jm, km) bind(C, name="adp_nodal_upd")
+      import; type(c_ptr), value :: ctx; integer(c_int), value :: nmode
+      real(c_double), intent(out) :: ndmax; integer(c_int), intent(out) :: im, jm, km
+    end function
+    integer(c_int) function adp_powdis(ctx, p, fixedsrc_mode) bind(C, name="adp_powdis")
+      import; type(c_ptr), value :: ctx; real(c_double), intent(out) :: p(*); integer(c_int), value :: fixedsrc_mode
+    end function
+    integer(c_int) function adp_integrate(ctx, s, res) bind(C, name="adp_integrate")
+      import; type(c_ptr), value :: ctx; real(c_double), intent(in) :: s(*); real(c_double), intent(out) :: res
+    end function
+    integer(c_int) function adp_set_kinetics(ctx, ibeta, lamb, velo, tbeta, sth, bth) bind(C, name="adp_set_kinetics")
+      import; type(c_ptr), value :: ctx
+      real(c_double), intent(in) :: ibeta(6), lamb(6), velo(*), tbeta(*); real(c_double), value :: sth, bth
+    end function
+    integer(c_int) function adp_set_transient(ctx, c0, ft, fst, omeg, sigrp, L) bind(C, name="adp_set_transient")
+      import; type(c_ptr), value :: ctx
+      real(c_double), intent(in) :: c0(*), ft(*), fst(*), omeg(*), sigrp(*), L(*)
+    end function
+    integer(c_int) function adp_get_exsrc(ctx, ht) bind(C, name="adp_get_exsrc")
+      import; type(c_ptr), value :: ctx; real(c_double), value :: ht
+    end function
+    integer(c_int) function adp_get_exsrc_arrays(ctx, exsrc, dfis) bind(C, name="adp_get_exsrc_arrays")
+      import; type(c_ptr), value :: ctx; real(c_double), intent(out) :: exsrc(*), dfis(*)
+    end function
+    integer(c_int) function adp_get_state(ctx, f0, fs0, s0, Ke) bind(C, name="adp_get_state")
+      import; type(c_ptr), value :: ctx; real(c_double), intent(out) :: f0(*), fs0(*), s0(*), Ke
+    end function
+    integer(c_int) function adp_set_state(ctx, f0, fs0, Ke) bind(C, name="adp_set_state")
+      import; type(c_ptr), value :: ctx; real(c_double), intent(in) :: f0(*), fs0(*); real(c_double), value :: Ke
+    end function
+    integer(c_int) function adp_set_s0(ctx, s0, g) bind(C, name="adp_set_s0")
+      import; type(c_ptr), value :: ctx; real(c_double), intent(in) :: s0(*); integer(c_int), value :: g
+    end function
+    integer(c_int) function adp_get_nod(ctx, df, dn) bind(C, name="adp_get_nod")
+      import; type(c_ptr), value :: ctx; real(c_double), intent(out) :: df(*), dn(*)
+    end function
+    integer(c_int) function adp_set_nod_dn(ctx, dn) bind(C, name="adp_set_nod_dn")
+      import; type(c_ptr), value :: ctx; real(c_double), intent(in) :: dn(*)
+    end function
+    integer(c_int) function adp_get_ndmax(ctx, ndmax) bind(C, name="adp_get_ndmax")
+      import; type(c_ptr), value :: ctx; real(c_double), intent(out) :: ndmax
+    end function
+  end interface
+
+contains
+
+  !> First call: create the context and hand over the geometry (what inp_geom1/2 + misc left in sdata).
+  subroutine gpu_init()
+    use sdata, only: nxx, nyy, nzz, nnod, ng, nmat, ix, iy, iz, ystag, xstag, xdel, ydel, zdel, &
+                     xeast, xwest, ynorth, ysouth, zbott, ztop, mat
+    integer(c_int) :: ierr, bc(6), i
+    integer(c_int), allocatable :: ysmin(:), ysmax(:), xsmin(:), xsmax(:)
+    if (c_associated(ctx)) return
+    ierr = adp_create(ctx, -1_c_int)      ! device = LOCAL_RANK (one process per GPU), else 0
+    if (ierr /= 0) stop 'adpres_b200: no CUDA device (there is no CPU fallback)'
+    ierr = adp_comm_init_env(ctx)
+    if (ierr /= 0) stop 'adpres_b200: multi-GPU initialisation failed'
+    allocate(ysmin(nyy), ysmax(nyy), xsmin(nxx), xsmax(nxx))
+    do i = 1, nyy; ysmin(i) = ystag(i)%smin; ysmax(i) = ystag(i)%smax; end do
+    do i = 1, nxx; xsmin(i) = xstag(i)%smin; xsmax(i) = xstag(i)%smax; end do
+    bc = (/ xeast, xwest, ynorth, ysouth, zbott, ztop /)
+    ierr = adp_set_geometry(ctx, nxx, nyy, nzz, nnod, ng, nmat, ix, iy, iz, ysmin, ysmax, xsmin, xsmax, &
+                            xdel, ydel, zdel, bc, mat)
+    if (ierr /= 0) stop 'adpres_b200: adp_set_geometry failed'
+  end subroutine gpu_init
+
+  !> Before every outer*(): cross sections as XS_updt left them + the iteration control.
+  subroutine gpu_push_inputs()
+    use sdata, only: D, sigr, nuf, sigf, sigs, chi, dc, exsrc, nout, nin, nac, nupd, serc, ferc, kern
+    integer(c_int) :: ierr, k
+    call gpu_init()
+    ierr = adp_set_xs(ctx, D, sigr, nuf, sigf, sigs, chi, dc, exsrc)
+    if (ierr /= 0) stop 'adpres_b200: adp_set_xs failed'
+    k = ADP_KERN_SANM
+    if (kern == ' FDM') k = ADP_KERN_FDM
+    if (kern == ' PNM') k = ADP_KERN_PNM
+    ierr = adp_set_control(ctx, nout, nin, nac, nupd, serc, ferc, k)
+  end subroutine gpu_push_inputs
+
+  !> After an outer*(): results the drivers read from sdata (f0, fs0, s0, Ke, nod%df/dn).
+  subroutine gpu_pull_results()
+    use sdata, only: f0, fs0, s0, Ke, nod, nnod, ng
+    integer(c_int) :: ierr
+    real(c_double), allocatable :: df(:,:,:), dn(:,:,:)
+    integer :: n, g
+    ierr = adp_get_state(ctx, f0, fs0, s0, Ke)
+    allocate(df(6,nnod,ng), dn(6,nnod,ng))
+    ierr = adp_get_nod(ctx, df, dn)
+    do g = 1, ng
+      do n = 1, nnod
+        nod(n,g)%df = df(:,n,g)
+        nod(n,g)%dn = dn(:,n,g)
+      end do
+    end do
+  end subroutine gpu_pull_results
+
+end module adpres_b200

@@ -59,7 +59,7 @@ enum {
 };
 
 /* ---- lifecycle ---------------------------------------------------------------------- */
-int adp_create(adp_ctx **ctx, int device);
+int adp_create(adp_ctx **ctx, int device /* -1: from ADP_LOCAL_RANK / LOCAL_RANK, else 0 */);
 int adp_destroy(adp_ctx *ctx);
 const char *adp_last_error(const adp_ctx *ctx);
 const char *adp_version(void);
@@ -69,6 +69,9 @@ const char *adp_version(void);
  * MPI / a file).  Must be called before adp_set_geometry().  Not calling it = 1 rank. */
 int adp_comm_unique_id(void *uid128);
 int adp_comm_init(adp_ctx *ctx, int nranks, int rank, const void *uid128);
+/* the same from the environment (ADP_NRANKS|WORLD_SIZE, ADP_RANK|RANK, ADP_UID_FILE): what the
+ * Fortran driver calls when it is started once per GPU */
+int adp_comm_init_env(adp_ctx *ctx);
 /* planes [k0, k1) (0-based) owned by this rank, valid after adp_set_geometry() */
 int adp_slab(const adp_ctx *ctx, int *k0, int *k1);
 

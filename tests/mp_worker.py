@@ -28,9 +28,10 @@ def main():
     uid = bytes(t.cpu().tolist())
 
     deck = sys.argv[1] if len(sys.argv) > 1 else "IAEA3Ds"
-    p = load_problem(deck)
-    if deck == "IAEA2D":                      # only 2 planes: refine axially so that every rank gets >= 2
-        p = p.refine(zdiv=[4, 4])
+    if deck == "IAEA3Ds_z2":                  # 38 planes: uneven slabs at 4 ranks, 2 planes per axial assembly
+        p = load_problem("IAEA3Ds").refine(zdiv=[2] * 19)
+    else:
+        p = load_problem(deck)
     s = capi.Solver(p, device=local, nranks=world, rank=rank, uid=uid)
     o = Oracle(p)
     own = s.own
@@ -56,7 +57,6 @@ def main():
     assert np.abs(dn_s[:, own, :] - dn_o[:, own, :]).max() < 1e-9, np.abs(dn_s[:, own, :] - dn_o[:, own, :]).max()
     assert abs(ndmax - o.ndmax) < 1e-9 * max(1.0, o.ndmax), (ndmax, o.ndmax)
     # 4. the whole eigenvalue solve
-    s2 = capi.Solver(p, device=local, nranks=world, rank=rank, uid=None) if False else None
     del s
     dist.barrier()
     buf2 = (capi.C.c_ubyte * 128)()

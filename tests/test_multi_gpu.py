@@ -1,5 +1,9 @@
 """z-slab decomposition over 2 GPUs (NCCL halo planes + scalar all-reduces) against the
-single-process oracle.  Needs >= 2 GPUs; run with `gpurun --gpus 2`."""
+single-process oracle.  Needs >= 2 GPUs; run with `gpurun --gpus 2`.
+
+(A z-refined IAEA2D -- a 2-D problem replicated axially -- is deliberately NOT used: the
+reference algorithm itself is unstable on it; summing its dot products four-way instead of
+serially makes the CPU oracle STOP with ndmax > 1e3, so no iteration-path parity exists.)"""
 import os
 import subprocess
 import sys
@@ -16,7 +20,7 @@ def _ngpu():
     return torch.cuda.device_count() if torch.cuda.is_available() else 0
 
 
-@pytest.mark.parametrize("deck", ["IAEA3Ds", "IAEA2D"])
+@pytest.mark.parametrize("deck", ["IAEA3Ds", "IAEA3Ds_z2"])
 def test_two_rank_slabs_match_oracle(deck):
     if _ngpu() < 2:
         pytest.skip("needs 2 GPUs")
