@@ -114,6 +114,9 @@ struct adp_ctx {
     double *d_dc = nullptr;                // [f][g][NV]
     double *d_chi = nullptr;               // [g][nmat]
     double *d_S = nullptr;                 // [3][G][NV]
+    double *d_nd = nullptr;                // [3][G*G+7G][NV] node-direction store of the nodal update
+    double *d_abefgh = nullptr;            // [3][6][G][NV] SANM constants, valid until D / sigr change
+    bool abefgh_valid = false;
     // transient
     double *d_c0 = nullptr, *d_ft = nullptr, *d_fst = nullptr, *d_omeg = nullptr, *d_sigrp = nullptr,
            *d_L = nullptr, *d_dfis = nullptr, *d_tbeta = nullptr, *d_velo = nullptr;

@@ -88,7 +88,7 @@ extern "C" int adp_destroy(adp_ctx *c)
                     c->d_f0[0], c->d_f0[1], c->d_fs[0], c->d_fs[1], c->d_r, c->d_rs, c->d_p, c->d_v, c->d_s, c->d_t,
                     c->d_s0, c->d_a, c->d_df, c->d_dn, c->d_D, c->d_sigr, c->d_nuf, c->d_sigf, c->d_exsrc, c->d_sigs,
                     c->d_dc, c->d_chi, c->d_S, c->d_c0, c->d_ft, c->d_fst, c->d_omeg, c->d_sigrp, c->d_L, c->d_dfis,
-                    c->d_tbeta, c->d_velo, c->d_scal, c->d_part, c->d_ticket, c->d_argidx, c->d_errflag, c->d_stage};
+                    c->d_tbeta, c->d_velo, c->d_nd, c->d_abefgh, c->d_scal, c->d_part, c->d_ticket, c->d_argidx, c->d_errflag, c->d_stage};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (c->h_scal) cudaFreeHost(c->h_scal);
     if (c->h_flags) cudaFreeHost(c->h_flags);
@@ -248,6 +248,9 @@ extern "C" int adp_set_geometry(adp_ctx *c, int nxx, int nyy, int nzz, int nnod,
     TRY(dev_alloc(c, &c->d_stage, NV));
     // D must stay non-zero on ghost planes outside the core (divisions in coup_coef never use
     // them, but keep every table finite): initialise to 1
+    if (c->d_nd) { cudaFree(c->d_nd); c->d_nd = nullptr; }
+    if (c->d_abefgh) { cudaFree(c->d_abefgh); c->d_abefgh = nullptr; }
+    c->abefgh_valid = false;
     c->geometry_set = true;
     c->xs_set = false; c->matrix_ready = false; c->have_flux = false; c->coup_first = true;
     c->outer_first = c->outer_ad_first = true;
@@ -276,6 +279,7 @@ extern "C" int adp_set_xs(adp_ctx *c, const double *D, const double *sigr, const
     const int G = c->ng;
     if (D) TRY(upload_nodes(c, c->d_D, D, G, true));
     if (sigr) TRY(upload_nodes(c, c->d_sigr, sigr, G, true));
+    if (D || sigr) c->abefgh_valid = false;   // the SANM constants A..H depend on sigr/D only
     if (nuf) TRY(upload_nodes(c, c->d_nuf, nuf, G, true));
     if (sigf) TRY(upload_nodes(c, c->d_sigf, sigf, G, true));
     if (sigs) TRY(upload_nodes(c, c->d_sigs, sigs, G * G, true));   // host (n,g,h): column g + G*h = device [h][g]

@@ -367,39 +367,59 @@ struct FsrcArgs {
     double *fs_new;
 };
 
+// RelE / RelEg take the maximum of |new-old|/|new| over all entries; an fp64 division per entry
+// (3 per row at G = 2) made this kernel instruction-bound (ncu: 40 M warp instructions, DRAM 36 %).
+// Each thread therefore tracks its maximum as a fraction (num, den), comparing candidates by
+// cross-multiplication, and divides once at the end.  The value returned is exactly the
+// reference's quotient of the selected entry; only between candidates whose quotients agree to
+// ~1 ulp can the selection differ.
+struct FracMax {
+    double num = 0.0, den = 1.0;
+    __device__ __forceinline__ void take(double n, double d)
+    {
+        if (n * den > num * d) { num = n; den = d; }
+    }
+    __device__ __forceinline__ double value() const { return num / den; }
+};
+
+template <int NG>   // NG > 0: compile-time group count (all loads of a row issue together); 0: runtime
 __global__ void __launch_bounds__(ADP_TILE) k_fsrc_norms(Geo G, FsrcArgs A, int do_norms, RedOut ro)
 {
     double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    FracMax mser, mfer;
+    const int ng = NG > 0 ? NG : A.ng;
     FOR_EACH_ROW(G, 0, G.nzl)
     {
         const long long idx = node_idx(G, kl, r);
         const int m = A.adjoint ? A.mat[idx] - 1 : 0;
-        double fs = 0.0, fer = 0.0;
-        for (int g = 0; g < A.ng; ++g) {
+        double fs = 0.0;
+#pragma unroll
+        for (int g = 0; g < ng; ++g) {
             const double fn = A.fnew[g][idx];
             const double w = A.adjoint ? A.w[g][m] : A.w[g][idx];
             fs = fs + fn * w;
-            if (do_norms && fabs(fn) > 1.e-10) {
-                const double e = fabs(fn - A.fold[g][idx]) / fabs(fn);
-                fer = fmax(fer, e);
-            }
+            if (do_norms && fabs(fn) > 1.e-10) mfer.take(fabs(fn - A.fold[g][idx]), fabs(fn));
         }
         A.fs_new[idx] = fs;
         if (do_norms) {
             const double errn = fs - A.fs_old[idx];
             acc[0] = acc[0] + errn * errn;
             acc[1] = acc[1] + (G.area[r] * G.hz[1 + G.k0 + kl]) * fs;
-            if (fabs(fs) > 1.e-10) acc[2] = fmax(acc[2], fabs(errn) / fabs(fs));
-            acc[3] = fmax(acc[3], fer);
+            if (fabs(fs) > 1.e-10) mser.take(fabs(errn), fabs(fs));
         }
     }
-    if (do_norms) grid_reduce<2, 2>(acc, ro);
+    if (do_norms) {
+        acc[2] = mser.value();
+        acc[3] = mfer.value();
+        grid_reduce<2, 2>(acc, ro);
+    }
 }
 
 // E: fiss_extrp (mod_cmfd.f90:326-329): fs = fs + domiR/(1-domiR) * errn, then Integrate + RelE
 __global__ void __launch_bounds__(ADP_TILE) k_extrap(Geo G, const double *__restrict__ fs_old, double *__restrict__ fs_new, RedOut ro)
 {
     double acc[2] = {0.0, 0.0};
+    FracMax mser;
     const double c = ro.scal[S_EXC];
     FOR_EACH_ROW(G, 0, G.nzl)
     {
@@ -409,8 +429,9 @@ __global__ void __launch_bounds__(ADP_TILE) k_extrap(Geo G, const double *__rest
         const double fs = fs_new[idx] + c * errn;
         fs_new[idx] = fs;
         acc[0] = acc[0] + (G.area[r] * G.hz[1 + G.k0 + kl]) * fs;
-        if (fabs(fs) > 1.e-10) acc[1] = fmax(acc[1], fabs(fs - fo) / fabs(fs));
+        if (fabs(fs) > 1.e-10) mser.take(fabs(fs - fo), fabs(fs));
     }
+    acc[1] = mser.value();
     grid_reduce<1, 1>(acc, ro);
 }
 
@@ -602,8 +623,14 @@ static int launch_fsrc(adp_ctx *c, bool adjoint, bool do_norms, int fs_in, int f
     }
     A.fs_old = c->d_fs[fs_in];
     A.fs_new = c->d_fs[fs_out];
-    k_fsrc_norms<<<adp_grid(c, k_fsrc_norms, c->geo.ntiles), ADP_TILE, 0, c->stream>>>(c->geo, A, do_norms ? 1 : 0,
-                                                                         make_red(c, S_E2SQ, S_FINT, S_SER, S_FER));
+    const RedOut ro = make_red(c, S_E2SQ, S_FINT, S_SER, S_FER);
+    const int nt = c->geo.ntiles, dn = do_norms ? 1 : 0;
+    switch (c->ng) {
+    case 1: k_fsrc_norms<1><<<adp_grid(c, k_fsrc_norms<1>, nt), ADP_TILE, 0, c->stream>>>(c->geo, A, dn, ro); break;
+    case 2: k_fsrc_norms<2><<<adp_grid(c, k_fsrc_norms<2>, nt), ADP_TILE, 0, c->stream>>>(c->geo, A, dn, ro); break;
+    case 4: k_fsrc_norms<4><<<adp_grid(c, k_fsrc_norms<4>, nt), ADP_TILE, 0, c->stream>>>(c->geo, A, dn, ro); break;
+    default: k_fsrc_norms<0><<<adp_grid(c, k_fsrc_norms<0>, nt), ADP_TILE, 0, c->stream>>>(c->geo, A, dn, ro); break;
+    }
     LAUNCH_CHECK(c);
     return ADP_OK;
 }
@@ -864,7 +891,8 @@ int adp_k_bench_one(adp_ctx *c, int what, int g)
             A.fnew[h] = f0ptr(c, c->cur[h], h); A.fold[h] = f0ptr(c, cur_old[h], h); A.w[h] = c->d_nuf + (size_t)h * c->NV;
         }
         A.fs_old = c->d_fs[c->fcur]; A.fs_new = c->d_stage;
-        k_fsrc_norms<<<adp_grid(c, k_fsrc_norms, nt), ADP_TILE, 0, c->stream>>>(c->geo, A, 1, make_red(c, S_TMP0, S_TMP1, S_TMP0, S_TMP1));
+        if (c->ng == 2) k_fsrc_norms<2><<<adp_grid(c, k_fsrc_norms<2>, nt), ADP_TILE, 0, c->stream>>>(c->geo, A, 1, make_red(c, S_TMP0, S_TMP1, S_TMP0, S_TMP1));
+        else k_fsrc_norms<0><<<adp_grid(c, k_fsrc_norms<0>, nt), ADP_TILE, 0, c->stream>>>(c->geo, A, 1, make_red(c, S_TMP0, S_TMP1, S_TMP0, S_TMP1));
         break;
     }
     default:
@@ -880,6 +908,7 @@ void adp_k_preload_cmfd(adp_ctx *c)
 {
     adp_grid(c, k_coup_coef, 1); adp_grid(c, k_matrix_setup, 1); adp_grid(c, k_residual, 1); adp_grid(c, k_update_p, 1);
     adp_grid(c, k_spmv_dot, 1); adp_grid(c, k_st, 1); adp_grid(c, k_s, 1); adp_grid(c, k_t, 1); adp_grid(c, k_update_xr, 1);
-    adp_grid(c, k_fsrc_norms, 1); adp_grid(c, k_extrap, 1); adp_grid(c, k_integrate, 1); adp_grid(c, k_fill, 1);
+    adp_grid(c, k_fsrc_norms<0>, 1); adp_grid(c, k_fsrc_norms<1>, 1); adp_grid(c, k_fsrc_norms<2>, 1); adp_grid(c, k_fsrc_norms<4>, 1);
+    adp_grid(c, k_extrap, 1); adp_grid(c, k_integrate, 1); adp_grid(c, k_fill, 1);
     adp_grid(c, k_scalar, 1); adp_grid(c, k_powdis, 1); adp_grid(c, k_scale, 1); adp_grid(c, k_get_exsrc, 1);
 }

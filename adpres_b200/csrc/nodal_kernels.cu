@@ -6,10 +6,16 @@
 // frozen by get_source before any dn is overwritten (mod_nodal.f90:49), so all surfaces are
 // independent.  Here:
 //   k_nodal_source    one thread per node: Lxyz -> S1,S2,S3              mod_nodal.f90:901-1043
+//   k_nodal_abefgh    one thread per node: the SANM constants A,B,E,F,G,H per (direction, group)
+//                     (sinh/cosh); they depend only on sigr, D and the mesh, so they are cached
+//                     until the cross sections change                      :1409-1451
+//   k_nodal_nodedir   one thread per (node, direction): everything the sweep carries for that
+//                     node -- B matrix, transverse-leakage moments, a2 (GxG LU), a4 -- computed
+//                     ONCE and stored ([3][G*G+7G][NV] doubles)            :1047-1405,740-825
 //   k_nodal_surfaces  one thread per (node, direction): the surface on the node's "+" side
 //                     (two-node 2Gx2G problem, or the one-node boundary problem), plus the
-//                     "-" boundary surface if the node is the first of its line.  The
-//                     4th-order expansion coefficients live in registers.      :282-897,1047-1451
+//                     "-" boundary surface if the node is the first of its line; a1, a3, the
+//                     surface current and the new dn live in registers.    :282-698
 // Each surface is evaluated with the reference's operation order (same Doolittle LU without
 // pivoting, same accumulation order), so results differ from the sweep only through the libm
 // (sinh/cosh) and not at all for PNM.
@@ -41,6 +47,8 @@ struct NodalArgs {
     const double *df;                    // [g][6][NV]
     double *dn;                          // [g][6][NV]
     double *S;                           // [3][G][NV]
+    double *nd;                          // [3][G*G+7G][NV]  per (direction, node): Bc, A, F, G, H, a2, a4, L1
+    double *abefgh;                      // [3][6][G][NV]    SANM constants cache
     const double *scal;
     int *errflag;
 };
@@ -221,18 +229,13 @@ __device__ __forceinline__ bool node_dir(const Geo &G, const NodalArgs &A, int u
 #pragma unroll
     for (int g = 0; g < NG; ++g) {
         if (KERN == ADP_KERN_SANM) {
-            const double alp = 0.5 * sqrt(sigr[g] / nd.D[g]) * q.h;
-            const double alp2 = alp * alp;
-            const double sh = sinh(alp), ch = cosh(alp);
-            const double m0c = sh / alp;
-            const double m1s = 3.0 * (ch / alp - sh / alp2);
-            const double m2c = 5.0 * (sh / alp - 3.0 * ch / alp2 + 3.0 * sh / (alp * alp * alp));
-            nd.A[g] = (sh - m1s) / (alp2 * m1s);
-            nd.B[g] = (ch - m0c - m2c) / (alp2 * m2c);
-            nd.E[g] = (m0c / m2c - 3.0 / alp2);
-            nd.F[g] = (alp * ch - m1s) / (alp2 * m1s);
-            nd.Gc[g] = (alp * sh - 3.0 * m2c) / (ch - m0c - m2c);
-            nd.H[g] = (alp * ch - m1s) / (sh - m1s);
+            const double *cc = A.abefgh + ((size_t)u * 6 * NG + g) * NV + idx;   // [u][c][g][NV]
+            nd.A[g] = cc[0];
+            nd.B[g] = cc[(size_t)1 * NG * NV];
+            nd.E[g] = cc[(size_t)2 * NG * NV];
+            nd.F[g] = cc[(size_t)3 * NG * NV];
+            nd.Gc[g] = cc[(size_t)4 * NG * NV];
+            nd.H[g] = cc[(size_t)5 * NG * NV];
         } else {
             nd.A[g] = 1.0 / 15.0; nd.B[g] = 1.0 / 35.0; nd.E[g] = 2.0 / 7.0;
             nd.F[g] = 2.0 / 5.0; nd.Gc[g] = 10.0; nd.H[g] = 6.0;
@@ -317,6 +320,112 @@ __device__ __forceinline__ void get_a3(const NodeDir<NG> &nd, const double (&a1)
     }
 }
 
+
+// get_ABEFGH (mod_nodal.f90:1409-1451) for every direction and group of one node
+template <int NG>
+__global__ void __launch_bounds__(ADP_TILE, 3) k_nodal_abefgh(Geo G, const double *__restrict__ D, const double *__restrict__ sigr,
+                                                              double *__restrict__ out, int klo, int npl)
+{
+    const long long NV = G.NV;
+    FOR_EACH_ROW(G, klo, npl)
+    {
+        const long long idx = node_idx(G, kl, r);
+        const double hu[3] = {G.hx[r], G.hy[r], G.hz[1 + G.k0 + kl]};
+#pragma unroll
+        for (int g = 0; g < NG; ++g) {
+            const double ratio = sigr[(size_t)g * NV + idx] / D[(size_t)g * NV + idx];
+            double c[3][6];
+#pragma unroll
+            for (int u = 0; u < 3; ++u) {
+                bool reuse = false;
+#pragma unroll
+                for (int w = 0; w < u; ++w)
+                    if (!reuse && hu[w] == hu[u]) {   // same inputs -> same bits; skip the transcendental work
+#pragma unroll
+                        for (int k = 0; k < 6; ++k) c[u][k] = c[w][k];
+                        reuse = true;
+                    }
+                if (reuse) continue;
+                const double alp = 0.5 * sqrt(ratio) * hu[u];
+                const double alp2 = alp * alp;
+                const double sh = sinh(alp), ch = cosh(alp);
+                const double m0c = sh / alp;
+                const double m1s = 3.0 * (ch / alp - sh / alp2);
+                const double m2c = 5.0 * (sh / alp - 3.0 * ch / alp2 + 3.0 * sh / (alp * alp * alp));
+                c[u][0] = (sh - m1s) / (alp2 * m1s);
+                c[u][1] = (ch - m0c - m2c) / (alp2 * m2c);
+                c[u][2] = (m0c / m2c - 3.0 / alp2);
+                c[u][3] = (alp * ch - m1s) / (alp2 * m1s);
+                c[u][4] = (alp * sh - 3.0 * m2c) / (ch - m0c - m2c);
+                c[u][5] = (alp * ch - m1s) / (sh - m1s);
+            }
+#pragma unroll
+            for (int u = 0; u < 3; ++u)
+#pragma unroll
+                for (int k = 0; k < 6; ++k) out[(((size_t)u * 6 + k) * NG + g) * NV + idx] = c[u][k];
+        }
+    }
+}
+
+// store layout of one (direction, node): slots [0,NG*NG) Bc(g,h); then A, F, G, H, a2, a4, L1 (NG each)
+template <int NG>
+__device__ __forceinline__ void nd_store(const NodeDir<NG> &nd, double *__restrict__ base, long long NV, long long idx)
+{
+    int sl = 0;
+#pragma unroll
+    for (int g = 0; g < NG; ++g)
+#pragma unroll
+        for (int h = 0; h < NG; ++h) base[(size_t)(sl++) * NV + idx] = nd.Bc[g][h];
+#pragma unroll
+    for (int g = 0; g < NG; ++g) {
+        base[(size_t)(sl + 0 * NG + g) * NV + idx] = nd.A[g];
+        base[(size_t)(sl + 1 * NG + g) * NV + idx] = nd.F[g];
+        base[(size_t)(sl + 2 * NG + g) * NV + idx] = nd.Gc[g];
+        base[(size_t)(sl + 3 * NG + g) * NV + idx] = nd.H[g];
+        base[(size_t)(sl + 4 * NG + g) * NV + idx] = nd.a2[g];
+        base[(size_t)(sl + 5 * NG + g) * NV + idx] = nd.a4[g];
+        base[(size_t)(sl + 6 * NG + g) * NV + idx] = nd.L1[g];
+    }
+}
+template <int NG>
+__device__ __forceinline__ void nd_load(NodeDir<NG> &nd, const double *__restrict__ base, long long NV, long long idx,
+                                        const NodalArgs &A)
+{
+    int sl = 0;
+#pragma unroll
+    for (int g = 0; g < NG; ++g)
+#pragma unroll
+        for (int h = 0; h < NG; ++h) nd.Bc[g][h] = base[(size_t)(sl++) * NV + idx];
+#pragma unroll
+    for (int g = 0; g < NG; ++g) {
+        nd.A[g] = base[(size_t)(sl + 0 * NG + g) * NV + idx];
+        nd.F[g] = base[(size_t)(sl + 1 * NG + g) * NV + idx];
+        nd.Gc[g] = base[(size_t)(sl + 2 * NG + g) * NV + idx];
+        nd.H[g] = base[(size_t)(sl + 3 * NG + g) * NV + idx];
+        nd.a2[g] = base[(size_t)(sl + 4 * NG + g) * NV + idx];
+        nd.a4[g] = base[(size_t)(sl + 5 * NG + g) * NV + idx];
+        nd.L1[g] = base[(size_t)(sl + 6 * NG + g) * NV + idx];
+        nd.f0[g] = A.f0[g][idx];
+        nd.D[g] = A.D[(size_t)g * NV + idx];
+    }
+}
+
+// one thread per (node, direction): compute and store what the sweep carries for that node
+template <int NG, int KERN>
+__global__ void __launch_bounds__(ADP_TILE, (NG <= 2) ? 3 : 1) k_nodal_nodedir(Geo G, NodalArgs A, int u, int klo, int npl)
+{
+    bool ok = true;
+    FOR_EACH_ROW(G, klo, npl)
+    {
+        const long long idx = node_idx(G, kl, r);
+        const Line q = line_of(G, u, kl, r);
+        NodeDir<NG> nd;
+        ok = node_dir<NG, KERN>(G, A, u, idx, q, nd) && ok;
+        nd_store<NG>(nd, A.nd + (size_t)u * (NG * NG + 7 * NG) * G.NV, G.NV, idx);
+    }
+    if (!ok) atomicExch(A.errflag, ADP_STOP_LU_DIAG);
+}
+
 struct ArgMax {
     double *scal;
     double *part;              // [ADP_MAXPART]
@@ -382,10 +491,11 @@ __device__ __forceinline__ void grid_argmax(double v, long long l, const ArgMax 
 // of the first node of a line).  get_coefs / get_coefs_first / get_coefs_last +
 // nodal_coup_upd (mod_nodal.f90:282-698).
 // ---------------------------------------------------------------------------------------
-template <int NG, int KERN>
+template <int NG>
 __global__ void __launch_bounds__(ADP_TILE, (NG <= 2) ? 2 : 1) k_nodal_surfaces(Geo G, NodalArgs A, int u, int klo, int npl, ArgMax am)
 {
     const long long NV = G.NV;
+    const double *ndbase = A.nd + (size_t)u * (NG * NG + 7 * NG) * NV;
     double best = -1.0;
     long long best_loc = 0x7fffffffffffffffLL;
     bool ok = true;
@@ -397,7 +507,7 @@ __global__ void __launch_bounds__(ADP_TILE, (NG <= 2) ? 2 : 1) k_nodal_surfaces(
         const Line qn = line_of(G, u, kl, r);
         const int sf = 2 * u;                                         // 0-based "+" face; "-" face = sf + 1
         NodeDir<NG> n;
-        ok = node_dir<NG, KERN>(G, A, u, idx, qn, n) && ok;
+        nd_load<NG>(n, ndbase, NV, idx, A);
         double a1[NG], a3[NG];
 
         if (!qn.has_m && owned) {
@@ -448,7 +558,7 @@ __global__ void __launch_bounds__(ADP_TILE, (NG <= 2) ? 2 : 1) k_nodal_surfaces(
             const int rp = (u == 0) ? r + 1 : (u == 1) ? r + (int)qn.off_p : r;
             const Line qp = line_of(G, u, klp, rp);
             NodeDir<NG> p;
-            ok = node_dir<NG, KERN>(G, A, u, idp, qp, p) && ok;
+            nd_load<NG>(p, ndbase, NV, idp, A);
             double R[2 * NG][2 * NG], s[2 * NG], sx[2 * NG];
 #pragma unroll
             for (int g = 0; g < NG; ++g) {
@@ -548,12 +658,37 @@ __global__ void __launch_bounds__(ADP_TILE, (NG <= 2) ? 2 : 1) k_nodal_surfaces(
 }
 
 template <int NG>
-void launch_surfaces(adp_ctx *c, const NodalArgs &A, int u, int klo, int npl, int ntiles, const ArgMax &am)
+void launch_nodal(adp_ctx *c, const NodalArgs &A, const ArgMax &am, bool refresh_abefgh)
 {
-    if (A.kern == ADP_KERN_SANM)
-        k_nodal_surfaces<NG, ADP_KERN_SANM><<<adp_grid(c, k_nodal_surfaces<NG, ADP_KERN_SANM>, ntiles), ADP_TILE, 0, c->stream>>>(c->geo, A, u, klo, npl, am);
-    else
-        k_nodal_surfaces<NG, ADP_KERN_PNM><<<adp_grid(c, k_nodal_surfaces<NG, ADP_KERN_PNM>, ntiles), ADP_TILE, 0, c->stream>>>(c->geo, A, u, klo, npl, am);
+    // planes that need node-direction data: own planes, plus the neighbour's boundary plane for
+    // the z surfaces shared with the slabs below / above
+    const int zlo = (c->k0 > 0) ? -1 : 0, zhi = (c->k1 < c->nzz) ? c->nzl + 1 : c->nzl;
+    const int tpp = c->geo.tpp;
+    if (A.kern == ADP_KERN_SANM && refresh_abefgh) {
+        k_nodal_abefgh<NG><<<adp_grid(c, k_nodal_abefgh<NG>, tpp * (zhi - zlo)), ADP_TILE, 0, c->stream>>>(
+            c->geo, c->d_D, c->d_sigr, A.abefgh, zlo, zhi - zlo);
+        c->launches++;
+    }
+    for (int u = 0; u < 3; ++u) {
+        const int klo = (u == 2) ? zlo : 0, npl = ((u == 2) ? zhi : c->nzl) - klo;
+        if (A.kern == ADP_KERN_SANM)
+            k_nodal_nodedir<NG, ADP_KERN_SANM><<<adp_grid(c, k_nodal_nodedir<NG, ADP_KERN_SANM>, tpp * npl), ADP_TILE, 0, c->stream>>>(c->geo, A, u, klo, npl);
+        else
+            k_nodal_nodedir<NG, ADP_KERN_PNM><<<adp_grid(c, k_nodal_nodedir<NG, ADP_KERN_PNM>, tpp * npl), ADP_TILE, 0, c->stream>>>(c->geo, A, u, klo, npl);
+        c->launches++;
+    }
+    for (int u = 0; u < 3; ++u) {
+        const int klo = (u == 2) ? zlo : 0, npl = c->nzl - klo;     // kl = -1: the surface shared with the slab below
+        k_nodal_surfaces<NG><<<adp_grid(c, k_nodal_surfaces<NG>, tpp * npl), ADP_TILE, 0, c->stream>>>(c->geo, A, u, klo, npl, am);
+        c->launches++;
+    }
+}
+
+template <int NG>
+void preload_nodal(adp_ctx *c)
+{
+    adp_grid(c, k_nodal_abefgh<NG>, 1); adp_grid(c, k_nodal_nodedir<NG, ADP_KERN_SANM>, 1);
+    adp_grid(c, k_nodal_nodedir<NG, ADP_KERN_PNM>, 1); adp_grid(c, k_nodal_surfaces<NG>, 1);
 }
 
 }  // namespace
@@ -567,6 +702,7 @@ static NodalArgs make_args(adp_ctx *c, int cmode)
     A.D = c->d_D; A.sigr = c->d_sigr; A.nuf = c->d_nuf; A.exsrc = c->d_exsrc; A.sigs = c->d_sigs;
     A.chi = c->d_chi; A.dc = c->d_dc; A.mat = c->d_mat; A.tbeta = c->d_tbeta; A.dfis = c->d_dfis;
     A.df = c->d_df; A.dn = c->d_dn; A.S = c->d_S; A.scal = c->d_scal; A.errflag = c->d_errflag;
+    A.nd = c->d_nd; A.abefgh = c->d_abefgh;
     return A;
 }
 
@@ -592,6 +728,17 @@ int adp_k_nodal_source(adp_ctx *c, int cmode)
 
 int adp_k_nodal_update(adp_ctx *c, int cmode)
 {
+    if (c->ng > 8) { c->err = "nodal update supports 1..8 energy groups"; return ADP_ERR_UNSUPPORTED; }
+    // scratch of the update, allocated on first use: node-direction store and SANM constants cache
+    const size_t NS = (size_t)c->ng * c->ng + 7 * c->ng;
+    if (!c->d_nd) {
+        if (cudaMalloc((void **)&c->d_nd, 3 * NS * c->NV * sizeof(double)) != cudaSuccess ||
+            cudaMalloc((void **)&c->d_abefgh, (size_t)3 * 6 * c->ng * c->NV * sizeof(double)) != cudaSuccess) {
+            c->err = "adp_k_nodal_update: out of device memory for the nodal scratch";
+            return ADP_ERR_CUDA;
+        }
+        c->abefgh_valid = false;
+    }
     int rc = adp_k_nodal_source(c, cmode);
     if (rc) return rc;
     NodalArgs A = make_args(c, cmode);
@@ -603,26 +750,22 @@ int adp_k_nodal_update(adp_ctx *c, int cmode)
     ArgMax am;
     am.scal = c->d_scal; am.part = c->d_part; am.part_loc = (long long *)(c->d_part + ADP_MAXPART);
     am.ticket = c->d_ticket; am.loc_out = c->d_argidx;
-    for (int u = 0; u < 3; ++u) {
-        int klo = 0, npl = c->nzl;
-        if (u == 2 && c->k0 > 0) { klo = -1; npl = c->nzl + 1; }   // the surface shared with the slab below
-        const int grid = c->geo.tpp * npl;
-        switch (c->ng) {
-        case 1: launch_surfaces<1>(c, A, u, klo, npl, grid, am); break;
-        case 2: launch_surfaces<2>(c, A, u, klo, npl, grid, am); break;
-        case 3: launch_surfaces<3>(c, A, u, klo, npl, grid, am); break;
-        case 4: launch_surfaces<4>(c, A, u, klo, npl, grid, am); break;
-        case 5: launch_surfaces<5>(c, A, u, klo, npl, grid, am); break;
-        case 6: launch_surfaces<6>(c, A, u, klo, npl, grid, am); break;
-        case 7: launch_surfaces<7>(c, A, u, klo, npl, grid, am); break;
-        case 8: launch_surfaces<8>(c, A, u, klo, npl, grid, am); break;
-        default: c->err = "nodal update supports 1..8 energy groups"; return ADP_ERR_UNSUPPORTED;
-        }
-        c->launches++;
-        if (cudaPeekAtLastError() != cudaSuccess) {
-            c->err = std::string("k_nodal_surfaces launch failed: ") + cudaGetErrorString(cudaGetLastError());
-            return ADP_ERR_CUDA;
-        }
+    const bool refresh = !c->abefgh_valid;
+    switch (c->ng) {
+    case 1: launch_nodal<1>(c, A, am, refresh); break;
+    case 2: launch_nodal<2>(c, A, am, refresh); break;
+    case 3: launch_nodal<3>(c, A, am, refresh); break;
+    case 4: launch_nodal<4>(c, A, am, refresh); break;
+    case 5: launch_nodal<5>(c, A, am, refresh); break;
+    case 6: launch_nodal<6>(c, A, am, refresh); break;
+    case 7: launch_nodal<7>(c, A, am, refresh); break;
+    case 8: launch_nodal<8>(c, A, am, refresh); break;
+    default: break;
+    }
+    if (c->kern == ADP_KERN_SANM) c->abefgh_valid = true;
+    if (cudaPeekAtLastError() != cudaSuccess) {
+        c->err = std::string("nodal update launch failed: ") + cudaGetErrorString(cudaGetLastError());
+        return ADP_ERR_CUDA;
     }
     return ADP_OK;
 }
@@ -630,9 +773,9 @@ int adp_k_nodal_update(adp_ctx *c, int cmode)
 void adp_k_preload_nodal(adp_ctx *c)
 {
     adp_grid(c, k_nodal_source, 1);
-    const bool sanm = c->kern != ADP_KERN_PNM;
-#define PRE(NG_) \
-    case NG_: if (sanm) adp_grid(c, k_nodal_surfaces<NG_, ADP_KERN_SANM>, 1); else adp_grid(c, k_nodal_surfaces<NG_, ADP_KERN_PNM>, 1); break;
-    switch (c->ng) { PRE(1) PRE(2) PRE(3) PRE(4) PRE(5) PRE(6) PRE(7) PRE(8) default: break; }
-#undef PRE
+    switch (c->ng) {
+    case 1: preload_nodal<1>(c); break; case 2: preload_nodal<2>(c); break; case 3: preload_nodal<3>(c); break;
+    case 4: preload_nodal<4>(c); break; case 5: preload_nodal<5>(c); break; case 6: preload_nodal<6>(c); break;
+    case 7: preload_nodal<7>(c); break; case 8: preload_nodal<8>(c); break; default: break;
+    }
 }
