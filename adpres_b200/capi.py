@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libadpres_b200.so")
+LIB_PATH = os.environ.get("ADPRES_B200_LIB", os.path.join(_HERE, "libadpres_b200.so"))   # override: A/B builds
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int)

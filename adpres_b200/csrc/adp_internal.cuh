@@ -18,6 +18,7 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdio>
+#include <cstring>
 #include <string>
 #include <vector>
 #include <map>
@@ -68,6 +69,33 @@ struct Geo {
     const double *hz;              // [nzz + 2] node size in z, hz[1 + kg]; ends padded
     const double *area;            // [np] xdel*ydel
     const int *ixr, *iyr;          // [np] 1-based i, j of plane position r
+};
+
+// Destination of a boundary-plane "push": the ghost planes of the z-neighbours' copy of the same
+// vector, mapped into this process over NVLink peer memory (CUDA IPC).  lo = the lower
+// neighbour's upper ghost plane, hi = the upper neighbour's lower ghost plane; nullptr = none.
+struct Push {
+    double *lo = nullptr, *hi = nullptr;
+};
+enum { PB_RS = 0, PB_V0, PB_V1, PB_R, PB_F0A, PB_F0B, PB_COUNT };
+
+// In-kernel all-reduce over peer memory.  Every rank owns a mailbox
+//     mail[ADP_MAIL_SLOTS][nranks][ADP_MAIL_WORDS]   (doubles; word 7 = sequence number)
+// mapped into all other ranks.  The last CTA of a reduction posts its local results into slot
+// (seq % ADP_MAIL_SLOTS), row `rank`, of EVERY rank's mailbox (values, system fence, sequence
+// number) and then waits until all rows of its own mailbox carry that sequence number; the
+// results are combined in rank order (deterministic).  Two consecutive reductions use different
+// slots and a rank cannot run two reductions ahead of another, so slots are never overwritten early.
+#define ADP_MAIL_SLOTS 4
+#define ADP_MAIL_WORDS 8
+#define ADP_MAX_RANKS 8
+struct Mail {
+    double *const *box;               // device table: box[q] = rank q's mailbox (box[rank] is local).  A table in
+                                      // global memory, NOT an array inside the kernel parameters: indexing a
+                                      // parameter array with a runtime q makes every thread copy it to a stack frame
+    unsigned long long *seq;          // device counter of reductions done on this rank
+    int *errflag;
+    int nranks = 1, rank = 0;
 };
 
 #define FLAG_XM 1
@@ -140,6 +168,17 @@ struct adp_ctx {
     // multi-rank
     adp_comm *comm = nullptr;
     int nranks = 1, rank = 0;
+    double *d_v2 = nullptr;                // second v buffer (iteration parity; see bicg_core)
+    bool peer_ok = false;                  // neighbours' vectors are mapped: halos are pushed by the kernels
+    double *peer_lo[PB_COUNT] = {nullptr}, *peer_hi[PB_COUNT] = {nullptr};
+    int nzl_lo = 0, nzl_hi = 0;            // planes owned by the lower / upper neighbour
+    long long NV_lo = 0, NV_hi = 0;
+    bool xghost_valid[2][ADP_MAXG] = {{false}};   // ghost planes of f0[which][g] are current
+    bool peer_ar = false;                  // reductions are all-reduced inside the kernels (mailboxes)
+    double *d_mail = nullptr;              // this rank's mailbox
+    double *mail_peer[ADP_MAX_RANKS] = {nullptr};
+    double **d_mail_table = nullptr;       // device copy of mail_peer[]
+    unsigned long long *d_arseq = nullptr;
     // CUDA graphs of one outer iteration, keyed by (mode, parity pattern, extrapolate)
     std::map<unsigned long long, cudaGraphExec_t> graphs;
     std::map<unsigned long long, long long> graph_launches;   // kernels inside each graph
@@ -215,4 +254,15 @@ int adp_comm_halo(adp_ctx *c, double *d_vec, int nplanes);            // exchang
 int adp_comm_allreduce_sum(adp_ctx *c, double *d_scal, int count);
 int adp_comm_allreduce_max(adp_ctx *c, double *d_scal, int count);
 int adp_comm_allreduce_min_ll(adp_ctx *c, long long *d_val, int count);
+int adp_comm_allreduce_max_nccl(adp_ctx *c, double *d_scal, int count);
 void adp_comm_destroy(adp_ctx *c);
+int adp_comm_map_peers(adp_ctx *c);                                     // after the vectors are allocated
+void adp_comm_unmap_peers(adp_ctx *c);
+static inline Push adp_push(const adp_ctx *c, int buf, long long goff_lo = 0, long long goff_hi = 0)
+{
+    Push ps;
+    if (!c->peer_ok) return ps;
+    if (c->peer_lo[buf]) ps.lo = c->peer_lo[buf] + goff_lo + (long long)(ADP_GH + c->nzl_lo) * c->np;
+    if (c->peer_hi[buf]) ps.hi = c->peer_hi[buf] + goff_hi + (long long)(ADP_GH - 1) * c->np;
+    return ps;
+}

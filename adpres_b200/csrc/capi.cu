@@ -85,10 +85,10 @@ extern "C" int adp_destroy(adp_ctx *c)
     free_graphs(c);
     adp_comm_destroy(c);
     void *ptrs[] = {c->d_ypm, c->d_ypp, c->d_ixr, c->d_iyr, c->d_mat, c->d_flag, c->d_hx, c->d_hy, c->d_hz, c->d_area,
-                    c->d_f0[0], c->d_f0[1], c->d_fs[0], c->d_fs[1], c->d_r, c->d_rs, c->d_p, c->d_v, c->d_s, c->d_t,
+                    c->d_f0[0], c->d_f0[1], c->d_fs[0], c->d_fs[1], c->d_r, c->d_rs, c->d_p, c->d_v, c->d_v2, c->d_s, c->d_t,
                     c->d_s0, c->d_a, c->d_df, c->d_dn, c->d_D, c->d_sigr, c->d_nuf, c->d_sigf, c->d_exsrc, c->d_sigs,
                     c->d_dc, c->d_chi, c->d_S, c->d_c0, c->d_ft, c->d_fst, c->d_omeg, c->d_sigrp, c->d_L, c->d_dfis,
-                    c->d_tbeta, c->d_velo, c->d_nd, c->d_abefgh, c->d_scal, c->d_part, c->d_ticket, c->d_argidx, c->d_errflag, c->d_stage};
+                    c->d_tbeta, c->d_velo, c->d_nd, c->d_abefgh, c->d_mail, c->d_arseq, c->d_mail_table, c->d_scal, c->d_part, c->d_ticket, c->d_argidx, c->d_errflag, c->d_stage};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (c->h_scal) cudaFreeHost(c->h_scal);
     if (c->h_flags) cudaFreeHost(c->h_flags);
@@ -152,6 +152,7 @@ extern "C" int adp_set_geometry(adp_ctx *c, int nxx, int nyy, int nzz, int nnod,
 {
     if (!c) return ADP_ERR_USAGE;
     CUDA_TRY(c, cudaSetDevice(c->device));
+    adp_comm_unmap_peers(c);
     ADP_REQUIRE(c, ng >= 1 && ng <= ADP_MAXG, "adp_set_geometry: ng must be 1..16");
     ADP_REQUIRE(c, nnod > 0 && nzz > 0 && nnod % nzz == 0, "adp_set_geometry: nnod must be np*nzz (plane-invariant core outline)");
     free_graphs(c);
@@ -237,6 +238,7 @@ extern "C" int adp_set_geometry(adp_ctx *c, int nxx, int nyy, int nzz, int nnod,
     for (int w = 0; w < 2; ++w) { TRY(dev_alloc(c, &c->d_f0[w], Gn * NV)); TRY(dev_alloc(c, &c->d_fs[w], NV)); }
     TRY(dev_alloc(c, &c->d_r, NV)); TRY(dev_alloc(c, &c->d_rs, NV)); TRY(dev_alloc(c, &c->d_p, NV));
     TRY(dev_alloc(c, &c->d_v, NV)); TRY(dev_alloc(c, &c->d_s, NV)); TRY(dev_alloc(c, &c->d_t, NV));
+    if (c->nranks > 1) TRY(dev_alloc(c, &c->d_v2, NV));
     TRY(dev_alloc(c, &c->d_s0, NV));
     TRY(dev_alloc(c, &c->d_a, Gn * 7 * NV));
     TRY(dev_alloc(c, &c->d_df, Gn * 6 * NV)); TRY(dev_alloc(c, &c->d_dn, Gn * 6 * NV));
@@ -257,7 +259,9 @@ extern "C" int adp_set_geometry(adp_ctx *c, int nxx, int nyy, int nzz, int nnod,
     c->ndmax = 0.0; c->s0_group = 0;
     for (int g = 0; g < ADP_MAXG; ++g) c->cur[g] = 0;
     c->fcur = 0;
+    memset(c->xghost_valid, 0, sizeof(c->xghost_valid));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    TRY(adp_comm_map_peers(c));
     return ADP_OK;
 }
 
@@ -367,7 +371,13 @@ extern "C" int adp_outer_iter(adp_ctx *c, int mode, int p, double *Ke, double *s
     ADP_REQUIRE(c, mode != ADP_MODE_TRANSIENT || c->kinetics_set, "adp_outer_iter: transient mode needs adp_set_kinetics");
     CUDA_TRY(c, cudaSetDevice(c->device));
     const bool extrap = (p % c->nac) == 0;
-    bool use_graph = c->use_graphs && c->nranks == 1;
+    // multi-rank: graphs only once no NCCL call is left inside the iteration (halos pushed by the
+    // kernels, reductions through the mailboxes, ghost flux planes current)
+    bool use_graph = c->use_graphs;
+    if (c->nranks > 1) {
+        use_graph = use_graph && c->peer_ok && c->peer_ar;
+        for (int g = 0; g < c->ng && use_graph; ++g) use_graph = c->xghost_valid[c->cur[g]][g];
+    }
     if (use_graph) {
         unsigned long long key = (unsigned long long)mode | ((unsigned long long)(extrap ? 1 : 0) << 4) |
                                  ((unsigned long long)c->fcur << 5);
@@ -398,6 +408,7 @@ extern "C" int adp_outer_iter(adp_ctx *c, int mode, int p, double *Ke, double *s
         for (int g = 0; g < c->ng; ++g) c->cur[g] ^= 1;
         c->fcur ^= 1;
         c->s0_group = (mode == ADP_MODE_ADJOINT) ? 1 : c->ng;
+        if (c->nranks > 1) for (int g = 0; g < c->ng; ++g) c->xghost_valid[c->cur[g]][g] = true;
         c->launches += c->graph_launches[key];
     } else {
         TRY(issue_outer_iter(c, mode, extrap));
@@ -406,6 +417,7 @@ extern "C" int adp_outer_iter(adp_ctx *c, int mode, int p, double *Ke, double *s
     if (Ke) *Ke = c->h_scal[S_KE];
     if (ser) *ser = c->h_scal[S_SER];
     if (fer) *fer = c->h_scal[S_FER];
+    if (c->nranks > 1 && !std::isfinite(c->h_scal[S_KE])) { c->err = "adp_outer_iter: non-finite k-eff (peer all-reduce timeout?)"; return ADP_ERR_NCCL; }
     return ADP_OK;
 }
 
@@ -423,7 +435,7 @@ extern "C" int adp_nodal_upd(adp_ctx *c, int nmode, double *ndmax, int *im, int 
     if (c->nranks > 1) {
         // global maximum and, among the ranks holding it, the lowest node number
         CUDA_TRY(c, cudaMemcpyAsync(c->d_scal + S_TMP0, c->d_scal + S_NDMAX, sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
-        TRY(adp_comm_allreduce_max(c, c->d_scal + S_NDMAX, 1));
+        TRY(adp_comm_allreduce_max_nccl(c, c->d_scal + S_NDMAX, 1));
         CUDA_TRY(c, cudaMemcpyAsync(c->h_scal, c->d_scal, S_COUNT * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
         CUDA_TRY(c, cudaStreamSynchronize(c->stream));
         if (c->h_scal[S_TMP0] != c->h_scal[S_NDMAX]) {
@@ -436,7 +448,7 @@ extern "C" int adp_nodal_upd(adp_ctx *c, int nmode, double *ndmax, int *im, int 
         CUDA_TRY(c, cudaStreamSynchronize(c->stream));
         double f = flag;
         CUDA_TRY(c, cudaMemcpyAsync(c->d_scal + S_TMP1, &f, sizeof(double), cudaMemcpyHostToDevice, c->stream));
-        TRY(adp_comm_allreduce_max(c, c->d_scal + S_TMP1, 1));
+        TRY(adp_comm_allreduce_max_nccl(c, c->d_scal + S_TMP1, 1));
         CUDA_TRY(c, cudaMemcpyAsync(&f, c->d_scal + S_TMP1, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
         CUDA_TRY(c, cudaStreamSynchronize(c->stream));
         flag = (int)f;
@@ -584,6 +596,7 @@ extern "C" int adp_set_state(adp_ctx *c, const double *f0, const double *fs0, do
     if (fs0) TRY(upload_nodes(c, c->d_fs[c->fcur], fs0, 1, false));
     CUDA_TRY(c, cudaMemcpyAsync(c->d_scal + S_KE, &Ke, sizeof(double), cudaMemcpyHostToDevice, c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    if (f0) memset(c->xghost_valid, 0, sizeof(c->xghost_valid));
     if (f0 && fs0) c->have_flux = true;
     c->outer_first = false;
     return ADP_OK;
@@ -735,6 +748,8 @@ extern "C" int adp_set_option(adp_ctx *c, const char *name, int value)
 {
     if (!c || !name) return ADP_ERR_USAGE;
     if (!strcmp(name, "graphs")) { c->use_graphs = value != 0; free_graphs(c); return ADP_OK; }
+    if (!strcmp(name, "peer_push")) { if (!value) c->peer_ok = false; return ADP_OK; }
+    if (!strcmp(name, "peer_allreduce")) { if (!value) c->peer_ar = false; return ADP_OK; }
     if (!strcmp(name, "bench_warmup")) { c->bench_warmup = value; return ADP_OK; }
     if (!strcmp(name, "fuse_st")) { c->fuse_st = value != 0; free_graphs(c); return ADP_OK; }
     if (!strcmp(name, "grid_blocks")) {
@@ -750,7 +765,7 @@ static int enqueue_nodal_upd(adp_ctx *c, int nmode)
 {
     CUDA_TRY(c, cudaMemsetAsync(c->d_scal + S_NDMAX, 0, sizeof(double), c->stream));
     TRY(adp_k_nodal_update(c, nmode));
-    if (c->nranks > 1) TRY(adp_comm_allreduce_max(c, c->d_scal + S_NDMAX, 1));
+    if (c->nranks > 1) TRY(adp_comm_allreduce_max_nccl(c, c->d_scal + S_NDMAX, 1));
     TRY(adp_k_matrix_setup(c));
     return ADP_OK;
 }

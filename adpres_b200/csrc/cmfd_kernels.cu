@@ -90,13 +90,17 @@ __device__ __forceinline__ void grid_reduce(double (&val)[NS + NM], const RedOut
     }
     __syncthreads();
     if (wid == 0) {
+        double res[NVAL];
 #pragma unroll
         for (int i = 0; i < NVAL; ++i) {
             double w = (lane < ADP_TILE / 32) ? sm[i][lane] : 0.0;
-            w = (i < NS) ? warp_sum(w) : warp_max(w);
-            if (lane == 0) ro.scal[ro.slot[i]] = w;
+            res[i] = (i < NS) ? warp_sum(w) : warp_max(w);
         }
-        if (lane == 0) *ro.ticket = 0u;
+        if (lane == 0) {
+#pragma unroll
+            for (int i = 0; i < NVAL; ++i) ro.scal[ro.slot[i]] = res[i];
+            *ro.ticket = 0u;
+        }
     }
 }
 
@@ -112,6 +116,28 @@ __device__ __forceinline__ void grid_reduce(double (&val)[NS + NM], const RedOut
 __device__ __forceinline__ long long node_idx(const Geo &G, int kl, int r)
 {
     return (long long)(kl + ADP_GH) * G.np + r;
+}
+
+// Boundary planes go straight into the z-neighbours' ghost planes (NVLink peer stores); the
+// all-reduce that ends every such kernel is the barrier that orders them before the reads.
+// The stores are kept OUT of the streaming loop (a possibly-aliasing store there cost the SpMV
+// kernel 10 us, ncu A/B): after its tiles a CTA walks its boundary-plane tiles again, re-reads
+// the values it has just written itself (L1/L2 hits) and forwards them.
+__device__ __forceinline__ void push_tail(const Geo &G, const Push &ps, const double *vec)
+{
+#ifndef ADP_NO_PUSH
+    if (!ps.lo && !ps.hi) return;
+    for (int tile = blockIdx.x; tile < G.ntiles; tile += gridDim.x) {
+        const int kl = tile / G.tpp;
+        if (kl != 0 && kl != G.nzl - 1) continue;
+        const int r = (tile % G.tpp) * ADP_TILE + threadIdx.x;
+        if (r >= G.np) continue;
+        const double val = vec[node_idx(G, kl, r)];
+        if (ps.lo && kl == 0) ps.lo[r] = val;
+        if (ps.hi && kl == G.nzl - 1) ps.hi[r] = val;
+    }
+    __threadfence_system();
+#endif
 }
 
 // y = A_g x at row idx, terms added in set_ind order (z-,y-,x-,diag,x+,y+,z+) from 0,
@@ -211,7 +237,7 @@ struct SrcArgs {
 };
 
 __global__ void __launch_bounds__(ADP_TILE) k_residual(Geo G, SrcArgs A, const double *__restrict__ a,
-                                                        const double *__restrict__ x, double *__restrict__ rs, RedOut ro)
+                                                        const double *__restrict__ x, double *__restrict__ rs, Push ps, RedOut ro)
 {
     double acc[1] = {0.0};
     const double Ke = ro.scal[S_KE];
@@ -237,19 +263,20 @@ __global__ void __launch_bounds__(ADP_TILE) k_residual(Geo G, SrcArgs A, const d
         rs[idx] = res;      // r0 = rs = p1: one store serves all three (see bicg_core)
         acc[0] = acc[0] + res * res;
     }
+    push_tail(G, ps, rs);
     grid_reduce<1, 0>(acc, ro);
 }
 
 // A: p = r + beta (p - omega v), beta = (rho/rho_prev)(alpha/omega)   (mod_cmfd.f90:1231-1232)
 __global__ void __launch_bounds__(ADP_TILE) k_update_p(Geo G, const double *__restrict__ scal, int slot_rho, int slot_rho_prev,
                                                         const double *__restrict__ rv, const double *__restrict__ v,
-                                                        const double *p_in, double *p_out)
+                                                        const double *p_in, double *p_out, int klo, int npl)
 {
     const double rho = scal[slot_rho], rho_prev = scal[slot_rho_prev];
     const double alpha = rho_prev / scal[S_RSV];
     const double omega = scal[S_TS] / scal[S_TT];
     const double beta = (rho / rho_prev) * (alpha / omega);
-    FOR_EACH_ROW(G, 0, G.nzl)
+    FOR_EACH_ROW(G, klo, npl)
     {
         const long long idx = node_idx(G, kl, r);
         p_out[idx] = rv[idx] + beta * (p_in[idx] - omega * v[idx]);
@@ -258,7 +285,7 @@ __global__ void __launch_bounds__(ADP_TILE) k_update_p(Geo G, const double *__re
 
 // B: v = A p and the partial sums of (rs, v)   (mod_cmfd.f90:1233-1234)
 __global__ void __launch_bounds__(ADP_TILE) k_spmv_dot(Geo G, const double *__restrict__ a, const double *__restrict__ pv,
-                                                        const double *__restrict__ rs, double *__restrict__ v, RedOut ro)
+                                                        const double *__restrict__ rs, double *__restrict__ v, Push ps, RedOut ro)
 {
     double acc[1] = {0.0};
     FOR_EACH_ROW(G, 0, G.nzl)
@@ -268,6 +295,7 @@ __global__ void __launch_bounds__(ADP_TILE) k_spmv_dot(Geo G, const double *__re
         v[idx] = y;
         if (rs) acc[0] = acc[0] + rs[idx] * y;
     }
+    push_tail(G, ps, v);
     if (rs) grid_reduce<1, 0>(acc, ro);
 }
 
@@ -335,7 +363,7 @@ __global__ void __launch_bounds__(ADP_TILE) k_t(Geo G, const double *__restrict_
 __global__ void __launch_bounds__(ADP_TILE) k_update_xr(Geo G, int slot_rho, int last, const double *x_in,
                                                          double *x_out, const double *__restrict__ pv,
                                                          const double *__restrict__ s, const double *__restrict__ t,
-                                                         const double *__restrict__ rs, double *__restrict__ rv, RedOut ro)
+                                                         const double *__restrict__ rs, double *__restrict__ rv, Push ps, RedOut ro)
 {
     double acc[1] = {0.0};
     const double alpha = ro.scal[slot_rho] / ro.scal[S_RSV];
@@ -344,13 +372,15 @@ __global__ void __launch_bounds__(ADP_TILE) k_update_xr(Geo G, int slot_rho, int
     {
         const long long idx = node_idx(G, kl, r);
         const double sv = s[idx];
-        x_out[idx] = x_in[idx] + alpha * pv[idx] + omega * sv;
+        const double xn = x_in[idx] + alpha * pv[idx] + omega * sv;
+        x_out[idx] = xn;
         if (!last) {
             const double rn = sv - omega * t[idx];
             rv[idx] = rn;
             acc[0] = acc[0] + rs[idx] * rn;
         }
     }
+    push_tail(G, ps, last ? x_out : rv);   // the neighbours' copy of r, or (last sweep) of this flux buffer
     if (!last) grid_reduce<1, 0>(acc, ro);
 }
 
@@ -644,6 +674,7 @@ int adp_k_init_flux(adp_ctx *c, int adjoint)
         LAUNCH_CHECK(c);
     }
     c->fcur = 0;
+    memset(c->xghost_valid, 0, sizeof(c->xghost_valid));
     double one = 1.0;
     CUDA_TRY(c, cudaMemcpyAsync(c->d_scal + S_KE, &one, sizeof(double), cudaMemcpyHostToDevice, c->stream));
     int rc = launch_fsrc(c, adjoint != 0, false, 0, 0, c->cur, c->cur);
@@ -676,48 +707,66 @@ int adp_k_outer_begin(adp_ctx *c, int mode)
 
 // One bicg(nin, g, bs, f0(:,g)) including the source construction.  After the call the new
 // flux of group g lives in the other ping-pong buffer and c->cur[g] has been flipped.
-static int bicg_core(adp_ctx *c, const SrcArgs &src, const double *a, const double *x_in, double *x_out, int nin)
+static int bicg_core(adp_ctx *c, const SrcArgs &src, const double *a, const double *x_in, double *x_out, int nin,
+                     bool x_ghost_valid, Push push_x)
 {
     const int nt = c->geo.ntiles;
     const bool multi = c->nranks > 1;
+    const bool peer = multi && c->peer_ok;       // halos are pushed by the producing kernels
+    const Push none;
     int rc;
-    if (multi && (rc = adp_comm_halo(c, const_cast<double *>(x_in), 1))) return rc;
+    // ghost planes of x: pushed by the previous bicg's last D kernel, else exchanged here
+    if (multi && !(peer && x_ghost_valid) && (rc = adp_comm_halo(c, const_cast<double *>(x_in), 1))) return rc;
     // iteration i uses rho slot S_RHO0 + (i & 1); P produces the one of iteration 1
-    k_residual<<<adp_grid(c, k_residual, nt), ADP_TILE, 0, c->stream>>>(c->geo, src, a, x_in, c->d_rs, make_red(c, S_RHO1));
+    k_residual<<<adp_grid(c, k_residual, nt), ADP_TILE, 0, c->stream>>>(c->geo, src, a, x_in, c->d_rs,
+                                                                      peer ? adp_push(c, PB_RS) : none, make_red(c, S_RHO1));
     LAUNCH_CHECK(c);
     if (multi && (rc = adp_comm_allreduce_sum(c, c->d_scal + S_RHO1, 1))) return rc;
     if (nin <= 0) {
         if (x_in != x_out) CUDA_TRY(c, cudaMemcpyAsync(x_out, x_in, sizeof(double) * c->NV, cudaMemcpyDeviceToDevice, c->stream));
         return ADP_OK;
     }
+    // rows A runs over: with pushed halos p is also formed on the neighbours' boundary planes
+    // (from the pushed r, v and the previous p), which saves exchanging it
+    const int a_klo = (peer && c->k0 > 0) ? -1 : 0;
+    const int a_npl = c->nzl - a_klo + ((peer && c->k1 < c->nzz) ? 1 : 0);
     for (int i = 1; i <= nin; ++i) {
         const int slot = S_RHO0 + (i & 1), slot_prev = S_RHO0 + ((i - 1) & 1), slot_next = S_RHO0 + ((i + 1) & 1);
         // first iteration: r = p = rs (one vector); afterwards the separate r and p buffers
         const double *r_cur = (i == 1) ? c->d_rs : c->d_r;
         double *p_cur = (i == 1) ? c->d_rs : c->d_p;
+        // v alternates between two buffers when halos are pushed: B of iteration i+1 stores into a
+        // neighbour's ghost plane while that neighbour may still run A of iteration i+1, which
+        // reads the ghost plane of v_i (there is no all-reduce between A and B)
+        double *v_cur = (peer && !(i & 1)) ? c->d_v2 : c->d_v;
+        const double *v_prev = (peer && (i & 1)) ? c->d_v2 : c->d_v;
+        const int pb_v = (peer && !(i & 1)) ? PB_V1 : PB_V0;
         if (i > 1) {
-            k_update_p<<<adp_grid(c, k_update_p, nt), ADP_TILE, 0, c->stream>>>(c->geo, c->d_scal, slot, slot_prev, c->d_r, c->d_v,
-                                                                              (i == 2) ? c->d_rs : c->d_p, c->d_p);
+            k_update_p<<<adp_grid(c, k_update_p, c->geo.tpp * a_npl), ADP_TILE, 0, c->stream>>>(
+                c->geo, c->d_scal, slot, slot_prev, c->d_r, v_prev, (i == 2) ? c->d_rs : c->d_p, c->d_p, a_klo, a_npl);
             LAUNCH_CHECK(c);
         }
-        if (multi && (rc = adp_comm_halo(c, p_cur, 1))) return rc;
-        k_spmv_dot<<<adp_grid(c, k_spmv_dot, nt), ADP_TILE, 0, c->stream>>>(c->geo, a, p_cur, c->d_rs, c->d_v, make_red(c, S_RSV));
+        if (multi && !peer && (rc = adp_comm_halo(c, p_cur, 1))) return rc;
+        k_spmv_dot<<<adp_grid(c, k_spmv_dot, nt), ADP_TILE, 0, c->stream>>>(c->geo, a, p_cur, c->d_rs, v_cur,
+                                                                          peer ? adp_push(c, pb_v) : none, make_red(c, S_RSV));
         LAUNCH_CHECK(c);
-        if (multi || !c->fuse_st) {
-            if (multi && (rc = adp_comm_allreduce_sum(c, c->d_scal + S_RSV, 1))) return rc;
-            k_s<<<adp_grid(c, k_s, nt), ADP_TILE, 0, c->stream>>>(c->geo, c->d_scal, slot, r_cur, c->d_v, c->d_s);
+        if (multi && (rc = adp_comm_allreduce_sum(c, c->d_scal + S_RSV, 1))) return rc;
+        if ((multi && !peer) || !c->fuse_st) {
+            k_s<<<adp_grid(c, k_s, nt), ADP_TILE, 0, c->stream>>>(c->geo, c->d_scal, slot, r_cur, v_cur, c->d_s);
             LAUNCH_CHECK(c);
             if (multi && (rc = adp_comm_halo(c, c->d_s, 1))) return rc;
             k_t<<<adp_grid(c, k_t, nt), ADP_TILE, 0, c->stream>>>(c->geo, a, c->d_s, c->d_t, make_red(c, S_TT, S_TS));
             LAUNCH_CHECK(c);
-            if (multi && (rc = adp_comm_allreduce_sum(c, c->d_scal + S_TT, 2))) return rc;
         } else {
-            k_st<<<adp_grid(c, k_st, nt), ADP_TILE, 0, c->stream>>>(c->geo, a, slot, r_cur, c->d_v, c->d_s, c->d_t, make_red(c, S_TT, S_TS));
+            // s = r - alpha v on the fly, on ghost planes from the pushed r and v
+            k_st<<<adp_grid(c, k_st, nt), ADP_TILE, 0, c->stream>>>(c->geo, a, slot, r_cur, v_cur, c->d_s, c->d_t, make_red(c, S_TT, S_TS));
             LAUNCH_CHECK(c);
         }
+        if (multi && (rc = adp_comm_allreduce_sum(c, c->d_scal + S_TT, 2))) return rc;
         const int last = (i == nin) ? 1 : 0;
-        k_update_xr<<<adp_grid(c, k_update_xr, nt), ADP_TILE, 0, c->stream>>>(c->geo, slot, last, (i == 1) ? x_in : x_out, x_out, p_cur, c->d_s,
-                                                                            c->d_t, c->d_rs, c->d_r, make_red(c, slot_next));
+        k_update_xr<<<adp_grid(c, k_update_xr, nt), ADP_TILE, 0, c->stream>>>(
+            c->geo, slot, last, (i == 1) ? x_in : x_out, x_out, p_cur, c->d_s, c->d_t, c->d_rs, c->d_r,
+            peer ? (last ? push_x : adp_push(c, PB_R)) : none, make_red(c, slot_next));
         LAUNCH_CHECK(c);
         if (!last && multi && (rc = adp_comm_allreduce_sum(c, c->d_scal + slot_next, 1))) return rc;
     }
@@ -743,8 +792,11 @@ int adp_k_bicg_group(adp_ctx *c, int mode, int g, int nin, bool write_s0)
     S.b = nullptr;
     const double *x_in = f0ptr(c, c->cur[g], g);
     double *x_out = f0ptr(c, c->cur[g] ^ 1, g);
-    int rc = bicg_core(c, S, a_of(c, g), x_in, x_out, nin);
+    const int wout = c->cur[g] ^ 1;
+    const Push push_x = adp_push(c, PB_F0A + wout, (long long)g * c->NV_lo, (long long)g * c->NV_hi);
+    int rc = bicg_core(c, S, a_of(c, g), x_in, x_out, nin, c->xghost_valid[c->cur[g]][g], push_x);
     if (rc) return rc;
+    c->xghost_valid[wout][g] = (c->nranks > 1 && c->peer_ok && nin > 0);
     c->cur[g] ^= 1;
     if (write_s0) c->s0_group = g + 1;
     return ADP_OK;
@@ -756,14 +808,14 @@ int adp_k_bicg_raw(adp_ctx *c, int g, int imax, const double *d_b, double *d_x)
     SrcArgs S{};
     S.b = d_b;
     // D's first iteration reads x_in and writes x_out; in-place is fine (same element)
-    return bicg_core(c, S, a_of(c, g), d_x, d_x, imax);
+    return bicg_core(c, S, a_of(c, g), d_x, d_x, imax, false, Push());
 }
 
 int adp_k_spmv(adp_ctx *c, int g, const double *d_x, double *d_v)
 {
     int rc;
     if (c->nranks > 1 && (rc = adp_comm_halo(c, const_cast<double *>(d_x), 1))) return rc;
-    k_spmv_dot<<<adp_grid(c, k_spmv_dot, c->geo.ntiles), ADP_TILE, 0, c->stream>>>(c->geo, a_of(c, g), d_x, nullptr, d_v, make_red(c, S_TMP1));
+    k_spmv_dot<<<adp_grid(c, k_spmv_dot, c->geo.ntiles), ADP_TILE, 0, c->stream>>>(c->geo, a_of(c, g), d_x, nullptr, d_v, Push(), make_red(c, S_TMP1));
     LAUNCH_CHECK(c);
     return ADP_OK;
 }
@@ -854,20 +906,20 @@ int adp_k_bench_one(adp_ctx *c, int what, int g)
     const double *a = a_of(c, g);
     switch (what) {
     case 0:
-        k_spmv_dot<<<adp_grid(c, k_spmv_dot, nt), ADP_TILE, 0, c->stream>>>(c->geo, a, c->d_p, c->d_rs, c->d_v, make_red(c, S_TMP1));
+        k_spmv_dot<<<adp_grid(c, k_spmv_dot, nt), ADP_TILE, 0, c->stream>>>(c->geo, a, c->d_p, c->d_rs, c->d_v, Push(), make_red(c, S_TMP1));
         break;
     case 8:
-        k_spmv_dot<<<adp_grid(c, k_spmv_dot, nt), ADP_TILE, 0, c->stream>>>(c->geo, a, c->d_p, nullptr, c->d_v, make_red(c, S_TMP1));
+        k_spmv_dot<<<adp_grid(c, k_spmv_dot, nt), ADP_TILE, 0, c->stream>>>(c->geo, a, c->d_p, nullptr, c->d_v, Push(), make_red(c, S_TMP1));
         break;
     case 1:
         k_st<<<adp_grid(c, k_st, nt), ADP_TILE, 0, c->stream>>>(c->geo, a, S_RHO1, c->d_r, c->d_v, c->d_s, c->d_t, make_red(c, S_TMP0, S_TMP1));
         break;
     case 2:
         k_update_xr<<<adp_grid(c, k_update_xr, nt), ADP_TILE, 0, c->stream>>>(c->geo, S_RHO1, 0, c->d_stage, c->d_stage, c->d_p, c->d_s, c->d_t, c->d_rs,
-                                                      c->d_S, make_red(c, S_TMP1));
+                                                      c->d_S, Push(), make_red(c, S_TMP1));
         break;
     case 3:
-        k_update_p<<<adp_grid(c, k_update_p, nt), ADP_TILE, 0, c->stream>>>(c->geo, c->d_scal, S_RHO0, S_RHO1, c->d_r, c->d_v, c->d_p, c->d_S);
+        k_update_p<<<adp_grid(c, k_update_p, nt), ADP_TILE, 0, c->stream>>>(c->geo, c->d_scal, S_RHO0, S_RHO1, c->d_r, c->d_v, c->d_p, c->d_S, 0, c->nzl);
         break;
     case 4: {
         SrcArgs S{};
@@ -879,7 +931,7 @@ int adp_k_bench_one(adp_ctx *c, int what, int g)
         S.fs = c->d_fs[c->fcur]; S.exsrc = c->d_exsrc + (size_t)g * c->NV; S.nuf_g = c->d_nuf + (size_t)g * c->NV;
         S.chi_g = c->d_chi + (size_t)g * c->nmat; S.tbeta = c->d_tbeta; S.dfis = c->d_dfis; S.mat = c->d_mat;
         S.s0 = nullptr; S.b = nullptr;
-        k_residual<<<adp_grid(c, k_residual, nt), ADP_TILE, 0, c->stream>>>(c->geo, S, a, f0ptr(c, c->cur[g], g), c->d_S, make_red(c, S_TMP1));
+        k_residual<<<adp_grid(c, k_residual, nt), ADP_TILE, 0, c->stream>>>(c->geo, S, a, f0ptr(c, c->cur[g], g), c->d_S, Push(), make_red(c, S_TMP1));
         break;
     }
     case 5: {

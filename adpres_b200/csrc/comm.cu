@@ -14,7 +14,7 @@ namespace {
 typedef struct ncclComm *ncclComm_t;
 typedef struct { char internal[128]; } ncclUniqueId;
 enum { ncclSuccess = 0 };
-enum { ncclInt64 = 4, ncclFloat64 = 8 };
+enum { ncclInt8 = 0, ncclInt64 = 4, ncclFloat64 = 8 };
 enum { ncclSum = 0, ncclMax = 2, ncclMin = 3 };
 
 struct Nccl {
@@ -23,6 +23,7 @@ struct Nccl {
     int (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
     int (*CommDestroy)(ncclComm_t) = nullptr;
     int (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*AllGather)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
     int (*Send)(const void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     int (*Recv)(void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     int (*GroupStart)() = nullptr;
@@ -44,7 +45,7 @@ bool load_nccl(std::string &err)
     *(void **)(&g_nccl.field) = dlsym(g_nccl.h, name);                      \
     if (!g_nccl.field) { err = std::string("NCCL symbol missing: ") + name; return false; }
     SYM(GetUniqueId, "ncclGetUniqueId") SYM(CommInitRank, "ncclCommInitRank") SYM(CommDestroy, "ncclCommDestroy")
-    SYM(AllReduce, "ncclAllReduce") SYM(Send, "ncclSend") SYM(Recv, "ncclRecv") SYM(GroupStart, "ncclGroupStart")
+    SYM(AllReduce, "ncclAllReduce") SYM(AllGather, "ncclAllGather") SYM(Send, "ncclSend") SYM(Recv, "ncclRecv") SYM(GroupStart, "ncclGroupStart")
     SYM(GroupEnd, "ncclGroupEnd") SYM(GetErrorString, "ncclGetErrorString")
 #undef SYM
     g_nccl.ok = true;
@@ -130,8 +131,112 @@ extern "C" int adp_comm_init_env(adp_ctx *c)
     return rc;
 }
 
+// Map the z-neighbours' BiCGSTAB vectors and flux buffers into this process (CUDA IPC over
+// NVLink) so that kernels can store their boundary plane straight into the neighbour's ghost
+// plane.  All ranks must agree, so the outcome is min-reduced; on any failure the NCCL
+// send/recv halo path stays in use.
+int adp_comm_map_peers(adp_ctx *c)
+{
+    c->peer_ok = false;
+    if (c->nranks == 1) return ADP_OK;
+    if (getenv("ADP_NO_PEER")) return ADP_OK;
+    double *bufs[PB_COUNT] = {c->d_rs, c->d_v, c->d_v2, c->d_r, c->d_f0[0], c->d_f0[1]};
+    const size_t HB = sizeof(cudaIpcMemHandle_t), per = PB_COUNT * HB;
+    std::vector<char> mine(per), all(per * c->nranks);
+    int ok = 1;
+    for (int b = 0; b < PB_COUNT; ++b)
+        if (cudaIpcGetMemHandle((cudaIpcMemHandle_t *)(mine.data() + b * HB), bufs[b]) != cudaSuccess) { ok = 0; cudaGetLastError(); }
+    char *d_send = nullptr, *d_recv = nullptr;
+    CUDA_TRY(c, cudaMalloc((void **)&d_send, per));
+    CUDA_TRY(c, cudaMalloc((void **)&d_recv, per * c->nranks));
+    CUDA_TRY(c, cudaMemcpyAsync(d_send, mine.data(), per, cudaMemcpyHostToDevice, c->stream));
+    NCCL_TRY(c, g_nccl.AllGather(d_send, d_recv, per, ncclInt8, c->comm->comm, c->stream));
+    CUDA_TRY(c, cudaMemcpyAsync(all.data(), d_recv, per * c->nranks, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    cudaFree(d_send); cudaFree(d_recv);
+    auto open_rank = [&](int peer, double **dst) {
+        for (int b = 0; b < PB_COUNT; ++b) {
+            void *ptr = nullptr;
+            cudaIpcMemHandle_t h;
+            memcpy(&h, all.data() + (size_t)peer * per + b * HB, HB);
+            if (cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; cudaGetLastError(); ptr = nullptr; }
+            dst[b] = (double *)ptr;
+        }
+    };
+    for (int b = 0; b < PB_COUNT; ++b) c->peer_lo[b] = c->peer_hi[b] = nullptr;
+    if (ok && c->rank > 0) open_rank(c->rank - 1, c->peer_lo);
+    if (ok && c->rank + 1 < c->nranks) open_rank(c->rank + 1, c->peer_hi);
+    // neighbours' slab sizes (same partition formula as adp_set_geometry)
+    auto planes = [&](int r) { const int base = c->nzz / c->nranks, rem = c->nzz % c->nranks; return base + (r < rem ? 1 : 0); };
+    c->nzl_lo = c->rank > 0 ? planes(c->rank - 1) : 0;
+    c->nzl_hi = c->rank + 1 < c->nranks ? planes(c->rank + 1) : 0;
+    c->NV_lo = (long long)c->np * (c->nzl_lo + 2 * ADP_GH);
+    c->NV_hi = (long long)c->np * (c->nzl_hi + 2 * ADP_GH);
+    // agreement
+    double flag = ok;
+    CUDA_TRY(c, cudaMemcpyAsync(c->d_scal + S_TMP1, &flag, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    NCCL_TRY(c, g_nccl.AllReduce(c->d_scal + S_TMP1, c->d_scal + S_TMP1, 1, ncclFloat64, ncclMin, c->comm->comm, c->stream));
+    CUDA_TRY(c, cudaMemcpyAsync(&flag, c->d_scal + S_TMP1, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    c->peer_ok = flag > 0.5;
+    if (!c->peer_ok) { adp_comm_unmap_peers(c); return ADP_OK; }
+    // ---- mailboxes of the in-kernel all-reduce: every rank maps every other rank's
+    c->peer_ar = false;
+    if (c->nranks > ADP_MAX_RANKS || getenv("ADP_NO_PEER_AR")) return ADP_OK;
+    const size_t mail_bytes = (size_t)ADP_MAIL_SLOTS * c->nranks * ADP_MAIL_WORDS * sizeof(double);
+    if (!c->d_mail) {
+        CUDA_TRY(c, cudaMalloc((void **)&c->d_mail, mail_bytes));
+        CUDA_TRY(c, cudaMalloc((void **)&c->d_arseq, sizeof(unsigned long long)));
+    }
+    CUDA_TRY(c, cudaMemsetAsync(c->d_mail, 0, mail_bytes, c->stream));
+    CUDA_TRY(c, cudaMemsetAsync(c->d_arseq, 0, sizeof(unsigned long long), c->stream));
+    int ok2 = 1;
+    std::vector<char> hm(HB), hall(HB * c->nranks);
+    if (cudaIpcGetMemHandle((cudaIpcMemHandle_t *)hm.data(), c->d_mail) != cudaSuccess) { ok2 = 0; cudaGetLastError(); }
+    CUDA_TRY(c, cudaMalloc((void **)&d_send, HB));
+    CUDA_TRY(c, cudaMalloc((void **)&d_recv, HB * c->nranks));
+    CUDA_TRY(c, cudaMemcpyAsync(d_send, hm.data(), HB, cudaMemcpyHostToDevice, c->stream));
+    NCCL_TRY(c, g_nccl.AllGather(d_send, d_recv, HB, ncclInt8, c->comm->comm, c->stream));
+    CUDA_TRY(c, cudaMemcpyAsync(hall.data(), d_recv, HB * c->nranks, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    cudaFree(d_send); cudaFree(d_recv);
+    for (int q = 0; q < c->nranks; ++q) {
+        if (q == c->rank) { c->mail_peer[q] = c->d_mail; continue; }
+        void *ptr = nullptr;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, hall.data() + (size_t)q * HB, HB);
+        if (!ok2 || cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok2 = 0; cudaGetLastError(); ptr = nullptr; }
+        c->mail_peer[q] = (double *)ptr;
+    }
+    if (!c->d_mail_table) CUDA_TRY(c, cudaMalloc((void **)&c->d_mail_table, ADP_MAX_RANKS * sizeof(double *)));
+    CUDA_TRY(c, cudaMemcpyAsync(c->d_mail_table, c->mail_peer, ADP_MAX_RANKS * sizeof(double *), cudaMemcpyHostToDevice, c->stream));
+    flag = ok2;
+    CUDA_TRY(c, cudaMemcpyAsync(c->d_scal + S_TMP1, &flag, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    NCCL_TRY(c, g_nccl.AllReduce(c->d_scal + S_TMP1, c->d_scal + S_TMP1, 1, ncclFloat64, ncclMin, c->comm->comm, c->stream));
+    CUDA_TRY(c, cudaMemcpyAsync(&flag, c->d_scal + S_TMP1, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    c->peer_ar = flag > 0.5;      // the min-all-reduce also guarantees every mailbox is zeroed before first use
+    return ADP_OK;
+}
+
+void adp_comm_unmap_peers(adp_ctx *c)
+{
+    for (int b = 0; b < PB_COUNT; ++b) {
+        if (c->peer_lo[b]) cudaIpcCloseMemHandle(c->peer_lo[b]);
+        if (c->peer_hi[b]) cudaIpcCloseMemHandle(c->peer_hi[b]);
+        c->peer_lo[b] = c->peer_hi[b] = nullptr;
+    }
+    for (int q = 0; q < ADP_MAX_RANKS; ++q) {
+        if (c->mail_peer[q] && c->mail_peer[q] != c->d_mail) cudaIpcCloseMemHandle(c->mail_peer[q]);
+        c->mail_peer[q] = nullptr;
+    }
+    c->peer_ar = false;
+    c->peer_ok = false;
+}
+
 void adp_comm_destroy(adp_ctx *c)
 {
+    adp_comm_unmap_peers(c);
     if (c->comm) {
         if (c->comm->comm && g_nccl.ok) g_nccl.CommDestroy(c->comm->comm);
         delete c->comm;
@@ -162,13 +267,70 @@ int adp_comm_halo(adp_ctx *c, double *v, int n)
     return ADP_OK;
 }
 
+// Scalar all-reduce over peer memory: ONE warp posts this rank's values into row `rank` of slot
+// (seq % ADP_MAIL_SLOTS) of every rank's mailbox (values, system fence, sequence number) and
+// waits until every row of its own mailbox carries that sequence number; rows are combined in
+// rank order (deterministic).  ~2-3 us instead of ~20 us for an 8-byte ncclAllReduce, and like
+// it a barrier: it completes only after every rank's preceding kernel (and its halo pushes) has.
+// A separate tiny kernel on purpose: inlined into the tails of the streaming kernels this code
+// raised their register count and cost k_st / k_residual 10-13 % (A/B measured).
+template <bool MAX>
+__global__ void k_mail_allreduce(double *vals, int count, Mail m)
+{
+    if (threadIdx.x != 0) return;
+    const unsigned long long seq = *m.seq + 1ull;
+    const size_t slot = (size_t)(seq % ADP_MAIL_SLOTS) * m.nranks;
+    double v[4];
+    for (int i = 0; i < count; ++i) v[i] = vals[i];
+    for (int q = 0; q < m.nranks; ++q) {
+        volatile double *dst = m.box[q] + (slot + m.rank) * ADP_MAIL_WORDS;
+        for (int i = 0; i < count; ++i) dst[i] = v[i];
+    }
+    __threadfence_system();
+    for (int q = 0; q < m.nranks; ++q)
+        *(volatile unsigned long long *)(m.box[q] + (slot + m.rank) * ADP_MAIL_WORDS + (ADP_MAIL_WORDS - 1)) = seq;
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    const long long t0 = clock64();
+    for (int q = 0; q < m.nranks; ++q) {
+        volatile double *src = m.box[m.rank] + (slot + q) * ADP_MAIL_WORDS;
+        volatile unsigned long long *flag = (volatile unsigned long long *)(src + (ADP_MAIL_WORDS - 1));
+        while (*flag != seq)
+            if (clock64() - t0 > 8000000000LL) { atomicExch(m.errflag, ADP_ERR_NCCL); break; }   // ~4 s: never hang the GPU
+        __threadfence_system();
+        for (int i = 0; i < count; ++i) acc[i] = MAX ? fmax(acc[i], src[i]) : acc[i] + src[i];
+    }
+    for (int i = 0; i < count; ++i) vals[i] = acc[i];
+    *m.seq = seq;
+}
+
+static int mail_allreduce(adp_ctx *c, double *d, int count, bool is_max)
+{
+    Mail m;
+    m.box = c->d_mail_table; m.seq = c->d_arseq; m.errflag = c->d_errflag; m.nranks = c->nranks; m.rank = c->rank;
+    if (count > 4) { c->err = "mail_allreduce: at most 4 values"; return ADP_ERR_USAGE; }
+    if (is_max) k_mail_allreduce<true><<<1, 32, 0, c->stream>>>(d, count, m);
+    else k_mail_allreduce<false><<<1, 32, 0, c->stream>>>(d, count, m);
+    c->launches++;
+    if (cudaPeekAtLastError() != cudaSuccess) { c->err = "k_mail_allreduce launch failed"; return ADP_ERR_CUDA; }
+    return ADP_OK;
+}
+
 int adp_comm_allreduce_sum(adp_ctx *c, double *d, int count)
 {
     if (c->nranks == 1) return ADP_OK;
+    if (c->peer_ar) return mail_allreduce(c, d, count, false);
     NCCL_TRY(c, g_nccl.AllReduce(d, d, count, ncclFloat64, ncclSum, c->comm->comm, c->stream));
     return ADP_OK;
 }
 int adp_comm_allreduce_max(adp_ctx *c, double *d, int count)
+{
+    if (c->nranks == 1) return ADP_OK;
+    if (c->peer_ar) return mail_allreduce(c, d, count, true);
+    NCCL_TRY(c, g_nccl.AllReduce(d, d, count, ncclFloat64, ncclMax, c->comm->comm, c->stream));
+    return ADP_OK;
+}
+// explicit NCCL all-reduce (results that do NOT come out of grid_reduce, e.g. the ndmax arg-max)
+int adp_comm_allreduce_max_nccl(adp_ctx *c, double *d, int count)
 {
     if (c->nranks == 1) return ADP_OK;
     NCCL_TRY(c, g_nccl.AllReduce(d, d, count, ncclFloat64, ncclMax, c->comm->comm, c->stream));

@@ -224,6 +224,11 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    # nvidia-smi takes driver locks while it starts up (kernel launches stall for tens of ms):
+    # start the sampler now, long before the timed region, and let it reach its steady loop
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+
     # ---------------------------------------------------------------- problem
     p = load_c2(planes_factor=world)
     s = capi.Solver(p, device=local_rank, nranks=world, rank=rank, uid=uid, **CTL)
@@ -236,8 +241,10 @@ def main():
 
     # ---------------------------------------------------------------- value (device resident)
     s.outer_steps(capi.MODE_FORWARD, 1, W)
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    t_wait = time.time()
+    while not sampler.lines and time.time() - t_wait < 5.0:
+        time.sleep(0.05)
+    n_before = len(sampler.lines)
     barrier()
     l0 = s.launch_count()
     s.timer_start()
@@ -245,7 +252,8 @@ def main():
     ms = s.timer_stop()
     barrier()
     launches = s.launch_count() - l0
-    clocks = sampler.stop()
+    time.sleep(0.12)                       # let the 100 ms sampler take one more reading of the loaded state
+    n_after = len(sampler.lines)
     assert rc == 0 and np.isfinite(ke), (rc, ke)
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device="cuda")
@@ -340,6 +348,8 @@ def main():
         cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port", "sample": desc, "seconds": dt,
                "host_cores_available": host_cores()}
 
+    clocks = sampler.stop()
+    clocks["samples_during_value_region"] = max(0, n_after - n_before)
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
