@@ -363,14 +363,9 @@ static int issue_outer_iter(adp_ctx *c, int mode, bool extrap, bool readback = t
     return ADP_OK;
 }
 
-extern "C" int adp_outer_iter(adp_ctx *c, int mode, int p, double *Ke, double *ser, double *fer)
+// Launch one outer iteration: CUDA-graph replay when possible, direct launches otherwise.
+static int launch_outer_iter(adp_ctx *c, int mode, bool extrap)
 {
-    if (!c) return ADP_ERR_USAGE;
-    ADP_REQUIRE(c, c->have_flux && c->matrix_ready, "adp_outer_iter: needs adp_matrix_setup and a flux");
-    ADP_REQUIRE(c, mode >= ADP_MODE_FORWARD && mode <= ADP_MODE_TRANSIENT, "adp_outer_iter: bad mode");
-    ADP_REQUIRE(c, mode != ADP_MODE_TRANSIENT || c->kinetics_set, "adp_outer_iter: transient mode needs adp_set_kinetics");
-    CUDA_TRY(c, cudaSetDevice(c->device));
-    const bool extrap = (p % c->nac) == 0;
     // multi-rank: graphs only once no NCCL call is left inside the iteration (halos pushed by the
     // kernels, reductions through the mailboxes, ghost flux planes current)
     bool use_graph = c->use_graphs;
@@ -378,46 +373,64 @@ extern "C" int adp_outer_iter(adp_ctx *c, int mode, int p, double *Ke, double *s
         use_graph = use_graph && c->peer_ok && c->peer_ar;
         for (int g = 0; g < c->ng && use_graph; ++g) use_graph = c->xghost_valid[c->cur[g]][g];
     }
-    if (use_graph) {
-        unsigned long long key = (unsigned long long)mode | ((unsigned long long)(extrap ? 1 : 0) << 4) |
-                                 ((unsigned long long)c->fcur << 5);
-        for (int g = 0; g < c->ng; ++g) key |= (unsigned long long)c->cur[g] << (8 + g);
-        auto it = c->graphs.find(key);
-        if (it == c->graphs.end()) {
-            cudaGraph_t graph = nullptr;
-            const long long l0 = c->launches;
-            const int s0g = c->s0_group, fcur = c->fcur;
-            int cur[ADP_MAXG];
-            memcpy(cur, c->cur, sizeof(cur));
-            CUDA_TRY(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
-            int rc = issue_outer_iter(c, mode, extrap);
-            cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
-            if (rc) return rc;
-            CUDA_TRY(c, e);
-            cudaGraphExec_t exec = nullptr;
-            CUDA_TRY(c, cudaGraphInstantiate(&exec, graph, 0));
-            cudaGraphDestroy(graph);
-            // capture advanced the host-side bookkeeping once; undo it, the launch below redoes it
-            c->graph_launches[key] = c->launches - l0;
-            c->launches = l0; c->s0_group = s0g; c->fcur = fcur;
-            memcpy(c->cur, cur, sizeof(cur));
-            it = c->graphs.emplace(key, exec).first;
-        }
-        CUDA_TRY(c, cudaGraphLaunch(it->second, c->stream));
-        // host bookkeeping of what the graph did
-        for (int g = 0; g < c->ng; ++g) c->cur[g] ^= 1;
-        c->fcur ^= 1;
-        c->s0_group = (mode == ADP_MODE_ADJOINT) ? 1 : c->ng;
-        if (c->nranks > 1) for (int g = 0; g < c->ng; ++g) c->xghost_valid[c->cur[g]][g] = true;
-        c->launches += c->graph_launches[key];
-    } else {
-        TRY(issue_outer_iter(c, mode, extrap));
+    if (!use_graph) return issue_outer_iter(c, mode, extrap);
+    unsigned long long key = (unsigned long long)mode | ((unsigned long long)(extrap ? 1 : 0) << 4) |
+                             ((unsigned long long)c->fcur << 5);
+    for (int g = 0; g < c->ng; ++g) key |= (unsigned long long)c->cur[g] << (8 + g);
+    auto it = c->graphs.find(key);
+    if (it == c->graphs.end()) {
+        cudaGraph_t graph = nullptr;
+        const long long l0 = c->launches;
+        const int s0g = c->s0_group, fcur = c->fcur;
+        int cur[ADP_MAXG];
+        memcpy(cur, c->cur, sizeof(cur));
+        CUDA_TRY(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+        int rc = issue_outer_iter(c, mode, extrap);
+        cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
+        if (rc) return rc;
+        CUDA_TRY(c, e);
+        cudaGraphExec_t exec = nullptr;
+        CUDA_TRY(c, cudaGraphInstantiate(&exec, graph, 0));
+        cudaGraphDestroy(graph);
+        // capture advanced the host-side bookkeeping once; undo it, the launch below redoes it
+        c->graph_launches[key] = c->launches - l0;
+        c->launches = l0; c->s0_group = s0g; c->fcur = fcur;
+        memcpy(c->cur, cur, sizeof(cur));
+        it = c->graphs.emplace(key, exec).first;
     }
+    CUDA_TRY(c, cudaGraphLaunch(it->second, c->stream));
+    // host bookkeeping of what the graph did
+    for (int g = 0; g < c->ng; ++g) c->cur[g] ^= 1;
+    c->fcur ^= 1;
+    c->s0_group = (mode == ADP_MODE_ADJOINT) ? 1 : c->ng;
+    if (c->nranks > 1) for (int g = 0; g < c->ng; ++g) c->xghost_valid[c->cur[g]][g] = true;
+    c->launches += c->graph_launches[key];
+    return ADP_OK;
+}
+
+extern "C" int adp_outer_iter(adp_ctx *c, int mode, int p, double *Ke, double *ser, double *fer)
+{
+    if (!c) return ADP_ERR_USAGE;
+    ADP_REQUIRE(c, c->have_flux && c->matrix_ready, "adp_outer_iter: needs adp_matrix_setup and a flux");
+    ADP_REQUIRE(c, mode >= ADP_MODE_FORWARD && mode <= ADP_MODE_TRANSIENT, "adp_outer_iter: bad mode");
+    ADP_REQUIRE(c, mode != ADP_MODE_TRANSIENT || c->kinetics_set, "adp_outer_iter: transient mode needs adp_set_kinetics");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    TRY(launch_outer_iter(c, mode, (p % c->nac) == 0));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     if (Ke) *Ke = c->h_scal[S_KE];
     if (ser) *ser = c->h_scal[S_SER];
     if (fer) *fer = c->h_scal[S_FER];
-    if (c->nranks > 1 && !std::isfinite(c->h_scal[S_KE])) { c->err = "adp_outer_iter: non-finite k-eff (peer all-reduce timeout?)"; return ADP_ERR_NCCL; }
+    if (c->nranks > 1 && !std::isfinite(c->h_scal[S_KE])) {
+        int flag = 0;
+        cudaMemcpy(&flag, c->d_errflag, sizeof(int), cudaMemcpyDeviceToHost);
+        char buf[512];
+        snprintf(buf, sizeof(buf), "adp_outer_iter: non-finite k-eff at p=%d rank %d (errflag %d%s): Ke %g F %g FC %g FINT %g E2SQ %g RSV %g TT %g TS %g RHO %g %g SER %g FER %g",
+                 p, c->rank, flag, flag == ADP_ERR_NCCL ? " = peer all-reduce timeout" : "", c->h_scal[S_KE], c->h_scal[S_F], c->h_scal[S_FC],
+                 c->h_scal[S_FINT], c->h_scal[S_E2SQ], c->h_scal[S_RSV], c->h_scal[S_TT], c->h_scal[S_TS], c->h_scal[S_RHO0], c->h_scal[S_RHO1],
+                 c->h_scal[S_SER], c->h_scal[S_FER]);
+        c->err = buf;
+        return ADP_ERR_NCCL;
+    }
     return ADP_OK;
 }
 
@@ -782,7 +795,7 @@ extern "C" int adp_outer_steps(adp_ctx *c, int mode, int p_first, int nsteps, do
     CUDA_TRY(c, cudaMemsetAsync(c->d_errflag, 0, sizeof(int), c->stream));
     for (int p = p_first; p < p_first + nsteps; ++p) {
         const bool extrap = (p % c->nac) == 0;
-        TRY(issue_outer_iter(c, mode, extrap, false));
+        TRY(launch_outer_iter(c, mode, extrap));
         if (p % c->nupd == 0 && c->kern != ADP_KERN_FDM) {
             const int nmode = (mode == ADP_MODE_ADJOINT) ? 0 : (mode == ADP_MODE_TRANSIENT) ? 2 : 1;
             TRY(enqueue_nodal_upd(c, nmode));

@@ -4,7 +4,7 @@
 Metric (BASELINE.json): node-group unknowns per second per outer iteration, on the
 configuration the metric is quoted on: IAEA-3D refined to 1 cm x 1 cm x 2 cm nodes
 (170 x 170 x 190 mesh, 4 579 000 nodes, 2 groups = 9.158 M node-groups, SANM kernel),
-iteration control `%ITER . 2 1e-5 1e-5 5 50` (nin = 2, nac = 5, nupd = 50).
+iteration control `%ITER . 10 1e-5 1e-5 5 50` (nin = 10, nac = 5, nupd = 50; the stable choice, see CTL).
 
 A "step" is one pass of the reference's `do p = 1, nout` loop body (mod_cmfd.f90:465-496):
 G x (TSrc + bicg(nin)), FSrc, l2norm, [fiss_extrp], Integrate, k-eff, RelE, RelEg and, whenever
@@ -23,8 +23,9 @@ mod(p, nupd) == 0, the SANM nodal update + matrix_setup(0).
           exists in the image, so oracle/_ref cannot be built) on 1 host core -- the reference
           is serial -- on a bounded sample (same radial mesh, 19 of the 190 planes).
 
-N > 1 (torchrun): z-slab decomposition, one rank per GPU, weak scaling (190 planes per rank:
-the axial mesh is refined to 190*N planes); halo planes + scalar all-reduces over NCCL.
+N > 1 (torchrun): z-slab decomposition, one rank per GPU, weak scaling: N copies of the core
+stacked axially (190 planes per rank, same node sizes); halo planes are pushed by the kernels
+over NVLink peer memory, scalar all-reduces go through peer-memory mailboxes (NCCL fallback).
 
 `--impl reference` times the reference algorithm on the host CPU (oracle port, 1 thread).
 """
@@ -45,19 +46,70 @@ sys.path.insert(0, ROOT)
 
 METRIC = "node_group_unknowns_per_s_per_outer_iteration"
 UNIT = "unknowns/s"
-CTL = dict(nin=2, nac=5, nupd=50, nout=1000000, serc=1e-5, ferc=1e-5)
+# %ITER: nin = 10 inner BiCGSTAB sweeps, extrapolation every 5, nodal update every 50 outers.  Chosen by
+# measurement: on this 1 cm mesh the reference's default (nin = 2, nupd = 212) and nin = 2..5 with
+# nupd = 50..100 make its two-node iteration unstable (ndmax > 1e3, the reference's own STOP, at the
+# 1st-3rd nodal update); nin = 10 converges to k-eff 1.029069 in ~380 outer iterations.
+CTL = dict(nin=10, nac=5, nupd=50, nout=1000000, serc=1e-5, ferc=1e-5)
 SPMV_BYTES_PER_ROW = 72.0   # 7 coefficients + x + y, fp64
 
 
-def load_c2(planes_factor=1, sample_planes=None):
+def load_c2(stack=1, sample_planes=None):
     """IAEA-3D (smpl/static/IAEA3Ds) with %GEOM lines 3/5/7 changed to `10 8*20`, `8*20 10`,
-    `19*10`  (BASELINE.json configs[1]); planes_factor multiplies the axial refinement (weak
-    scaling); sample_planes = 19 coarsens the axial mesh to one plane per assembly (CPU sample)."""
+    `19*10` (BASELINE.json configs[1]: 1 cm x 1 cm x 2 cm nodes, 170 x 170 x 190).
+    stack = n repeats the 19 axial assemblies n times (n cores on top of each other, same node
+    sizes): the weak-scaling workload, one core copy per GPU.  (Refining the axial mesh n-fold
+    instead is NOT a valid fixed-%ITER workload: the reference's two-node iteration goes unstable
+    on 0.5 / 0.25 cm planes at nin = 10 -- ndmax > 1e3, its own STOP -- see DESIGN.md.)
+    sample_planes = 19 coarsens the axial mesh to one plane per assembly (bounded CPU sample)."""
+    import dataclasses
     from adpres_b200.deck import Problem
     with open(os.path.join(ROOT, "tests", "golden", "IAEA3Ds.spec.json")) as fh:
         p = Problem.from_spec(json.load(fh))
-    zdiv = [10 * planes_factor] * 19 if sample_planes is None else [sample_planes // 19] * 19
+    if stack > 1:
+        p = dataclasses.replace(p, nz=p.nz * stack, zsize=np.tile(p.zsize, stack), zdiv=np.tile(p.zdiv, stack),
+                                zpln=np.tile(p.zpln, stack))
+    zdiv = [10] * p.nz if sample_planes is None else [sample_planes // 19] * p.nz
     return p.refine(xdiv=[10] + [20] * 8, ydiv=[20] * 8 + [10], zdiv=zdiv)
+
+
+class SlabProblem:
+    """Weak-scaling workload for rank `rank` of `world`: `world` copies of the C2 core stacked
+    axially (190*world planes, same 1 cm x 1 cm x 2 cm nodes) == load_c2(stack=world).  The C ABI
+    takes the GLOBAL sdata arrays, but a rank only ever reads its own z-slab (+2 ghost planes) of
+    them, so the global arrays are allocated uncommitted (np.empty) and only that plane range is
+    filled -- host memory per rank stays at the size of the slab instead of growing with N."""
+
+    def __init__(self, base, world, rank):
+        from adpres_b200.slab import slab_planes
+        self.base, self.world = base, world
+        for k in ("mode", "ng", "nmat", "nxx", "nyy", "npl", "bc", "xdel", "ydel", "ystag_smin", "ystag_smax",
+                  "xstag_smin", "xstag_smax", "chi", "nout", "nin", "serc", "ferc", "nac", "kern"):
+            setattr(self, k, getattr(base, k))
+        self.nzz = base.nzz * world
+        self.nnod = base.nnod * world
+        self.nupd = base.nupd
+        self.zdel = np.tile(base.zdel, world)
+        npl = base.npl
+        self.ix = np.tile(base.ix[:npl], self.nzz)
+        self.iy = np.tile(base.iy[:npl], self.nzz)
+        self.iz = np.repeat(np.arange(1, self.nzz + 1, dtype=np.int32), npl)
+        k0, k1 = slab_planes(self.nzz, world, rank)
+        self.k0, self.k1 = k0, k1
+        ka, kb = max(0, k0 - 2), min(self.nzz, k1 + 2)
+        self.rows = slice(ka * npl, kb * npl)                     # global node range this rank touches
+        planes = np.arange(ka, kb) % base.nzz                     # plane of the stack -> plane of the single core
+        src = (planes[:, None] * npl + np.arange(npl)[None, :]).reshape(-1)
+        self.mat = np.empty(self.nnod, dtype=np.int32)
+        self.mat[self.rows] = base.mat[src]
+        for k in ("D", "sigr", "nuf", "sigf", "exsrc"):
+            a = np.empty((self.nnod, base.ng), order="F")
+            a[self.rows, :] = getattr(base, k)[src, :]
+            setattr(self, k, a)
+        self.sigs = np.empty((self.nnod, base.ng, base.ng), order="F")
+        self.sigs[self.rows] = base.sigs[src]
+        self.dc = np.empty((self.nnod, base.ng, 6), order="F")
+        self.dc[self.rows] = base.dc[src]
 
 
 class ClockSampler:
@@ -187,11 +239,12 @@ def main():
         os.write(real_stdout, (json.dumps(line) + "\n").encode())
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-solve", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
 
@@ -230,7 +283,7 @@ def main():
     sampler.start()
 
     # ---------------------------------------------------------------- problem
-    p = load_c2(planes_factor=world)
+    p = load_c2() if world == 1 else SlabProblem(load_c2(), world, rank)
     s = capi.Solver(p, device=local_rank, nranks=world, rank=rank, uid=uid, **CTL)
     units_per_step = p.nnod * p.ng
     N_own = (s.k1 - s.k0) * p.npl
@@ -265,13 +318,37 @@ def main():
     e2e = None
     if not args.no_e2e:
         keep, hx = [], {}
-        for k in ("D", "sigr", "nuf", "sigf", "sigs", "chi", "dc", "exsrc"):
-            t, hx[k] = pinned(getattr(p, k))
-            keep.append(t)
-        st0 = s.state()
-        t1, f0_h = pinned(st0["f0"]); t2, fs0_h = pinned(st0["fs0"])
-        t3, f0_out = pinned(np.zeros((p.nnod, p.ng), order="F")); t4, fs0_out = pinned(np.zeros(p.nnod))
-        t5, pw_out = pinned(np.zeros(p.nnod))
+        cudart = torch.cuda.cudart()
+
+        def host_buffer(a):
+            """Page-locked host buffer with the contents of `a`: a pinned copy at N = 1; at N > 1 the
+            (uncommitted) global array itself with only this rank's slab rows registered."""
+            if world == 1:
+                t, v = pinned(a)
+                keep.append(t)
+                return v
+            a2 = a.reshape(a.shape[0], -1, order="F")
+            for col in range(a2.shape[1]):
+                seg = a2[p.rows, col]
+                rc_ = cudart.cudaHostRegister(seg.ctypes.data, seg.nbytes, 0)
+                assert int(rc_) == 0, f"cudaHostRegister failed: {rc_}"
+            return a
+        for k in ("D", "sigr", "nuf", "sigf", "sigs", "dc", "exsrc"):
+            hx[k] = host_buffer(getattr(p, k))
+        hx["chi"] = np.asfortranarray(p.chi)
+        st0 = s.state() if world == 1 else None
+        if world == 1:
+            f0_h, fs0_h = host_buffer(st0["f0"]), host_buffer(st0["fs0"])
+            ke0 = st0["Ke"]
+        else:
+            f0_h, fs0_h = np.empty((p.nnod, p.ng), order="F"), np.empty(p.nnod)
+            ke_ = capi.C.c_double()
+            s._chk(s.L.adp_get_state(s.h, capi._d(f0_h), capi._d(fs0_h), None, capi.C.byref(ke_)))
+            ke0 = ke_.value
+            host_buffer(f0_h); host_buffer(fs0_h)
+        f0_out = host_buffer(np.empty((p.nnod, p.ng), order="F") if world > 1 else np.zeros((p.nnod, p.ng), order="F"))
+        fs0_out = host_buffer(np.empty(p.nnod) if world > 1 else np.zeros(p.nnod))
+        pw_out = host_buffer(np.empty(p.nnod) if world > 1 else np.zeros(p.nnod))
         L = s.L
         d = capi._d
 
@@ -279,7 +356,7 @@ def main():
             # what the patched Fortran outer() does: hand over sdata, iterate, take the results back
             s._chk(L.adp_set_xs(s.h, d(hx["D"]), d(hx["sigr"]), d(hx["nuf"]), d(hx["sigf"]), d(hx["sigs"]), d(hx["chi"]),
                                 d(hx["dc"]), d(hx["exsrc"])))
-            s._chk(L.adp_set_state(s.h, d(f0_h), d(fs0_h), capi.C.c_double(st0["Ke"])))
+            s._chk(L.adp_set_state(s.h, d(f0_h), d(fs0_h), capi.C.c_double(ke0)))
             s.matrix_setup(1)
             s.outer_begin(capi.MODE_FORWARD)
             for q in range(p_first, p_first + nsteps):
@@ -341,10 +418,24 @@ def main():
     roofline["outer_iteration"] = {"alg_bytes_per_row": row_bytes, "GBps_per_gpu": step_gbps, "frac": step_gbps / peak,
                                    "note": "includes the nodal updates that fall inside the timed steps"}
 
+    # ---------------------------------------------------------------- seconds to k-eff convergence (N = 1)
+    solve = None
+    if world == 1 and not args.no_solve:
+        s3 = capi.Solver(p, device=local_rank, **dict(CTL, nout=5000))
+        s3.matrix_setup(1)                      # warm: allocations, module load
+        t0 = time.perf_counter()
+        rc3, n3 = s3.outer(0)                   # the reference's outer(): exit test every iteration, from f0 = 1
+        torch.cuda.synchronize()
+        dt3 = time.perf_counter() - t0
+        solve = {"seconds_to_keff_convergence": dt3, "outer_iterations": n3, "keff": s3.state()["Ke"], "status": rc3,
+                 "serc": CTL["serc"], "ferc": CTL["ferc"], "unknowns": units_per_step,
+                 "what": "adp_outer(): full eigenvalue solve from flat flux incl. nodal updates, per-iteration exit test on the host"}
+        s3.close()
+
     # ---------------------------------------------------------------- CPU baseline (rank 0, N = 1)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, dt, desc = run_oracle_sample(steps=50, warmup=2)
+        v, dt, desc = run_oracle_sample(steps=30, warmup=2)
         cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port", "sample": desc, "seconds": dt,
                "host_cores_available": host_cores()}
 
@@ -355,13 +446,13 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": f"IAEA-3D refined 1cm x 1cm x {2.0 / world:g}cm ({p.nxx}x{p.nyy}x{p.nzz} mesh, "
-                                   f"{p.nnod} nodes, {p.ng} groups = {units_per_step} node-groups), SANM kernel; "
-                                   f"{s.k1 - s.k0} planes per GPU",
+            "config": {"workload": f"IAEA-3D refined 1cm x 1cm x 2cm" + (f", {world} cores stacked axially" if world > 1 else "") +
+                                   f" ({p.nxx}x{p.nyy}x{p.nzz} mesh, {p.nnod} nodes, {p.ng} groups = {units_per_step} "
+                                   f"node-groups), SANM kernel; {s.k1 - s.k0} planes per GPU",
                        "nin": CTL["nin"], "nac": CTL["nac"], "nupd": CTL["nupd"], "parallelism": f"z-slab x{world}",
                        "l2": "inputs larger than L2 (each kernel streams >= 290 MB per launch; 126 MB L2)",
                        "keff_after_steps": ke},
-            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "solve": solve,
         }
         emit(line)
     if world > 1:

@@ -8,14 +8,14 @@ from adpres_b200 import capi
 
 opts = dict(a.split("=") for a in sys.argv[1:] if "=" in a)
 planes = int(opts.pop("planes", 1))
-p = bench.load_c2(planes_factor=planes)
+p = bench.load_c2(stack=planes)
 s = capi.Solver(p, **bench.CTL)
 for k, v in opts.items():
     s.set_option(k, int(v))
 s.matrix_setup(1); s.init_flux(); s.outer_begin(0)
 s.outer_steps(0, 1, 5)
 s.timer_start(); s.outer_steps(0, 6, 40); ms = s.timer_stop()
-print("opts", opts, "ms/step (no nodal)", ms / 40)
+print("opts", opts, "nin", bench.CTL["nin"], "ms/step (no nodal)", ms / 40)
 s.timer_start(); s.outer_steps(0, 46, 10); ms = s.timer_stop()
 print("10 steps incl. 1 nodal update: ms", ms)
 names = {0: "B spmv_dot", 8: "spmv plain", 1: "C st fused", 2: "D update_xr", 3: "A update_p", 4: "P residual", 5: "F fsrc_norms",
