@@ -127,16 +127,20 @@ __device__ __forceinline__ void push_tail(const Geo &G, const Push &ps, const do
 {
 #ifndef ADP_NO_PUSH
     if (!ps.lo && !ps.hi) return;
-    for (int tile = blockIdx.x; tile < G.ntiles; tile += gridDim.x) {
-        const int kl = tile / G.tpp;
-        if (kl != 0 && kl != G.nzl - 1) continue;
-        const int r = (tile % G.tpp) * ADP_TILE + threadIdx.x;
-        if (r >= G.np) continue;
-        const double val = vec[node_idx(G, kl, r)];
-        if (ps.lo && kl == 0) ps.lo[r] = val;
-        if (ps.hi && kl == G.nzl - 1) ps.hi[r] = val;
+    bool pushed = false;
+    // boundary-plane tiles are [0, tpp) and [(nzl-1) tpp, nzl tpp): visit only those of this CTA
+    for (int side = 0; side < 2; ++side) {
+        const int kl = side ? G.nzl - 1 : 0;
+        double *dst = side ? ps.hi : ps.lo;
+        if (!dst) continue;
+        const int t0 = kl * G.tpp;
+        int first = t0 + ((int)blockIdx.x - t0 % (int)gridDim.x + (int)gridDim.x) % (int)gridDim.x;   // first tile >= t0 of this CTA
+        for (int tile = first; tile < t0 + G.tpp; tile += gridDim.x) {
+            const int r = (tile - t0) * ADP_TILE + threadIdx.x;
+            if (r < G.np) { dst[r] = vec[node_idx(G, kl, r)]; pushed = true; }
+        }
     }
-    __threadfence_system();
+    if (pushed) __threadfence_system();      // only the threads that stored to a neighbour pay for the fence
 #endif
 }
 

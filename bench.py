@@ -409,7 +409,12 @@ def main():
         "GBps": rows * 8.0 * (41 * p.ng + p.ng ** 2) / (nodal_ms * 1e-3) / 1e9}
     dom = kern["k_spmv_dot (B: v=Ap,(rs,v))"]
     roofline = {"bound": "hbm", "kernel": "k_spmv_dot", "achieved": dom["GBps"], "peak": peak, "unit": "GB/s",
-                "frac": dom["GBps"] / peak, "traffic": None, "peak_source": peak_src,
+                "frac": dom["GBps"] / peak,
+                # dram__bytes_read.sum + dram__bytes_write.sum of k_spmv_dot per launch on this workload, from the
+                # committed `ncu --set full` capture profiles/r01_ncu_full.txt (330.28 MB + 30.44 MB); algorithmic
+                # 72 B/row x 4.579 M rows = 329.7 MB (+ 36.6 MB for the dot-product operand rs it also reads)
+                "traffic": 360.72e6 if (world == 1 and rows == 4579000) else None, "traffic_unit": "bytes/launch",
+                "peak_source": peak_src,
                 "alg_bytes_per_launch": rows * SPMV_BYTES_PER_ROW, "ms_per_launch": dom["ms"],
                 "kernels": kern}
     # whole outer iteration: SURVEY.md 8(d): bicg 8(8+32 nin) + TSrc 8(2(G-1)+4) + tail 8(3G+4)/G per node-group row
