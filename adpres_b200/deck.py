@@ -155,6 +155,9 @@ class Problem:
     mdc: Optional[np.ndarray] = None     # (nmat, ng, 6) ADF per material
     adf_rot: Optional[list] = None       # [(rot, x1,x2,y1,y2,z1,z2), ...]
     esrc: Optional[list] = None          # [(sden, spec[ng], [(zpos, [(xpos, ypos), ...]), ...]), ...]
+    crod: Optional[dict] = None          # %CROD: nb, nstep, pos0, ssize, bpos[nb], bmap(nx,ny), dsigtr/dsiga/dnuf/dsigf (nmat,ng), dsigs (nmat,ng,ng)
+    ejct: Optional[dict] = None          # %EJCT: fbpos, tmove, bspeed, ttot, tstep1, tdiv, tstep2, ibeta, lamb, velo
+    bextr: int = 0
     cards: Optional[Dict[str, List[str]]] = None
     # ---- node-wise (filled by build())
     nxx: int = 0
@@ -188,7 +191,7 @@ class Problem:
     _SPEC_FIELDS = ("mode", "ng", "nmat", "nx", "ny", "nz", "xsize", "ysize", "zsize", "xdiv", "ydiv",
                     "zdiv", "zpln", "planars", "bc", "xsigtr", "xsiga", "xnuf", "xsigf", "xsigs", "chi",
                     "nout", "nin", "serc", "ferc", "nac", "nupd", "th_niter", "nth", "kern", "biter",
-                    "sth", "bth", "mdc", "adf_rot", "esrc")
+                    "sth", "bth", "mdc", "adf_rot", "esrc", "crod", "ejct", "bextr")
 
     def to_spec(self) -> dict:
         """JSON-able problem specification (what the deck says, before node expansion).
@@ -199,6 +202,8 @@ class Problem:
             v = getattr(self, k)
             if k == "nupd" and not self.biter:
                 v = 0
+            if isinstance(v, dict):
+                v = {kk: (vv.tolist() if isinstance(vv, np.ndarray) else vv) for kk, vv in v.items()}
             d[k] = v.tolist() if isinstance(v, np.ndarray) else v
         return d
 
@@ -215,6 +220,11 @@ class Problem:
             kw["mdc"] = np.array(kw["mdc"], dtype=np.float64)
         if kw.get("adf_rot") is not None:
             kw["adf_rot"] = [tuple(r) for r in kw["adf_rot"]]
+        for card in ("crod", "ejct"):
+            if kw.get(card) is not None:
+                kw[card] = {kk: (np.array(vv) if isinstance(vv, list) else vv) for kk, vv in kw[card].items()}
+                if card == "crod":
+                    kw[card]["bmap"] = kw[card]["bmap"].astype(np.int32)
         return Problem(**kw).build()
 
     # ------------------------------------------------------------------ geometry
@@ -286,8 +296,9 @@ class Problem:
         self._build_esrc()
         return self
 
-    def update_xs(self) -> None:
-        """base_updt + Dsigr_updt (mod_xsec.f90:172-226)."""
+    def update_xs(self, bpos=None) -> None:
+        """XS_updt for the cards in scope: base_updt [+ crod_updt(bpos)] + Dsigr_updt
+        (mod_xsec.f90:11-46,172-296)."""
         m = self.mat - 1
         N, G = self.nnod, self.ng
         self.sigtr = np.asfortranarray(self.xsigtr[m, :])
@@ -295,7 +306,61 @@ class Problem:
         self.nuf = np.asfortranarray(self.xnuf[m, :])
         self.sigf = np.asfortranarray(self.xsigf[m, :])
         self.sigs = np.asfortranarray(self.xsigs[m, :, :])
+        if self.crod is not None:
+            self.crod_updt(self.crod["bpos"] if bpos is None else bpos)
         self.finish_xs()
+
+    @property
+    def coreh(self) -> float:
+        h = 0.0
+        for z in self.zdel:          # mod_io.f90:1274-1277
+            h = h + z
+        return h
+
+    def crod_updt(self, bpos) -> None:
+        """crod_updt (mod_xsec.f90:230-296): volume-weighted rodded cross sections, rods enter from
+        the top; the partially rodded node gets the fraction vfrac of the increment."""
+        c = self.crod
+        ia, ja, _ = self._node_assembly_maps()
+        fbmap = c["bmap"][np.ix_(ia, ja)]                 # (nxx, nyy) node-wise bank map
+        coreh = self.coreh
+        # node number of (i, j, k): plane-invariant position + k * npl
+        pos = np.full((self.nxx + 1, self.nyy + 1), -1, dtype=np.int64)
+        pos[self.ix[:self.npl], self.iy[:self.npl]] = np.arange(self.npl)
+        for j in range(1, self.nyy + 1):
+            for i in range(1, self.nxx + 1):
+                b = fbmap[i - 1, j - 1]
+                if b <= 0 or pos[i, j] < 0:
+                    continue
+                rodh = coreh - c["pos0"] - bpos[b - 1] * c["ssize"]
+                dum = 0.0
+                for k in range(self.nzz, 0, -1):
+                    n = pos[i, j] + (k - 1) * self.npl
+                    mm = self.mat[n] - 1
+                    if rodh >= dum and rodh <= dum + self.zdel[k - 1]:
+                        vfrac = (rodh - dum) / self.zdel[k - 1]
+                    else:
+                        vfrac = None
+                    w = 1.0 if vfrac is None else vfrac
+                    if vfrac is None:
+                        self.sigtr[n, :] = self.sigtr[n, :] + c["dsigtr"][mm, :]
+                        self.siga[n, :] = self.siga[n, :] + c["dsiga"][mm, :]
+                        self.nuf[n, :] = self.nuf[n, :] + c["dnuf"][mm, :]
+                        self.sigf[n, :] = self.sigf[n, :] + c["dsigf"][mm, :]
+                        self.sigs[n, :, :] = self.sigs[n, :, :] + c["dsigs"][mm, :, :]
+                        dum = dum + self.zdel[k - 1]
+                    else:
+                        self.sigtr[n, :] = self.sigtr[n, :] + w * c["dsigtr"][mm, :]
+                        self.siga[n, :] = self.siga[n, :] + w * c["dsiga"][mm, :]
+                        self.nuf[n, :] = self.nuf[n, :] + w * c["dnuf"][mm, :]
+                        self.sigf[n, :] = self.sigf[n, :] + w * c["dsigf"][mm, :]
+                        self.sigs[n, :, :] = self.sigs[n, :, :] + w * c["dsigs"][mm, :, :]
+                        break
+                col = pos[i, j] + np.arange(self.nzz) * self.npl
+                for a in (self.siga, self.nuf, self.sigf, self.sigs):
+                    blk = a[col]
+                    blk[blk < 0.0] = 0.0
+                    a[col] = blk
 
     def finish_xs(self) -> None:
         """Dsigr_updt: D = 1/(3 sigtr); sigr = siga + sum_{h != g} sigs(g -> h), h ascending."""
@@ -472,6 +537,34 @@ def parse_deck(text: str, base_dir: str = ".") -> Problem:
                     break
                 rots.append((rot, *v))
         p.mdc, p.adf_rot = mdc, rots
+    if "CROD" in cards:                 # mod_io.f90:2148-2330 (%XSEC decks: material-wise increments)
+        r = _Reader(cards["CROD"], "CROD")
+        v = r.rec(2)
+        nb, nstep = int(v[0]), _f(v[1])
+        pos0, ssize = r.floats(2)
+        bpos = np.array(r.floats(nb))
+        bmap = np.zeros((nx, ny), dtype=np.int32)
+        for j in range(ny - 1, -1, -1):
+            bmap[:, j] = r.ints(nx)
+        dsigtr = np.zeros((nmat, ng)); dsiga = np.zeros((nmat, ng)); dnuf = np.zeros((nmat, ng))
+        dsigf = np.zeros((nmat, ng)); dsigs = np.zeros((nmat, ng, ng))
+        for i in range(nmat):
+            for g in range(ng):
+                v = r.floats(4 + ng)
+                dsigtr[i, g], dsiga[i, g], dnuf[i, g], dsigf[i, g] = v[:4]
+                dsigs[i, g, :] = v[4:]
+        p.crod = dict(nb=nb, nstep=nstep, pos0=pos0, ssize=ssize, bpos=bpos, bmap=bmap, dsigtr=dsigtr, dsiga=dsiga,
+                      dnuf=dnuf, dsigf=dsigf, dsigs=dsigs)
+    if "EJCT" in cards and mode == "RODEJECT":   # mod_io.f90:2332-2440
+        r = _Reader(cards["EJCT"], "EJCT")
+        nb = p.crod["nb"]
+        fb = np.array([r.floats(3) for _ in range(nb)])
+        ttot, tstep1, tdiv, tstep2 = r.floats(4)
+        ibeta = np.array(r.floats(6)); lamb = np.array(r.floats(6)); velo = np.array(r.floats(ng))
+        p.ejct = dict(fbpos=fb[:, 0].copy(), tmove=fb[:, 1].copy(), bspeed=fb[:, 2].copy(), ttot=ttot, tstep1=tstep1,
+                      tdiv=tdiv, tstep2=tstep2, ibeta=ibeta, lamb=lamb, velo=velo)
+    if "EXTR" in cards:
+        p.bextr = 1
     if "ESRC" in cards and mode == "FIXEDSRC":   # mod_io.f90:1369-1517
         r = _Reader(cards["ESRC"], "ESRC")
         nsrc = r.ints(1)[0]

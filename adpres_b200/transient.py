@@ -1,0 +1,174 @@
+"""Rod-ejection transient driver for the harness (reference: src/mod_trans.f90).
+
+In the drop-in deployment `rod_eject` / `trans_calc` stay Fortran and call `outer`, `outer_ad`
+and `outer_tr` of the replaced `mod_cmfd`.  This module restates that *caller* (mode RODEJECT,
+no TH feedback, %XSEC decks) so that the reference's transient decks can be run end to end
+against any object exposing the hot-path entry points -- the CUDA library
+(`adpres_b200.capi.Solver`) or the CPU oracle (`oracle.Oracle`):
+
+    set_xs(**arrays)  set_kinetics(...)  set_transient(...)
+    outer(popt)  outer_ad(popt)  outer_tr(ht)  state()  nod()
+
+The glue between the calls (control-rod motion, `iPden`, `uPden`, `PowTot`, `reactivity` with
+`Lxyz`) is numpy, identical for both back ends, so a trace comparison isolates the hot path.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def lxyz_total(p, f0, df, dn):
+    """L(n,g) = L1 + L2 + L3 of Lxyz (mod_nodal.f90:901-1005), vectorised over all nodes.
+    df, dn: (6, nnod, ng) as adp_get_nod returns them."""
+    N, G, npl = p.nnod, p.ng, p.npl
+    i, j, k = p.ix, p.iy, p.iz
+    first_x = i == p.ystag_smin[j - 1]
+    last_x = i == p.ystag_smax[j - 1]
+    first_y = j == p.xstag_smin[i - 1]
+    last_y = j == p.xstag_smax[i - 1]
+    first_z, last_z = k == 1, k == p.nzz
+    # neighbour node numbers (0-based); y neighbours through the plane table
+    pos = np.zeros((p.nxx + 2, p.nyy + 2), dtype=np.int64)
+    pos[p.ix[:npl], p.iy[:npl]] = np.arange(npl)
+    base = (k - 1).astype(np.int64) * npl
+    n = np.arange(N)
+    xp, xm = np.where(last_x, n, n + 1), np.where(first_x, n, n - 1)
+    yp = np.where(last_y, n, base + pos[i, np.minimum(j + 1, p.nyy + 1)])
+    ym = np.where(first_y, n, base + pos[i, j - 1])
+    zp, zm = np.where(last_z, n, n + npl), np.where(first_z, n, n - npl)
+    bc = p.bc  # xeast, xwest, ynorth, ysouth, zbott, ztop
+    L = np.zeros((N, G), order="F")
+    for g in range(G):
+        f = f0[:, g]
+
+        def lead(face_p, face_m, nb_p, nb_m, last, first, bcp, bcm, h):
+            dfp, dnp_, dfm, dnm = df[face_p, :, g], dn[face_p, :, g], df[face_m, :, g], dn[face_m, :, g]
+            jp_int = -dfp * (f[nb_p] - f) - dnp_ * (f[nb_p] + f)
+            jp_bnd = np.zeros(N) if bcp == 2 else dfp * f - dnp_ * f
+            jm_int = -dfm * (f - f[nb_m]) - dnm * (f + f[nb_m])
+            jm_bnd = np.zeros(N) if bcm == 2 else -dfm * f - dnm * f
+            jp = np.where(last, jp_bnd, jp_int)
+            jm = np.where(first, jm_bnd, jm_int)
+            return (jp - jm) / h
+        L1 = lead(0, 1, xp, xm, last_x, first_x, bc[0], bc[1], p.xdel[i - 1])
+        L2 = lead(2, 3, yp, ym, last_y, first_y, bc[2], bc[3], p.ydel[j - 1])
+        L3 = lead(4, 5, zp, zm, last_z, first_z, bc[5], bc[4], p.zdel[k - 1])
+        L[:, g] = L1 + L2 + L3
+    return L
+
+
+def powtot(p, f0):
+    """PowTot (mod_trans.f90:523-557)."""
+    pw = np.zeros(p.nnod)
+    for g in range(p.ng):
+        pw = pw + np.maximum(f0[:, g] * p.sigf[:, g] * p.vdel, 0.0)
+    return float(pw.sum())
+
+
+def reactivity(p, af, sigrp, f0, fs0, L):
+    """reactivity (mod_trans.f90:648-688) with L already evaluated."""
+    src = rem = lea = fde = 0.0
+    chi_n = p.chi[p.mat - 1, :]
+    for g in range(p.ng):
+        scg = np.zeros(p.nnod)
+        for h in range(p.ng):
+            if h != g:
+                scg = scg + p.sigs[:, h, g] * f0[:, h]
+        src += float((af[:, g] * (scg + chi_n[:, g] * fs0) * p.vdel).sum())
+        rem += float((af[:, g] * sigrp[:, g] * f0[:, g] * p.vdel).sum())
+        lea += float((af[:, g] * L[:, g] * p.vdel).sum())
+        fde += float((af[:, g] * chi_n[:, g] * fs0 * p.vdel).sum())
+    return (src - lea - rem) / fde
+
+
+def _push_xs(solver, p, **override):
+    kw = dict(D=p.D, sigr=p.sigr, nuf=p.nuf, sigf=p.sigf, sigs=p.sigs, chi=p.chi, dc=p.dc, exsrc=p.exsrc)
+    kw.update(override)
+    solver.set_xs(**kw)
+
+
+def rod_eject(p, solver, max_steps=None, log=None):
+    """rod_eject (mod_trans.f90:17-160) + trans_calc (:332-479), thc = 0.  Returns a list of
+    (step, t, reactivity [$], relative power, outer iterations, maxi)."""
+    e, c = p.ejct, p.crod
+    ibeta, lamb, velo = e["ibeta"], e["lamb"], e["velo"]
+    bpos = c["bpos"].astype(np.float64).copy()
+    fbpos, tmove, bspeed = e["fbpos"], e["tmove"], e["bspeed"]
+    mdir = np.where(np.abs(fbpos - bpos) < 1e-5, 0, np.where(fbpos - bpos > 1e-5, 2, 1))
+    say = log or (lambda *a: None)
+
+    p.update_xs(bpos)
+    _push_xs(solver, p)
+    rc, n = solver.outer(0)
+    assert rc == 0, rc
+    ke = solver.state()["Ke"]
+    say(f"steady state: {n} outers, k-eff {ke:.6f}")
+    # KNE1 (mod_trans.f90:483-518): force k-eff to 1 by scaling nu*sigf
+    if abs(ke - 1.0) > 1e-5:
+        for it in range(10):
+            p.xnuf = p.xnuf / ke
+            c["dnuf"] = c["dnuf"] / ke
+            p.update_xs(bpos)
+            _push_xs(solver, p)
+            rc, n = solver.outer(0)
+            ke = solver.state()["Ke"]
+            say(f"KNE1 pass {it + 1}: {n} outers, k-eff {ke:.6f}")
+            if abs(ke - 1.0) < 1e-5:
+                break
+    rc, n = solver.outer_ad(0)
+    af = solver.state()["f0"].copy()
+    say(f"adjoint: {n} outers")
+    rc, n = solver.outer(0)
+    st = solver.state()
+    f0, fs0 = st["f0"], st["fs0"]
+    say(f"forward again: {n} outers, k-eff {st['Ke']:.6f}")
+    c0 = np.asfortranarray((ibeta / lamb)[None, :] * fs0[:, None])        # iPden
+    tpow1 = powtot(p, f0)
+    tbeta = np.full(p.nmat, 0.0)
+    for jf in range(6):
+        tbeta = tbeta + ibeta[jf]
+    ctbeta = tbeta[0]
+    df, dn = solver.nod()
+    L = lxyz_total(p, f0, df, dn)
+    rho = reactivity(p, af, p.sigr, f0, fs0, L)
+    trace = [(0, 0.0, rho / ctbeta, 1.0, 0, False)]
+    solver.set_kinetics(ibeta, lamb, velo, tbeta, p.sth, p.bth)
+
+    steps = [(i, e["tstep1"], i * e["tstep1"]) for i in range(1, int(round(e["tdiv"] / e["tstep1"])) + 1)]
+    steps += [(i, e["tstep2"], e["tdiv"] + i * e["tstep2"]) for i in range(1, int(round((e["ttot"] - e["tdiv"]) / e["tstep2"])) + 1)]
+    omeg = np.zeros((p.nnod, p.ng), order="F")                             # bextr == 0
+    for step, (_, ht, t2) in enumerate(steps, start=1):
+        if max_steps is not None and step > max_steps:
+            break
+        # rod bank changes (mod_trans.f90:374-388)
+        for b in range(c["nb"]):
+            if mdir[b] == 1 and t2 - tmove[b] > 1e-5 and fbpos[b] - bpos[b] < 1e-5:
+                bpos[b] = max(bpos[b] - ht * bspeed[b], fbpos[b])
+            elif mdir[b] == 2 and t2 - tmove[b] > 1e-5 and fbpos[b] - bpos[b] > 1e-5:
+                bpos[b] = min(bpos[b] + ht * bspeed[b], fbpos[b])
+        p.update_xs(bpos)
+        sigrp = p.sigr.copy(order="F")
+        sigr = p.sigr.copy(order="F")
+        for g in range(p.ng):
+            sigr[:, g] = sigr[:, g] + 1.0 / (p.sth * velo[g] * ht) + omeg[:, g] / velo[g]
+        ft, fst = f0.copy(order="F"), fs0.copy()
+        _push_xs(solver, p, sigr=sigr)
+        solver.set_transient(c0=c0, ft=ft, fst=fst, omeg=omeg, sigrp=sigrp, L=L)
+        rc, maxi, n = solver.outer_tr(ht)
+        assert rc == 0, rc
+        st = solver.state()
+        f0, fs0 = st["f0"], st["fs0"]
+        # uPden (mod_trans.f90:601-644)
+        for i in range(6):
+            pxe = np.exp(-lamb[i] * ht)
+            a1 = (1.0 - pxe) / (lamb[i] * ht)
+            a2 = 1.0 - a1
+            a1 = a1 - pxe
+            c0[:, i] = c0[:, i] * pxe + ibeta[i] / lamb[i] * (a1 * fst + a2 * fs0)
+        tpow2 = powtot(p, f0)
+        df, dn = solver.nod()
+        L = lxyz_total(p, f0, df, dn)
+        rho = reactivity(p, af, sigrp, f0, fs0, L)
+        trace.append((step, t2, rho / ctbeta, tpow2 / tpow1, n, maxi))
+        say(f"{step:4d} {t2:10.3f} {rho / ctbeta:10.4f} {tpow2 / tpow1:15.4E}  outers {n}")
+    return trace
