@@ -602,12 +602,6 @@ static inline RedOut make_red(adp_ctx *c, int s0, int s1 = S_TMP1, int s2 = S_TM
     ro.slot[0] = s0; ro.slot[1] = s1; ro.slot[2] = s2; ro.slot[3] = s3;
     return ro;
 }
-static inline int grid_for(adp_ctx *c, int ntiles)
-{
-    int g = c->grid_blocks;
-    if (ntiles < g) g = ntiles;
-    return g < 1 ? 1 : g;
-}
 #define LAUNCH_CHECK(c)                                                                     \
     do {                                                                                    \
         (c)->launches++;                                                                    \

@@ -277,30 +277,38 @@ int adp_comm_halo(adp_ctx *c, double *v, int n)
 template <bool MAX>
 __global__ void k_mail_allreduce(double *vals, int count, Mail m)
 {
-    if (threadIdx.x != 0) return;
+    // one warp; lane q talks to rank q: posts this rank's values into rank q's mailbox and polls
+    // the row rank q writes into this rank's mailbox -- all ranks in parallel, one fence each way
+    const int q = threadIdx.x;
     const unsigned long long seq = *m.seq + 1ull;
     const size_t slot = (size_t)(seq % ADP_MAIL_SLOTS) * m.nranks;
-    double v[4];
-    for (int i = 0; i < count; ++i) v[i] = vals[i];
-    for (int q = 0; q < m.nranks; ++q) {
+    double mine[4] = {0.0, 0.0, 0.0, 0.0}, got[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int i = 0; i < count; ++i) mine[i] = vals[i];
+    if (q < m.nranks) {
         volatile double *dst = m.box[q] + (slot + m.rank) * ADP_MAIL_WORDS;
-        for (int i = 0; i < count; ++i) dst[i] = v[i];
-    }
-    __threadfence_system();
-    for (int q = 0; q < m.nranks; ++q)
-        *(volatile unsigned long long *)(m.box[q] + (slot + m.rank) * ADP_MAIL_WORDS + (ADP_MAIL_WORDS - 1)) = seq;
-    double acc[4] = {0.0, 0.0, 0.0, 0.0};
-    const long long t0 = clock64();
-    for (int q = 0; q < m.nranks; ++q) {
+        for (int i = 0; i < count; ++i) dst[i] = mine[i];
+        __threadfence_system();
+        *(volatile unsigned long long *)(dst + (ADP_MAIL_WORDS - 1)) = seq;
         volatile double *src = m.box[m.rank] + (slot + q) * ADP_MAIL_WORDS;
         volatile unsigned long long *flag = (volatile unsigned long long *)(src + (ADP_MAIL_WORDS - 1));
+        const long long t0 = clock64();
         while (*flag != seq)
             if (clock64() - t0 > 8000000000LL) { atomicExch(m.errflag, ADP_ERR_NCCL); break; }   // ~4 s: never hang the GPU
         __threadfence_system();
-        for (int i = 0; i < count; ++i) acc[i] = MAX ? fmax(acc[i], src[i]) : acc[i] + src[i];
+        for (int i = 0; i < count; ++i) got[i] = src[i];
     }
-    for (int i = 0; i < count; ++i) vals[i] = acc[i];
-    *m.seq = seq;
+    __syncwarp();
+    // combine in rank order on lane 0 (deterministic)
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int r = 0; r < m.nranks; ++r)
+        for (int i = 0; i < 4; ++i) {
+            const double w = __shfl_sync(0xffffffffu, got[i], r);
+            acc[i] = MAX ? fmax(acc[i], w) : acc[i] + w;
+        }
+    if (q == 0) {
+        for (int i = 0; i < count; ++i) vals[i] = acc[i];
+        *m.seq = seq;
+    }
 }
 
 static int mail_allreduce(adp_ctx *c, double *d, int count, bool is_max)

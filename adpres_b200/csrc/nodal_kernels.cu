@@ -706,12 +706,6 @@ static NodalArgs make_args(adp_ctx *c, int cmode)
     return A;
 }
 
-static inline int grid_for(adp_ctx *c, int ntiles)
-{
-    int g = c->grid_blocks;
-    if (ntiles < g) g = ntiles;
-    return g < 1 ? 1 : g;
-}
 
 int adp_k_nodal_source(adp_ctx *c, int cmode)
 {

@@ -274,3 +274,50 @@ def test_transient_outer_tr_synthetic_state(mods):
     pw_o = o.powtot(o.state()["f0"]) / pw0
     assert 1.05 < pw_o < 1.25
     assert abs(pw_s / pw_o - 1) < 1e-4
+
+
+# ------------------------------------------------------------------ multigroup with ADFs (BASELINE configs[3])
+@pytest.mark.parametrize("ng", [4, 8])
+def test_synthetic_multigroup_with_adf(mods, ng):
+    """4 and 8 energy groups with assembly discontinuity factors on every face (synthetic cross
+    sections, tests/synth.py): matrix, one SANM update (2G x 2G un-pivoted LU, 16 x 16 at G = 8,
+    including the reference's ADF cross terms of mod_nodal.f90:693-694) and the whole solve.
+    Synthetic, so GPU-vs-oracle only ("parity unpinned" by the reference)."""
+    capi, Oracle = mods
+    from synth import iaea3d_multigroup
+    p = iaea3d_multigroup(ng)
+    assert p.dc.min() < 0.96 and p.dc.max() > 1.04
+    s, o = capi.Solver(p), Oracle(p)
+    s.matrix_setup(1); o.matrix_setup(1)
+    assert np.array_equal(s.matrix_dia(), o.matrix_dia())
+    # one nodal update from an identical state
+    o.set_control(nout=8, nupd=1000)
+    o.outer(0)
+    st = o.state()
+    s.set_state(st["f0"], st["fs0"], st["Ke"])
+    assert o.nodal_upd(1) == 0
+    rc, ndmax, _ = s.nodal_upd(1)
+    assert rc == 0
+    dn_s, dn_o = s.nod()[1], o.nod()[1]
+    assert np.abs(dn_s - dn_o).max() < 1e-9 * max(1.0, np.abs(dn_o).max())
+    assert abs(ndmax - o.ndmax) < 1e-9 * max(1.0, o.ndmax)
+    # the whole eigenvalue solve
+    s2, o2 = capi.Solver(p), Oracle(p)
+    rc_s, n_s = s2.outer(0)
+    rc_o, n_o = o2.outer(0)
+    assert rc_s == rc_o == 0 and abs(n_s - n_o) <= 1, (n_s, n_o)
+    assert abs(s2.state()["Ke"] - o2.state()["Ke"]) < 1e-5 * o2.state()["Ke"]
+    _, pw_s = s2.powdis()
+    _, pw_o = o2.powdis()
+    nz = pw_o > 1e-12
+    assert np.abs(pw_s[nz] / pw_o[nz] - 1).max() < 1e-5
+
+
+def test_outer_th_runs_maxn_iterations_without_stop(mods):
+    """outer_th(maxn) (mod_cmfd.f90:703-796): at most maxn iterations, no STOP on non-convergence."""
+    p, s, o = _pair(mods, "IAEA3Ds")
+    rc_s, n_s = s.outer_th(30)
+    rc_o, n_o = o.outer_th(30)
+    assert rc_s == rc_o == 0 and n_s == n_o == 30
+    assert abs(s.state()["Ke"] - o.state()["Ke"]) < 1e-9
+    assert s.ndmax > 0 and abs(s.ndmax - o.ndmax) < 1e-9      # nodal update at p = 22 happened in both
