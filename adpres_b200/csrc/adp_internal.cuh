@@ -164,6 +164,7 @@ struct adp_ctx {
     size_t stage_elems = 0;
     int grid_blocks = 0;                   // persistent grid size override (option "grid_blocks")
     bool grid_override = false;
+    bool balance_rounds = false;   // measured: no effect on these bandwidth-bound kernels (A/B, tools/kbench.py)
     int sm_count = 0;
     // multi-rank
     adp_comm *comm = nullptr;
@@ -230,7 +231,15 @@ static inline int adp_grid(adp_ctx *c, K kernel, int ntiles)
     if (c->grid_blocks > 0 && c->grid_override) g = c->grid_blocks;
     if (g > ADP_MAXPART) g = ADP_MAXPART;
     if (ntiles < g) g = ntiles;
-    return g < 1 ? 1 : (int)g;
+    if (g < 1) g = 1;
+    // balance the rounds of the tile loop: with g CTAs the loop takes ceil(ntiles/g) rounds and the
+    // last one is generally almost empty (18 050 tiles on 1 184 CTAs: 16 rounds, the last 24 % full);
+    // the smallest grid that needs the same number of rounds fills all of them
+    if (!c->grid_override && c->balance_rounds) {
+        const long long rounds = (ntiles + g - 1) / g;
+        g = (ntiles + rounds - 1) / rounds;
+    }
+    return (int)g;
 }
 
 // ---- launch wrappers implemented in the kernel files ---------------------------------------

@@ -763,6 +763,7 @@ extern "C" int adp_set_option(adp_ctx *c, const char *name, int value)
     if (!strcmp(name, "graphs")) { c->use_graphs = value != 0; free_graphs(c); return ADP_OK; }
     if (!strcmp(name, "peer_push")) { if (!value) c->peer_ok = false; return ADP_OK; }
     if (!strcmp(name, "peer_allreduce")) { if (!value) c->peer_ar = false; return ADP_OK; }
+    if (!strcmp(name, "balance_rounds")) { c->balance_rounds = value != 0; free_graphs(c); return ADP_OK; }
     if (!strcmp(name, "bench_warmup")) { c->bench_warmup = value; return ADP_OK; }
     if (!strcmp(name, "fuse_st")) { c->fuse_st = value != 0; free_graphs(c); return ADP_OK; }
     if (!strcmp(name, "grid_blocks")) {

@@ -397,25 +397,35 @@ def main():
         peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
     kern = {}
     rows = N_own
-    for name, what, bytes_per_row in (("k_spmv_dot (B: v=Ap,(rs,v))", 0, 72.0), ("k_spmv (plain v=Ap)", 8, 72.0),
-                                      ("k_st (C: s,t fused)", 1, 88.0), ("k_update_xr (D)", 2, 56.0),
-                                      ("k_update_p (A)", 3, 32.0), ("k_residual (P)", 4, 8.0 * (7 + 1 + 1 + 2 * (p.ng - 1) + 1 + 3) + 4.0),
-                                      ("k_fsrc_norms (F)", 5, 8.0 * (3 * p.ng + 2))):
+    G, nin = p.ng, CTL["nin"]
+    # (name, bench id, algorithmic bytes/row per SURVEY.md 8(d) BiCGSTAB phase table, launches per outer iteration,
+    #  dram bytes per launch from the committed ncu --set full capture profiles/r01_ncu_full.txt at the N = 1 size)
+    table = (("k_st (C: s = r - alpha v on the fly, t = A s, (t,t), (t,s))", 1, 88.0, G * nin, 391.76e6),
+             ("k_spmv_dot (B: v = A p, (rs,v))", 0, 80.0, G * nin, 360.72e6),
+             ("k_spmv (plain v = A p, no dot product)", 8, 72.0, 0, 322.52e6),
+             ("k_update_xr (D: x, r update, rho)", 2, 56.0, G * nin, 226.82e6),
+             ("k_update_p (A: p update)", 3, 32.0, G * (nin - 1), 126.46e6),
+             ("k_residual (P: source + residual)", 4, 8.0 * (7 + 1 + 1 + 2 * (G - 1) + 1 + 1) + 4.0, G, 491.38e6),
+             ("k_fsrc_norms (F: fission source + norms)", 5, 8.0 * (3 * G + 2), 1, 286.86e6))
+    for name, what, bytes_per_row, per_step, traffic in table:
         kms = s.bench_kernel(what, 20)
-        kern[name] = {"ms": kms, "alg_bytes_per_row": bytes_per_row, "GBps": rows * bytes_per_row / (kms * 1e-3) / 1e9}
+        kern[name] = {"ms": kms, "alg_bytes_per_row": bytes_per_row, "GBps": rows * bytes_per_row / (kms * 1e-3) / 1e9,
+                      "frac": rows * bytes_per_row / (kms * 1e-3) / 1e9 / peak, "launches_per_step": per_step,
+                      "ms_per_step": kms * per_step,
+                      "ncu_dram_bytes_per_launch": traffic if (world == 1 and rows == 4579000) else None}
     nodal_ms = s.bench_kernel(7, 3)
-    kern["nodal update (source + 3 surface sweeps)"] = {
-        "ms": nodal_ms, "alg_bytes_per_node": 8.0 * (41 * p.ng + p.ng ** 2),
-        "GBps": rows * 8.0 * (41 * p.ng + p.ng ** 2) / (nodal_ms * 1e-3) / 1e9}
-    dom = kern["k_spmv_dot (B: v=Ap,(rs,v))"]
-    roofline = {"bound": "hbm", "kernel": "k_spmv_dot", "achieved": dom["GBps"], "peak": peak, "unit": "GB/s",
-                "frac": dom["GBps"] / peak,
-                # dram__bytes_read.sum + dram__bytes_write.sum of k_spmv_dot per launch on this workload, from the
-                # committed `ncu --set full` capture profiles/r01_ncu_full.txt (330.28 MB + 30.44 MB); algorithmic
-                # 72 B/row x 4.579 M rows = 329.7 MB (+ 36.6 MB for the dot-product operand rs it also reads)
-                "traffic": 360.72e6 if (world == 1 and rows == 4579000) else None, "traffic_unit": "bytes/launch",
-                "peak_source": peak_src,
-                "alg_bytes_per_launch": rows * SPMV_BYTES_PER_ROW, "ms_per_launch": dom["ms"],
+    kern["nodal update (source + 3 node-direction + 3 surface launches)"] = {
+        "ms": nodal_ms, "alg_bytes_per_node": 8.0 * (41 * G + G ** 2), "launches_per_step": 1.0 / CTL["nupd"],
+        "GBps": rows * 8.0 * (41 * G + G ** 2) / (nodal_ms * 1e-3) / 1e9, "ms_per_step": nodal_ms / CTL["nupd"]}
+    # the dominant kernel = largest share of the step (agrees with the committed launch list
+    # profiles/r01_launches_summary.txt: k_st 20 %, k_spmv_dot 19 %)
+    dom_name = max((k for k in kern if "alg_bytes_per_row" in kern[k]), key=lambda k: kern[k]["ms_per_step"])
+    dom = kern[dom_name]
+    roofline = {"bound": "hbm", "kernel": dom_name.split(" ")[0], "achieved": dom["GBps"], "peak": peak, "unit": "GB/s",
+                "frac": dom["frac"], "traffic": dom["ncu_dram_bytes_per_launch"], "traffic_unit": "bytes/launch (ncu dram read+write)",
+                "alg_bytes_per_launch": rows * dom["alg_bytes_per_row"], "ms_per_launch": dom["ms"], "peak_source": peak_src,
+                "spmv_on_72B_basis": {"k_spmv_dot": rows * SPMV_BYTES_PER_ROW / (kern["k_spmv_dot (B: v = A p, (rs,v))"]["ms"] * 1e-3) / 1e9 / peak,
+                                      "k_spmv": kern["k_spmv (plain v = A p, no dot product)"]["frac"]},
                 "kernels": kern}
     # whole outer iteration: SURVEY.md 8(d): bicg 8(8+32 nin) + TSrc 8(2(G-1)+4) + tail 8(3G+4)/G per node-group row
     row_bytes = 8.0 * (8 + 32 * CTL["nin"]) + 8.0 * (2 * (p.ng - 1) + 4) + 8.0 * (3 * p.ng + 4) / p.ng
