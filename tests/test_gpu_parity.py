@@ -321,3 +321,74 @@ def test_outer_th_runs_maxn_iterations_without_stop(mods):
     assert rc_s == rc_o == 0 and n_s == n_o == 30
     assert abs(s.state()["Ke"] - o.state()["Ke"]) < 1e-9
     assert s.ndmax > 0 and abs(s.ndmax - o.ndmax) < 1e-9      # nodal update at p = 22 happened in both
+
+
+# ------------------------------------------------------------------ iteration-control / boundary-condition matrix
+@pytest.mark.parametrize("nin,nac,nupd,kern", [(1, 4, 12, 1), (3, 4, 6, 2), (5, 2, 2, 1), (2, 5, 10, 2), (4, 7, 5, 1), (6, 5, 3, 2)])
+def test_iteration_control_matrix(mods, nin, nac, nupd, kern):
+    """Odd / even BiCGSTAB sweep counts (rho slot and v buffer parity), frequent extrapolation and
+    nodal updates, PNM and SANM: 14 outer iterations iterate-for-iterate."""
+    capi, Oracle = mods
+    p = load_problem("IAEA3Ds")
+    kw = dict(nin=nin, nac=nac, nupd=nupd, kern=kern, nout=14)
+    s, o = capi.Solver(p, **kw), Oracle(p, **kw)
+    s.enable_trace()
+    rc_s, n_s = s.outer(1)
+    rc_o, n_o = o.outer(1)
+    assert (rc_s, n_s) == (rc_o, n_o)
+    ke_o, ser_o, fer_o = o.trace()
+    for (q, ke, ser, fer) in s.trace_rows:
+        assert abs(ke - ke_o[q - 1]) < 1e-9 * max(1.0, abs(ke_o[q - 1])), (q, ke, ke_o[q - 1])
+        assert abs(ser - ser_o[q - 1]) < 1e-6 * max(1.0, ser_o[q - 1])
+    assert [u[0] for u in s.trace_nodal] == [u[0] for u in o.nodal_trace()]
+    for a, b in zip(s.trace_nodal, o.nodal_trace()):
+        assert abs(a[1] - b[1]) < 1e-7 * max(1.0, b[1]), (a, b)
+    assert _rel(s.state()["f0"], o.state()["f0"]) < 1e-8
+
+
+@pytest.mark.parametrize("bc", [(0, 0, 0, 0, 0, 0), (1, 1, 1, 1, 1, 1), (2, 2, 2, 2, 0, 1), (0, 2, 1, 2, 2, 0)])
+@pytest.mark.parametrize("deck", ["IAEA3Ds", "KOEBERG"])
+def test_boundary_condition_matrix(mods, deck, bc):
+    """Every boundary code (0 zero flux, 1 zero incoming current, 2 reflective) on every face:
+    coup_coef boundary forms, Lxyz boundary currents, one-node boundary problems of the nodal
+    update (get_a1matvec_first/_last, three branches each) and the one-sided TL fits."""
+    capi, Oracle = mods
+    p = load_problem(deck)
+    p.bc = np.array(bc, dtype=np.int32)
+    kw = dict(nupd=5, nout=12)
+    s, o = capi.Solver(p, **kw), Oracle(p, **kw)
+    s.matrix_setup(1); o.matrix_setup(1)
+    assert np.array_equal(s.nod()[0], o.nod()[0])
+    assert np.array_equal(s.matrix_dia(), o.matrix_dia())
+    rc_s, n_s = s.outer(0)
+    rc_o, n_o = o.outer(0)
+    assert (rc_s, n_s) == (rc_o, n_o)
+    assert abs(s.state()["Ke"] - o.state()["Ke"]) < 1e-9
+    assert np.abs(s.nod()[1] - o.nod()[1]).max() < 1e-8
+    assert _rel(s.state()["f0"], o.state()["f0"]) < 1e-8
+
+
+def test_adjoint_with_adf_and_nodal_updates(mods):
+    """outer_ad(1) on the ADF deck: cmode 0 B matrix (transposed scattering / fission operator),
+    groups swept G..1, nodal updates with discontinuity factors."""
+    p, s, o = _pair(mods, "DVP")
+    rc_s, n_s = s.outer_ad(1)
+    rc_o, n_o = o.outer_ad(1)
+    assert rc_s == rc_o == 0 and abs(n_s - n_o) <= 1
+    assert abs(s.state()["Ke"] - o.state()["Ke"]) * 1e5 < 1.0
+    assert _rel(s.state()["f0"], o.state()["f0"]) < 1e-5
+
+
+def test_unstable_nodal_iteration_gives_the_reference_stop(mods):
+    """nupd = 1 (a nodal update after the very first, unconverged outer iteration) blows the
+    two-node iteration up: the reference STOPs with "Max. change in nodal coupling coefficient"
+    > 1e3 (mod_nodal.f90:131-142).  Same stop code at the same iteration on the GPU."""
+    capi, Oracle = mods
+    p = load_problem("IAEA3Ds")
+    kw = dict(nin=2, nac=3, nupd=1, nout=14)
+    s, o = capi.Solver(p, **kw), Oracle(p, **kw)
+    rc_s, n_s = s.outer(0)
+    rc_o, n_o = o.outer(0)
+    assert rc_o == 3 and rc_s == capi.STOP_NDMAX
+    assert s.ndmax > 1e3 and o.ndmax > 1e3          # (the diverging iterates themselves amplify round-off)
+    assert "not stable" in s.last_error()
