@@ -258,6 +258,7 @@ int adp_k_integrate(adp_ctx *c, const double *d_vec, int slot);
 // nodal_kernels.cu
 int adp_k_nodal_source(adp_ctx *c, int cmode);
 int adp_k_nodal_update(adp_ctx *c, int cmode);
+int adp_k_lxyz_total(adp_ctx *c, double *d_L);
 // comm.cu
 int adp_comm_halo(adp_ctx *c, double *d_vec, int nplanes);            // exchange ghost planes of one vector
 int adp_comm_allreduce_sum(adp_ctx *c, double *d_scal, int count);

@@ -743,6 +743,21 @@ extern "C" int adp_get_source(adp_ctx *c, int cmode, double *S1, double *S2, dou
     return ADP_OK;
 }
 
+// L(n,g) = L1 + L2 + L3 of Lxyz (mod_nodal.f90:901-1005) for all nodes, as `reactivity`
+// (mod_trans.f90:677-678) forms it -- on the device, so that the time-step driver reads back
+// nnod*ng doubles instead of nod%df/dn (24x as much) and loops over Lxyz on the host.
+extern "C" int adp_lxyz_total(adp_ctx *c, double *L)
+{
+    if (!c || !L) return ADP_ERR_USAGE;
+    ADP_REQUIRE(c, c->have_flux && c->matrix_ready, "adp_lxyz_total: needs matrix and flux");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    TRY(ensure_transient(c));
+    TRY(adp_k_lxyz_total(c, c->d_L));
+    TRY(download_nodes(c, L, c->d_L, c->ng));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return ADP_OK;
+}
+
 extern "C" int adp_set_trace(adp_ctx *c, adp_trace_fn fn, void *user)
 {
     if (!c) return ADP_ERR_USAGE;

@@ -56,7 +56,7 @@ struct NodalArgs {
 // ---------------------------------------------------------------------------------------
 // Lxyz + get_source (mod_nodal.f90:901-1043)
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(ADP_TILE, 4) k_nodal_source(Geo G, NodalArgs A)
+__global__ void __launch_bounds__(ADP_TILE, 4) k_nodal_source(Geo G, NodalArgs A, double *__restrict__ Ltot)
 {
     const long long NV = G.NV;
     const int np = G.np;
@@ -90,6 +90,10 @@ __global__ void __launch_bounds__(ADP_TILE, 4) k_nodal_source(Geo G, NodalArgs A
             if (kg == 0) jm = (G.bc[4] == 2) ? 0.0 : -df[5 * NV + idx] * fn - dn[5 * NV + idx] * fn;
             else { const double fm = f0[idx - np]; jm = -df[5 * NV + idx] * (fn - fm) - dn[5 * NV + idx] * (fn + fm); }
             const double L3 = (jp - jm) / hz;
+            if (Ltot) {            // reactivity (mod_trans.f90:677-678): L(n,g) = L1 + L2 + L3
+                Ltot[(size_t)g * NV + idx] = L1 + L2 + L3;
+                continue;
+            }
             double *S1 = A.S + ((size_t)0 * A.ng + g) * NV, *S2 = A.S + ((size_t)1 * A.ng + g) * NV,
                    *S3 = A.S + ((size_t)2 * A.ng + g) * NV;
             if (A.cmode == 2) {
@@ -714,9 +718,23 @@ int adp_k_nodal_source(adp_ctx *c, int cmode)
     if (c->nranks > 1)
         for (int g = 0; g < c->ng; ++g)
             if ((rc = adp_comm_halo(c, c->d_f0[c->cur[g]] + (size_t)g * c->NV, 1))) return rc;
-    k_nodal_source<<<adp_grid(c, k_nodal_source, c->geo.ntiles), ADP_TILE, 0, c->stream>>>(c->geo, A);
+    k_nodal_source<<<adp_grid(c, k_nodal_source, c->geo.ntiles), ADP_TILE, 0, c->stream>>>(c->geo, A, nullptr);
     c->launches++;
     if (cudaPeekAtLastError() != cudaSuccess) { c->err = "k_nodal_source launch failed"; return ADP_ERR_CUDA; }
+    return ADP_OK;
+}
+
+// L(n,g) = L1 + L2 + L3 of Lxyz for every node (what `reactivity` needs), into d_L
+int adp_k_lxyz_total(adp_ctx *c, double *d_L)
+{
+    NodalArgs A = make_args(c, 1);
+    int rc;
+    if (c->nranks > 1)
+        for (int g = 0; g < c->ng; ++g)
+            if ((rc = adp_comm_halo(c, c->d_f0[c->cur[g]] + (size_t)g * c->NV, 1))) return rc;
+    k_nodal_source<<<adp_grid(c, k_nodal_source, c->geo.ntiles), ADP_TILE, 0, c->stream>>>(c->geo, A, d_L);
+    c->launches++;
+    if (cudaPeekAtLastError() != cudaSuccess) { c->err = "k_nodal_source (Lxyz) launch failed"; return ADP_ERR_CUDA; }
     return ADP_OK;
 }
 

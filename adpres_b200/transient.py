@@ -81,6 +81,15 @@ def reactivity(p, af, sigrp, f0, fs0, L):
     return (src - lea - rem) / fde
 
 
+def _leakage(p, solver, f0):
+    """L(n,g) for `reactivity`: on the device when the back end offers it (adp_lxyz_total), else
+    from nod%df/dn copied back, as the reference does."""
+    if hasattr(solver, "lxyz_total"):
+        return solver.lxyz_total()
+    df, dn = solver.nod()
+    return lxyz_total(p, f0, df, dn)
+
+
 def _push_xs(solver, p, **override):
     kw = dict(D=p.D, sigr=p.sigr, nuf=p.nuf, sigf=p.sigf, sigs=p.sigs, chi=p.chi, dc=p.dc, exsrc=p.exsrc)
     kw.update(override)
@@ -128,8 +137,7 @@ def rod_eject(p, solver, max_steps=None, log=None):
     for jf in range(6):
         tbeta = tbeta + ibeta[jf]
     ctbeta = tbeta[0]
-    df, dn = solver.nod()
-    L = lxyz_total(p, f0, df, dn)
+    L = _leakage(p, solver, f0)
     rho = reactivity(p, af, p.sigr, f0, fs0, L)
     trace = [(0, 0.0, rho / ctbeta, 1.0, 0, False)]
     solver.set_kinetics(ibeta, lamb, velo, tbeta, p.sth, p.bth)
@@ -166,8 +174,7 @@ def rod_eject(p, solver, max_steps=None, log=None):
             a1 = a1 - pxe
             c0[:, i] = c0[:, i] * pxe + ibeta[i] / lamb[i] * (a1 * fst + a2 * fs0)
         tpow2 = powtot(p, f0)
-        df, dn = solver.nod()
-        L = lxyz_total(p, f0, df, dn)
+        L = _leakage(p, solver, f0)
         rho = reactivity(p, af, sigrp, f0, fs0, L)
         trace.append((step, t2, rho / ctbeta, tpow2 / tpow1, n, maxi))
         say(f"{step:4d} {t2:10.3f} {rho / ctbeta:10.4f} {tpow2 / tpow1:15.4E}  outers {n}")

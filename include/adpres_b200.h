@@ -149,6 +149,9 @@ int adp_set_s0(adp_ctx *ctx, const double *s0, int g);
 /* nod(n,g)%df / %dn as df(6,nnod,ng), dn(6,nnod,ng) (Lxyz in reactivity, mod_trans.f90:677) */
 int adp_get_nod(adp_ctx *ctx, double *df, double *dn);
 int adp_set_nod_dn(adp_ctx *ctx, const double *dn);
+/* L(nnod,ng) = L1+L2+L3 of Lxyz for every node, evaluated on the device and left there as the L
+ * that get_exsrc uses (reactivity, mod_trans.f90:677-678; saves copying nod%df/dn back) */
+int adp_lxyz_total(adp_ctx *ctx, double *L);
 /* exsrc(nnod,ng), dfis(nnod) after adp_get_exsrc */
 int adp_get_exsrc_arrays(adp_ctx *ctx, double *exsrc, double *dfis);
 /* ndmax persists across outer*() calls and starts at 0 (mod_data.f90:199) */

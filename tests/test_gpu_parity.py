@@ -392,3 +392,37 @@ def test_unstable_nodal_iteration_gives_the_reference_stop(mods):
     assert rc_o == 3 and rc_s == capi.STOP_NDMAX
     assert s.ndmax > 1e3 and o.ndmax > 1e3          # (the diverging iterates themselves amplify round-off)
     assert "not stable" in s.last_error()
+
+
+def test_integrate_powdis_and_usage_errors(mods):
+    capi, Oracle = mods
+    p = load_problem("IAEA3Ds")
+    s = capi.Solver(p)
+    x = np.random.default_rng(2).random(p.nnod)
+    assert abs(s.integrate(x) / float(np.dot(p.vdel, x)) - 1) < 1e-13          # Integrate (mod_cmfd.f90:1120-1139)
+    with pytest.raises(capi.AdpresError):                                      # no matrix / flux yet
+        s.outer_iter(0, 1)
+    with pytest.raises(capi.AdpresError):
+        s.nodal_upd(1)
+    with pytest.raises(capi.AdpresError):                                      # transient mode without kinetics data
+        s.matrix_setup(1); s.init_flux(); s.outer_begin(3); s.outer_iter(3, 1)
+    # PowDis STOP: zero fission cross section everywhere -> "TOTAL NODES POWER IS ZERO OR LESS"
+    s2 = capi.Solver(p)
+    s2.set_xs(sigf=np.zeros_like(p.sigf))
+    s2.matrix_setup(1); s2.init_flux()
+    rc, _ = s2.powdis()
+    assert rc == capi.STOP_ZERO_POWER
+    rc, _ = s2.powdis(fixedsrc=True)                                           # tolerated in FIXEDSRC mode
+    assert rc == 0
+
+
+def test_lxyz_total_on_device(mods):
+    """adp_lxyz_total: L = L1 + L2 + L3 of Lxyz for all nodes (reactivity, mod_trans.f90:677-678)."""
+    p, s, o = _pair(mods, "IAEA3Ds")
+    o.set_control(nout=30); o.outer(0)
+    st = o.state()
+    s.matrix_setup(1)
+    s.set_state(st["f0"], st["fs0"], st["Ke"])
+    s.set_nod_dn(o.nod()[1])
+    o.reactivity(st["f0"], p.sigr)
+    assert np.array_equal(s.lxyz_total(), o.transient()["L"])
