@@ -25,7 +25,8 @@ SYMBOLS = [
     "adp_create", "adp_destroy", "adp_last_error", "adp_version", "adp_comm_unique_id", "adp_comm_init", "adp_comm_init_env", "adp_slab",
     "adp_set_geometry", "adp_set_xs", "adp_set_control", "adp_matrix_setup", "adp_init_flux", "adp_outer_begin",
     "adp_outer_iter", "adp_nodal_upd", "adp_powdis", "adp_integrate", "adp_set_kinetics", "adp_set_transient",
-    "adp_get_exsrc", "adp_get_state", "adp_set_state", "adp_set_s0", "adp_get_nod", "adp_set_nod_dn", "adp_lxyz_total", "adp_get_exsrc_arrays",
+    "adp_get_exsrc", "adp_save_adjoint", "adp_ipden", "adp_begin_time_step", "adp_upden", "adp_powtot",
+    "adp_reactivity", "adp_get_state", "adp_set_state", "adp_set_s0", "adp_get_nod", "adp_set_nod_dn", "adp_lxyz_total", "adp_get_exsrc_arrays",
     "adp_get_ndmax", "adp_set_trace", "adp_outer", "adp_outer_ad", "adp_outer_fs", "adp_outer_th", "adp_outer_tr",
     "adp_sp_matvec", "adp_bicg", "adp_get_matrix", "adp_get_source", "adp_set_option", "adp_launch_count",
     "adp_bench_kernel", "adp_outer_steps", "adp_timer_start", "adp_timer_stop",
@@ -306,3 +307,26 @@ class Solver:
         L = np.zeros((self.N, self.G), order="F")
         self._chk(self.L.adp_lxyz_total(self.h, _d(L)))
         return L
+
+    # ---- time-step glue on the device (mod_trans.f90 callers)
+    def save_adjoint(self):
+        self._chk(self.L.adp_save_adjoint(self.h))
+
+    def ipden(self):
+        self._chk(self.L.adp_ipden(self.h))
+
+    def begin_time_step(self, ht):
+        self._chk(self.L.adp_begin_time_step(self.h, C.c_double(ht)))
+
+    def upden(self, ht):
+        self._chk(self.L.adp_upden(self.h, C.c_double(ht)))
+
+    def powtot(self):
+        r = C.c_double()
+        self._chk(self.L.adp_powtot(self.h, C.byref(r)))
+        return r.value
+
+    def reactivity(self, use_sigrp):
+        r = C.c_double()
+        self._chk(self.L.adp_reactivity(self.h, int(use_sigrp), C.byref(r)))
+        return r.value

@@ -146,6 +146,7 @@ struct adp_ctx {
     double *d_abefgh = nullptr;            // [3][6][G][NV] SANM constants, valid until D / sigr change
     bool abefgh_valid = false;
     // transient
+    double *d_af = nullptr;                // adjoint flux kept for reactivity() [G][NV]
     double *d_c0 = nullptr, *d_ft = nullptr, *d_fst = nullptr, *d_omeg = nullptr, *d_sigrp = nullptr,
            *d_L = nullptr, *d_dfis = nullptr, *d_tbeta = nullptr, *d_velo = nullptr;
     double ibeta[ADP_NF] = {0}, lamb[ADP_NF] = {0};
@@ -255,6 +256,10 @@ int adp_k_outer_tail(adp_ctx *c, int mode, bool extrapolate);
 int adp_k_powdis(adp_ctx *c, double *d_pow);
 int adp_k_get_exsrc(adp_ctx *c, double ht);
 int adp_k_integrate(adp_ctx *c, const double *d_vec, int slot);
+int adp_k_ipden(adp_ctx *c);
+int adp_k_upden(adp_ctx *c, double ht);
+int adp_k_begin_step(adp_ctx *c, double ht);
+int adp_k_reactivity(adp_ctx *c, const double *d_af, const double *d_sigr_for_rem);
 // nodal_kernels.cu
 int adp_k_nodal_source(adp_ctx *c, int cmode);
 int adp_k_nodal_update(adp_ctx *c, int cmode);

@@ -88,7 +88,7 @@ extern "C" int adp_destroy(adp_ctx *c)
                     c->d_f0[0], c->d_f0[1], c->d_fs[0], c->d_fs[1], c->d_r, c->d_rs, c->d_p, c->d_v, c->d_v2, c->d_s, c->d_t,
                     c->d_s0, c->d_a, c->d_df, c->d_dn, c->d_D, c->d_sigr, c->d_nuf, c->d_sigf, c->d_exsrc, c->d_sigs,
                     c->d_dc, c->d_chi, c->d_S, c->d_c0, c->d_ft, c->d_fst, c->d_omeg, c->d_sigrp, c->d_L, c->d_dfis,
-                    c->d_tbeta, c->d_velo, c->d_nd, c->d_abefgh, c->d_mail, c->d_arseq, c->d_mail_table, c->d_scal, c->d_part, c->d_ticket, c->d_argidx, c->d_errflag, c->d_stage};
+                    c->d_tbeta, c->d_velo, c->d_af, c->d_nd, c->d_abefgh, c->d_mail, c->d_arseq, c->d_mail_table, c->d_scal, c->d_part, c->d_ticket, c->d_argidx, c->d_errflag, c->d_stage};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (c->h_scal) cudaFreeHost(c->h_scal);
     if (c->h_flags) cudaFreeHost(c->h_flags);
@@ -570,6 +570,69 @@ extern "C" int adp_get_exsrc_arrays(adp_ctx *c, double *exsrc, double *dfis)
     if (exsrc) TRY(download_nodes(c, exsrc, c->d_exsrc, c->ng));
     if (dfis) TRY(download_nodes(c, dfis, c->d_dfis, 1));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return ADP_OK;
+}
+
+// ---- transient time-step glue on the device -----------------------------
+// These replace, optionally, host loops of mod_trans.f90 so that a time step does not move
+// flux-sized arrays over PCIe: only the new cross sections go up and a few scalars come back.
+extern "C" int adp_save_adjoint(adp_ctx *c)
+{   // `af = f0` after outer_ad (mod_trans.f90:65-66), kept on the device
+    if (!c) return ADP_ERR_USAGE;
+    ADP_REQUIRE(c, c->have_flux, "adp_save_adjoint: no flux");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    if (!c->d_af) TRY(dev_alloc(c, &c->d_af, (size_t)c->ng * c->NV));
+    for (int g = 0; g < c->ng; ++g)
+        CUDA_TRY(c, cudaMemcpyAsync(c->d_af + (size_t)g * c->NV, c->d_f0[c->cur[g]] + (size_t)g * c->NV, c->NV * sizeof(double),
+                                    cudaMemcpyDeviceToDevice, c->stream));
+    return ADP_OK;
+}
+extern "C" int adp_ipden(adp_ctx *c)
+{   // iPden (mod_trans.f90:561-597)
+    if (!c) return ADP_ERR_USAGE;
+    ADP_REQUIRE(c, c->kinetics_set && c->have_flux, "adp_ipden: needs adp_set_kinetics and a flux");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    return adp_k_ipden(c);
+}
+extern "C" int adp_upden(adp_ctx *c, double ht)
+{   // uPden (mod_trans.f90:601-644); fst is the fission source saved by adp_begin_time_step
+    if (!c) return ADP_ERR_USAGE;
+    ADP_REQUIRE(c, c->kinetics_set && c->have_flux, "adp_upden: needs adp_set_kinetics and a flux");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    return adp_k_upden(c, ht);
+}
+extern "C" int adp_begin_time_step(adp_ctx *c, double ht)
+{   // trans_calc (mod_trans.f90:398-416) after XS_updt: sigrp = sigr; sigr += 1/(sth v ht) + omeg/v; ft = f0; fst = fs0
+    if (!c) return ADP_ERR_USAGE;
+    ADP_REQUIRE(c, c->kinetics_set && c->have_flux, "adp_begin_time_step: needs adp_set_kinetics and a flux");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    return adp_k_begin_step(c, ht);
+}
+extern "C" int adp_powtot(adp_ctx *c, double *tpow)
+{   // PowTot (mod_trans.f90:523-557) of the current flux
+    if (!c || !tpow) return ADP_ERR_USAGE;
+    ADP_REQUIRE(c, c->have_flux, "adp_powtot: no flux");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    TRY(adp_k_powdis(c, c->d_stage));
+    CUDA_TRY(c, cudaMemcpyAsync(c->h_scal, c->d_scal, S_COUNT * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    *tpow = c->h_scal[S_POW];
+    return ADP_OK;
+}
+extern "C" int adp_reactivity(adp_ctx *c, int use_sigrp, double *rho)
+{   // reactivity(af, sigr | sigrp, rho) (mod_trans.f90:648-688): fills L (Lxyz) and returns rho;
+    // use_sigrp = 0: the removal term uses the current sigr (before the first step, :95), 1: sigrp
+    if (!c || !rho) return ADP_ERR_USAGE;
+    ADP_REQUIRE(c, c->d_af != nullptr, "adp_reactivity: call adp_save_adjoint after outer_ad first");
+    ADP_REQUIRE(c, c->have_flux && c->matrix_ready, "adp_reactivity: needs matrix and flux");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    TRY(ensure_transient(c));
+    TRY(adp_k_lxyz_total(c, c->d_L));
+    TRY(adp_k_reactivity(c, c->d_af, use_sigrp ? c->d_sigrp : c->d_sigr));
+    CUDA_TRY(c, cudaMemcpyAsync(c->h_scal, c->d_scal, S_COUNT * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    const double src = c->h_scal[S_TMP0], rem = c->h_scal[S_TMP1], lea = c->h_scal[S_E2SQ], fde = c->h_scal[S_FINT];
+    *rho = (src - lea - rem) / fde;
     return ADP_OK;
 }
 

@@ -590,6 +590,105 @@ __global__ void __launch_bounds__(ADP_TILE) k_get_exsrc(Geo G, ExsrcArgs A)
     }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// transient time-step glue (callers of outer_tr in mod_trans.f90), SURVEY section 8(f)-1
+// ------------------------------------------------------------------------------------------
+struct KinConst {
+    double lamb[ADP_NF], ibeta[ADP_NF];
+};
+
+// iPden (mod_trans.f90:561-597, bxtab == 0): c0(n,j) = iBeta(j)/lamb(j) * fs0(n)
+__global__ void __launch_bounds__(ADP_TILE) k_ipden(Geo G, KinConst K, const double *__restrict__ fs, double *__restrict__ c0)
+{
+    FOR_EACH_ROW(G, 0, G.nzl)
+    {
+        const long long idx = node_idx(G, kl, r);
+#pragma unroll
+        for (int j = 0; j < ADP_NF; ++j) {
+            const double blamb = K.ibeta[j] / K.lamb[j];
+            c0[(size_t)j * G.NV + idx] = blamb * fs[idx];
+        }
+    }
+}
+
+// uPden (mod_trans.f90:601-644, bxtab == 0)
+__global__ void __launch_bounds__(ADP_TILE) k_upden(Geo G, KinConst K, double ht, const double *__restrict__ fst,
+                                                     const double *__restrict__ fs, double *__restrict__ c0)
+{
+    FOR_EACH_ROW(G, 0, G.nzl)
+    {
+        const long long idx = node_idx(G, kl, r);
+#pragma unroll
+        for (int i = 0; i < ADP_NF; ++i) {
+            const double pxe = exp(-K.lamb[i] * ht);
+            double a1 = (1.0 - pxe) / (K.lamb[i] * ht);
+            const double a2 = 1.0 - a1;
+            a1 = a1 - pxe;
+            double *c = c0 + (size_t)i * G.NV + idx;
+            *c = *c * pxe + K.ibeta[i] / K.lamb[i] * (a1 * fst[idx] + a2 * fs[idx]);
+        }
+    }
+}
+
+// trans_calc (mod_trans.f90:398-416): sigrp = sigr ; sigr += 1/(sth v ht) + omeg/v ; ft = f0 ; fst = fs0
+struct StepArgs {
+    int ng;
+    double sth, ht;
+    const double *velo, *omeg;          // [G], [G][NV]
+    double *sigr, *sigrp, *ft;          // [G][NV]
+    const double *f0[ADP_MAXG];
+    const double *fs;
+    double *fst;
+};
+__global__ void __launch_bounds__(ADP_TILE) k_begin_step(Geo G, StepArgs A)
+{
+    const long long NV = G.NV;
+    FOR_EACH_ROW(G, 0, G.nzl)
+    {
+        const long long idx = node_idx(G, kl, r);
+        for (int g = 0; g < A.ng; ++g) {
+            const double sr = A.sigr[(size_t)g * NV + idx];
+            A.sigrp[(size_t)g * NV + idx] = sr;
+            A.sigr[(size_t)g * NV + idx] = sr + 1.0 / (A.sth * A.velo[g] * A.ht) + A.omeg[(size_t)g * NV + idx] / A.velo[g];
+            A.ft[(size_t)g * NV + idx] = A.f0[g][idx];
+        }
+        A.fst[idx] = A.fs[idx];
+    }
+}
+
+// reactivity (mod_trans.f90:648-688): the four adjoint-weighted integrals; L is already on the device
+struct ReacArgs {
+    int ng, nmat;
+    const double *af, *sigrp, *L;       // [G][NV]
+    const double *f0[ADP_MAXG];
+    const double *sigs, *chi, *fs;
+    const int *mat;
+};
+__global__ void __launch_bounds__(ADP_TILE) k_reactivity(Geo G, ReacArgs A, RedOut ro)
+{
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};   // src, rem, lea, fde
+    const long long NV = G.NV;
+    FOR_EACH_ROW(G, 0, G.nzl)
+    {
+        const long long idx = node_idx(G, kl, r);
+        const int m = A.mat[idx] - 1;
+        const double vdel = G.area[r] * G.hz[1 + G.k0 + kl];
+        const double fs = A.fs[idx];
+        for (int g = 0; g < A.ng; ++g) {
+            double scg = 0.0;
+            for (int h = 0; h < A.ng; ++h)
+                if (h != g) scg = scg + A.sigs[((size_t)g * A.ng + h) * NV + idx] * A.f0[h][idx];   // sigs(n,h,g)
+            const double af = A.af[(size_t)g * NV + idx], chi = A.chi[g * A.nmat + m];
+            acc[0] = acc[0] + af * (scg + chi * fs) * vdel;
+            acc[1] = acc[1] + af * A.sigrp[(size_t)g * NV + idx] * A.f0[g][idx] * vdel;
+            acc[2] = acc[2] + af * A.L[(size_t)g * NV + idx] * vdel;
+            acc[3] = acc[3] + af * chi * fs * vdel;
+        }
+    }
+    grid_reduce<4, 0>(acc, ro);
+}
+
 }  // namespace
 
 // =========================================================================================
@@ -961,4 +1060,58 @@ void adp_k_preload_cmfd(adp_ctx *c)
     adp_grid(c, k_fsrc_norms<0>, 1); adp_grid(c, k_fsrc_norms<1>, 1); adp_grid(c, k_fsrc_norms<2>, 1); adp_grid(c, k_fsrc_norms<4>, 1);
     adp_grid(c, k_extrap, 1); adp_grid(c, k_integrate, 1); adp_grid(c, k_fill, 1);
     adp_grid(c, k_scalar, 1); adp_grid(c, k_powdis, 1); adp_grid(c, k_scale, 1); adp_grid(c, k_get_exsrc, 1);
+    adp_grid(c, k_ipden, 1); adp_grid(c, k_upden, 1); adp_grid(c, k_begin_step, 1); adp_grid(c, k_reactivity, 1);
+}
+
+// ---- transient time-step glue -------------------------------------------------------------
+static KinConst kin_of(adp_ctx *c)
+{
+    KinConst K;
+    for (int i = 0; i < ADP_NF; ++i) { K.lamb[i] = c->lamb[i]; K.ibeta[i] = c->ibeta[i]; }
+    return K;
+}
+int adp_k_ipden(adp_ctx *c)
+{
+    k_ipden<<<adp_grid(c, k_ipden, c->geo.ntiles), ADP_TILE, 0, c->stream>>>(c->geo, kin_of(c), c->d_fs[c->fcur], c->d_c0);
+    LAUNCH_CHECK(c);
+    return ADP_OK;
+}
+int adp_k_upden(adp_ctx *c, double ht)
+{
+    k_upden<<<adp_grid(c, k_upden, c->geo.ntiles), ADP_TILE, 0, c->stream>>>(c->geo, kin_of(c), ht, c->d_fst, c->d_fs[c->fcur], c->d_c0);
+    LAUNCH_CHECK(c);
+    return ADP_OK;
+}
+int adp_k_begin_step(adp_ctx *c, double ht)
+{
+    StepArgs A{};
+    A.ng = c->ng; A.sth = c->sth; A.ht = ht; A.velo = c->d_velo; A.omeg = c->d_omeg;
+    A.sigr = c->d_sigr; A.sigrp = c->d_sigrp; A.ft = c->d_ft;
+    for (int g = 0; g < c->ng; ++g) A.f0[g] = f0ptr(c, c->cur[g], g);
+    A.fs = c->d_fs[c->fcur]; A.fst = c->d_fst;
+    k_begin_step<<<adp_grid(c, k_begin_step, c->geo.ntiles), ADP_TILE, 0, c->stream>>>(c->geo, A);
+    LAUNCH_CHECK(c);
+    // the nodal kernels read sigr on the neighbour's boundary plane (A..H, B matrix)
+    if (c->nranks > 1)
+        for (int g = 0; g < c->ng; ++g) {
+            int rc = adp_comm_halo(c, c->d_sigr + (size_t)g * c->NV, 2);
+            if (rc) return rc;
+        }
+    c->abefgh_valid = false;
+    return ADP_OK;
+}
+int adp_k_reactivity(adp_ctx *c, const double *d_af, const double *d_sigr_for_rem)
+{
+    ReacArgs A{};
+    A.ng = c->ng; A.nmat = c->nmat; A.af = d_af; A.sigrp = d_sigr_for_rem; A.L = c->d_L;
+    for (int g = 0; g < c->ng; ++g) A.f0[g] = f0ptr(c, c->cur[g], g);
+    A.sigs = c->d_sigs; A.chi = c->d_chi; A.fs = c->d_fs[c->fcur]; A.mat = c->d_mat;
+    k_reactivity<<<adp_grid(c, k_reactivity, c->geo.ntiles), ADP_TILE, 0, c->stream>>>(c->geo, A, make_red(c, S_TMP0, S_TMP1, S_E2SQ, S_FINT));
+    LAUNCH_CHECK(c);
+    if (c->nranks > 1) {
+        int rc = adp_comm_allreduce_sum(c, c->d_scal + S_TMP0, 2);
+        if (rc) return rc;
+        if ((rc = adp_comm_allreduce_sum(c, c->d_scal + S_E2SQ, 2))) return rc;
+    }
+    return ADP_OK;
 }

@@ -96,6 +96,66 @@ def _push_xs(solver, p, **override):
     solver.set_xs(**kw)
 
 
+def rod_eject_device_glue(p, solver, max_steps=None, log=None):
+    """The same transient with the time-step glue on the device (adp_save_adjoint, adp_ipden,
+    adp_begin_time_step, adp_upden, adp_powtot, adp_reactivity): per step only the new cross
+    sections go up and three scalars come back.  Same return value as rod_eject()."""
+    e, c = p.ejct, p.crod
+    ibeta, lamb, velo = e["ibeta"], e["lamb"], e["velo"]
+    bpos = c["bpos"].astype(np.float64).copy()
+    fbpos, tmove, bspeed = e["fbpos"], e["tmove"], e["bspeed"]
+    mdir = np.where(np.abs(fbpos - bpos) < 1e-5, 0, np.where(fbpos - bpos > 1e-5, 2, 1))
+    p.update_xs(bpos)
+    _push_xs(solver, p)
+    rc, n = solver.outer(0)
+    assert rc == 0, rc
+    ke = solver.state()["Ke"]
+    if abs(ke - 1.0) > 1e-5:                                  # KNE1
+        for it in range(10):
+            p.xnuf = p.xnuf / ke
+            c["dnuf"] = c["dnuf"] / ke
+            p.update_xs(bpos)
+            _push_xs(solver, p)
+            rc, n = solver.outer(0)
+            ke = solver.state()["Ke"]
+            if abs(ke - 1.0) < 1e-5:
+                break
+    solver.outer_ad(0)
+    solver.save_adjoint()
+    solver.outer(0)
+    tbeta = np.full(p.nmat, 0.0)
+    for jf in range(6):
+        tbeta = tbeta + ibeta[jf]
+    ctbeta = tbeta[0]
+    solver.set_kinetics(ibeta, lamb, velo, tbeta, p.sth, p.bth)
+    solver.ipden()
+    tpow1 = solver.powtot()
+    rho = solver.reactivity(0)
+    trace = [(0, 0.0, rho / ctbeta, 1.0, 0, False)]
+    steps = [(i, e["tstep1"], i * e["tstep1"]) for i in range(1, int(round(e["tdiv"] / e["tstep1"])) + 1)]
+    steps += [(i, e["tstep2"], e["tdiv"] + i * e["tstep2"]) for i in range(1, int(round((e["ttot"] - e["tdiv"]) / e["tstep2"])) + 1)]
+    for step, (_, ht, t2) in enumerate(steps, start=1):
+        if max_steps is not None and step > max_steps:
+            break
+        for b in range(c["nb"]):
+            if mdir[b] == 1 and t2 - tmove[b] > 1e-5 and fbpos[b] - bpos[b] < 1e-5:
+                bpos[b] = max(bpos[b] - ht * bspeed[b], fbpos[b])
+            elif mdir[b] == 2 and t2 - tmove[b] > 1e-5 and fbpos[b] - bpos[b] > 1e-5:
+                bpos[b] = min(bpos[b] + ht * bspeed[b], fbpos[b])
+        p.update_xs(bpos)
+        _push_xs(solver, p)                 # XS_updt result; the time terms are added on the device
+        solver.begin_time_step(ht)
+        rc, maxi, n = solver.outer_tr(ht)
+        assert rc == 0, rc
+        solver.upden(ht)
+        tpow2 = solver.powtot()
+        rho = solver.reactivity(1)
+        trace.append((step, t2, rho / ctbeta, tpow2 / tpow1, n, maxi))
+        if log:
+            log(f"{step:4d} {t2:10.3f} {rho / ctbeta:10.4f} {tpow2 / tpow1:15.4E}  outers {n}")
+    return trace
+
+
 def rod_eject(p, solver, max_steps=None, log=None):
     """rod_eject (mod_trans.f90:17-160) + trans_calc (:332-479), thc = 0.  Returns a list of
     (step, t, reactivity [$], relative power, outer iterations, maxi)."""

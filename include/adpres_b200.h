@@ -138,6 +138,21 @@ int adp_set_transient(adp_ctx *ctx, const double *c0, const double *ft, const do
 /* get_exsrc(ht, exsrc): fills exsrc and dfis on the device (mod_cmfd.f90:872-952, bxtab=0) */
 int adp_get_exsrc(adp_ctx *ctx, double ht);
 
+/* ---- optional: the time-step glue of mod_trans.f90 on the device ------------- */
+/* With these a time step uploads only the new cross sections and reads back scalars.
+ *   adp_save_adjoint      af = f0 after outer_ad                       mod_trans.f90:65-66
+ *   adp_ipden             iPden                                        mod_trans.f90:561-597
+ *   adp_begin_time_step   sigrp = sigr; sigr += 1/(sth v ht) + omeg/v; ft = f0; fst = fs0   :398-416
+ *   adp_upden             uPden(ht)                                    mod_trans.f90:601-644
+ *   adp_powtot            PowTot(f0, tpow)                             mod_trans.f90:523-557
+ *   adp_reactivity        reactivity(af, sigr|sigrp, rho), fills L     mod_trans.f90:648-688   */
+int adp_save_adjoint(adp_ctx *ctx);
+int adp_ipden(adp_ctx *ctx);
+int adp_begin_time_step(adp_ctx *ctx, double ht);
+int adp_upden(adp_ctx *ctx, double ht);
+int adp_powtot(adp_ctx *ctx, double *tpow);
+int adp_reactivity(adp_ctx *ctx, int use_sigrp, double *rho);
+
 /* ---- state exchange with the Fortran side ----------------------------------------------- */
 /* f0(nnod,ng), fs0(nnod), s0(nnod,ng); NULL = skip.  (drivers read them after outer*) */
 int adp_get_state(adp_ctx *ctx, double *f0, double *fs0, double *s0, double *Ke);

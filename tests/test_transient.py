@@ -85,3 +85,19 @@ def test_lmw_gpu_power_trace_deck_as_shipped(lmw_oracle_trace):
         assert a[1] == b[1]
         assert abs(a[3] / b[3] - 1) < 3e-3, (a, b)
         assert abs(a[2] - b[2]) < 2e-3, (a, b)
+
+
+@pytest.mark.gpu
+def test_lmw_device_side_time_step_glue():
+    """iPden, uPden, PowTot, reactivity (+Lxyz) and the sigr / ft / fst bookkeeping
+    of trans_calc run on the device; the trace must equal the host-glue run (converged steps)."""
+    from adpres_b200 import capi, transient
+    from oracle import Oracle
+    p1, p2 = _tight(load_problem("LMW")), _tight(load_problem("LMW"))
+    tr_o = transient.rod_eject(p1, Oracle(p1), max_steps=6)
+    tr_d = transient.rod_eject_device_glue(p2, capi.Solver(p2), max_steps=6)
+    assert len(tr_d) == len(tr_o) == 7
+    for a, b in zip(tr_d, tr_o):
+        assert a[1] == b[1]
+        assert abs(a[3] / b[3] - 1) < 1e-5, (a, b)
+        assert abs(a[2] - b[2]) < 1e-5, (a, b)
