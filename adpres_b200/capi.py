@@ -25,7 +25,7 @@ SYMBOLS = [
     "adp_create", "adp_destroy", "adp_last_error", "adp_version", "adp_comm_unique_id", "adp_comm_init", "adp_comm_init_env", "adp_slab",
     "adp_set_geometry", "adp_set_xs", "adp_set_control", "adp_matrix_setup", "adp_init_flux", "adp_outer_begin",
     "adp_outer_iter", "adp_nodal_upd", "adp_powdis", "adp_integrate", "adp_set_kinetics", "adp_set_transient",
-    "adp_get_exsrc", "adp_save_adjoint", "adp_ipden", "adp_begin_time_step", "adp_upden", "adp_powtot",
+    "adp_get_exsrc", "adp_set_material_xs", "adp_set_crod", "adp_xs_update", "adp_get_xs", "adp_save_adjoint", "adp_ipden", "adp_begin_time_step", "adp_upden", "adp_powtot",
     "adp_reactivity", "adp_get_state", "adp_set_state", "adp_set_s0", "adp_get_nod", "adp_set_nod_dn", "adp_lxyz_total", "adp_get_exsrc_arrays",
     "adp_get_ndmax", "adp_set_trace", "adp_outer", "adp_outer_ad", "adp_outer_fs", "adp_outer_th", "adp_outer_tr",
     "adp_sp_matvec", "adp_bicg", "adp_get_matrix", "adp_get_source", "adp_set_option", "adp_launch_count",
@@ -330,3 +330,29 @@ class Solver:
         r = C.c_double()
         self._chk(self.L.adp_reactivity(self.h, int(use_sigrp), C.byref(r)))
         return r.value
+
+    # ---- XS update on the device (%XSEC + %CROD decks)
+    def set_material_xs(self, p=None):
+        p = p or self.p
+        a = [np.asfortranarray(x, dtype=np.float64) for x in (p.xsigtr, p.xsiga, p.xnuf, p.xsigf, p.xsigs)]
+        self._chk(self.L.adp_set_material_xs(self.h, *[_d(x) for x in a]))
+
+    def set_crod(self, p=None):
+        p = p or self.p
+        c = p.crod
+        ia, ja, _ = p._node_assembly_maps()
+        fbmap = np.asfortranarray(c["bmap"][np.ix_(ia, ja)].astype(np.int32))          # (nxx, nyy) column-major
+        a = [np.asfortranarray(c[k], dtype=np.float64) for k in ("dsigtr", "dsiga", "dnuf", "dsigf", "dsigs")]
+        self._chk(self.L.adp_set_crod(self.h, int(c["nb"]), C.c_double(c["pos0"]), C.c_double(c["ssize"]),
+                                      fbmap.ctypes.data_as(_ip), *[_d(x) for x in a]))
+
+    def xs_update(self, bpos=None):
+        b = None if bpos is None else np.ascontiguousarray(bpos, dtype=np.float64)
+        self._chk(self.L.adp_xs_update(self.h, _d(b)))
+
+    def get_xs(self):
+        N, G = self.N, self.G
+        out = dict(D=np.zeros((N, G), order="F"), sigr=np.zeros((N, G), order="F"), nuf=np.zeros((N, G), order="F"),
+                   sigf=np.zeros((N, G), order="F"), sigs=np.zeros((N, G, G), order="F"))
+        self._chk(self.L.adp_get_xs(self.h, _d(out["D"]), _d(out["sigr"]), _d(out["nuf"]), _d(out["sigf"]), _d(out["sigs"])))
+        return out

@@ -147,6 +147,12 @@ struct adp_ctx {
     bool abefgh_valid = false;
     // transient
     double *d_af = nullptr;                // adjoint flux kept for reactivity() [G][NV]
+    // material tables and control-rod data for the device-side XS update (adp_xs_update)
+    double *d_xtab = nullptr, *d_dtab = nullptr;   // [xsigtr|xsiga|xnuf|xsigf (nmat,ng)] + xsigs (nmat,ng,ng); same for the rod increments
+    int *d_fb = nullptr;                   // [np] control-rod bank of each plane position (0: none)
+    double *d_bpos = nullptr, *d_dumtop = nullptr;
+    int nb = 0;
+    double coreh = 0.0, pos0 = 0.0, ssize = 0.0;
     double *d_c0 = nullptr, *d_ft = nullptr, *d_fst = nullptr, *d_omeg = nullptr, *d_sigrp = nullptr,
            *d_L = nullptr, *d_dfis = nullptr, *d_tbeta = nullptr, *d_velo = nullptr;
     double ibeta[ADP_NF] = {0}, lamb[ADP_NF] = {0};
@@ -256,6 +262,7 @@ int adp_k_outer_tail(adp_ctx *c, int mode, bool extrapolate);
 int adp_k_powdis(adp_ctx *c, double *d_pow);
 int adp_k_get_exsrc(adp_ctx *c, double ht);
 int adp_k_integrate(adp_ctx *c, const double *d_vec, int slot);
+int adp_k_xs_update(adp_ctx *c);
 int adp_k_ipden(adp_ctx *c);
 int adp_k_upden(adp_ctx *c, double ht);
 int adp_k_begin_step(adp_ctx *c, double ht);

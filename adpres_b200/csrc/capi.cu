@@ -88,7 +88,7 @@ extern "C" int adp_destroy(adp_ctx *c)
                     c->d_f0[0], c->d_f0[1], c->d_fs[0], c->d_fs[1], c->d_r, c->d_rs, c->d_p, c->d_v, c->d_v2, c->d_s, c->d_t,
                     c->d_s0, c->d_a, c->d_df, c->d_dn, c->d_D, c->d_sigr, c->d_nuf, c->d_sigf, c->d_exsrc, c->d_sigs,
                     c->d_dc, c->d_chi, c->d_S, c->d_c0, c->d_ft, c->d_fst, c->d_omeg, c->d_sigrp, c->d_L, c->d_dfis,
-                    c->d_tbeta, c->d_velo, c->d_af, c->d_nd, c->d_abefgh, c->d_mail, c->d_arseq, c->d_mail_table, c->d_scal, c->d_part, c->d_ticket, c->d_argidx, c->d_errflag, c->d_stage};
+                    c->d_tbeta, c->d_velo, c->d_af, c->d_xtab, c->d_dtab, c->d_fb, c->d_bpos, c->d_dumtop, c->d_nd, c->d_abefgh, c->d_mail, c->d_arseq, c->d_mail_table, c->d_scal, c->d_part, c->d_ticket, c->d_argidx, c->d_errflag, c->d_stage};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (c->h_scal) cudaFreeHost(c->h_scal);
     if (c->h_flags) cudaFreeHost(c->h_flags);
@@ -569,6 +569,83 @@ extern "C" int adp_get_exsrc_arrays(adp_ctx *c, double *exsrc, double *dfis)
     CUDA_TRY(c, cudaSetDevice(c->device));
     if (exsrc) TRY(download_nodes(c, exsrc, c->d_exsrc, c->ng));
     if (dfis) TRY(download_nodes(c, dfis, c->d_dfis, 1));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return ADP_OK;
+}
+
+// ---- XS update on the device: %XSEC material tables + %CROD -------------
+static int upload_tables(adp_ctx *c, double **dst, const double *a, const double *b, const double *d, const double *e,
+                         const double *s5)
+{
+    const size_t mg = (size_t)c->nmat * c->ng, tot = 4 * mg + mg * c->ng;
+    if (!*dst) TRY(dev_alloc(c, dst, tot));
+    const double *src[4] = {a, b, d, e};
+    for (int i = 0; i < 4; ++i)
+        CUDA_TRY(c, cudaMemcpyAsync(*dst + i * mg, src[i], mg * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(c, cudaMemcpyAsync(*dst + 4 * mg, s5, mg * c->ng * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return ADP_OK;
+}
+
+extern "C" int adp_set_material_xs(adp_ctx *c, const double *xsigtr, const double *xsiga, const double *xnuf,
+                                   const double *xsigf, const double *xsigs)
+{
+    if (!c || !xsigtr || !xsiga || !xnuf || !xsigf || !xsigs) return ADP_ERR_USAGE;
+    ADP_REQUIRE(c, c->geometry_set, "adp_set_material_xs: geometry not set");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    return upload_tables(c, &c->d_xtab, xsigtr, xsiga, xnuf, xsigf, xsigs);
+}
+
+extern "C" int adp_set_crod(adp_ctx *c, int nb, double pos0, double ssize, const int *fbmap, const double *dsigtr,
+                            const double *dsiga, const double *dnuf, const double *dsigf, const double *dsigs)
+{
+    if (!c || !fbmap || nb < 1) return ADP_ERR_USAGE;
+    ADP_REQUIRE(c, c->geometry_set, "adp_set_crod: geometry not set");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    TRY(upload_tables(c, &c->d_dtab, dsigtr, dsiga, dnuf, dsigf, dsigs));
+    c->nb = nb; c->pos0 = pos0; c->ssize = ssize;
+    // bank of every plane position, rod length above every plane, core height -- accumulated in the
+    // reference's order (mod_io.f90:1274-1277, mod_xsec.f90:252-277)
+    std::vector<int> fb(c->np);
+    for (int r = 0; r < c->np; ++r) fb[r] = fbmap[(size_t)(c->h_iy[r] - 1) * c->nxx + (c->h_ix[r] - 1)];
+    std::vector<double> hz(c->nzz + 2), dumtop(c->nzz);
+    CUDA_TRY(c, cudaMemcpy(hz.data(), c->d_hz, (c->nzz + 2) * sizeof(double), cudaMemcpyDeviceToHost));
+    double coreh = 0.0;
+    for (int k = 0; k < c->nzz; ++k) coreh = coreh + hz[1 + k];
+    c->coreh = coreh;
+    double dum = 0.0;
+    for (int k = c->nzz - 1; k >= 0; --k) { dumtop[k] = dum; dum = dum + hz[1 + k]; }
+    if (!c->d_fb) { TRY(dev_alloc(c, &c->d_fb, c->np)); TRY(dev_alloc(c, &c->d_dumtop, c->nzz)); }
+    if (c->d_bpos) { cudaFree(c->d_bpos); c->d_bpos = nullptr; }
+    TRY(dev_alloc(c, &c->d_bpos, nb));
+    CUDA_TRY(c, cudaMemcpy(c->d_fb, fb.data(), c->np * sizeof(int), cudaMemcpyHostToDevice));
+    CUDA_TRY(c, cudaMemcpy(c->d_dumtop, dumtop.data(), c->nzz * sizeof(double), cudaMemcpyHostToDevice));
+    return ADP_OK;
+}
+
+extern "C" int adp_xs_update(adp_ctx *c, const double *bpos)
+{
+    if (!c) return ADP_ERR_USAGE;
+    ADP_REQUIRE(c, c->d_xtab != nullptr, "adp_xs_update: call adp_set_material_xs first");
+    ADP_REQUIRE(c, c->xs_set, "adp_xs_update: chi / dc / exsrc come from adp_set_xs (call it once)");
+    ADP_REQUIRE(c, !c->d_fb || bpos, "adp_xs_update: bank positions missing");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    if (c->d_fb) CUDA_TRY(c, cudaMemcpyAsync(c->d_bpos, bpos, c->nb * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    TRY(adp_k_xs_update(c));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return ADP_OK;
+}
+
+extern "C" int adp_get_xs(adp_ctx *c, double *D, double *sigr, double *nuf, double *sigf, double *sigs)
+{
+    if (!c) return ADP_ERR_USAGE;
+    ADP_REQUIRE(c, c->xs_set, "adp_get_xs: cross sections not set");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    if (D) TRY(download_nodes(c, D, c->d_D, c->ng));
+    if (sigr) TRY(download_nodes(c, sigr, c->d_sigr, c->ng));
+    if (nuf) TRY(download_nodes(c, nuf, c->d_nuf, c->ng));
+    if (sigf) TRY(download_nodes(c, sigf, c->d_sigf, c->ng));
+    if (sigs) TRY(download_nodes(c, sigs, c->d_sigs, c->ng * c->ng));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     return ADP_OK;
 }

@@ -689,6 +689,68 @@ __global__ void __launch_bounds__(ADP_TILE) k_reactivity(Geo G, ReacArgs A, RedO
     grid_reduce<4, 0>(acc, ro);
 }
 
+
+// ------------------------------------------------------------------------------------------
+// XS_updt for %XSEC + %CROD decks on the device:
+// base_updt (mod_xsec.f90:172-195) + crod_updt (:230-296) + Dsigr_updt (:199-226)
+// ------------------------------------------------------------------------------------------
+struct XsArgs {
+    int ng, nmat, nb, has_rods;
+    const double *xsigtr, *xsiga, *xnuf, *xsigf, *xsigs;        // (nmat,ng[,ng]) column-major
+    const double *dsigtr, *dsiga, *dnuf, *dsigf, *dsigs;
+    const int *mat, *fb;                                         // fb[r]: bank of plane position r (0 none)
+    const double *bpos, *dumtop;                                 // [nb], [nzz]: rod length above plane k
+    double coreh, pos0, ssize;
+    double *D, *sigr, *nuf, *sigf, *sigs;                        // node-wise outputs
+};
+__global__ void __launch_bounds__(ADP_TILE) k_xs_update(Geo G, XsArgs A, int klo, int npl)
+{
+    const long long NV = G.NV;
+    FOR_EACH_ROW(G, klo, npl)
+    {
+        const long long idx = node_idx(G, kl, r);
+        const int kg = G.k0 + kl;
+        const int m = A.mat[idx] - 1;
+        // rod state of this node: w < 0 none, else the volume fraction (1 = fully rodded)
+        double w = -1.0;
+        const int b = A.has_rods ? A.fb[r] : 0;
+        if (b > 0) {
+            const double rodh = A.coreh - A.pos0 - A.bpos[b - 1] * A.ssize;   // rod tip below the core top
+            const double dum = A.dumtop[kg], hz = G.hz[1 + kg];
+            if (rodh < 0.0) w = 1.0;                                            // (reference quirk: never "partial")
+            else if (rodh > dum + hz) w = 1.0;
+            else if (rodh > dum || (rodh == dum && kg == G.nzz - 1)) w = (rodh - dum) / hz;
+            // rodh == dum below the top: the node above took it with vfrac = 1 and the sweep EXITed
+        }
+        for (int g = 0; g < A.ng; ++g) {
+            const int t = g * A.nmat + m;
+            double sigtr = A.xsigtr[t], siga = A.xsiga[t], nuf = A.xnuf[t], sigf = A.xsigf[t];
+            if (w >= 0.0) {
+                if (w == 1.0) { sigtr = sigtr + A.dsigtr[t]; siga = siga + A.dsiga[t]; nuf = nuf + A.dnuf[t]; sigf = sigf + A.dsigf[t]; }
+                else { sigtr = sigtr + w * A.dsigtr[t]; siga = siga + w * A.dsiga[t]; nuf = nuf + w * A.dnuf[t]; sigf = sigf + w * A.dsigf[t]; }
+            }
+            if (b > 0) {     // negative cross sections are suppressed in rodded columns (mod_xsec.f90:280-290)
+                if (siga < 0.0) siga = 0.0;
+                if (nuf < 0.0) nuf = 0.0;
+                if (sigf < 0.0) sigf = 0.0;
+            }
+            double dum = 0.0;
+            for (int h = 0; h < A.ng; ++h) {
+                const int t2 = m + A.nmat * (g + A.ng * h);                    // xsigs(mat, g, h): g -> h
+                double ss = A.xsigs[t2];
+                if (w >= 0.0) ss = (w == 1.0) ? ss + A.dsigs[t2] : ss + w * A.dsigs[t2];
+                if (b > 0 && ss < 0.0) ss = 0.0;
+                A.sigs[((size_t)h * A.ng + g) * NV + idx] = ss;
+                if (h != g) dum = dum + ss;
+            }
+            A.D[(size_t)g * NV + idx] = 1.0 / (3.0 * sigtr);
+            A.sigr[(size_t)g * NV + idx] = siga + dum;
+            A.nuf[(size_t)g * NV + idx] = nuf;
+            A.sigf[(size_t)g * NV + idx] = sigf;
+        }
+    }
+}
+
 }  // namespace
 
 // =========================================================================================
@@ -1060,7 +1122,7 @@ void adp_k_preload_cmfd(adp_ctx *c)
     adp_grid(c, k_fsrc_norms<0>, 1); adp_grid(c, k_fsrc_norms<1>, 1); adp_grid(c, k_fsrc_norms<2>, 1); adp_grid(c, k_fsrc_norms<4>, 1);
     adp_grid(c, k_extrap, 1); adp_grid(c, k_integrate, 1); adp_grid(c, k_fill, 1);
     adp_grid(c, k_scalar, 1); adp_grid(c, k_powdis, 1); adp_grid(c, k_scale, 1); adp_grid(c, k_get_exsrc, 1);
-    adp_grid(c, k_ipden, 1); adp_grid(c, k_upden, 1); adp_grid(c, k_begin_step, 1); adp_grid(c, k_reactivity, 1);
+    adp_grid(c, k_xs_update, 1); adp_grid(c, k_ipden, 1); adp_grid(c, k_upden, 1); adp_grid(c, k_begin_step, 1); adp_grid(c, k_reactivity, 1);
 }
 
 // ---- transient time-step glue -------------------------------------------------------------
@@ -1113,5 +1175,30 @@ int adp_k_reactivity(adp_ctx *c, const double *d_af, const double *d_sigr_for_re
         if (rc) return rc;
         if ((rc = adp_comm_allreduce_sum(c, c->d_scal + S_E2SQ, 2))) return rc;
     }
+    return ADP_OK;
+}
+
+// ---- XS update on the device ----------------------------------------------------------------
+int adp_k_xs_update(adp_ctx *c)
+{
+    XsArgs A{};
+    A.ng = c->ng; A.nmat = c->nmat; A.nb = c->nb; A.has_rods = c->d_fb != nullptr;
+    const size_t mg = (size_t)c->nmat * c->ng;
+    A.xsigtr = c->d_xtab; A.xsiga = c->d_xtab + mg; A.xnuf = c->d_xtab + 2 * mg; A.xsigf = c->d_xtab + 3 * mg;
+    A.xsigs = c->d_xtab + 4 * mg;
+    if (A.has_rods) {
+        A.dsigtr = c->d_dtab; A.dsiga = c->d_dtab + mg; A.dnuf = c->d_dtab + 2 * mg; A.dsigf = c->d_dtab + 3 * mg;
+        A.dsigs = c->d_dtab + 4 * mg;
+        A.fb = c->d_fb; A.bpos = c->d_bpos; A.dumtop = c->d_dumtop;
+        A.coreh = c->coreh; A.pos0 = c->pos0; A.ssize = c->ssize;
+    }
+    A.mat = c->d_mat;
+    A.D = c->d_D; A.sigr = c->d_sigr; A.nuf = c->d_nuf; A.sigf = c->d_sigf; A.sigs = c->d_sigs;
+    // own planes and the ghost planes that lie inside the core (static data: no communication)
+    const int klo = -((c->k0 >= ADP_GH) ? ADP_GH : c->k0);
+    const int khi = c->nzl + ((c->nzz - c->k1 >= ADP_GH) ? ADP_GH : (c->nzz - c->k1));
+    k_xs_update<<<adp_grid(c, k_xs_update, c->geo.tpp * (khi - klo)), ADP_TILE, 0, c->stream>>>(c->geo, A, klo, khi - klo);
+    LAUNCH_CHECK(c);
+    c->abefgh_valid = false;
     return ADP_OK;
 }

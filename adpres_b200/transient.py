@@ -96,17 +96,27 @@ def _push_xs(solver, p, **override):
     solver.set_xs(**kw)
 
 
-def rod_eject_device_glue(p, solver, max_steps=None, log=None):
+def rod_eject_device_glue(p, solver, max_steps=None, log=None, device_xs=False):
     """The same transient with the time-step glue on the device (adp_save_adjoint, adp_ipden,
     adp_begin_time_step, adp_upden, adp_powtot, adp_reactivity): per step only the new cross
-    sections go up and three scalars come back.  Same return value as rod_eject()."""
+    sections go up and three scalars come back.  With device_xs the cross-section update itself
+    (base_updt + crod_updt + Dsigr_updt) runs on the device too (adp_xs_update): per step only the
+    bank positions go up.  Same return value as rod_eject()."""
+    if device_xs:
+        def _push(solver_, p_, bpos_):
+            solver_.set_material_xs(p_)
+            solver_.set_crod(p_)
+            solver_.xs_update(bpos_)
+    else:
+        def _push(solver_, p_, bpos_):
+            p_.update_xs(bpos_)
+            _push_xs(solver_, p_)
     e, c = p.ejct, p.crod
     ibeta, lamb, velo = e["ibeta"], e["lamb"], e["velo"]
     bpos = c["bpos"].astype(np.float64).copy()
     fbpos, tmove, bspeed = e["fbpos"], e["tmove"], e["bspeed"]
     mdir = np.where(np.abs(fbpos - bpos) < 1e-5, 0, np.where(fbpos - bpos > 1e-5, 2, 1))
-    p.update_xs(bpos)
-    _push_xs(solver, p)
+    _push(solver, p, bpos)
     rc, n = solver.outer(0)
     assert rc == 0, rc
     ke = solver.state()["Ke"]
@@ -114,8 +124,7 @@ def rod_eject_device_glue(p, solver, max_steps=None, log=None):
         for it in range(10):
             p.xnuf = p.xnuf / ke
             c["dnuf"] = c["dnuf"] / ke
-            p.update_xs(bpos)
-            _push_xs(solver, p)
+            _push(solver, p, bpos)
             rc, n = solver.outer(0)
             ke = solver.state()["Ke"]
             if abs(ke - 1.0) < 1e-5:
@@ -142,8 +151,7 @@ def rod_eject_device_glue(p, solver, max_steps=None, log=None):
                 bpos[b] = max(bpos[b] - ht * bspeed[b], fbpos[b])
             elif mdir[b] == 2 and t2 - tmove[b] > 1e-5 and fbpos[b] - bpos[b] > 1e-5:
                 bpos[b] = min(bpos[b] + ht * bspeed[b], fbpos[b])
-        p.update_xs(bpos)
-        _push_xs(solver, p)                 # XS_updt result; the time terms are added on the device
+        _push(solver, p, bpos)              # XS_updt result; the time terms are added on the device
         solver.begin_time_step(ht)
         rc, maxi, n = solver.outer_tr(ht)
         assert rc == 0, rc

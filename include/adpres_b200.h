@@ -138,6 +138,18 @@ int adp_set_transient(adp_ctx *ctx, const double *c0, const double *ft, const do
 /* get_exsrc(ht, exsrc): fills exsrc and dfis on the device (mod_cmfd.f90:872-952, bxtab=0) */
 int adp_get_exsrc(adp_ctx *ctx, double ht);
 
+/* ---- optional: XS_updt on the device for %XSEC (+ %CROD) decks --------------- */
+/* material tables xsigtr..xsigf (nmat,ng), xsigs (nmat,ng,ng) [g -> h]           mod_io.f90:683-762 */
+int adp_set_material_xs(adp_ctx *ctx, const double *xsigtr, const double *xsiga, const double *xnuf,
+                        const double *xsigf, const double *xsigs);
+/* %CROD: node-wise bank map fbmap(nxx,nyy), rod increments per material          mod_io.f90:2148-2330 */
+int adp_set_crod(adp_ctx *ctx, int nb, double pos0, double ssize, const int *fbmap, const double *dsigtr,
+                 const double *dsiga, const double *dnuf, const double *dsigf, const double *dsigs);
+/* base_updt + crod_updt(bpos) + Dsigr_updt -> D, sigr, nuf, sigf, sigs on the device
+ * (mod_xsec.f90:172-296); chi, dc, exsrc stay as adp_set_xs left them */
+int adp_xs_update(adp_ctx *ctx, const double *bpos /* (nb) or NULL without rods */);
+int adp_get_xs(adp_ctx *ctx, double *D, double *sigr, double *nuf, double *sigf, double *sigs);
+
 /* ---- optional: the time-step glue of mod_trans.f90 on the device ------------- */
 /* With these a time step uploads only the new cross sections and reads back scalars.
  *   adp_save_adjoint      af = f0 after outer_ad                       mod_trans.f90:65-66

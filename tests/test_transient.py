@@ -101,3 +101,36 @@ def test_lmw_device_side_time_step_glue():
         assert a[1] == b[1]
         assert abs(a[3] / b[3] - 1) < 1e-5, (a, b)
         assert abs(a[2] - b[2]) < 1e-5, (a, b)
+
+
+@pytest.mark.gpu
+def test_device_xs_update_bit_exact_for_rod_positions():
+    """base_updt + crod_updt + Dsigr_updt on the device (adp_xs_update) against the
+    harness restatement of mod_xsec.f90:172-296, for rod tips inside nodes, on node boundaries
+    (the EXIT tie), fully inserted and fully withdrawn."""
+    from adpres_b200 import capi
+    p = load_problem("LMW")
+    s = capi.Solver(p)
+    s.set_material_xs(); s.set_crod()
+    for bpos in ([180.0, 100.0], [60.0, 180.0], [100.0, 100.0], [0.0, 37.3], [177.0, 2.5], [180.0, 180.0], [95.0, 105.0]):
+        b = np.array(bpos)
+        p.update_xs(b)
+        s.xs_update(b)
+        got = s.get_xs()
+        for k in ("D", "sigr", "nuf", "sigf", "sigs"):
+            assert np.array_equal(got[k], getattr(p, k)), (bpos, k)
+
+
+@pytest.mark.gpu
+def test_lmw_fully_device_resident_time_stepping():
+    """XS update + time-step glue + outer_tr all on the device: per step only the two bank
+    positions go up and (reactivity, power) come back."""
+    from adpres_b200 import capi, transient
+    from oracle import Oracle
+    p1, p2 = _tight(load_problem("LMW")), _tight(load_problem("LMW"))
+    tr_o = transient.rod_eject(p1, Oracle(p1), max_steps=6)
+    tr_d = transient.rod_eject_device_glue(p2, capi.Solver(p2), max_steps=6, device_xs=True)
+    for a, b in zip(tr_d, tr_o):
+        assert a[1] == b[1]
+        assert abs(a[3] / b[3] - 1) < 1e-5, (a, b)
+        assert abs(a[2] - b[2]) < 1e-5, (a, b)
