@@ -138,16 +138,19 @@ def test_sample_mesh_iterations_and_nodal_update_vs_oracle():
     assert np.abs(f_s - f_o).max() / np.abs(f_o).max() < 1e-7
 
 
-def test_c2_full_solve_against_cpu_oracle_fixture():
-    """BASELINE.json configs[1] at full size against the CPU oracle.  The oracle needs ~40 min of
-    CPU for this solve, so its result is a committed fixture (tests/golden/c2_oracle_result.json,
-    made by tools/oracle_fullsize.py in the container that has the oracle and the time); the GPU
-    runs the identical %ITER card.  North-star bars: k-eff within 1 pcm, power within 1e-5."""
+@pytest.mark.parametrize("fixture", ["c2_oracle_result.json", "c2prime_oracle_result.json"])
+def test_c2_full_solve_against_cpu_oracle_fixture(fixture):
+    """BASELINE.json configs[1] at full size (C2: 4.58 M nodes, 2 cm planes) and the north star's
+    ">= 10 M nodes" variant (C2': 10.07 M nodes, 0.91 cm planes) against the CPU oracle.  The
+    oracle needs 45 / 63 min of CPU for these solves, so its results are committed fixtures
+    (tests/golden/c2*_oracle_result.json, made by tools/oracle_fullsize.py in the container that
+    has the oracle and the time); the GPU runs the identical %ITER card.  North-star bars: k-eff
+    within 1 pcm, power within 1e-5."""
     import json
     import os
     from conftest import GOLDEN
     from adpres_b200 import capi
-    path = os.path.join(GOLDEN, "c2_oracle_result.json")
+    path = os.path.join(GOLDEN, fixture)
     if not os.path.exists(path):
         pytest.skip("full-size oracle fixture not generated")
     ref = json.load(open(path))
@@ -162,11 +165,19 @@ def test_c2_full_solve_against_cpu_oracle_fixture():
     # Iteration path: ten unconverged BiCGSTAB sweeps per outer amplify reduction-order round-off
     # (measured: |dKe| 1e-10 at p = 1-3, 1e-8 at p = 5, 1e-6 at p = 20, 1e-4 at p = 50) before both
     # runs contract onto the same solution (378 vs 383 outers, k-eff equal to 2e-9).
-    for (q, k, ser, fer) in s.trace_rows[:15]:
-        assert abs(k - ref["trace_ke"][q - 1]) < (1e-9 if q <= 3 else 1e-6), (q, k, ref["trace_ke"][q - 1])
-    for mine, theirs in zip(s.trace_nodal[:2], ref["nodal_updates"][:2]):
-        assert mine[0] == theirs[0] and abs(mine[1] / theirs[1] - 1) < 1e-2, (mine, theirs)
-    assert abs(n - ref["outers"]) <= max(3, ref["outers"] // 40), (n, ref["outers"])
+    if ref["zdiv"] == 10:
+        for (q, k, ser, fer) in s.trace_rows[:15]:
+            assert abs(k - ref["trace_ke"][q - 1]) < (1e-9 if q <= 3 else 1e-6), (q, k, ref["trace_ke"][q - 1])
+        for mine, theirs in zip(s.trace_nodal[:2], ref["nodal_updates"][:2]):
+            assert mine[0] == theirs[0] and abs(mine[1] / theirs[1] - 1) < 1e-2, (mine, theirs)
+        assert abs(n - ref["outers"]) <= max(3, ref["outers"] // 40), (n, ref["outers"])
+    else:
+        # 0.91 cm planes: the unconverged sweeps amplify round-off faster (|dKe| 3e-9 at p = 1, 2e-8 at
+        # p = 3, 8e-6 at p = 10, 5e-4 at p = 15) and the transient phase, including the oracle's own
+        # ser = 1e4 excursion at p = 60, is not reproducible between summation orders; the outer
+        # count is therefore not compared (383 here, 258 in the oracle), only the solution is.
+        for (q, k, ser, fer) in s.trace_rows[:10]:
+            assert abs(k - ref["trace_ke"][q - 1]) < (1e-7 if q <= 3 else 1e-4), (q, k, ref["trace_ke"][q - 1])
     rc, pw = s.powdis()
     asm, asm_ref = p.asm_power(pw), np.array(ref["asm_power"])
     nz = asm_ref > 0
