@@ -25,7 +25,7 @@ SYMBOLS = [
     "adp_create", "adp_destroy", "adp_last_error", "adp_version", "adp_comm_unique_id", "adp_comm_init", "adp_comm_init_env", "adp_slab",
     "adp_set_geometry", "adp_set_xs", "adp_set_control", "adp_matrix_setup", "adp_init_flux", "adp_outer_begin",
     "adp_outer_iter", "adp_nodal_upd", "adp_powdis", "adp_integrate", "adp_set_kinetics", "adp_set_transient",
-    "adp_get_exsrc", "adp_set_material_xs", "adp_set_crod", "adp_xs_update", "adp_get_xs", "adp_save_adjoint", "adp_ipden", "adp_begin_time_step", "adp_upden", "adp_powtot",
+    "adp_get_exsrc", "adp_set_material_xs", "adp_set_crod", "adp_xs_update", "adp_get_xs", "adp_save_adjoint", "adp_ipden", "adp_update_omeg", "adp_begin_time_step", "adp_upden", "adp_powtot", "adp_asm_pow", "adp_axi_pow", "adp_asm_flux",
     "adp_reactivity", "adp_get_state", "adp_set_state", "adp_set_s0", "adp_get_nod", "adp_set_nod_dn", "adp_lxyz_total", "adp_get_exsrc_arrays",
     "adp_get_ndmax", "adp_set_trace", "adp_outer", "adp_outer_ad", "adp_outer_fs", "adp_outer_th", "adp_outer_tr",
     "adp_sp_matvec", "adp_bicg", "adp_get_matrix", "adp_get_source", "adp_set_option", "adp_launch_count",
@@ -227,6 +227,31 @@ class Solver:
         rc = self._chk(self.L.adp_powdis(self.h, _d(pw), int(fixedsrc)))
         return rc, pw
 
+    # ---- result reductions (mod_io.f90 AsmPow / AxiPow / AsmFlux)
+    def asm_pow(self):
+        p = self.p
+        fasm = np.zeros((p.nx, p.ny), order="F")
+        im, jm = C.c_int(), C.c_int()
+        self._chk(self.L.adp_asm_pow(self.h, p.nx, p.ny, _i(np.ascontiguousarray(p.xdiv, dtype=np.int32)),
+                                     _i(np.ascontiguousarray(p.ydiv, dtype=np.int32)), _d(fasm), C.byref(im), C.byref(jm)))
+        return fasm, im.value, jm.value
+
+    def axi_pow(self):
+        p = self.p
+        faxi = np.zeros(p.nz)
+        am = C.c_int()
+        self._chk(self.L.adp_axi_pow(self.h, p.nz, _i(np.ascontiguousarray(p.zdiv, dtype=np.int32)), _d(faxi), C.byref(am)))
+        return faxi, am.value
+
+    def asm_flux(self, norm=None):
+        p = self.p
+        fasm = np.zeros((p.nx, p.ny, p.ng), order="F")
+        neg = C.c_int()
+        self._chk(self.L.adp_asm_flux(self.h, p.nx, p.ny, _i(np.ascontiguousarray(p.xdiv, dtype=np.int32)),
+                                      _i(np.ascontiguousarray(p.ydiv, dtype=np.int32)), int(norm is not None),
+                                      C.c_double(norm if norm is not None else 0.0), _d(fasm), C.byref(neg)))
+        return fasm, neg.value
+
     def integrate(self, s):
         r = C.c_double()
         self._chk(self.L.adp_integrate(self.h, _d(np.ascontiguousarray(s, dtype=np.float64)), C.byref(r)))
@@ -314,6 +339,9 @@ class Solver:
 
     def ipden(self):
         self._chk(self.L.adp_ipden(self.h))
+
+    def update_omeg(self, ht, bextr):
+        self._chk(self.L.adp_update_omeg(self.h, C.c_double(ht), int(bextr)))
 
     def begin_time_step(self, ht):
         self._chk(self.L.adp_begin_time_step(self.h, C.c_double(ht)))

@@ -117,6 +117,8 @@ struct adp_ctx {
     int bc[6] = {0, 0, 0, 0, 0, 0};
     // host copies of small geometry
     std::vector<int> h_ix, h_iy, h_iz;
+    std::vector<int> h_nodp;               // (nxx,nyy) -> 1-based plane position, 0 outside the core outline
+    std::vector<double> h_xdel, h_ydel, h_zdel;
     // control
     int nout = 500, nin = 2, nac = 5, nupd = 1000000, kern = ADP_KERN_SANM;
     double serc = 1e-5, ferc = 1e-5;
@@ -158,6 +160,9 @@ struct adp_ctx {
     double ibeta[ADP_NF] = {0}, lamb[ADP_NF] = {0};
     double sth = 1.0, bth = 0.0;
     bool kinetics_set = false;
+    // result reductions (results.cu): column / plane sums
+    double *d_res = nullptr, *h_res = nullptr;
+    size_t res_elems = 0;
     // reductions
     double *d_scal = nullptr;              // [S_COUNT]
     double *d_part = nullptr;              // [4][ADP_MAXPART]
@@ -260,12 +265,14 @@ int adp_k_bicg_raw(adp_ctx *c, int g, int imax, const double *d_b, double *d_x);
 int adp_k_spmv(adp_ctx *c, int g, const double *d_x, double *d_v);
 int adp_k_outer_tail(adp_ctx *c, int mode, bool extrapolate);
 int adp_k_powdis(adp_ctx *c, double *d_pow);
+int adp_k_scale_by_slot(adp_ctx *c, double *d_vec, int slot);
 int adp_k_get_exsrc(adp_ctx *c, double ht);
 int adp_k_integrate(adp_ctx *c, const double *d_vec, int slot);
 int adp_k_xs_update(adp_ctx *c);
 int adp_k_ipden(adp_ctx *c);
 int adp_k_upden(adp_ctx *c, double ht);
 int adp_k_begin_step(adp_ctx *c, double ht);
+int adp_k_omeg(adp_ctx *c, double ht, int bextr);
 int adp_k_reactivity(adp_ctx *c, const double *d_af, const double *d_sigr_for_rem);
 // nodal_kernels.cu
 int adp_k_nodal_source(adp_ctx *c, int cmode);
@@ -277,6 +284,7 @@ int adp_comm_allreduce_sum(adp_ctx *c, double *d_scal, int count);
 int adp_comm_allreduce_max(adp_ctx *c, double *d_scal, int count);
 int adp_comm_allreduce_min_ll(adp_ctx *c, long long *d_val, int count);
 int adp_comm_allreduce_max_nccl(adp_ctx *c, double *d_scal, int count);
+int adp_comm_allreduce_sum_nccl(adp_ctx *c, double *d_vec, int count);   // any length (not a grid_reduce result)
 void adp_comm_destroy(adp_ctx *c);
 int adp_comm_map_peers(adp_ctx *c);                                     // after the vectors are allocated
 void adp_comm_unmap_peers(adp_ctx *c);

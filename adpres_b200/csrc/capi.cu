@@ -6,7 +6,6 @@
 
 #include "adp_internal.cuh"
 
-int adp_k_scale_by_slot(adp_ctx *c, double *d_vec, int slot);
 void adp_k_preload_cmfd(adp_ctx *c);
 void adp_k_preload_nodal(adp_ctx *c);
 
@@ -93,6 +92,8 @@ extern "C" int adp_destroy(adp_ctx *c)
     if (c->h_scal) cudaFreeHost(c->h_scal);
     if (c->h_flags) cudaFreeHost(c->h_flags);
     if (c->h_stage) cudaFreeHost(c->h_stage);
+    if (c->h_res) cudaFreeHost(c->h_res);
+    if (c->d_res) cudaFree(c->d_res);
     cudaStreamDestroy(c->stream);
     delete c;
     return ADP_OK;
@@ -186,6 +187,8 @@ extern "C" int adp_set_geometry(adp_ctx *c, int nxx, int nyy, int nzz, int nnod,
     std::vector<unsigned char> flag(np);
     std::vector<double> hx(np), hy(np), area(np), hz(nzz + 2, 0.0);
     for (int r = 0; r < np; ++r) nodp[(size_t)(iy[r] - 1) * nxx + (ix[r] - 1)] = r + 1;
+    c->h_nodp = nodp;
+    c->h_xdel.assign(xdel, xdel + nxx); c->h_ydel.assign(ydel, ydel + nyy); c->h_zdel.assign(zdel, zdel + nzz);
     for (int r = 0; r < np; ++r) {
         const int i = ix[r], j = iy[r];
         unsigned f = 0;
@@ -684,6 +687,16 @@ extern "C" int adp_begin_time_step(adp_ctx *c, double ht)
     ADP_REQUIRE(c, c->kinetics_set && c->have_flux, "adp_begin_time_step: needs adp_set_kinetics and a flux");
     CUDA_TRY(c, cudaSetDevice(c->device));
     return adp_k_begin_step(c, ht);
+}
+extern "C" int adp_update_omeg(adp_ctx *c, double ht, int bextr)
+{   // rod_eject (mod_trans.f90:128-134,150-154): omeg = LOG(f0 / ft) / ht (%EXTR) or 0; ft is the flux
+    // saved by the previous adp_begin_time_step, so call it before the next one
+    if (!c) return ADP_ERR_USAGE;
+    ADP_REQUIRE(c, c->have_flux, "adp_update_omeg: no flux");
+    ADP_REQUIRE(c, ht > 0.0, "adp_update_omeg: time step must be positive");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    TRY(ensure_transient(c));
+    return adp_k_omeg(c, ht, bextr);
 }
 extern "C" int adp_powtot(adp_ctx *c, double *tpow)
 {   // PowTot (mod_trans.f90:523-557) of the current flux

@@ -636,6 +636,7 @@ struct StepArgs {
     int ng;
     double sth, ht;
     const double *velo, *omeg;          // [G], [G][NV]
+    double *omeg_out;                   // k_omeg only
     double *sigr, *sigrp, *ft;          // [G][NV]
     const double *f0[ADP_MAXG];
     const double *fs;
@@ -654,6 +655,18 @@ __global__ void __launch_bounds__(ADP_TILE) k_begin_step(Geo G, StepArgs A)
             A.ft[(size_t)g * NV + idx] = A.f0[g][idx];
         }
         A.fst[idx] = A.fs[idx];
+    }
+}
+
+// rod_eject (mod_trans.f90:128-134,150-154): omeg = LOG(f0 / ft) / tstep with %EXTR, else 0
+__global__ void __launch_bounds__(ADP_TILE) k_omeg(Geo G, StepArgs A, int bextr)
+{
+    const long long NV = G.NV;
+    FOR_EACH_ROW(G, 0, G.nzl)
+    {
+        const long long idx = node_idx(G, kl, r);
+        for (int g = 0; g < A.ng; ++g)
+            A.omeg_out[(size_t)g * NV + idx] = bextr ? log(A.f0[g][idx] / A.ft[(size_t)g * NV + idx]) / A.ht : 0.0;
     }
 }
 
@@ -1160,6 +1173,15 @@ int adp_k_begin_step(adp_ctx *c, double ht)
             if (rc) return rc;
         }
     c->abefgh_valid = false;
+    return ADP_OK;
+}
+int adp_k_omeg(adp_ctx *c, double ht, int bextr)
+{
+    StepArgs A{};
+    A.ng = c->ng; A.ht = ht; A.ft = c->d_ft; A.omeg_out = c->d_omeg;
+    for (int g = 0; g < c->ng; ++g) A.f0[g] = f0ptr(c, c->cur[g], g);
+    k_omeg<<<adp_grid(c, k_omeg, c->geo.ntiles), ADP_TILE, 0, c->stream>>>(c->geo, A, bextr);
+    LAUNCH_CHECK(c);
     return ADP_OK;
 }
 int adp_k_reactivity(adp_ctx *c, const double *d_af, const double *d_sigr_for_rem)

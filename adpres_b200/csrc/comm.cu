@@ -351,6 +351,12 @@ int adp_comm_allreduce_max_nccl(adp_ctx *c, double *d, int count)
     NCCL_TRY(c, g_nccl.AllReduce(d, d, count, ncclFloat64, ncclMax, c->comm->comm, c->stream));
     return ADP_OK;
 }
+int adp_comm_allreduce_sum_nccl(adp_ctx *c, double *d, int count)
+{
+    if (c->nranks == 1) return ADP_OK;
+    NCCL_TRY(c, g_nccl.AllReduce(d, d, count, ncclFloat64, ncclSum, c->comm->comm, c->stream));
+    return ADP_OK;
+}
 int adp_comm_allreduce_min_ll(adp_ctx *c, long long *d, int count)
 {
     if (c->nranks == 1) return ADP_OK;

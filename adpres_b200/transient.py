@@ -152,6 +152,7 @@ def rod_eject_device_glue(p, solver, max_steps=None, log=None, device_xs=False):
             elif mdir[b] == 2 and t2 - tmove[b] > 1e-5 and fbpos[b] - bpos[b] > 1e-5:
                 bpos[b] = min(bpos[b] + ht * bspeed[b], fbpos[b])
         _push(solver, p, bpos)              # XS_updt result; the time terms are added on the device
+        solver.update_omeg(ht, p.bextr and step > 1)          # mod_trans.f90:127-135,150-154
         solver.begin_time_step(ht)
         rc, maxi, n = solver.outer_tr(ht)
         assert rc == 0, rc
@@ -212,10 +213,15 @@ def rod_eject(p, solver, max_steps=None, log=None):
 
     steps = [(i, e["tstep1"], i * e["tstep1"]) for i in range(1, int(round(e["tdiv"] / e["tstep1"])) + 1)]
     steps += [(i, e["tstep2"], e["tdiv"] + i * e["tstep2"]) for i in range(1, int(round((e["ttot"] - e["tdiv"]) / e["tstep2"])) + 1)]
-    omeg = np.zeros((p.nnod, p.ng), order="F")                             # bextr == 0
+    ft = f0
     for step, (_, ht, t2) in enumerate(steps, start=1):
         if max_steps is not None and step > max_steps:
             break
+        # exponential transformation (%EXTR, mod_trans.f90:127-135,150-154): not in the very first step
+        if p.bextr and step > 1:
+            omeg = np.asfortranarray(np.log(f0 / ft) / ht)
+        else:
+            omeg = np.zeros((p.nnod, p.ng), order="F")
         # rod bank changes (mod_trans.f90:374-388)
         for b in range(c["nb"]):
             if mdir[b] == 1 and t2 - tmove[b] > 1e-5 and fbpos[b] - bpos[b] < 1e-5:

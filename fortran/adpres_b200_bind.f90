@@ -103,6 +103,34 @@ module adpres_b200
     integer(c_int) function adp_get_ndmax(ctx, ndmax) bind(C, name="adp_get_ndmax")
       import; type(c_ptr), value :: ctx; real(c_double), intent(out) :: ndmax
     end function
+    ! ---- optional: time-step glue of mod_trans.f90 and XS_updt on the device (INTEGRATION.md) ----
+    integer(c_int) function adp_lxyz_total(ctx, L) bind(C, name="adp_lxyz_total")
+      import; type(c_ptr), value :: ctx; real(c_double), intent(out) :: L(*)
+    end function
+    integer(c_int) function adp_save_adjoint(ctx) bind(C, name="adp_save_adjoint")
+      import; type(c_ptr), value :: ctx
+    end function
+    integer(c_int) function adp_ipden(ctx) bind(C, name="adp_ipden")
+      import; type(c_ptr), value :: ctx
+    end function
+    integer(c_int) function adp_update_omeg(ctx, ht, bextr) bind(C, name="adp_update_omeg")
+      import; type(c_ptr), value :: ctx; real(c_double), value :: ht; integer(c_int), value :: bextr
+    end function
+    integer(c_int) function adp_begin_time_step(ctx, ht) bind(C, name="adp_begin_time_step")
+      import; type(c_ptr), value :: ctx; real(c_double), value :: ht
+    end function
+    integer(c_int) function adp_upden(ctx, ht) bind(C, name="adp_upden")
+      import; type(c_ptr), value :: ctx; real(c_double), value :: ht
+    end function
+    integer(c_int) function adp_powtot(ctx, tpow) bind(C, name="adp_powtot")
+      import; type(c_ptr), value :: ctx; real(c_double), intent(out) :: tpow
+    end function
+    integer(c_int) function adp_reactivity(ctx, use_sigrp, rho) bind(C, name="adp_reactivity")
+      import; type(c_ptr), value :: ctx; integer(c_int), value :: use_sigrp; real(c_double), intent(out) :: rho
+    end function
+    integer(c_int) function adp_xs_update(ctx, bpos) bind(C, name="adp_xs_update")
+      import; type(c_ptr), value :: ctx; real(c_double), intent(in) :: bpos(*)
+    end function
   end interface
 
 contains

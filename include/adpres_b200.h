@@ -154,16 +154,31 @@ int adp_get_xs(adp_ctx *ctx, double *D, double *sigr, double *nuf, double *sigf,
 /* With these a time step uploads only the new cross sections and reads back scalars.
  *   adp_save_adjoint      af = f0 after outer_ad                       mod_trans.f90:65-66
  *   adp_ipden             iPden                                        mod_trans.f90:561-597
+ *   adp_update_omeg       omeg = bextr ? LOG(f0/ft)/ht : 0 (%EXTR)        mod_trans.f90:128-134,150-154
  *   adp_begin_time_step   sigrp = sigr; sigr += 1/(sth v ht) + omeg/v; ft = f0; fst = fs0   :398-416
  *   adp_upden             uPden(ht)                                    mod_trans.f90:601-644
  *   adp_powtot            PowTot(f0, tpow)                             mod_trans.f90:523-557
  *   adp_reactivity        reactivity(af, sigr|sigrp, rho), fills L     mod_trans.f90:648-688   */
 int adp_save_adjoint(adp_ctx *ctx);
 int adp_ipden(adp_ctx *ctx);
+int adp_update_omeg(adp_ctx *ctx, double ht, int bextr);
 int adp_begin_time_step(adp_ctx *ctx, double ht);
 int adp_upden(adp_ctx *ctx, double ht);
 int adp_powtot(adp_ctx *ctx, double *tpow);
 int adp_reactivity(adp_ctx *ctx, int use_sigrp, double *rho);
+
+/* ---- optional: result reductions on the device ------------------------------- */
+/* The reference prints assembly / axial averages of PowDis and of the flux through dense
+ * fx(nxx,nyy,nzz[,ng]) boxes on the host.  Here the O(nnod) stage (column sums over z, plane
+ * sums) runs on the device and only np or nzz values come back; the assembly loops and the
+ * normalisation follow in the reference's order.  Outputs are Fortran column-major.
+ *   adp_asm_pow   CALL PowDis(pow); CALL AsmPow(pow): fasm(nx,ny), location of the maximum   mod_io.f90:3267-3405
+ *   adp_axi_pow   CALL PowDis(pow); CALL AxiPow(pow): faxi(nz), plane of the maximum         mod_io.f90:3409-3494
+ *   adp_asm_flux  CALL AsmFlux(f0 [, norm]): fasm(nx,ny,ng), negf = 1 if a value is negative  mod_io.f90:3498-3644 */
+int adp_asm_pow(adp_ctx *ctx, int nx, int ny, const int *xdiv, const int *ydiv, double *fasm, int *xmax, int *ymax);
+int adp_axi_pow(adp_ctx *ctx, int nz, const int *zdiv, double *faxi, int *amax);
+int adp_asm_flux(adp_ctx *ctx, int nx, int ny, const int *xdiv, const int *ydiv, int use_norm, double norm,
+                 double *fasm, int *negf);
 
 /* ---- state exchange with the Fortran side ----------------------------------------------- */
 /* f0(nnod,ng), fs0(nnod), s0(nnod,ng); NULL = skip.  (drivers read them after outer*) */

@@ -134,3 +134,24 @@ def test_lmw_fully_device_resident_time_stepping():
         assert a[1] == b[1]
         assert abs(a[3] / b[3] - 1) < 1e-5, (a, b)
         assert abs(a[2] - b[2]) < 1e-5, (a, b)
+
+
+@pytest.mark.gpu
+def test_lmw_exponential_transformation_on_device():
+    """%EXTR (mod_trans.f90:127-135,150-154): omeg = LOG(f0 / ft) / tstep from the second step on,
+    formed on the device by adp_update_omeg and consumed by adp_begin_time_step (sigr += omeg / v)
+    and get_exsrc (exp(omeg ht) ft).  The oracle run forms omeg in numpy and uploads it."""
+    from adpres_b200 import capi, transient
+    from oracle import Oracle
+    p1, p2, p3 = (_tight(load_problem("LMW")) for _ in range(3))
+    p1.bextr = p2.bextr = 1
+    tr_o = transient.rod_eject(p1, Oracle(p1), max_steps=6)
+    tr_d = transient.rod_eject_device_glue(p2, capi.Solver(p2), max_steps=6, device_xs=True)
+    tr_0 = transient.rod_eject(p3, Oracle(p3), max_steps=6)
+    for a, b in zip(tr_d, tr_o):
+        assert a[1] == b[1]
+        assert abs(a[3] / b[3] - 1) < 1e-5, (a, b)
+        assert abs(a[2] - b[2]) < 1e-5, (a, b)
+    # the transformation is active: the converged iterates are the same solution of the time-discrete
+    # equations only to discretisation order, so the traces with and without %EXTR differ measurably
+    assert max(abs(a[3] - b[3]) for a, b in zip(tr_o, tr_0)) > 1e-7
