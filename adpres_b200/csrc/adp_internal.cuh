@@ -197,6 +197,7 @@ struct adp_ctx {
     std::map<unsigned long long, long long> graph_launches;   // kernels inside each graph
     bool use_graphs = true;
     int bench_warmup = 3;
+    int nodal_coop = -1;                   // surfaces kernel with 16 lanes per surface: -1 = for G >= 7, 0 never, 1 always
     bool fuse_st = true;                   // C kernel: s on the fly inside t = A s (false: k_s then k_t)
     // bookkeeping
     long long launches = 0;

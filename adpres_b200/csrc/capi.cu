@@ -933,6 +933,7 @@ extern "C" int adp_set_option(adp_ctx *c, const char *name, int value)
     if (!strcmp(name, "peer_allreduce")) { if (!value) c->peer_ar = false; return ADP_OK; }
     if (!strcmp(name, "balance_rounds")) { c->balance_rounds = value != 0; free_graphs(c); return ADP_OK; }
     if (!strcmp(name, "bench_warmup")) { c->bench_warmup = value; return ADP_OK; }
+    if (!strcmp(name, "nodal_coop")) { c->nodal_coop = value; free_graphs(c); return ADP_OK; }
     if (!strcmp(name, "fuse_st")) { c->fuse_st = value != 0; free_graphs(c); return ADP_OK; }
     if (!strcmp(name, "grid_blocks")) {
         ADP_REQUIRE(c, value >= 1 && value <= ADP_MAXPART, "grid_blocks out of range");

@@ -38,6 +38,8 @@ struct NodalArgs {
     int ng, nmat, cmode, kern;
     long long nnod_total;
     const double *f0[ADP_MAXG];          // current flux per group
+    const double *f0a, *f0b;             // the two flux buffers [G][NV]; bit g of curmask: group g lives in f0b
+    unsigned curmask;                    // (a pointer array indexed by a runtime g would be copied to a stack frame)
     const double *D, *sigr, *nuf, *exsrc; // [G][NV]
     const double *sigs;                  // [h][g][NV] = sigs(n,g,h)
     const double *chi;                   // [g][nmat]
@@ -661,6 +663,281 @@ __global__ void __launch_bounds__(ADP_TILE, (NG <= 2) ? 2 : 1) k_nodal_surfaces(
     grid_argmax(best, best_loc, am);
 }
 
+
+// ---------------------------------------------------------------------------------------
+// Cooperative surfaces kernel for many groups.  One thread per surface keeps two node-direction
+// records and a 2G x 2G system in registers; at G = 8 that is 3.2 KB of local memory per thread
+// (ptxas: 17 KB spill stores, 29 KB spill loads) and the three launches took 88 ms on the C2 mesh
+// (45 ms here, at 2 CTAs per SM; the kernel is bound by the latency of the dependent shuffle /
+// division chain, so occupancy matters: 1 CTA per SM 63 ms, 3 CTAs per SM with spills 63 ms).  A group
+// of 16 lanes owns one surface: lane l < 2G holds ROW l of the system (G rows of current
+// continuity, G rows of flux continuity), the Doolittle elimination broadcasts the pivot row
+// with shuffles, and forward / back substitution pass y(k), x(k) from lane to lane.  Every matrix
+// element sees exactly the operations of LU_solve (mod_nodal.f90:829-897) in the same order, so
+// the result is bit-identical to the one-thread-per-surface kernel.
+// ---------------------------------------------------------------------------------------
+#define COOP_W 16
+#define COOP_FULL 0xffffffffu
+// Both 16-lane groups of a warp always run the same code (a group without work computes on a
+// valid dummy item and discards the result), so every shuffle uses the constant full mask; a
+// per-group mask costs a MATCH/VOTE validity check per shuffle.
+__device__ __forceinline__ double shfl16(double v, int src)
+{
+    return __shfl_sync(COOP_FULL, v, src, COOP_W);
+}
+
+// compile-time loop: the body receives std::integral_constant<int, I>, so every array index is a
+// constant and the rows stay in registers ("#pragma unroll" alone left the 120-body elimination
+// nest of the 16 x 16 system partially rolled, with the row in local memory)
+template <int I, int N, typename F>
+__device__ __forceinline__ void static_for(F &&f)
+{
+    if constexpr (I < N) {
+        f(std::integral_constant<int, I>{});
+        static_for<I + 1, N>(f);
+    }
+}
+
+// rows 0..M-1 of U in lanes 0..M-1 of the 16-lane group (lanes >= M carry dummy rows and only
+// take part in the shuffles); b, x: one element per lane.  Returns false on the 1e-4 diagonal abort.
+template <int M>
+__device__ __forceinline__ bool coop_lu_solve(int sl, double (&row)[M], double b, double &x)
+{
+    // NOTE: never write "if (sl == i) ... row[i]": the compiler turns that chain into row[sl] and
+    // moves the row to local memory.  A lane gets its own diagonal from the broadcast instead.
+    double diag = 1.0;
+    static_for<0, M>([&](auto ic) {
+        constexpr int i = decltype(ic)::value;
+        const double d = shfl16(row[i], i);
+        if (sl == i) diag = d;
+    });
+    const bool ok = !(fabs(diag) < (double)10e-5f);          // original diagonal (mod_nodal.f90:856)
+    // decomposition: U(j,k) = U(j,k) - piv U(i,k), piv = U(j,i) / U(i,i) kept in U(j,i)
+    static_for<0, M>([&](auto ic) {
+        constexpr int i = decltype(ic)::value;
+        const double uii = shfl16(row[i], i);
+        if (sl == i) diag = uii;                             // U(i,i) is final from step i on
+        const double piv = row[i] / uii;
+        static_for<i + 1, M>([&](auto kc) {
+            constexpr int k = decltype(kc)::value;
+            const double uik = shfl16(row[k], i);
+            if (sl > i) row[k] = row[k] - piv * uik;
+        });
+        if (sl > i) row[i] = piv;
+    });
+    // forward substitution: y(i) = b(i) - sum_{k<i} L(i,k) y(k), k ascending
+    double isum = 0.0, y = b;
+    static_for<0, M>([&](auto kc) {
+        constexpr int k = decltype(kc)::value;
+        if (sl == k && k > 0) y = b - isum;
+        const double yk = shfl16(y, k);
+        if (sl > k) isum = isum + row[k] * yk;
+    });
+    // back substitution: x(i) = (y(i) - sum_{k>i} U(i,k) x(k)) / U(i,i), k ascending: lane i adds
+    // up only once all x(k > i) have arrived
+    double xs[M];
+    x = 0.0;
+    static_for<0, M>([&](auto tc) {
+        constexpr int i = M - 1 - decltype(tc)::value;
+        double bs = 0.0;
+        static_for<i + 1, M>([&](auto kc) {
+            constexpr int k = decltype(kc)::value;
+            bs = bs + row[k] * xs[k];
+        });
+        if (sl == i) x = (i == M - 1) ? y / diag : (y - bs) / diag;
+        xs[i] = shfl16(x, i);
+    });
+    return ok;
+}
+
+// what one lane keeps of a node-direction record: row g of Bc and the group-g scalars
+template <int NG>
+struct NodeDirRow {
+    double Bc[NG];
+    double A, F, Gc, H, a2, a4, L1, f0, D;
+};
+template <int NG>
+__device__ __forceinline__ void nd_load_row(NodeDirRow<NG> &nd, int g, const double *__restrict__ base, long long NV,
+                                            long long idx, const NodalArgs &A)
+{
+#pragma unroll
+    for (int h = 0; h < NG; ++h) nd.Bc[h] = base[(size_t)(g * NG + h) * NV + idx];
+    const double *sc = base + (size_t)(NG * NG + g) * NV + idx;
+    nd.A = sc[0];
+    nd.F = sc[(size_t)1 * NG * NV];
+    nd.Gc = sc[(size_t)2 * NG * NV];
+    nd.H = sc[(size_t)3 * NG * NV];
+    nd.a2 = sc[(size_t)4 * NG * NV];
+    nd.a4 = sc[(size_t)5 * NG * NV];
+    nd.L1 = sc[(size_t)6 * NG * NV];
+    nd.f0 = (((A.curmask >> g) & 1u) ? A.f0b : A.f0a)[(size_t)g * NV + idx];
+    nd.D = A.D[(size_t)g * NV + idx];
+}
+
+// one-node boundary problem (get_a1matvec_first / _last), G rows in lanes 0..G-1, then get_a3,
+// the boundary current and the dn update of nodal_coup_upd.  first: "-" face of the first node.
+template <int NG>
+__device__ __forceinline__ bool coop_boundary(const NodalArgs &A, bool active, int sl, int g, bool first, int bc,
+                                              const NodeDirRow<NG> &n, double h, int sf, long long NV, long long idx,
+                                              double &nder_out)
+{
+    const double P = 2.0 * n.D / h;
+    const int face = first ? sf + 1 : sf;
+    const double dcf = A.dc[((size_t)face * NG + g) * NV + idx];
+    double row[NG], b;
+    if (first) {
+        if (bc == 2) {
+#pragma unroll
+            for (int hh = 0; hh < NG; ++hh) row[hh] = (hh == g) ? P * (n.Bc[hh] * n.F + 1.0) : P * n.Bc[hh] * n.F;
+            b = P * (3.0 * n.a2 + n.Gc * n.a4 - n.F * n.L1);
+        } else if (bc == 1) {
+#pragma unroll
+            for (int hh = 0; hh < NG; ++hh)
+                row[hh] = (hh == g) ? -dcf * (1.0 + n.A * n.Bc[hh]) - 2.0 * P * (n.A * n.Bc[hh] * n.H + 1.0)
+                                    : -dcf * n.A * n.Bc[hh] - 2.0 * P * n.A * n.Bc[hh] * n.H;
+            b = 2.0 * P * (n.A * n.H * n.L1 - 3.0 * n.a2 - n.Gc * n.a4) - dcf * (n.a2 + n.a4 + n.f0 - n.A * n.L1);
+        } else {
+#pragma unroll
+            for (int hh = 0; hh < NG; ++hh) row[hh] = (hh == g) ? dcf * (1.0 + n.A * n.Bc[hh]) : dcf * n.A * n.Bc[hh];
+            b = dcf * (n.a2 + n.a4 + n.f0 - n.A * n.L1);
+        }
+    } else {
+        if (bc == 2) {
+#pragma unroll
+            for (int hh = 0; hh < NG; ++hh) row[hh] = (hh == g) ? -P * (n.Bc[hh] * n.F + 1.0) : -P * n.Bc[hh] * n.F;
+            b = P * (3.0 * n.a2 + n.Gc * n.a4 + n.F * n.L1);
+        } else if (bc == 1) {
+#pragma unroll
+            for (int hh = 0; hh < NG; ++hh)
+                row[hh] = (hh == g) ? dcf * (1.0 + n.A * n.Bc[hh]) + 2.0 * P * (n.A * n.Bc[hh] * n.H + 1.0)
+                                    : dcf * n.A * n.Bc[hh] + 2.0 * P * n.A * n.Bc[hh] * n.H;
+            b = -2.0 * P * (n.A * n.H * n.L1 + 3.0 * n.a2 + n.Gc * n.a4) - dcf * (n.a2 + n.a4 + n.f0 + n.A * n.L1);
+        } else {
+#pragma unroll
+            for (int hh = 0; hh < NG; ++hh) row[hh] = (hh == g) ? dcf * (1.0 + n.A * n.Bc[hh]) : dcf * n.A * n.Bc[hh];
+            b = -dcf * (n.a2 + n.a4 + n.f0 + n.A * n.L1);
+        }
+    }
+    double a1;
+    bool ok = coop_lu_solve<NG>(sl, row, b, a1);
+    if (sl >= NG || !active) ok = true;            // dummy rows / dummy item
+    // get_a3: a3(g) = A(g) (sum_h B(g,h) a1(h) + L1(g))
+    double Bf = 0.0;
+#pragma unroll
+    for (int hh = 0; hh < NG; ++hh) Bf = Bf + n.Bc[hh] * shfl16(a1, hh);
+    const double a3 = n.A * (Bf + n.L1);
+    nder_out = -1.0;
+    if (sl < NG && active) {
+        double *dn = A.dn + ((size_t)g * 6 + face) * NV;
+        const double dff = A.df[((size_t)g * 6 + face) * NV + idx];
+        const double ndpr = dn[idx];
+        double nw;
+        if (first) {
+            const double jp = -2.0 * n.D / h * (a1 - 3.0 * n.a2 + n.H * a3 - n.Gc * n.a4);
+            nw = -(jp / n.f0 + dff);
+        } else {
+            const double jp = -2.0 * n.D / h * (a1 + 3.0 * n.a2 + n.H * a3 + n.Gc * n.a4);
+            nw = -(jp / n.f0 - dff);
+        }
+        dn[idx] = nw;
+        nder_out = fabs(nw - ndpr);
+    }
+    return ok;
+}
+
+template <int NG>
+__global__ void __launch_bounds__(ADP_TILE, 2) k_nodal_surfaces_coop(Geo G, NodalArgs A, int u, int klo, int npl, ArgMax am)
+{
+    static_assert(2 * NG <= COOP_W, "a 16-lane group holds at most 16 rows");
+    const long long NV = G.NV;
+    const double *ndbase = A.nd + (size_t)u * (NG * NG + 7 * NG) * NV;
+    const int sl = threadIdx.x & (COOP_W - 1);
+    const int grp = threadIdx.x / COOP_W;                      // group within the CTA
+    constexpr int GPB = ADP_TILE / COOP_W;                     // groups per CTA
+    const int g = sl % NG;                                     // lanes >= 2 NG repeat rows, results unused
+    const bool lower = sl < NG;                                // current-continuity rows / the lanes that own group g
+    const int sf = 2 * u;
+    double best = -1.0;
+    long long best_loc = 0x7fffffffffffffffLL;
+    bool ok = true;
+    const long long total = (long long)npl * G.np;
+    // the trip count is the same for every thread of the CTA; a group past the end repeats the last item as a dummy
+    for (long long base = (long long)blockIdx.x * GPB; base < total; base += (long long)gridDim.x * GPB) {
+        const bool live = base + grp < total;
+        const long long item = live ? base + grp : total - 1;
+        const int kl = klo + (int)(item / G.np), r = (int)(item % G.np);
+        const long long idx = node_idx(G, kl, r);
+        const bool owned = (kl >= 0 && kl < G.nzl);
+        const long long gnode = (long long)(G.k0 + kl) * G.np + r;
+        const Line qn = line_of(G, u, kl, r);
+        NodeDirRow<NG> n;
+        nd_load_row<NG>(n, g, ndbase, NV, idx, A);
+        const bool do_first = live && !qn.has_m && owned;
+        const bool do_inner = live && qn.has_p;
+        const bool do_last = live && !qn.has_p && owned;
+        double nder;
+        if (__any_sync(COOP_FULL, do_first)) {
+            ok = coop_boundary<NG>(A, do_first, sl, g, true, qn.bcm, n, qn.h, sf, NV, idx, nder) && ok;
+            if (nder > best || (nder == best && gnode < best_loc)) { best = nder; best_loc = gnode; }
+        }
+        if (__any_sync(COOP_FULL, do_inner)) {
+            // a group without a "+" neighbour pairs the node with itself and discards the result
+            const long long idp = do_inner ? idx + qn.off_p : idx;
+            const int klp = (do_inner && u == 2) ? kl + 1 : kl;
+            const int rp = !do_inner ? r : (u == 0) ? r + 1 : (u == 1) ? r + (int)qn.off_p : r;
+            const Line qp = line_of(G, u, klp, rp);
+            NodeDirRow<NG> p;
+            nd_load_row<NG>(p, g, ndbase, NV, idp, A);
+            const double Pn = 2.0 * n.D / qn.h, Pp = 2.0 * p.D / qp.h;
+            const double dcn = A.dc[((size_t)sf * NG + g) * NV + idx];
+            const double dcp = A.dc[((size_t)(sf + 1) * NG + g) * NV + idp];
+            double row[2 * NG], b;
+            if (lower) {
+#pragma unroll
+                for (int h = 0; h < NG; ++h) {
+                    row[h] = (h == g) ? -Pn * (n.Bc[h] * n.F + 1.0) : -Pn * n.Bc[h] * n.F;
+                    row[h + NG] = (h == g) ? Pp * (p.Bc[h] * p.F + 1.0) : Pp * p.Bc[h] * p.F;
+                }
+                b = Pn * (3.0 * n.a2 + n.Gc * n.a4 + n.F * n.L1) + Pp * (3.0 * p.a2 + p.Gc * p.a4 - p.F * p.L1);
+            } else {
+#pragma unroll
+                for (int h = 0; h < NG; ++h) {
+                    row[h] = (h == g) ? dcn * (n.Bc[h] * n.A + 1.0) : dcn * n.Bc[h] * n.A;
+                    row[h + NG] = (h == g) ? dcp * (p.Bc[h] * p.A + 1.0) : dcp * p.Bc[h] * p.A;
+                }
+                // ADF cross terms exactly as mod_nodal.f90:693-694 (An*Ln1 with dc_p, Ap*Lp1 with dc_n)
+                b = dcp * (p.a2 + p.a4 + p.f0 - n.A * n.L1) - dcn * (n.a2 + n.a4 + n.f0 + p.A * p.L1);
+            }
+            double sx;
+            const bool okl = coop_lu_solve<2 * NG>(sl, row, b, sx);
+            if (sl < 2 * NG && do_inner) ok = okl && ok;
+            double Bf = 0.0;
+#pragma unroll
+            for (int h = 0; h < NG; ++h) Bf = Bf + n.Bc[h] * shfl16(sx, h);      // a1(h) = sx(h)
+            const double a3 = n.A * (Bf + n.L1);
+            if (lower && do_inner) {
+                const double jp = -2.0 * n.D / qn.h * (sx + 3.0 * n.a2 + n.H * a3 + n.Gc * n.a4);
+                double *dn = A.dn + ((size_t)g * 6 + sf) * NV;
+                const double dfp = A.df[((size_t)g * 6 + sf) * NV + idx];
+                const double ndpr = dn[idx];
+                const double nw = (dfp * (n.f0 - p.f0) - jp) / (n.f0 + p.f0);
+                dn[idx] = nw;
+                A.dn[((size_t)g * 6 + sf + 1) * NV + idp] = nw;
+                if (owned) {
+                    const double nd2 = fabs(nw - ndpr);
+                    if (nd2 > best || (nd2 == best && gnode < best_loc)) { best = nd2; best_loc = gnode; }
+                }
+            }
+        }
+        if (__any_sync(COOP_FULL, do_last)) {
+            ok = coop_boundary<NG>(A, do_last, sl, g, false, qn.bcp, n, qn.h, sf, NV, idx, nder) && ok;
+            if (nder > best || (nder == best && gnode < best_loc)) { best = nder; best_loc = gnode; }
+        }
+    }
+    if (!ok) atomicExch(A.errflag, ADP_STOP_LU_DIAG);
+    grid_argmax(best, best_loc, am);
+}
+
 template <int NG>
 void launch_nodal(adp_ctx *c, const NodalArgs &A, const ArgMax &am, bool refresh_abefgh)
 {
@@ -683,7 +960,15 @@ void launch_nodal(adp_ctx *c, const NodalArgs &A, const ArgMax &am, bool refresh
     }
     for (int u = 0; u < 3; ++u) {
         const int klo = (u == 2) ? zlo : 0, npl = c->nzl - klo;     // kl = -1: the surface shared with the slab below
-        k_nodal_surfaces<NG><<<adp_grid(c, k_nodal_surfaces<NG>, tpp * npl), ADP_TILE, 0, c->stream>>>(c->geo, A, u, klo, npl, am);
+        // many groups: 16 lanes per surface (the one-thread version spills its 2G x 2G system)
+        // measured on the C2 mesh (whole update, ms): G = 8: 116 -> 77; G = 6: 46 -> 45; G = 4: 12 -> 44
+        const bool coop = (c->nodal_coop < 0) ? (NG >= 7) : (c->nodal_coop > 0);
+        if (coop) {
+            const long long items = (long long)npl * c->np;
+            const int tiles = (int)((items + ADP_TILE / COOP_W - 1) / (ADP_TILE / COOP_W));
+            k_nodal_surfaces_coop<NG><<<adp_grid(c, k_nodal_surfaces_coop<NG>, tiles), ADP_TILE, 0, c->stream>>>(c->geo, A, u, klo, npl, am);
+        } else
+            k_nodal_surfaces<NG><<<adp_grid(c, k_nodal_surfaces<NG>, tpp * npl), ADP_TILE, 0, c->stream>>>(c->geo, A, u, klo, npl, am);
         c->launches++;
     }
 }
@@ -693,6 +978,7 @@ void preload_nodal(adp_ctx *c)
 {
     adp_grid(c, k_nodal_abefgh<NG>, 1); adp_grid(c, k_nodal_nodedir<NG, ADP_KERN_SANM>, 1);
     adp_grid(c, k_nodal_nodedir<NG, ADP_KERN_PNM>, 1); adp_grid(c, k_nodal_surfaces<NG>, 1);
+    adp_grid(c, k_nodal_surfaces_coop<NG>, 1);
 }
 
 }  // namespace
@@ -703,6 +989,8 @@ static NodalArgs make_args(adp_ctx *c, int cmode)
     A.ng = c->ng; A.nmat = c->nmat; A.cmode = cmode; A.kern = c->kern;
     A.nnod_total = c->nnod;
     for (int g = 0; g < c->ng; ++g) A.f0[g] = c->d_f0[c->cur[g]] + (size_t)g * c->NV;
+    A.f0a = c->d_f0[0]; A.f0b = c->d_f0[1]; A.curmask = 0;
+    for (int g = 0; g < c->ng; ++g) if (c->cur[g]) A.curmask |= 1u << g;
     A.D = c->d_D; A.sigr = c->d_sigr; A.nuf = c->d_nuf; A.exsrc = c->d_exsrc; A.sigs = c->d_sigs;
     A.chi = c->d_chi; A.dc = c->d_dc; A.mat = c->d_mat; A.tbeta = c->d_tbeta; A.dfis = c->d_dfis;
     A.df = c->d_df; A.dn = c->d_dn; A.S = c->d_S; A.scal = c->d_scal; A.errflag = c->d_errflag;
