@@ -28,6 +28,8 @@ def main():
     uid = bytes(t.cpu().tolist())
 
     deck = sys.argv[1] if len(sys.argv) > 1 else "IAEA3Ds"
+    if deck == "LMW_tr":
+        return transient_main(rank, world, local, uid, dist)
     if deck == "IAEA3Ds_z2":                  # 38 planes: uneven slabs at 4 ranks, 2 planes per axial assembly
         p = load_problem("IAEA3Ds").refine(zdiv=[2] * 19)
     else:
@@ -75,7 +77,53 @@ def main():
     _, pw_o = o.powdis()
     nz = pw_o[own] > 1e-12
     assert np.abs(pw_s[own][nz] / pw_o[own][nz] - 1).max() < 1e-5
+    # 5. result reductions (AsmPow / AxiPow / AsmFlux): the slabs' partial column and plane sums are
+    #    all-reduced, every rank gets the whole map.  Inputs for the oracle: the GPU's own power and
+    #    flux, gathered from the slabs.
+    from oracle import results
+
+    def gather(a):
+        full = np.zeros_like(a)
+        full[own] = a[own]
+        tt = torch.from_numpy(np.ascontiguousarray(full.T)).cuda()
+        dist.all_reduce(tt)
+        return np.asfortranarray(tt.cpu().numpy().T) if a.ndim == 2 else tt.cpu().numpy()
+    pw_full, f0_full = gather(pw_s), gather(s.state()["f0"])
+    fasm, im, jm = s.asm_pow()
+    ref, ri, rj = results.asm_pow(p, pw_full)
+    assert np.abs(fasm - ref).max() < 1e-13 and (im, jm) == (ri, rj)
+    faxi, am = s.axi_pow()
+    ra, ram = results.axi_pow(p, pw_full)
+    assert np.abs(faxi - ra).max() < 1e-13 and am == ram
+    fa, neg = s.asm_flux()
+    rf, rneg = results.asm_flux(p, f0_full)
+    assert np.abs(fa - rf).max() < 1e-13 * np.abs(rf).max() and neg == rneg
     print(f"RANK {rank}/{world} OK deck={deck} planes=[{s.k0},{s.k1}) keff={ks:.6f} outers={n_s}", flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def transient_main(rank, world, local, uid, dist):
+    """Device-resident rod-ejection time steps (XS update, %EXTR, time-step glue, outer_tr, uPden,
+    PowTot, reactivity with Lxyz) on z-slabs against the single-process oracle with numpy glue."""
+    from conftest import load_problem
+    from adpres_b200 import capi, transient
+    from oracle import Oracle
+
+    def tight(p):
+        p.serc = p.ferc = 1e-9
+        p.nout = 5000
+        p.bextr = 1
+        return p
+    p1, p2 = tight(load_problem("LMW")), tight(load_problem("LMW"))
+    tr_o = transient.rod_eject(p1, Oracle(p1), max_steps=4)
+    s = capi.Solver(p2, device=local, nranks=world, rank=rank, uid=uid)
+    tr_d = transient.rod_eject_device_glue(p2, s, max_steps=4, device_xs=True)
+    for a, b in zip(tr_d, tr_o):
+        assert a[1] == b[1]
+        assert abs(a[3] / b[3] - 1) < 1e-5, (a, b)
+        assert abs(a[2] - b[2]) < 1e-5, (a, b)
+    print(f"RANK {rank}/{world} OK deck=LMW_tr planes=[{s.k0},{s.k1}) power={tr_d[-1][3]:.6f}", flush=True)
     dist.barrier()
     dist.destroy_process_group()
 
