@@ -86,6 +86,14 @@ class Solver:
         if nranks > 1:
             self._chk(self.L.adp_comm_init(self.h, nranks, rank, uid))
         self.nranks, self.rank = nranks, rank
+        self._trace_cb = None
+        self.load_problem(p, nupd=nupd, nout=nout, nin=nin, nac=nac, serc=serc, ferc=ferc, kern=kern)
+
+    def load_problem(self, p, **control):
+        """Geometry + cross sections + iteration control of `p` into this context (a context can be
+        re-used for another deck: adp_set_geometry re-sizes everything)."""
+        self.p = p
+        self.N, self.G = p.nnod, p.ng
         self._chk(self.L.adp_set_geometry(self.h, p.nxx, p.nyy, p.nzz, p.nnod, p.ng, p.nmat, _i(p.ix), _i(p.iy),
                                           _i(p.iz), _i(p.ystag_smin), _i(p.ystag_smax), _i(p.xstag_smin),
                                           _i(p.xstag_smax), _d(p.xdel), _d(p.ydel), _d(p.zdel), _i(p.bc), _i(p.mat)))
@@ -94,8 +102,7 @@ class Solver:
         self.k0, self.k1 = k0.value, k1.value
         self.own = slice(self.k0 * p.npl, self.k1 * p.npl)      # node range this rank owns
         self.set_xs()
-        self.set_control(nout=nout, nin=nin, nac=nac, nupd=nupd, serc=serc, ferc=ferc, kern=kern)
-        self._trace_cb = None
+        self.set_control(**control)
         self.trace_rows, self.trace_nodal, self.trace_extrp = [], [], []
 
     # ---- plumbing

@@ -253,8 +253,16 @@ extern "C" int adp_set_geometry(adp_ctx *c, int nxx, int nyy, int nzz, int nnod,
     TRY(dev_alloc(c, &c->d_stage, NV));
     // D must stay non-zero on ghost planes outside the core (divisions in coup_coef never use
     // them, but keep every table finite): initialise to 1
-    if (c->d_nd) { cudaFree(c->d_nd); c->d_nd = nullptr; }
-    if (c->d_abefgh) { cudaFree(c->d_abefgh); c->d_abefgh = nullptr; }
+    // buffers allocated on first use are sized by the geometry: drop them, they come back on demand
+    {
+        double **lazy[] = {&c->d_nd, &c->d_abefgh, &c->d_c0, &c->d_ft, &c->d_fst, &c->d_omeg, &c->d_sigrp, &c->d_L,
+                           &c->d_af, &c->d_xtab, &c->d_dtab, &c->d_bpos, &c->d_dumtop, &c->d_res};
+        for (double **q : lazy)
+            if (*q) { cudaFree(*q); *q = nullptr; }
+        if (c->d_fb) { cudaFree(c->d_fb); c->d_fb = nullptr; }
+        if (c->h_res) { cudaFreeHost(c->h_res); c->h_res = nullptr; }
+        c->res_elems = 0; c->nb = 0; c->kinetics_set = false;
+    }
     c->abefgh_valid = false;
     c->geometry_set = true;
     c->xs_set = false; c->matrix_ready = false; c->have_flux = false; c->coup_first = true;

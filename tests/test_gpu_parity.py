@@ -457,3 +457,31 @@ def test_cooperative_surfaces_kernel_is_bit_identical(mods, ng, bc, kern):
     assert a[4] == b[4] and len(a[4]) >= 2                      # (p, ndmax, i, j, k) of every update
     assert np.array_equal(a[3], b[3])
     assert np.array_equal(a[2]["f0"], b[2]["f0"]) and a[2]["Ke"] == b[2]["Ke"] and a[5] == b[5]
+
+
+def test_context_reuse_across_decks(mods):
+    """One context, three decks of different size, group count and mode in a row (adp_set_geometry
+    re-sizes the node arrays and drops every buffer that is allocated on first use: nodal scratch,
+    transient arrays, rod tables, result buffers).  Results must equal those of fresh contexts."""
+    capi, _ = mods
+    from adpres_b200 import transient
+    from synth import iaea3d_multigroup
+    import copy
+
+    def run(s, p):
+        if p.mode == "RODEJECT":
+            tr = transient.rod_eject_device_glue(p, s, max_steps=2, device_xs=True)
+            return [(r[2], r[3]) for r in tr], s.asm_pow()[0]
+        rc, n = s.outer(0)
+        assert rc == 0
+        return (n, s.state()["Ke"]), s.asm_pow()[0]
+    decks = [load_problem("LMW"), iaea3d_multigroup(4), load_problem("IAEA3Ds"), load_problem("LMW")]
+    fresh = [run(capi.Solver(copy.deepcopy(p)), copy.deepcopy(p)) for p in decks]
+    s = capi.Solver(copy.deepcopy(decks[0]))
+    for i, p in enumerate(decks):
+        q = copy.deepcopy(p)
+        if i:
+            s.load_problem(q)
+        got = run(s, q)
+        assert got[0] == fresh[i][0], (i, got[0], fresh[i][0])
+        assert np.array_equal(got[1], fresh[i][1])
