@@ -610,7 +610,7 @@ extern "C" int adp_set_material_xs(adp_ctx *c, const double *xsigtr, const doubl
 extern "C" int adp_set_crod(adp_ctx *c, int nb, double pos0, double ssize, const int *fbmap, const double *dsigtr,
                             const double *dsiga, const double *dnuf, const double *dsigf, const double *dsigs)
 {
-    if (!c || !fbmap || nb < 1) return ADP_ERR_USAGE;
+    if (!c || !fbmap || nb < 1 || !dsigtr || !dsiga || !dnuf || !dsigf || !dsigs) return ADP_ERR_USAGE;
     ADP_REQUIRE(c, c->geometry_set, "adp_set_crod: geometry not set");
     CUDA_TRY(c, cudaSetDevice(c->device));
     TRY(upload_tables(c, &c->d_dtab, dsigtr, dsiga, dnuf, dsigf, dsigs));
