@@ -49,3 +49,29 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src and "liboracle" not in src, f
+
+
+def test_header_is_plain_c_and_a_c_client_links(tmp_path):
+    """The boundary is a C ABI: include/adpres_b200.h compiles as C99 (no C++ or torch types in
+    the signatures) and a C program links against the library through it alone.  Without a GPU
+    the client reports the loud adp_create failure (exit code 3); with one it runs a usage-error
+    round trip (exit code 0)."""
+    import shutil
+    import subprocess
+    import torch
+    gcc = shutil.which("gcc")
+    if not gcc:
+        pytest.skip("no gcc")
+    capi.load()                                   # builds the library if needed
+    libdir = os.path.join(ROOT, "adpres_b200")
+    exe = str(tmp_path / "abi_probe")
+    cmd = [gcc, "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "examples", "abi_probe.c"), "-L", libdir, "-ladpres_b200", "-Wl,-rpath," + libdir, "-o", exe]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert "sm_100a" in r.stdout
+    if torch.cuda.is_available():
+        assert r.returncode == 0 and "cross sections not set" in r.stdout, r.stdout + r.stderr
+    else:
+        assert r.returncode == 3 and "no CPU fallback" in r.stdout, r.stdout + r.stderr
