@@ -16,7 +16,7 @@ _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int)
 
 MODE_FORWARD, MODE_ADJOINT, MODE_FIXEDSRC, MODE_TRANSIENT = 0, 1, 2, 3
-STOP_MAXOUTER, STOP_LU_DIAG, STOP_NDMAX, STOP_ZERO_POWER = 1, 2, 3, 4
+STOP_MAXOUTER, STOP_LU_DIAG, STOP_NDMAX, STOP_ZERO_POWER, STOP_STEAM_TABLE = 1, 2, 3, 4, 5
 
 TRACE_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int)
 
@@ -25,7 +25,8 @@ SYMBOLS = [
     "adp_create", "adp_destroy", "adp_last_error", "adp_version", "adp_comm_unique_id", "adp_comm_init", "adp_comm_init_env", "adp_slab",
     "adp_set_geometry", "adp_set_xs", "adp_set_control", "adp_matrix_setup", "adp_init_flux", "adp_outer_begin",
     "adp_outer_iter", "adp_nodal_upd", "adp_powdis", "adp_integrate", "adp_set_kinetics", "adp_set_transient",
-    "adp_get_exsrc", "adp_set_material_xs", "adp_set_crod", "adp_xs_update", "adp_get_xs", "adp_save_adjoint", "adp_ipden", "adp_update_omeg", "adp_begin_time_step", "adp_upden", "adp_powtot", "adp_asm_pow", "adp_axi_pow", "adp_asm_flux",
+    "adp_get_exsrc", "adp_set_material_xs", "adp_set_crod", "adp_xs_update", "adp_get_xs", "adp_save_adjoint", "adp_ipden", "adp_update_omeg", "adp_begin_time_step", "adp_upden", "adp_powtot", "adp_asm_pow", "adp_axi_pow", "adp_asm_flux", "adp_set_th", "adp_set_th_state", "adp_get_th_state", "adp_th_pline",
+    "adp_th_upd", "adp_th_trans",
     "adp_reactivity", "adp_get_state", "adp_set_state", "adp_set_s0", "adp_get_nod", "adp_set_nod_dn", "adp_lxyz_total", "adp_get_exsrc_arrays",
     "adp_get_ndmax", "adp_set_trace", "adp_outer", "adp_outer_ad", "adp_outer_fs", "adp_outer_th", "adp_outer_tr",
     "adp_sp_matvec", "adp_bicg", "adp_get_matrix", "adp_get_source", "adp_set_option", "adp_launch_count",
@@ -258,6 +259,44 @@ class Solver:
                                       _i(np.ascontiguousarray(p.ydiv, dtype=np.int32)), int(norm is not None),
                                       C.c_double(norm if norm is not None else 0.0), _d(fasm), C.byref(neg)))
         return fasm, neg.value
+
+    # ---- thermal-hydraulic channel solve (mod_th.f90 th_upd / th_trans)
+    def set_th(self, th):
+        """th: the dict of deck.Problem.th_setup()"""
+        self._th = th
+        stab = np.asfortranarray(th["stab"], dtype=np.float64)
+        rc = self.L.adp_set_th(self.h, C.c_double(th["pi"]), C.c_double(th["rf"]), C.c_double(th["rg"]), C.c_double(th["rc"]),
+                               C.c_double(th["dia"]), C.c_double(th["dh"]), C.c_double(th["farea"]), C.c_double(th["cflow"]),
+                               C.c_double(th["cf"]), C.c_double(th["tin"]), _d(np.ascontiguousarray(th["rpos"])),
+                               _d(np.ascontiguousarray(th["rdel"])), int(th["ntem"]), _d(stab))
+        return self._chk(rc)
+
+    def set_th_state(self, st):
+        keep = {k: np.asfortranarray(st[k], dtype=np.float64) for k in st if st.get(k) is not None}
+        g = lambda k: _d(keep[k]) if k in keep else None
+        self._chk(self.L.adp_set_th_state(self.h, g("tfm"), g("heatf"), g("ent"), g("ftem"), g("mtem"), g("cden"), g("frate")))
+
+    def th_state(self):
+        N = self.N
+        st = dict(tfm=np.zeros((N, 13), order="F"), heatf=np.zeros(N), ent=np.zeros(N), ftem=np.zeros(N), mtem=np.zeros(N),
+                  cden=np.zeros(N), frate=np.zeros(N))
+        self._chk(self.L.adp_get_th_state(self.h, _d(st["tfm"]), _d(st["heatf"]), _d(st["ent"]), _d(st["ftem"]), _d(st["mtem"]),
+                                          _d(st["cden"]), _d(st["frate"])))
+        return st
+
+    def th_pline(self, pow_, ppow, form=0):
+        nf = np.asfortranarray(self._th["node_nf"], dtype=np.float64)
+        return self._chk(self.L.adp_th_pline(self.h, C.c_double(pow_), C.c_double(ppow), int(form), _d(nf)))
+
+    def th_upd(self, xpline=None, want_err=True):
+        e = C.c_double()
+        x = None if xpline is None else np.ascontiguousarray(xpline, dtype=np.float64)
+        rc = self._chk(self.L.adp_th_upd(self.h, _d(x), C.byref(e) if want_err else None))
+        return rc, e.value
+
+    def th_trans(self, xpline, h):
+        x = None if xpline is None else np.ascontiguousarray(xpline, dtype=np.float64)
+        return self._chk(self.L.adp_th_trans(self.h, _d(x), C.c_double(h)))
 
     def integrate(self, s):
         r = C.c_double()

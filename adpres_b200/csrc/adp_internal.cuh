@@ -160,6 +160,17 @@ struct adp_ctx {
     double ibeta[ADP_NF] = {0}, lamb[ADP_NF] = {0};
     double sth = 1.0, bth = 0.0;
     bool kinetics_set = false;
+    // thermal-hydraulic channel solve (th.cu): parameters of %THER and the state the reference keeps in sdata
+    struct ThPar {
+        double pi = 0, rf = 0, rg = 0, rc = 0, dia = 0, dh = 0, farea = 0, cflow = 0, cf = 0, tin = 0, enti = 0;
+        double rpos[12] = {0}, rdel[12] = {0};
+        int ntem = 0;
+    } th;
+    bool th_set = false, th_state_set = false, th_pline_set = false;
+    double *d_stab = nullptr;              // (ntem, 6) column-major
+    double *d_tfm = nullptr;               // [nt+1][NV] radial pin temperatures
+    double *d_heatf = nullptr, *d_ent = nullptr, *d_ftem = nullptr, *d_mtem = nullptr, *d_cden = nullptr, *d_frate = nullptr,
+           *d_pline = nullptr, *d_nodenf = nullptr /*[np]*/, *d_chain = nullptr /*[2][np] entm, bfrate*/;
     // result reductions (results.cu): column / plane sums
     double *d_res = nullptr, *h_res = nullptr;
     size_t res_elems = 0;
@@ -275,6 +286,12 @@ int adp_k_upden(adp_ctx *c, double ht);
 int adp_k_begin_step(adp_ctx *c, double ht);
 int adp_k_omeg(adp_ctx *c, double ht, int bextr);
 int adp_k_reactivity(adp_ctx *c, const double *d_af, const double *d_sigr_for_rem);
+// capi.cu: host (nnod, ncol) column-major, global  <->  device [col][NV], own planes of this rank
+int adp_upload_nodes(adp_ctx *c, double *d, const double *h, int ncol);
+int adp_download_nodes(adp_ctx *c, double *h, const double *d, int ncol);
+// comm.cu: pass a per-channel vector up the z-slab chain (thermal-hydraulic march)
+int adp_comm_chain_recv(adp_ctx *c, double *d_buf, int count);   // from rank - 1 (no-op on rank 0)
+int adp_comm_chain_send(adp_ctx *c, const double *d_buf, int count);   // to rank + 1 (no-op on the last rank)
 // nodal_kernels.cu
 int adp_k_nodal_source(adp_ctx *c, int cmode);
 int adp_k_nodal_update(adp_ctx *c, int cmode);

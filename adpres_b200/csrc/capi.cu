@@ -94,6 +94,10 @@ extern "C" int adp_destroy(adp_ctx *c)
     if (c->h_stage) cudaFreeHost(c->h_stage);
     if (c->h_res) cudaFreeHost(c->h_res);
     if (c->d_res) cudaFree(c->d_res);
+    {
+        double *th[] = {c->d_stab, c->d_tfm, c->d_heatf, c->d_ent, c->d_ftem, c->d_mtem, c->d_cden, c->d_frate, c->d_pline, c->d_nodenf, c->d_chain};
+        for (double *q : th) if (q) cudaFree(q);
+    }
     cudaStreamDestroy(c->stream);
     delete c;
     return ADP_OK;
@@ -144,6 +148,10 @@ static int download_nodes(adp_ctx *c, double *h, const double *d, int ncol)
                                     cudaMemcpyDeviceToHost, c->stream));
     return ADP_OK;
 }
+
+// the same transfers for the other translation units (results.cu, th.cu)
+int adp_upload_nodes(adp_ctx *c, double *d, const double *h, int ncol) { return upload_nodes(c, d, h, ncol, false); }
+int adp_download_nodes(adp_ctx *c, double *h, const double *d, int ncol) { return download_nodes(c, h, d, ncol); }
 
 // ---------------------------------------------------------------------------------------------
 extern "C" int adp_set_geometry(adp_ctx *c, int nxx, int nyy, int nzz, int nnod, int ng, int nmat, const int *ix,
@@ -256,12 +264,15 @@ extern "C" int adp_set_geometry(adp_ctx *c, int nxx, int nyy, int nzz, int nnod,
     // buffers allocated on first use are sized by the geometry: drop them, they come back on demand
     {
         double **lazy[] = {&c->d_nd, &c->d_abefgh, &c->d_c0, &c->d_ft, &c->d_fst, &c->d_omeg, &c->d_sigrp, &c->d_L,
-                           &c->d_af, &c->d_xtab, &c->d_dtab, &c->d_bpos, &c->d_dumtop, &c->d_res};
+                           &c->d_af, &c->d_xtab, &c->d_dtab, &c->d_bpos, &c->d_dumtop, &c->d_res, &c->d_stab, &c->d_tfm,
+                           &c->d_heatf, &c->d_ent, &c->d_ftem, &c->d_mtem, &c->d_cden, &c->d_frate, &c->d_pline, &c->d_nodenf,
+                           &c->d_chain};
         for (double **q : lazy)
             if (*q) { cudaFree(*q); *q = nullptr; }
         if (c->d_fb) { cudaFree(c->d_fb); c->d_fb = nullptr; }
         if (c->h_res) { cudaFreeHost(c->h_res); c->h_res = nullptr; }
         c->res_elems = 0; c->nb = 0; c->kinetics_set = false;
+        c->th_set = c->th_state_set = c->th_pline_set = false;
     }
     c->abefgh_valid = false;
     c->geometry_set = true;

@@ -351,6 +351,18 @@ int adp_comm_allreduce_max_nccl(adp_ctx *c, double *d, int count)
     NCCL_TRY(c, g_nccl.AllReduce(d, d, count, ncclFloat64, ncclMax, c->comm->comm, c->stream));
     return ADP_OK;
 }
+int adp_comm_chain_recv(adp_ctx *c, double *d, int count)
+{
+    if (c->nranks == 1 || c->rank == 0) return ADP_OK;
+    NCCL_TRY(c, g_nccl.Recv(d, count, ncclFloat64, c->rank - 1, c->comm->comm, c->stream));
+    return ADP_OK;
+}
+int adp_comm_chain_send(adp_ctx *c, const double *d, int count)
+{
+    if (c->nranks == 1 || c->rank == c->nranks - 1) return ADP_OK;
+    NCCL_TRY(c, g_nccl.Send(d, count, ncclFloat64, c->rank + 1, c->comm->comm, c->stream));
+    return ADP_OK;
+}
 int adp_comm_allreduce_sum_nccl(adp_ctx *c, double *d, int count)
 {
     if (c->nranks == 1) return ADP_OK;

@@ -735,7 +735,7 @@ __device__ __forceinline__ bool coop_lu_solve(int sl, double (&row)[M], double b
     });
     // back substitution: x(i) = (y(i) - sum_{k>i} U(i,k) x(k)) / U(i,i), k ascending: lane i adds
     // up only once all x(k > i) have arrived
-    double xs[M];
+    double xs[M] = {};
     x = 0.0;
     static_for<0, M>([&](auto tc) {
         constexpr int i = M - 1 - decltype(tc)::value;

@@ -26,6 +26,19 @@ from typing import Dict, List, Optional
 import numpy as np
 
 KERN_FDM, KERN_PNM, KERN_SANM = 0, 1, 2
+TH_PI = float(np.float32(3.14159265))     # REAL(DP), PARAMETER :: pi = 3.14159265 (single-precision literal)
+TH_NM = 10                                 # fuel meat meshes (mod_data.f90:159); nt = nm + 2
+# steam table at 15.5 MPa (mod_io.f90:3124-3142): T [K], rho [g/cm3], h [J/kg], Pr, kin. viscosity [1e-6 m2/s], k [W/mK]
+TH_STAB = np.array([
+    [543.15, 0.78106745, 1182595.0, 0.820773, 0.128988, 0.60720],
+    [553.15, 0.76428125, 1232620.0, 0.829727, 0.126380, 0.59285],
+    [563.15, 0.74619716, 1284170.0, 0.846662, 0.124118, 0.57710],
+    [573.15, 0.72650785, 1337630.0, 0.863597, 0.121856, 0.55970],
+    [583.15, 0.70475081, 1393570.0, 0.915035, 0.120105, 0.54045],
+    [593.15, 0.68018488, 1452895.0, 0.966472, 0.118354, 0.51880],
+    [603.15, 0.65150307, 1517175.0, 1.166745, 0.143630, 0.49420],
+    [613.15, 0.61590149, 1589770.0, 1.515852, 0.195931, 0.46550],
+    [617.91, 0.59896404, 1624307.1, 1.681940, 0.220813, 0.45185]])
 _KERN_CODE = {"FDM": KERN_FDM, "PNM": KERN_PNM, "SANM": KERN_SANM}
 
 
@@ -158,6 +171,7 @@ class Problem:
     crod: Optional[dict] = None          # %CROD: nb, nstep, pos0, ssize, bpos[nb], bmap(nx,ny), dsigtr/dsiga/dnuf/dsigf (nmat,ng), dsigs (nmat,ng,ng)
     ejct: Optional[dict] = None          # %EJCT: fbpos, tmove, bspeed, ttot, tstep1, tdiv, tstep2, ibeta, lamb, velo
     bextr: int = 0
+    ther: Optional[dict] = None           # %THER raw inputs (ppow, pow, tin, cmflow, rf, tg, tc, ppitch, nfpin, ngt, cf)
     cards: Optional[Dict[str, List[str]]] = None
     # ---- node-wise (filled by build())
     nxx: int = 0
@@ -191,7 +205,7 @@ class Problem:
     _SPEC_FIELDS = ("mode", "ng", "nmat", "nx", "ny", "nz", "xsize", "ysize", "zsize", "xdiv", "ydiv",
                     "zdiv", "zpln", "planars", "bc", "xsigtr", "xsiga", "xnuf", "xsigf", "xsigs", "chi",
                     "nout", "nin", "serc", "ferc", "nac", "nupd", "th_niter", "nth", "kern", "biter",
-                    "sth", "bth", "mdc", "adf_rot", "esrc", "crod", "ejct", "bextr")
+                    "sth", "bth", "mdc", "adf_rot", "esrc", "crod", "ejct", "bextr", "ther")
 
     def to_spec(self) -> dict:
         """JSON-able problem specification (what the deck says, before node expansion).
@@ -433,6 +447,45 @@ class Problem:
                         self.exsrc[sel, g] += sden * spec[g]
 
     # ------------------------------------------------------------------ results
+    def th_setup(self) -> dict:
+        """Derived thermal-hydraulic data of inp_ther (mod_io.f90:3036-3146): pin geometry, sub-channel
+        flow, fuel pins per node, radial pin mesh, steam table at 15.5 MPa.  `pi` is the reference's
+        default-REAL literal 3.14159265 (mod_data.f90:169)."""
+        t = self.ther
+        if t is None:
+            raise ValueError("deck has no %THER card")
+        if t["tg"] > 0.25 * t["rf"] or t["tc"] > 0.25 * t["rf"]:
+            raise ValueError("ERROR: GAP / CLADDING THICKNESS IS TO LARGE (> 0.25*rf)")
+        pi = TH_PI
+        nm, nt = TH_NM, TH_NM + 2
+        rf, tg, tc, ppitch = t["rf"], t["tg"], t["tc"], t["ppitch"]
+        rg = rf + tg
+        rc = rg + tc
+        dia = 2.0 * rc
+        dh = dia * ((4.0 / pi) * (ppitch / dia) ** 2 - 1.0)
+        farea = ppitch ** 2 - 0.25 * pi * dia ** 2
+        cflow = t["cmflow"] / float(np.float32(t["nfpin"]))
+        area = self.xsize[:, None] * self.ysize[None, :]
+        barea = area.max()
+        ia = np.repeat(np.arange(self.nx), self.xdiv)
+        ja = np.repeat(np.arange(self.ny), self.ydiv)
+        div = (self.xdiv[:, None] * self.ydiv[None, :]).astype(np.float32).astype(np.float64)
+        node_nf = np.zeros((self.nxx, self.nyy), order="F")
+        for j in range(self.nyy):
+            for i in range(self.ystag_smin[j] - 1, self.ystag_smax[j]):
+                node_nf[i, j] = area[ia[i], ja[j]] * float(np.float32(t["nfpin"])) / (barea * div[ia[i], ja[j]])
+        rdel = np.zeros(nt)
+        rdel[:nm] = rf / float(np.float32(nm))
+        rdel[nm] = tg
+        rdel[nm + 1] = tc
+        rpos = np.zeros(nt)
+        rpos[0] = 0.5 * rdel[0]
+        for i in range(1, nt):
+            rpos[i] = rpos[i - 1] + 0.5 * (rdel[i - 1] + rdel[i])
+        return dict(pi=pi, nm=nm, nt=nt, rf=rf, rg=rg, rc=rc, dia=dia, dh=dh, farea=farea, cflow=cflow, cf=t["cf"],
+                    tin=t["tin"], pow=t["pow"], ppow=t["ppow"], node_nf=node_nf, rdel=rdel, rpos=rpos,
+                    stab=TH_STAB.copy(order="F"), ntem=TH_STAB.shape[0])
+
     def asm_power(self, pow_n: np.ndarray) -> np.ndarray:
         """AsmPow normalisation (mod_io.f90:3267-3363): axial average weighted by zdel,
         area-weighted per assembly, scaled so the mean over assemblies with power>0 is 1.
@@ -565,6 +618,16 @@ def parse_deck(text: str, base_dir: str = ".") -> Problem:
                       tdiv=tdiv, tstep2=tstep2, ibeta=ibeta, lamb=lamb, velo=velo)
     if "EXTR" in cards:
         p.bextr = 1
+    if "THER" in cards:                          # mod_io.f90:2996-3034 (derived data: Problem.th_setup)
+        r = _Reader(cards["THER"], "THER")
+        ppow = r.floats(1)[0]
+        pow_ = r.floats(1)[0]
+        tin, cmflow = r.floats(2)
+        rf, tg, tc, ppitch = r.floats(4)
+        nfpin, ngt = r.ints(2)
+        cf = r.floats(1)[0]
+        p.ther = dict(ppow=ppow, pow=pow_, tin=tin, cmflow=cmflow, rf=rf, tg=tg, tc=tc, ppitch=ppitch, nfpin=nfpin,
+                      ngt=ngt, cf=cf)
     if "ESRC" in cards and mode == "FIXEDSRC":   # mod_io.f90:1369-1517
         r = _Reader(cards["ESRC"], "ESRC")
         nsrc = r.ints(1)[0]

@@ -41,6 +41,7 @@ enum {
     ADP_STOP_LU_DIAG = 2,    /* "ERROR IN MATRIX DECOMP: DIAGONAL ELEMENTS CLOSE TO ZERO" mod_nodal.f90:856-862 */
     ADP_STOP_NDMAX = 3,      /* "Max. change in nodal coupling coefficient" > 1e3, mod_nodal.f90:131-142 */
     ADP_STOP_ZERO_POWER = 4, /* "TOTAL NODES POWER IS ZERO OR LESS" mod_cmfd.f90:1322-1326 */
+    ADP_STOP_STEAM_TABLE = 5, /* "ENTHALPY / MODERATOR TEMP. IS OUT OF THE RANGE ... IN THE STEAM TABLE" mod_th.f90:236-244,293-301 */
     ADP_ERR_CUDA = -1,
     ADP_ERR_USAGE = -2,
     ADP_ERR_NCCL = -3,
@@ -179,6 +180,30 @@ int adp_asm_pow(adp_ctx *ctx, int nx, int ny, const int *xdiv, const int *ydiv, 
 int adp_axi_pow(adp_ctx *ctx, int nz, const int *zdiv, double *faxi, int *amax);
 int adp_asm_flux(adp_ctx *ctx, int nx, int ny, const int *xdiv, const int *ydiv, int use_norm, double norm,
                  double *fasm, int *negf);
+
+/* ---- optional: thermal-hydraulic channel solve on the device ---------------- */
+/* th_upd / th_trans of mod_th.f90: per radial channel an axial enthalpy march, per node a 13-point
+ * tridiagonal solve of the radial pin conduction.  The XS feedback (XS_updt with ftem, mtem, cden,
+ * bcon) and the th_iter / cbsearch loops stay with the caller.
+ *   adp_set_th        what inp_ther leaves in sdata: pi (the reference's default-REAL 3.14159265),
+ *                     rf, rg, rc, dia, dh, farea, cflow, cf, tin, rpos(12), rdel(12), stab(ntem,6)   mod_io.f90:2958-3174
+ *   adp_set_th_state  tfm(nnod,13), heatf, ent, ftem, mtem, cden, frate (NULL = keep; frate NULL before
+ *                     the first transient step = cflow)                                              mod_io.f90:3101-3113
+ *   adp_th_pline      CALL PowDis(npow); pline = npow*pow*ppow*0.01/(node_nf*zdel) (form 0, th_iter,
+ *                     mod_th.f90:57-64) or npow*pow*xppow/(node_nf*zdel) (form 1, trans_calc,
+ *                     mod_trans.f90:430-441), kept on the device
+ *   adp_th_upd        CALL th_upd(pline); th_err = AbsE(ftem, otem) if requested                     mod_th.f90:594-699,94-119
+ *   adp_th_trans      CALL th_trans(pline, h)                                                        mod_th.f90:440-591
+ * xpline: host (nnod) linear power density in W/cm, or NULL = the one adp_th_pline left on the device. */
+int adp_set_th(adp_ctx *ctx, double pi, double rf, double rg, double rc, double dia, double dh, double farea, double cflow,
+               double cf, double tin, const double *rpos, const double *rdel, int ntem, const double *stab);
+int adp_set_th_state(adp_ctx *ctx, const double *tfm, const double *heatf, const double *ent, const double *ftem,
+                     const double *mtem, const double *cden, const double *frate);
+int adp_get_th_state(adp_ctx *ctx, double *tfm, double *heatf, double *ent, double *ftem, double *mtem, double *cden,
+                     double *frate);
+int adp_th_pline(adp_ctx *ctx, double pow, double ppow, int form, const double *node_nf);
+int adp_th_upd(adp_ctx *ctx, const double *xpline, double *th_err);
+int adp_th_trans(adp_ctx *ctx, const double *xpline, double h);
 
 /* ---- state exchange with the Fortran side ----------------------------------------------- */
 /* f0(nnod,ng), fs0(nnod), s0(nnod,ng); NULL = skip.  (drivers read them after outer*) */

@@ -25,7 +25,7 @@ DECKS = {
     "IAEA3Ds": "smpl/static/IAEA3Ds", "IAEA2D": "smpl/static/IAEA2D", "BIBLIS": "smpl/static/BIBLIS",
     "KOEBERG": "smpl/static/KOEBERG", "DVP": "smpl/static/DVP", "PNM": "smpl/static/PNM",
     "FDM": "smpl/static/FDM", "adjoint": "smpl/static/adjoint", "fixed_source": "smpl/static/fixed_source",
-    "LMW": "smpl/transient/LMW",
+    "LMW": "smpl/transient/LMW", "NEACRP_A1": "smpl/static/NEACRP/A1",
 }
 
 

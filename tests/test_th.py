@@ -1,0 +1,166 @@
+"""Thermal-hydraulic channel solve th_upd / th_trans (mod_th.f90:440-699) on the
+geometry and %THER card of smpl/static/NEACRP/A1.
+
+The reference holds no thermal-hydraulic output ("parity unpinned").  CPU tests check the numpy
+oracle (oracle/th.py, a statement-by-statement restatement) against conservation laws it does not
+use explicitly; GPU tests check the device kernels against the oracle from identical states."""
+import numpy as np
+import pytest
+
+from conftest import load_problem
+
+
+def _setup(ppow=100.0, seed=1):
+    """problem, TH data, state, a synthetic normalised power shape (chopped cosine x random radial)"""
+    from oracle import th as oth
+    p = load_problem("NEACRP_A1")
+    th = p.th_setup()
+    th["ppow"] = ppow
+    rng = np.random.default_rng(seed)
+    z = np.cumsum(p.zdel) - 0.5 * p.zdel
+    fuel = p.nuf[:, p.ng - 1] > 0
+    shape = np.zeros(p.nnod)
+    shape[fuel] = (np.sin(np.pi * z[p.iz - 1] / z[-1]) * (0.8 + 0.4 * rng.random(p.nnod)) * p.vdel)[fuel]
+    npow = shape / shape.sum()
+    return p, th, oth.initial_state(p, th), npow
+
+
+def test_ther_card_and_derived_data():
+    p = load_problem("NEACRP_A1")
+    th = p.th_setup()
+    assert (p.mode, p.nnod, th["nt"], th["ntem"]) == ("BCSEARCH", 3978, 12, 9)
+    assert th["pi"] == float(np.float32(3.14159265)) and th["pi"] != np.pi          # default-REAL literal
+    assert abs(th["rc"] - (4.1195e-3 + 6.8e-5 + 5.71e-4)) < 1e-18
+    assert abs(th["cflow"] - 82.12102 / 264) < 1e-15
+    # fuel pins: 264 per full assembly, shared among its nodes; the half-width assemblies on the symmetry lines hold half / a quarter
+    nf = th["node_nf"]
+    assert nf.max() == 66.0 and abs(nf[nf > 0].min() - 66.0) < 1e-12           # 2 x 2 nodes per full assembly, 1 node per quarter
+    assert abs(th["rpos"][9] + 0.5 * th["rdel"][9] - th["rf"]) < 1e-15          # the fuel meshes end at the pellet radius
+
+
+def test_oracle_energy_balance_and_convergence():
+    """Conservation checks the restatement does not use: (i) the coolant of every channel leaves with
+    the enthalpy the channel's linear power puts in; (ii) once the fixed point is reached the heat
+    flux through the cladding carries exactly the power generated in the pellet."""
+    from oracle import th as oth
+    p, th, st, npow = _setup()
+    xpl = oth.pline_static(p, th, npow)
+    assert 150.0 < xpl.max() < 450.0                       # W/cm, PWR-like
+    errs = []
+    for _ in range(12):
+        old = st["ftem"].copy()
+        oth.th_upd(p, th, st, xpl)
+        errs.append(oth.abs_e(st["ftem"], old))
+    assert errs[-1] < 1e-6 and all(b < a for a, b in zip(errs[2:], errs[3:]))
+    npl = p.npl
+    enti = oth.getent(th, th["tin"])
+    cpline = st["heatf"] * th["pi"] * th["dia"] + th["cf"] * xpl * 100.0
+    gain = (cpline * p.zdel[p.iz - 1] * 0.01).reshape(p.nzz, npl).sum(axis=0) / th["cflow"]
+    ent_top = st["ent"].reshape(p.nzz, npl)[-1]
+    cp_top = cpline.reshape(p.nzz, npl)[-1]
+    out = ent_top + 0.5 * cp_top * p.zdel[-1] * 0.01 / th["cflow"]          # upper boundary of the top node
+    assert np.abs(out - enti - gain).max() < 1e-6 * enti
+    fuel = xpl > 0
+    q_clad = st["heatf"][fuel] * th["pi"] * th["dia"]                        # W/m through the cladding surface
+    q_gen = (1.0 - th["cf"]) * xpl[fuel] * 100.0 * (th["pi"] * th["rf"] ** 2) / (th["pi"] * th["rf"] ** 2)
+    assert np.abs(q_clad / q_gen - 1.0).max() < 2e-3          # = 1 up to the pi / mesh-edge conventions of the reference
+    assert 560.0 < st["mtem"].max() < 617.0 and 900.0 < st["ftem"].max() < 1500.0
+
+
+def test_oracle_transient_relaxes_to_the_steady_state():
+    """th_trans with constant power and long time steps must reproduce th_upd's fixed point."""
+    from oracle import th as oth
+    p, th, st, npow = _setup()
+    xpl = oth.pline_static(p, th, npow)
+    for _ in range(12):
+        oth.th_upd(p, th, st, xpl)
+    ref = {k: v.copy() for k, v in st.items() if v is not None}
+    # th_trans deposits ALL power in the pellet (no (1 - cf) factor, mod_th.f90:509) -> compare with cf = 0 physics
+    th0 = dict(th, cf=0.0)
+    st0 = oth.initial_state(p, th0)
+    for _ in range(12):
+        oth.th_upd(p, th0, st0, xpl)
+    st0["frate"] = None
+    for _ in range(40):
+        oth.th_trans(p, th0, st0, xpl, 50.0)
+    st1 = {k: v.copy() for k, v in st0.items()}
+    oth.th_trans(p, th0, st1, xpl, 50.0)
+    assert np.abs(st1["ftem"] - st0["ftem"]).max() < 1e-3
+    assert abs(st0["ftem"].max() - ref["ftem"].max()) < 15.0        # same physics up to the heat split
+
+
+def test_oracle_steam_table_stop():
+    from oracle import th as oth
+    p, th, st, npow = _setup(ppow=2000.0)                    # twenty times nominal power: coolant leaves the table
+    with pytest.raises(oth.SteamTableError):
+        for _ in range(3):
+            oth.th_upd(p, th, st, oth.pline_static(p, th, npow))
+
+
+# ------------------------------------------------------------------ GPU
+def _cmp_state(a, b, tol):
+    for k in ("tfm", "heatf", "ent", "ftem", "mtem", "cden"):
+        d = np.abs(a[k] - b[k]).max() / max(np.abs(b[k]).max(), 1e-300)
+        assert d < tol, (k, d)
+
+
+@pytest.mark.gpu
+def test_gpu_th_upd_and_th_trans_against_oracle():
+    from adpres_b200 import capi
+    from oracle import th as oth
+    p, th, st, npow = _setup()
+    xpl = oth.pline_static(p, th, npow)
+    s = capi.Solver(p)
+    s.set_th(th)
+    s.set_th_state(st)
+    for it in range(5):
+        old = st["ftem"].copy()
+        oth.th_upd(p, th, st, xpl)
+        rc, err = s.th_upd(xpl)
+        assert rc == 0
+        assert abs(err - oth.abs_e(st["ftem"], old)) < 1e-9 * max(1.0, err)
+        _cmp_state(s.th_state(), st, 1e-12)                # pow() of the device library: <= 2 ulp
+    for it in range(4):
+        oth.th_trans(p, th, st, xpl * (1.0 + 0.3 * it), 0.05)
+        assert s.th_trans(xpl * (1.0 + 0.3 * it), 0.05) == 0
+        g = s.th_state()
+        _cmp_state(g, st, 1e-12)
+        assert np.abs(g["frate"] - st["frate"]).max() < 1e-12 * th["cflow"]
+
+
+@pytest.mark.gpu
+def test_gpu_th_pline_from_device_power():
+    """pline from the PowDis of the flux on the device, both operand orders (th_iter / trans_calc)."""
+    from adpres_b200 import capi
+    from oracle import th as oth
+    p, th, st, _ = _setup()
+    s = capi.Solver(p, nout=30)
+    s.outer(0)                                              # any flux will do
+    _, npow = s.powdis()
+    s.set_th(th)
+    s.set_th_state(st)
+    s.th_pline(th["pow"], th["ppow"], form=0)
+    rc, _ = s.th_upd(None)
+    assert rc == 0
+    oth.th_upd(p, th, st, oth.pline_static(p, th, npow))
+    _cmp_state(s.th_state(), st, 1e-12)
+    xppow = th["ppow"] * 1.25 * 0.01
+    s.th_pline(th["pow"], xppow, form=1)
+    assert s.th_trans(None, 0.01) == 0
+    nf = th["node_nf"][p.ix - 1, p.iy - 1]
+    oth.th_trans(p, th, st, npow * th["pow"] * xppow / (nf * p.zdel[p.iz - 1]), 0.01)
+    _cmp_state(s.th_state(), st, 1e-12)
+
+
+@pytest.mark.gpu
+def test_gpu_th_steam_table_stop_code():
+    from adpres_b200 import capi
+    from oracle import th as oth
+    p, th, st, npow = _setup(ppow=2000.0)
+    s = capi.Solver(p)
+    s.set_th(th)
+    s.set_th_state(st)
+    rcs = [s.th_upd(oth.pline_static(p, th, npow))[0] for _ in range(3)]
+    assert capi.STOP_STEAM_TABLE in rcs and b"STEAM TABLE" in s.L.adp_last_error(s.h)
+    th_bad = dict(th, tin=700.0)                            # inlet temperature outside the table: getent STOPs
+    assert s.set_th(th_bad) == capi.STOP_STEAM_TABLE
