@@ -131,6 +131,31 @@ module adpres_b200
     integer(c_int) function adp_xs_update(ctx, bpos) bind(C, name="adp_xs_update")
       import; type(c_ptr), value :: ctx; real(c_double), intent(in) :: bpos(*)
     end function
+    integer(c_int) function adp_set_th(ctx, pi, rf, rg, rc, dia, dh, farea, cflow, cf, tin, rpos, rdel, ntem, stab) &
+        bind(C, name="adp_set_th")
+      import; type(c_ptr), value :: ctx
+      real(c_double), value :: pi, rf, rg, rc, dia, dh, farea, cflow, cf, tin
+      real(c_double), intent(in) :: rpos(*), rdel(*), stab(*); integer(c_int), value :: ntem
+    end function
+    integer(c_int) function adp_set_th_state(ctx, tfm, heatf, ent, ftem, mtem, cden, frate) bind(C, name="adp_set_th_state")
+      import; type(c_ptr), value :: ctx, frate          ! frate: c_null_ptr before the first transient step
+      real(c_double), intent(in) :: tfm(*), heatf(*), ent(*), ftem(*), mtem(*), cden(*)
+    end function
+    integer(c_int) function adp_get_th_state(ctx, tfm, heatf, ent, ftem, mtem, cden, frate) bind(C, name="adp_get_th_state")
+      import; type(c_ptr), value :: ctx
+      real(c_double), intent(out) :: tfm(*), heatf(*), ent(*), ftem(*), mtem(*), cden(*), frate(*)
+    end function
+    integer(c_int) function adp_th_pline(ctx, pow, ppow, form, node_nf) bind(C, name="adp_th_pline")
+      import; type(c_ptr), value :: ctx; real(c_double), value :: pow, ppow; integer(c_int), value :: form
+      real(c_double), intent(in) :: node_nf(*)
+    end function
+    integer(c_int) function adp_th_upd(ctx, xpline, th_err) bind(C, name="adp_th_upd")
+      import; type(c_ptr), value :: ctx, xpline         ! xpline: c_null_ptr = the device's pline
+      real(c_double), intent(out) :: th_err
+    end function
+    integer(c_int) function adp_th_trans(ctx, xpline, h) bind(C, name="adp_th_trans")
+      import; type(c_ptr), value :: ctx, xpline; real(c_double), value :: h
+    end function
   end interface
 
 contains

@@ -30,6 +30,8 @@ def main():
     deck = sys.argv[1] if len(sys.argv) > 1 else "IAEA3Ds"
     if deck == "LMW_tr":
         return transient_main(rank, world, local, uid, dist)
+    if deck == "NEACRP_th":
+        return th_main(rank, world, local, uid, dist)
     if deck == "IAEA3Ds_z2":                  # 38 planes: uneven slabs at 4 ranks, 2 planes per axial assembly
         p = load_problem("IAEA3Ds").refine(zdiv=[2] * 19)
     else:
@@ -124,6 +126,42 @@ def transient_main(rank, world, local, uid, dist):
         assert abs(a[3] / b[3] - 1) < 1e-5, (a, b)
         assert abs(a[2] - b[2]) < 1e-5, (a, b)
     print(f"RANK {rank}/{world} OK deck=LMW_tr planes=[{s.k0},{s.k1}) power={tr_d[-1][3]:.6f}", flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def th_main(rank, world, local, uid, dist):
+    """th_upd / th_trans on z-slabs: the enthalpy march is a chain, every slab receives entm / bfrate
+    from the slab below and passes them on.  Owned nodes against the single-process oracle."""
+    import numpy as np
+    from adpres_b200 import capi
+    from oracle import th as oth
+    from test_th import _setup
+    p, th, st, npow = _setup()
+    xpl = oth.pline_static(p, th, npow)
+    s = capi.Solver(p, device=local, nranks=world, rank=rank, uid=uid)
+    s.set_th(th)
+    s.set_th_state(st)
+    own = s.own
+
+    def check():
+        g = s.th_state()
+        for k in ("tfm", "heatf", "ent", "ftem", "mtem", "cden", "frate"):
+            if st.get(k) is None:
+                continue
+            d = np.abs(g[k][own] - st[k][own]).max() / max(np.abs(st[k]).max(), 1e-300)
+            assert d < 1e-12, (k, d)
+    for it in range(4):
+        old = st["ftem"].copy()
+        oth.th_upd(p, th, st, xpl)
+        rc, err = s.th_upd(xpl)
+        assert rc == 0 and abs(err - oth.abs_e(st["ftem"], old)) < 1e-9 * max(1.0, err)      # all-reduced maximum
+        check()
+    for it in range(3):
+        oth.th_trans(p, th, st, xpl * 1.4, 0.05)
+        assert s.th_trans(xpl * 1.4, 0.05) == 0
+        check()
+    print(f"RANK {rank}/{world} OK deck=NEACRP_th planes=[{s.k0},{s.k1}) ftem_max={st['ftem'].max():.3f}", flush=True)
     dist.barrier()
     dist.destroy_process_group()
 
