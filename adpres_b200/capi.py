@@ -25,10 +25,10 @@ SYMBOLS = [
     "adp_create", "adp_destroy", "adp_last_error", "adp_version", "adp_comm_unique_id", "adp_comm_init", "adp_comm_init_env", "adp_slab",
     "adp_set_geometry", "adp_set_xs", "adp_set_control", "adp_matrix_setup", "adp_init_flux", "adp_outer_begin",
     "adp_outer_iter", "adp_nodal_upd", "adp_powdis", "adp_integrate", "adp_set_kinetics", "adp_set_transient",
-    "adp_get_exsrc", "adp_set_material_xs", "adp_set_crod", "adp_xs_update", "adp_get_xs", "adp_save_adjoint", "adp_ipden", "adp_update_omeg", "adp_begin_time_step", "adp_upden", "adp_powtot", "adp_asm_pow", "adp_axi_pow", "adp_asm_flux", "adp_set_th", "adp_set_th_state", "adp_get_th_state", "adp_th_pline",
+    "adp_get_exsrc", "adp_set_material_xs", "adp_set_crod", "adp_xs_update", "adp_set_feedback", "adp_xs_update_th", "adp_get_xs", "adp_save_adjoint", "adp_ipden", "adp_update_omeg", "adp_begin_time_step", "adp_upden", "adp_powtot", "adp_asm_pow", "adp_axi_pow", "adp_asm_flux", "adp_set_th", "adp_set_th_state", "adp_get_th_state", "adp_th_pline",
     "adp_th_upd", "adp_th_trans",
     "adp_reactivity", "adp_get_state", "adp_set_state", "adp_set_s0", "adp_get_nod", "adp_set_nod_dn", "adp_lxyz_total", "adp_get_exsrc_arrays",
-    "adp_get_ndmax", "adp_set_trace", "adp_outer", "adp_outer_ad", "adp_outer_fs", "adp_outer_th", "adp_outer_tr",
+    "adp_get_ndmax", "adp_get_errors", "adp_set_trace", "adp_outer", "adp_outer_ad", "adp_outer_fs", "adp_outer_th", "adp_outer_tr",
     "adp_sp_matvec", "adp_bicg", "adp_get_matrix", "adp_get_source", "adp_set_option", "adp_launch_count",
     "adp_bench_kernel", "adp_outer_steps", "adp_timer_start", "adp_timer_stop",
 ]
@@ -331,7 +331,9 @@ class Solver:
         s0 = np.zeros((self.N, self.G), order="F")
         ke = C.c_double()
         self._chk(self.L.adp_get_state(self.h, _d(f0), _d(fs0), _d(s0), C.byref(ke)))
-        return dict(f0=f0, fs0=fs0, s0=s0, Ke=ke.value)
+        ser, fer = C.c_double(), C.c_double()
+        self.L.adp_get_errors(self.h, C.byref(ser), C.byref(fer))
+        return dict(f0=f0, fs0=fs0, s0=s0, Ke=ke.value, ser=ser.value, fer=fer.value)
 
     def nod(self):
         df = np.zeros((6, self.N, self.G), order="F")
@@ -423,6 +425,21 @@ class Solver:
     def xs_update(self, bpos=None):
         b = None if bpos is None else np.ascontiguousarray(bpos, dtype=np.float64)
         self._chk(self.L.adp_xs_update(self.h, _d(b)))
+
+    def set_feedback(self, p=None):
+        """feedback cards of the deck (p.fbk) -> device tables"""
+        p = p or self.p
+        for which, key in enumerate(("bcon", "ftem", "mtem", "cden")):
+            t = (p.fbk or {}).get(key)
+            if t is None:
+                continue
+            a = [np.asfortranarray(t[k], dtype=np.float64) for k in ("sigtr", "siga", "nuf", "sigf", "sigs")]
+            self._chk(self.L.adp_set_feedback(self.h, which, C.c_double(t["ref"]), *[_d(x) for x in a]))
+
+    def xs_update_th(self, bcon, ftem=None, mtem=None, cden=None, bpos=None):
+        f = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float64)
+        ft, mt, cd, bp = f(ftem), f(mtem), f(cden), f(bpos)
+        self._chk(self.L.adp_xs_update_th(self.h, C.c_double(bcon), _d(ft), _d(mt), _d(cd), _d(bp)))
 
     def get_xs(self):
         N, G = self.N, self.G

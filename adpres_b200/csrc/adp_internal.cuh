@@ -122,6 +122,7 @@ struct adp_ctx {
     // control
     int nout = 500, nin = 2, nac = 5, nupd = 1000000, kern = ADP_KERN_SANM;
     double serc = 1e-5, ferc = 1e-5;
+    double last_ser = 1.0, last_fer = 1.0;   // source / flux error of the last outer iteration
     double ndmax = 0.0;  // persists across outer*() calls, starts at 0 (mod_data.f90:199)
     int im = 0, jm = 0, km = 0;
     bool coup_first = true, have_flux = false, geometry_set = false, xs_set = false, matrix_ready = false;
@@ -167,6 +168,9 @@ struct adp_ctx {
         int ntem = 0;
     } th;
     bool th_set = false, th_state_set = false, th_pline_set = false;
+    double *d_ftab[4] = {nullptr, nullptr, nullptr, nullptr};   // feedback tables: bcon, ftem, mtem, cden (layout of d_xtab)
+    double fref[4] = {0, 0, 0, 0}, bcon = 0.0;
+    bool xs_feedback = false;              // the current adp_xs_update applies the feedback tables
     double *d_stab = nullptr;              // (ntem, 6) column-major
     double *d_tfm = nullptr;               // [nt+1][NV] radial pin temperatures
     double *d_heatf = nullptr, *d_ent = nullptr, *d_ftem = nullptr, *d_mtem = nullptr, *d_cden = nullptr, *d_frate = nullptr,
@@ -281,6 +285,7 @@ int adp_k_scale_by_slot(adp_ctx *c, double *d_vec, int slot);
 int adp_k_get_exsrc(adp_ctx *c, double ht);
 int adp_k_integrate(adp_ctx *c, const double *d_vec, int slot);
 int adp_k_xs_update(adp_ctx *c);
+int adp_th_alloc(adp_ctx *c);            // th.cu: node arrays of the thermal-hydraulic state
 int adp_k_ipden(adp_ctx *c);
 int adp_k_upden(adp_ctx *c, double ht);
 int adp_k_begin_step(adp_ctx *c, double ht);

@@ -97,6 +97,7 @@ extern "C" int adp_destroy(adp_ctx *c)
     {
         double *th[] = {c->d_stab, c->d_tfm, c->d_heatf, c->d_ent, c->d_ftem, c->d_mtem, c->d_cden, c->d_frate, c->d_pline, c->d_nodenf, c->d_chain};
         for (double *q : th) if (q) cudaFree(q);
+        for (int f = 0; f < 4; ++f) if (c->d_ftab[f]) cudaFree(c->d_ftab[f]);
     }
     cudaStreamDestroy(c->stream);
     delete c;
@@ -273,6 +274,8 @@ extern "C" int adp_set_geometry(adp_ctx *c, int nxx, int nyy, int nzz, int nnod,
         if (c->h_res) { cudaFreeHost(c->h_res); c->h_res = nullptr; }
         c->res_elems = 0; c->nb = 0; c->kinetics_set = false;
         c->th_set = c->th_state_set = c->th_pline_set = false;
+        for (int f = 0; f < 4; ++f)
+            if (c->d_ftab[f]) { cudaFree(c->d_ftab[f]); c->d_ftab[f] = nullptr; }
     }
     c->abefgh_valid = false;
     c->geometry_set = true;
@@ -440,8 +443,9 @@ extern "C" int adp_outer_iter(adp_ctx *c, int mode, int p, double *Ke, double *s
     TRY(launch_outer_iter(c, mode, (p % c->nac) == 0));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     if (Ke) *Ke = c->h_scal[S_KE];
-    if (ser) *ser = c->h_scal[S_SER];
-    if (fer) *fer = c->h_scal[S_FER];
+    c->last_ser = c->h_scal[S_SER]; c->last_fer = c->h_scal[S_FER];
+    if (ser) *ser = c->last_ser;
+    if (fer) *fer = c->last_fer;
     if (c->nranks > 1 && !std::isfinite(c->h_scal[S_KE])) {
         int flag = 0;
         cudaMemcpy(&flag, c->d_errflag, sizeof(int), cudaMemcpyDeviceToHost);
@@ -512,6 +516,14 @@ extern "C" int adp_get_ndmax(adp_ctx *c, double *ndmax)
 {
     if (!c || !ndmax) return ADP_ERR_USAGE;
     *ndmax = c->ndmax;
+    return ADP_OK;
+}
+
+extern "C" int adp_get_errors(adp_ctx *c, double *ser, double *fer)
+{   // sdata's `ser`, `fer` after the last outer iteration (read by th_iter, cbsearch: mod_th.f90:77,789)
+    if (!c) return ADP_ERR_USAGE;
+    if (ser) *ser = c->last_ser;
+    if (fer) *fer = c->last_fer;
     return ADP_OK;
 }
 
@@ -654,6 +666,45 @@ extern "C" int adp_xs_update(adp_ctx *c, const double *bpos)
     CUDA_TRY(c, cudaSetDevice(c->device));
     if (c->d_fb) CUDA_TRY(c, cudaMemcpyAsync(c->d_bpos, bpos, c->nb * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     TRY(adp_k_xs_update(c));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return ADP_OK;
+}
+
+extern "C" int adp_set_feedback(adp_ctx *c, int which, double ref, const double *dsigtr, const double *dsiga,
+                                const double *dnuf, const double *dsigf, const double *dsigs)
+{   // %BCON / %CBCS (which 0), %FTEM (1), %MTEM (2), %CDEN (3): reference value and the cross-section
+    // changes per unit change of the parameter (mod_io.f90:2486-2957)
+    if (!c || !dsigtr || !dsiga || !dnuf || !dsigf || !dsigs) return ADP_ERR_USAGE;
+    ADP_REQUIRE(c, c->geometry_set, "adp_set_feedback: geometry not set");
+    ADP_REQUIRE(c, which >= 0 && which < 4, "adp_set_feedback: which must be 0 (bcon), 1 (ftem), 2 (mtem) or 3 (cden)");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    c->fref[which] = ref;
+    return upload_tables(c, &c->d_ftab[which], dsigtr, dsiga, dnuf, dsigf, dsigs);
+}
+
+extern "C" int adp_xs_update_th(adp_ctx *c, double bcon, const double *ftem, const double *mtem, const double *cden,
+                                const double *bpos)
+{   // XS_updt(bcon, ftem, mtem, cden, bpos) (mod_xsec.f90:11-46) with the feedback cards given by
+    // adp_set_feedback; ftem / mtem / cden: host (nnod) or NULL = the state adp_th_upd left on the device
+    if (!c) return ADP_ERR_USAGE;
+    ADP_REQUIRE(c, c->d_xtab != nullptr, "adp_xs_update_th: call adp_set_material_xs first");
+    ADP_REQUIRE(c, c->xs_set, "adp_xs_update_th: chi / dc / exsrc come from adp_set_xs (call it once)");
+    ADP_REQUIRE(c, !c->d_fb || bpos, "adp_xs_update_th: bank positions missing");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    TRY(adp_th_alloc(c));
+    const double *host[3] = {ftem, mtem, cden};
+    double *dev[3] = {c->d_ftem, c->d_mtem, c->d_cden};
+    for (int i = 0; i < 3; ++i) {
+        if (!c->d_ftab[1 + i]) continue;
+        ADP_REQUIRE(c, host[i] || c->th_state_set, "adp_xs_update_th: a feedback parameter is neither passed nor on the device");
+        if (host[i]) TRY(adp_upload_nodes(c, dev[i], host[i], 1));
+    }
+    c->bcon = bcon;
+    if (c->d_fb) CUDA_TRY(c, cudaMemcpyAsync(c->d_bpos, bpos, c->nb * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    c->xs_feedback = true;
+    const int rc = adp_k_xs_update(c);
+    c->xs_feedback = false;
+    if (rc) return rc;
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     return ADP_OK;
 }

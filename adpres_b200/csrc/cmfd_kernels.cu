@@ -715,6 +715,11 @@ struct XsArgs {
     const double *bpos, *dumtop;                                 // [nb], [nzz]: rod length above plane k
     double coreh, pos0, ssize;
     double *D, *sigr, *nuf, *sigf, *sigs;                        // node-wise outputs
+    // feedback (bcon_updt, ftem_updt, mtem_updt, cden_updt, mod_xsec.f90:396-516): tables laid out like
+    // xsigtr.. (nullptr = card absent), reference values, boron concentration, node-wise TH state
+    const double *ftab[4];
+    double fref[4], bcon;
+    const double *ftem, *mtem, *cden;
 };
 __global__ void __launch_bounds__(ADP_TILE) k_xs_update(Geo G, XsArgs A, int klo, int npl)
 {
@@ -735,9 +740,24 @@ __global__ void __launch_bounds__(ADP_TILE) k_xs_update(Geo G, XsArgs A, int klo
             else if (rodh > dum || (rodh == dum && kg == G.nzz - 1)) w = (rodh - dum) / hz;
             // rodh == dum below the top: the node above took it with vfrac = 1 and the sweep EXITed
         }
+        // parameter changes the feedback tables are multiplied with, in the reference's order
+        double dlt[4] = {0.0, 0.0, 0.0, 0.0};
+        if (A.ftab[0]) dlt[0] = A.bcon - A.fref[0];
+        if (A.ftab[1]) dlt[1] = sqrt(A.ftem[idx]) - sqrt(A.fref[1]);
+        if (A.ftab[2]) dlt[2] = A.mtem[idx] - A.fref[2];
+        if (A.ftab[3]) dlt[3] = A.cden[idx] - A.fref[3];
+        const int mg = A.nmat * A.ng;
         for (int g = 0; g < A.ng; ++g) {
             const int t = g * A.nmat + m;
             double sigtr = A.xsigtr[t], siga = A.xsiga[t], nuf = A.xnuf[t], sigf = A.xsigf[t];
+#pragma unroll
+            for (int f = 0; f < 4; ++f)
+                if (A.ftab[f]) {
+                    sigtr = sigtr + A.ftab[f][t] * dlt[f];
+                    siga = siga + A.ftab[f][mg + t] * dlt[f];
+                    nuf = nuf + A.ftab[f][2 * mg + t] * dlt[f];
+                    sigf = sigf + A.ftab[f][3 * mg + t] * dlt[f];
+                }
             if (w >= 0.0) {
                 if (w == 1.0) { sigtr = sigtr + A.dsigtr[t]; siga = siga + A.dsiga[t]; nuf = nuf + A.dnuf[t]; sigf = sigf + A.dsigf[t]; }
                 else { sigtr = sigtr + w * A.dsigtr[t]; siga = siga + w * A.dsiga[t]; nuf = nuf + w * A.dnuf[t]; sigf = sigf + w * A.dsigf[t]; }
@@ -751,6 +771,9 @@ __global__ void __launch_bounds__(ADP_TILE) k_xs_update(Geo G, XsArgs A, int klo
             for (int h = 0; h < A.ng; ++h) {
                 const int t2 = m + A.nmat * (g + A.ng * h);                    // xsigs(mat, g, h): g -> h
                 double ss = A.xsigs[t2];
+#pragma unroll
+                for (int f = 0; f < 4; ++f)
+                    if (A.ftab[f]) ss = ss + A.ftab[f][4 * mg + t2] * dlt[f];
                 if (w >= 0.0) ss = (w == 1.0) ? ss + A.dsigs[t2] : ss + w * A.dsigs[t2];
                 if (b > 0 && ss < 0.0) ss = 0.0;
                 A.sigs[((size_t)h * A.ng + g) * NV + idx] = ss;
@@ -1216,6 +1239,14 @@ int adp_k_xs_update(adp_ctx *c)
     }
     A.mat = c->d_mat;
     A.D = c->d_D; A.sigr = c->d_sigr; A.nuf = c->d_nuf; A.sigf = c->d_sigf; A.sigs = c->d_sigs;
+    for (int f = 0; f < 4; ++f) { A.ftab[f] = c->xs_feedback ? c->d_ftab[f] : nullptr; A.fref[f] = c->fref[f]; }
+    A.bcon = c->bcon; A.ftem = c->d_ftem; A.mtem = c->d_mtem; A.cden = c->d_cden;
+    if (c->xs_feedback && c->nranks > 1) {   // the ghost planes take the neighbours' temperatures and densities
+        int rc;
+        if (A.ftab[1] && (rc = adp_comm_halo(c, c->d_ftem, ADP_GH))) return rc;
+        if (A.ftab[2] && (rc = adp_comm_halo(c, c->d_mtem, ADP_GH))) return rc;
+        if (A.ftab[3] && (rc = adp_comm_halo(c, c->d_cden, ADP_GH))) return rc;
+    }
     // own planes and the ghost planes that lie inside the core (static data: no communication)
     const int klo = -((c->k0 >= ADP_GH) ? ADP_GH : c->k0);
     const int khi = c->nzl + ((c->nzz - c->k1 >= ADP_GH) ? ADP_GH : (c->nzz - c->k1));

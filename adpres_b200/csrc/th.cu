@@ -259,7 +259,7 @@ __global__ void __launch_bounds__(ADP_TILE) k_th_abse(Geo G, const double *__res
         if (rc__) return rc__; \
     } while (0)
 
-static int th_alloc(adp_ctx *c)
+int adp_th_alloc(adp_ctx *c)
 {
     if (c->d_tfm) return ADP_OK;
     const size_t NV = (size_t)c->NV;
@@ -304,7 +304,7 @@ extern "C" int adp_set_th(adp_ctx *c, double pi, double rf, double rg, double rc
     if (c->d_stab) { cudaFree(c->d_stab); c->d_stab = nullptr; }
     CUDA_TRY(c, cudaMalloc((void **)&c->d_stab, (size_t)ntem * 6 * sizeof(double)));
     CUDA_TRY(c, cudaMemcpy(c->d_stab, stab, (size_t)ntem * 6 * sizeof(double), cudaMemcpyHostToDevice));
-    TRY(th_alloc(c));
+    TRY(adp_th_alloc(c));
     c->th_set = true;
     return ADP_OK;
 }

@@ -171,6 +171,7 @@ class Problem:
     crod: Optional[dict] = None          # %CROD: nb, nstep, pos0, ssize, bpos[nb], bmap(nx,ny), dsigtr/dsiga/dnuf/dsigf (nmat,ng), dsigs (nmat,ng,ng)
     ejct: Optional[dict] = None          # %EJCT: fbpos, tmove, bspeed, ttot, tstep1, tdiv, tstep2, ibeta, lamb, velo
     bextr: int = 0
+    fbk: Optional[dict] = None            # %BCON / %CBCS / %FTEM / %MTEM / %CDEN: {name: dict(val, ref, sigtr, siga, nuf, sigf, sigs)}
     ther: Optional[dict] = None           # %THER raw inputs (ppow, pow, tin, cmflow, rf, tg, tc, ppitch, nfpin, ngt, cf)
     cards: Optional[Dict[str, List[str]]] = None
     # ---- node-wise (filled by build())
@@ -205,7 +206,7 @@ class Problem:
     _SPEC_FIELDS = ("mode", "ng", "nmat", "nx", "ny", "nz", "xsize", "ysize", "zsize", "xdiv", "ydiv",
                     "zdiv", "zpln", "planars", "bc", "xsigtr", "xsiga", "xnuf", "xsigf", "xsigs", "chi",
                     "nout", "nin", "serc", "ferc", "nac", "nupd", "th_niter", "nth", "kern", "biter",
-                    "sth", "bth", "mdc", "adf_rot", "esrc", "crod", "ejct", "bextr", "ther")
+                    "sth", "bth", "mdc", "adf_rot", "esrc", "crod", "ejct", "bextr", "ther", "fbk")
 
     def to_spec(self) -> dict:
         """JSON-able problem specification (what the deck says, before node expansion).
@@ -216,7 +217,9 @@ class Problem:
             v = getattr(self, k)
             if k == "nupd" and not self.biter:
                 v = 0
-            if isinstance(v, dict):
+            if k == "fbk" and v is not None:
+                v = {name: {kk: (vv.tolist() if isinstance(vv, np.ndarray) else vv) for kk, vv in t.items()} for name, t in v.items()}
+            elif isinstance(v, dict):
                 v = {kk: (vv.tolist() if isinstance(vv, np.ndarray) else vv) for kk, vv in v.items()}
             d[k] = v.tolist() if isinstance(v, np.ndarray) else v
         return d
@@ -239,6 +242,9 @@ class Problem:
                 kw[card] = {kk: (np.array(vv) if isinstance(vv, list) else vv) for kk, vv in kw[card].items()}
                 if card == "crod":
                     kw[card]["bmap"] = kw[card]["bmap"].astype(np.int32)
+        if kw.get("fbk") is not None:
+            kw["fbk"] = {name: {kk: (np.array(vv, dtype=np.float64) if isinstance(vv, list) else vv) for kk, vv in t.items()}
+                         for name, t in kw["fbk"].items()}
         return Problem(**kw).build()
 
     # ------------------------------------------------------------------ geometry
@@ -310,9 +316,10 @@ class Problem:
         self._build_esrc()
         return self
 
-    def update_xs(self, bpos=None) -> None:
-        """XS_updt for the cards in scope: base_updt [+ crod_updt(bpos)] + Dsigr_updt
-        (mod_xsec.f90:11-46,172-296)."""
+    def update_xs(self, bpos=None, bcon=None, ftem=None, mtem=None, cden=None) -> None:
+        """XS_updt (mod_xsec.f90:11-46): base_updt, then bcon_updt / ftem_updt / mtem_updt / cden_updt
+        (:396-516) for the feedback cards of the deck, crod_updt(bpos), Dsigr_updt.  A parameter
+        left at None takes the value of its card."""
         m = self.mat - 1
         N, G = self.nnod, self.ng
         self.sigtr = np.asfortranarray(self.xsigtr[m, :])
@@ -320,6 +327,22 @@ class Problem:
         self.nuf = np.asfortranarray(self.xnuf[m, :])
         self.sigf = np.asfortranarray(self.xsigf[m, :])
         self.sigs = np.asfortranarray(self.xsigs[m, :, :])
+        given = dict(bcon=bcon, ftem=ftem, mtem=mtem, cden=cden)
+        for key in ("bcon", "ftem", "mtem", "cden"):                     # the reference's order
+            t = (self.fbk or {}).get(key)
+            if t is None:
+                continue
+            x = t["val"] if given[key] is None else given[key]
+            if key == "ftem":
+                delta = np.sqrt(x) - np.sqrt(t["ref"])
+            else:
+                delta = x - t["ref"]
+            delta = np.broadcast_to(np.asarray(delta, dtype=np.float64), (N,))
+            self.sigtr = self.sigtr + t["sigtr"][m, :] * delta[:, None]
+            self.siga = self.siga + t["siga"][m, :] * delta[:, None]
+            self.nuf = self.nuf + t["nuf"][m, :] * delta[:, None]
+            self.sigf = self.sigf + t["sigf"][m, :] * delta[:, None]
+            self.sigs = self.sigs + t["sigs"][m, :, :] * delta[:, None, None]
         if self.crod is not None:
             self.crod_updt(self.crod["bpos"] if bpos is None else bpos)
         self.finish_xs()
@@ -618,6 +641,24 @@ def parse_deck(text: str, base_dir: str = ".") -> Problem:
                       tdiv=tdiv, tstep2=tstep2, ibeta=ibeta, lamb=lamb, velo=velo)
     if "EXTR" in cards:
         p.bextr = 1
+    # feedback cards (mod_io.f90:2486-2957): reference value(s), then nmat x ng records of
+    # d(sigtr, siga, nuf, sigf, sigs(1..ng)) per unit change of the parameter
+    fbk = {}
+    for card, key, nval in (("CBCS", "bcon", 1), ("BCON", "bcon", 2), ("FTEM", "ftem", 2), ("MTEM", "mtem", 2), ("CDEN", "cden", 2)):
+        if card not in cards:
+            continue
+        r = _Reader(cards[card], card)
+        v = r.floats(nval)
+        tab = dict(val=v[0], ref=v[-1], sigtr=np.zeros((nmat, ng)), siga=np.zeros((nmat, ng)), nuf=np.zeros((nmat, ng)),
+                   sigf=np.zeros((nmat, ng)), sigs=np.zeros((nmat, ng, ng)))
+        for i in range(nmat):
+            for g in range(ng):
+                w = r.floats(4 + ng)
+                tab["sigtr"][i, g], tab["siga"][i, g], tab["nuf"][i, g], tab["sigf"][i, g] = w[:4]
+                tab["sigs"][i, g, :] = w[4:]
+        fbk[key] = tab
+    if fbk:
+        p.fbk = fbk
     if "THER" in cards:                          # mod_io.f90:2996-3034 (derived data: Problem.th_setup)
         r = _Reader(cards["THER"], "THER")
         ppow = r.floats(1)[0]

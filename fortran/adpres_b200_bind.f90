@@ -131,6 +131,17 @@ module adpres_b200
     integer(c_int) function adp_xs_update(ctx, bpos) bind(C, name="adp_xs_update")
       import; type(c_ptr), value :: ctx; real(c_double), intent(in) :: bpos(*)
     end function
+    integer(c_int) function adp_set_feedback(ctx, which, ref, dsigtr, dsiga, dnuf, dsigf, dsigs) bind(C, name="adp_set_feedback")
+      import; type(c_ptr), value :: ctx; integer(c_int), value :: which; real(c_double), value :: ref
+      real(c_double), intent(in) :: dsigtr(*), dsiga(*), dnuf(*), dsigf(*), dsigs(*)
+    end function
+    integer(c_int) function adp_xs_update_th(ctx, bcon, ftem, mtem, cden, bpos) bind(C, name="adp_xs_update_th")
+      import; type(c_ptr), value :: ctx, ftem, mtem, cden      ! c_null_ptr = the TH state on the device
+      real(c_double), value :: bcon; real(c_double), intent(in) :: bpos(*)
+    end function
+    integer(c_int) function adp_get_errors(ctx, ser, fer) bind(C, name="adp_get_errors")
+      import; type(c_ptr), value :: ctx; real(c_double), intent(out) :: ser, fer
+    end function
     integer(c_int) function adp_set_th(ctx, pi, rf, rg, rc, dia, dh, farea, cflow, cf, tin, rpos, rdel, ntem, stab) &
         bind(C, name="adp_set_th")
       import; type(c_ptr), value :: ctx

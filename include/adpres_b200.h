@@ -149,6 +149,15 @@ int adp_set_crod(adp_ctx *ctx, int nb, double pos0, double ssize, const int *fbm
 /* base_updt + crod_updt(bpos) + Dsigr_updt -> D, sigr, nuf, sigf, sigs on the device
  * (mod_xsec.f90:172-296); chi, dc, exsrc stay as adp_set_xs left them */
 int adp_xs_update(adp_ctx *ctx, const double *bpos /* (nb) or NULL without rods */);
+/* feedback cards %BCON / %CBCS (which 0), %FTEM (1), %MTEM (2), %CDEN (3): reference value and
+ * d(sigtr, siga, nuf, sigf)(nmat,ng), dsigs(nmat,ng,ng) per unit change               mod_io.f90:2486-2957 */
+int adp_set_feedback(adp_ctx *ctx, int which, double ref, const double *dsigtr, const double *dsiga, const double *dnuf,
+                     const double *dsigf, const double *dsigs);
+/* XS_updt(bcon, ftem, mtem, cden, bpos): base_updt, bcon_updt, ftem_updt (SQRT), mtem_updt, cden_updt,
+ * crod_updt, Dsigr_updt (mod_xsec.f90:11-46,172-516); ftem / mtem / cden host (nnod) or NULL = the
+ * thermal-hydraulic state on the device (adp_th_upd / adp_set_th_state) */
+int adp_xs_update_th(adp_ctx *ctx, double bcon, const double *ftem, const double *mtem, const double *cden,
+                     const double *bpos);
 int adp_get_xs(adp_ctx *ctx, double *D, double *sigr, double *nuf, double *sigf, double *sigs);
 
 /* ---- optional: the time-step glue of mod_trans.f90 on the device ------------- */
@@ -223,6 +232,8 @@ int adp_lxyz_total(adp_ctx *ctx, double *L);
 int adp_get_exsrc_arrays(adp_ctx *ctx, double *exsrc, double *dfis);
 /* ndmax persists across outer*() calls and starts at 0 (mod_data.f90:199) */
 int adp_get_ndmax(adp_ctx *ctx, double *ndmax);
+/* sdata's ser / fer after the last outer iteration (th_iter, cbsearch read them: mod_th.f90:77,789) */
+int adp_get_errors(adp_ctx *ctx, double *ser, double *fer);
 
 /* ---- whole procedures (host loop in C++, adpres_b200/csrc/host_cmfd.cpp) ---------------- */
 /* Trace callback: called once per outer iteration with what the reference prints

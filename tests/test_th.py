@@ -164,3 +164,93 @@ def test_gpu_th_steam_table_stop_code():
     assert capi.STOP_STEAM_TABLE in rcs and b"STEAM TABLE" in s.L.adp_last_error(s.h)
     th_bad = dict(th, tin=700.0)                            # inlet temperature outside the table: getent STOPs
     assert s.set_th(th_bad) == capi.STOP_STEAM_TABLE
+
+
+# ------------------------------------------------------------------ XS feedback + boron search (NEACRP A1 deck)
+def test_feedback_cards_parsed():
+    p = load_problem("NEACRP_A1")
+    assert set(p.fbk) == {"bcon", "ftem", "mtem", "cden"}
+    assert (p.fbk["bcon"]["ref"], p.fbk["ftem"]["ref"], p.fbk["mtem"]["ref"], p.fbk["cden"]["ref"]) == (1200.2, 891.45, 579.75, 0.7125)
+    assert p.fbk["bcon"]["sigs"].shape == (p.nmat, p.ng, p.ng) and p.fbk["bcon"]["siga"][0, 1] == 1.02635e-05
+    # XS_updt order and signs: more boron -> more thermal absorption in the fuel; hotter fuel -> more fast absorption
+    p.update_xs(bcon=1200.2, ftem=np.full(p.nnod, 891.45), mtem=np.full(p.nnod, 579.75), cden=np.full(p.nnod, 0.7125))
+    base = p.sigr.copy()
+    p.update_xs(bcon=1300.2, ftem=np.full(p.nnod, 891.45), mtem=np.full(p.nnod, 579.75), cden=np.full(p.nnod, 0.7125))
+    fuel = p.nuf[:, 1] > 0
+    assert (p.sigr[fuel, 1] > base[fuel, 1]).all()
+    p.update_xs(bcon=1200.2, ftem=np.full(p.nnod, 1200.0), mtem=np.full(p.nnod, 579.75), cden=np.full(p.nnod, 0.7125))
+    assert (p.sigr[fuel, 0] > base[fuel, 0]).all()
+
+
+def test_oracle_critical_boron_search_with_th_feedback():
+    """cbsearcht on smpl/static/NEACRP/A1 end to end with the CPU oracle: the secant search converges
+    in a handful of boron guesses; at hot zero power (ppow = 1e-4 %) the core stays at the inlet
+    temperature.  (No reference output exists for this deck: parity unpinned.)"""
+    from adpres_b200 import thermal
+    from oracle import Oracle, th as oth
+    p = load_problem("NEACRP_A1")
+    g = thermal.HostGlue(p, Oracle(p), oth)
+    bc, rows = thermal.cbsearcht(g)
+    assert len(rows) <= 8 and abs(rows[-1][2] - 1.0) < 1e-5
+    assert 500.0 < bc < 800.0
+    f = g.th_fields()
+    assert abs(f["ftem"].max() - 559.15) < 0.05 and abs(f["mtem"].max() - 559.15) < 0.05
+    # rods out needs far more boron; a colder reference density less
+    p2 = load_problem("NEACRP_A1")
+    g2 = thermal.HostGlue(p2, Oracle(p2), oth)
+    g2.bpos = np.full(7, 228.0)
+    assert thermal.cbsearcht(g2)[0] > bc + 300.0
+
+
+@pytest.mark.gpu
+def test_gpu_xs_feedback_update_bit_exact():
+    """adp_xs_update_th (base + bcon + ftem(SQRT) + mtem + cden + rods + D/sigr on the device) against the
+    numpy XS_updt of the harness for random TH fields, several boron concentrations and rod positions."""
+    from adpres_b200 import capi
+    p = load_problem("NEACRP_A1")
+    s = capi.Solver(p)
+    s.set_material_xs(p); s.set_crod(p); s.set_feedback(p)
+    rng = np.random.default_rng(11)
+    for bcon, step in ((1200.2, 0.0), (567.7, 37.3), (0.0, 228.0), (2999.0, 100.5)):
+        ftem = 559.0 + 900.0 * rng.random(p.nnod)
+        mtem = 550.0 + 60.0 * rng.random(p.nnod)
+        cden = 0.60 + 0.18 * rng.random(p.nnod)
+        bpos = np.array([step, 0.0, 228.0, 114.0, step, 228.0, 0.0])
+        p.update_xs(bpos, bcon=bcon, ftem=ftem, mtem=mtem, cden=cden)
+        s.xs_update_th(bcon, ftem, mtem, cden, bpos)
+        x = s.get_xs()
+        for k in ("D", "sigr", "nuf", "sigf", "sigs"):
+            assert np.array_equal(x[k], getattr(p, k)), (k, bcon, np.abs(x[k] - getattr(p, k)).max())
+
+
+@pytest.mark.gpu
+def test_gpu_critical_boron_search_device_resident():
+    """The whole feedback loop on the device (XS update with feedback tables, outer_th, PowDis -> pline,
+    th_upd): per boron guess one number goes up, k-eff / ser / fer / th_err come back.  Against the
+    CPU oracle with numpy glue: same number of guesses, critical boron within 0.01 ppm, TH fields 1e-6."""
+    from adpres_b200 import capi, thermal
+    from oracle import Oracle, th as oth
+    p1, p2 = load_problem("NEACRP_A1"), load_problem("NEACRP_A1")
+    go = thermal.HostGlue(p1, Oracle(p1), oth)
+    gd = thermal.DeviceGlue(p2, capi.Solver(p2))
+    bo, ro = thermal.cbsearcht(go)
+    bd, rd = thermal.cbsearcht(gd)
+    assert len(ro) == len(rd)
+    assert abs(bo - bd) < 0.01, (bo, bd)
+    for a, b in zip(rd, ro):
+        assert abs(a[1] - b[1]) < 0.01 and abs(a[2] - b[2]) < 1e-6, (a, b)
+    fo, fd = go.th_fields(), gd.th_fields()
+    for k in fo:
+        assert np.abs(fd[k] / fo[k] - 1.0).max() < 1e-6, k
+    # a power case: 100 % power, full TH iteration (th_iter with convergence test)
+    for q in (p1, p2):
+        q.ther["ppow"] = 100.0
+    go = thermal.HostGlue(p1, Oracle(p1), oth)
+    gd = thermal.DeviceGlue(p2, capi.Solver(p2))
+    eo, lo = thermal.th_iter(go, 600.0, ind=0)
+    ed, ld = thermal.th_iter(gd, 600.0, ind=0)
+    assert lo == ld and abs(go.state()["Ke"] - gd.state()["Ke"]) < 1e-6
+    fo, fd = go.th_fields(), gd.th_fields()
+    assert fo["ftem"].max() > 900.0
+    for k in fo:
+        assert np.abs(fd[k] / fo[k] - 1.0).max() < 1e-5, k
