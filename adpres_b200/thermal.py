@@ -30,6 +30,16 @@ def _card(p, key):
     return None if t is None else t["val"]
 
 
+def _outer_th(p, solver, nth):
+    """CALL outer_th(nth).  Without a %ITER card outer_th itself sets nupd = int(nth/2), for good
+    (mod_cmfd.f90:743) -- otherwise the default nupd would leave the TH iterations without a single
+    nodal update."""
+    if not p.biter and p.nupd != p.nth // 2:
+        p.nupd = p.nth // 2
+        solver.set_control(nupd=p.nupd)
+    return solver.outer_th(nth)
+
+
 class HostGlue:
     def __init__(self, p, solver, th_module):
         self.p, self.s, self.thm = p, solver, th_module
@@ -53,7 +63,7 @@ class HostGlue:
         return self.s.outer(0)
 
     def outer_th(self, nth):
-        return self.s.outer_th(nth)
+        return _outer_th(self.p, self.s, nth)
 
     def th_step(self):
         p, th = self.p, self.th
@@ -104,7 +114,7 @@ class DeviceGlue:
         return self.s.outer(0)
 
     def outer_th(self, nth):
-        return self.s.outer_th(nth)
+        return _outer_th(self.p, self.s, nth)
 
     def th_step(self):
         rc = self.s.th_pline(self.th["pow"], self.th["ppow"], form=0)

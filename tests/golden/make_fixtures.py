@@ -25,7 +25,9 @@ DECKS = {
     "IAEA3Ds": "smpl/static/IAEA3Ds", "IAEA2D": "smpl/static/IAEA2D", "BIBLIS": "smpl/static/BIBLIS",
     "KOEBERG": "smpl/static/KOEBERG", "DVP": "smpl/static/DVP", "PNM": "smpl/static/PNM",
     "FDM": "smpl/static/FDM", "adjoint": "smpl/static/adjoint", "fixed_source": "smpl/static/fixed_source",
-    "LMW": "smpl/transient/LMW", "NEACRP_A1": "smpl/static/NEACRP/A1",
+    "LMW": "smpl/transient/LMW",
+    "NEACRP_A1": "smpl/static/NEACRP/A1", "NEACRP_A2": "smpl/static/NEACRP/A2", "NEACRP_B1": "smpl/static/NEACRP/B1",
+    "NEACRP_B2": "smpl/static/NEACRP/B2", "NEACRP_C1": "smpl/static/NEACRP/C1", "NEACRP_C2": "smpl/static/NEACRP/C2",
 }
 
 
@@ -34,6 +36,15 @@ def main():
         p = read_deck(os.path.join(REF, rel))
         with open(os.path.join(HERE, name + ".spec.json"), "w") as fh:
             json.dump(p.to_spec(), fh, separators=(",", ":"))
+    # ---- NEACRP: the boron concentration each TRANSIENT deck starts from is the critical boron the
+    # reference found for the matching static deck (%BCON first number, smpl/transient/NEACRP/*t)
+    bcon = {}
+    for case in ("A1", "A2", "B1", "B2", "C1", "C2"):
+        lines = open(os.path.join(REF, "smpl/transient/NEACRP", case + "t")).read().splitlines()
+        i = next(k for k, ln in enumerate(lines) if ln.strip().upper().startswith("%BCON"))
+        bcon[case] = float(lines[i + 1].split()[0])
+    with open(os.path.join(HERE, "neacrp_bcon.json"), "w") as fh:
+        json.dump({"source": "first number of the %BCON card of smpl/transient/NEACRP/<case>t", "ppm": bcon}, fh)
     # ---- docs trace
     text = open(os.path.join(REF, "docs/quick-guides.md")).read()
     rows = []
