@@ -1,8 +1,9 @@
 """CPU oracle for the thermal-hydraulic channel solve th_upd / th_trans (reference: src/mod_th.f90).
 
 TEST INFRASTRUCTURE ONLY (see oracle/__init__.py): the product (adp_th_upd, adp_th_trans in
-adpres_b200/csrc/th.cu) never imports this.  Parity unpinned: the reference repository holds no
-thermal-hydraulic output.  The functions restate the cited lines with the same operand order;
+adpres_b200/csrc/th.cu) never imports this.  Pinned (th_upd, with the XS feedback and the boron
+search around it) by the six critical boron concentrations the reference's NEACRP transient decks
+carry (tests/golden/neacrp_bcon.json, tests/test_th.py); th_trans is unpinned.  The functions restate the cited lines with the same operand order;
 the node loop of the reference (n = 1..nnod, k-major) is vectorised over the nodes of one plane
 and kept serial over the planes, which preserves the only dependence it has (the enthalpy /
 flow rate a channel hands from plane k to plane k + 1 through entm(i,j), bfrate(i,j)).

@@ -1,9 +1,11 @@
 """Thermal-hydraulic channel solve th_upd / th_trans (mod_th.f90:440-699) on the
 geometry and %THER card of smpl/static/NEACRP/A1.
 
-The reference holds no thermal-hydraulic output ("parity unpinned").  CPU tests check the numpy
-oracle (oracle/th.py, a statement-by-statement restatement) against conservation laws it does not
-use explicitly; GPU tests check the device kernels against the oracle from identical states."""
+Pinned by the reference's own numbers: the six NEACRP transient decks start from the critical
+boron concentration ADPRES found for the matching static deck; the oracle and the GPU reproduce
+all six (tests below).  CPU tests also check the numpy oracle (oracle/th.py, a statement-by-
+statement restatement) against conservation laws it does not use explicitly; GPU tests check the
+device kernels against the oracle from identical states."""
 import numpy as np
 import pytest
 
