@@ -253,3 +253,159 @@ def rod_eject(p, solver, max_steps=None, log=None):
         trace.append((step, t2, rho / ctbeta, tpow2 / tpow1, n, maxi))
         say(f"{step:4d} {t2:10.3f} {rho / ctbeta:10.4f} {tpow2 / tpow1:15.4E}  outers {n}")
     return trace
+
+
+# ------------------------------------------------------------------------------------------------
+# rod ejection with thermal-hydraulic feedback (mod_trans.f90:163-330 rod_eject_th, trans_calc with
+# thc = 1): the NEACRP decks smpl/transient/NEACRP/A1t ... C2t
+# ------------------------------------------------------------------------------------------------
+def _time_steps(e):
+    steps = [(i, e["tstep1"], i * e["tstep1"]) for i in range(1, int(round(e["tdiv"] / e["tstep1"])) + 1)]
+    steps += [(i, e["tstep2"], e["tdiv"] + i * e["tstep2"]) for i in range(1, int(round((e["ttot"] - e["tdiv"]) / e["tstep2"])) + 1)]
+    return steps
+
+
+def _move_rods(e, bpos, mdir, ht, t2):
+    """rod bank changes (mod_trans.f90:374-388)"""
+    fbpos, tmove, bspeed = e["fbpos"], e["tmove"], e["bspeed"]
+    for b in range(len(bpos)):
+        if mdir[b] == 1 and t2 - tmove[b] > 1e-5 and fbpos[b] - bpos[b] < 1e-5:
+            bpos[b] = max(bpos[b] - ht * bspeed[b], fbpos[b])
+        elif mdir[b] == 2 and t2 - tmove[b] > 1e-5 and fbpos[b] - bpos[b] > 1e-5:
+            bpos[b] = min(bpos[b] + ht * bspeed[b], fbpos[b])
+
+
+def rod_eject_th(p, g, max_steps=None, log=None):
+    """rod_eject_th + trans_calc(thc = 1) on a thermal.HostGlue `g` (numpy glue; g.s = oracle.Oracle or
+    capi.Solver, g.thm = the th module).  Returns rows (step, t, reactivity [$], relative power
+    xppow, outer iterations, maxi, max fuel-centreline temperature [K])."""
+    from . import thermal
+    s, thm, th = g.s, g.thm, g.th
+    e, c = p.ejct, p.crod
+    ibeta, lamb, velo = e["ibeta"], e["lamb"], e["velo"]
+    bcon = p.fbk["bcon"]["val"]
+    g.bpos = c["bpos"].astype(np.float64).copy()
+    mdir = np.where(np.abs(e["fbpos"] - g.bpos) < 1e-5, 0, np.where(e["fbpos"] - g.bpos > 1e-5, 2, 1))
+    thermal.th_iter(g, bcon, ind=0)
+    ke = s.state()["Ke"]
+    if abs(ke - 1.0) > 1e-5:                                  # KNE1 (mod_trans.f90:483-518)
+        for it in range(10):
+            p.xnuf = p.xnuf / ke
+            c["dnuf"] = c["dnuf"] / ke
+            g.xs_update(bcon)
+            s.outer(0)
+            ke = s.state()["Ke"]
+            if abs(ke - 1.0) < 1e-5:
+                break
+    s.outer_ad(0)
+    af = s.state()["f0"].copy()
+    s.outer(0)
+    st = s.state()
+    f0, fs0 = st["f0"], st["fs0"]
+    tpow1 = powtot(p, f0)
+    c0 = np.asfortranarray((ibeta / lamb)[None, :] * fs0[:, None])
+    tbeta = np.full(p.nmat, 0.0)
+    for jf in range(6):
+        tbeta = tbeta + ibeta[jf]
+    ctbeta = tbeta[0]
+    L = _leakage(p, s, f0)
+    rho = reactivity(p, af, p.sigr, f0, fs0, L)
+    trace = [(0, 0.0, rho / ctbeta, th["ppow"] * 0.01, 0, False, float(g.st["tfm"][:, 0].max()))]
+    s.set_kinetics(ibeta, lamb, velo, tbeta, p.sth, p.bth)
+    ft = f0
+    for step, (_, ht, t2) in enumerate(_time_steps(e), start=1):
+        if max_steps is not None and step > max_steps:
+            break
+        omeg = np.asfortranarray(np.log(f0 / ft) / ht) if (p.bextr and step > 1) else np.zeros((p.nnod, p.ng), order="F")
+        _move_rods(e, g.bpos, mdir, ht, t2)
+        p.update_xs(g.bpos, bcon=bcon, ftem=g.ftem, mtem=g.mtem, cden=g.cden)
+        sigrp = p.sigr.copy(order="F")
+        sigr = p.sigr.copy(order="F")
+        for gg in range(p.ng):
+            sigr[:, gg] = sigr[:, gg] + 1.0 / (p.sth * velo[gg] * ht) + omeg[:, gg] / velo[gg]
+        ft, fst = f0.copy(order="F"), fs0.copy()
+        _push_xs(s, p, sigr=sigr)
+        s.set_transient(c0=c0, ft=ft, fst=fst, omeg=omeg, sigrp=sigrp, L=L)
+        rc, maxi, n = s.outer_tr(ht)
+        assert rc == 0, rc
+        st = s.state()
+        f0, fs0 = st["f0"], st["fs0"]
+        for i in range(6):                                    # uPden
+            pxe = np.exp(-lamb[i] * ht)
+            a1 = (1.0 - pxe) / (lamb[i] * ht)
+            a2 = 1.0 - a1
+            a1 = a1 - pxe
+            c0[:, i] = c0[:, i] * pxe + ibeta[i] / lamb[i] * (a1 * fst + a2 * fs0)
+        tpow2 = powtot(p, f0)
+        L = _leakage(p, s, f0)
+        rho = reactivity(p, af, sigrp, f0, fs0, L)
+        rc, npow = s.powdis()
+        xppow = th["ppow"] * tpow2 / tpow1 * 0.01
+        nf = th["node_nf"][p.ix - 1, p.iy - 1]
+        pline = npow * th["pow"] * xppow / (nf * p.zdel[p.iz - 1])
+        thm.th_trans(p, th, g.st, pline, ht)
+        g.ftem, g.mtem, g.cden = g.st["ftem"], g.st["mtem"], g.st["cden"]
+        trace.append((step, t2, rho / ctbeta, xppow, n, maxi, float(g.st["tfm"][:, 0].max())))
+        if log:
+            log(f"{step:4d} {t2:9.4f} {rho / ctbeta:10.4f} {xppow:13.5E}  outers {n}  Tf,max {trace[-1][6]:.2f}")
+    return trace
+
+
+def rod_eject_th_device(p, g, max_steps=None, log=None):
+    """The same transient on a thermal.DeviceGlue `g`: XS update with feedback, time-step glue,
+    outer_tr, uPden, PowTot, reactivity, PowDis -> pline and th_trans all on the device; per step the
+    bank positions go up and (reactivity, power, max fuel temperature on request) come back."""
+    from . import thermal
+    s, th = g.s, g.th
+    e, c = p.ejct, p.crod
+    ibeta, lamb, velo = e["ibeta"], e["lamb"], e["velo"]
+    bcon = p.fbk["bcon"]["val"]
+    g.bpos = c["bpos"].astype(np.float64).copy()
+    mdir = np.where(np.abs(e["fbpos"] - g.bpos) < 1e-5, 0, np.where(e["fbpos"] - g.bpos > 1e-5, 2, 1))
+    thermal.th_iter(g, bcon, ind=0)
+    ke = s.state()["Ke"]
+    if abs(ke - 1.0) > 1e-5:
+        for it in range(10):
+            p.xnuf = p.xnuf / ke
+            c["dnuf"] = c["dnuf"] / ke
+            s.set_material_xs(p)
+            s.set_crod(p)
+            g.xs_update(bcon)
+            s.outer(0)
+            ke = s.state()["Ke"]
+            if abs(ke - 1.0) < 1e-5:
+                break
+    s.outer_ad(0)
+    s.save_adjoint()
+    s.outer(0)
+    tbeta = np.full(p.nmat, 0.0)
+    for jf in range(6):
+        tbeta = tbeta + ibeta[jf]
+    ctbeta = tbeta[0]
+    s.set_kinetics(ibeta, lamb, velo, tbeta, p.sth, p.bth)
+    tpow1 = s.powtot()
+    s.ipden()
+    rho = s.reactivity(0)
+    trace = [(0, 0.0, rho / ctbeta, th["ppow"] * 0.01, 0, False, float(s.th_state()["tfm"][:, 0].max()))]
+    for step, (_, ht, t2) in enumerate(_time_steps(e), start=1):
+        if max_steps is not None and step > max_steps:
+            break
+        _move_rods(e, g.bpos, mdir, ht, t2)
+        s.update_omeg(ht, p.bextr and step > 1)
+        g.xs_update(bcon)
+        s.begin_time_step(ht)
+        rc, maxi, n = s.outer_tr(ht)
+        assert rc == 0, rc
+        s.upden(ht)
+        tpow2 = s.powtot()
+        rho = s.reactivity(1)
+        xppow = th["ppow"] * tpow2 / tpow1 * 0.01
+        s.th_pline(th["pow"], xppow, form=1)
+        rc = s.th_trans(None, ht)
+        if rc > 0:
+            raise thermal.StopError(s.last_error())
+        tmax = float(s.th_state()["tfm"][:, 0].max()) if log or True else 0.0
+        trace.append((step, t2, rho / ctbeta, xppow, n, maxi, tmax))
+        if log:
+            log(f"{step:4d} {t2:9.4f} {rho / ctbeta:10.4f} {xppow:13.5E}  outers {n}  Tf,max {tmax:.2f}")
+    return trace

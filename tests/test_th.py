@@ -293,3 +293,52 @@ def test_gpu_critical_boron_search_device_resident():
     assert fo["ftem"].max() > 900.0
     for k in fo:
         assert np.abs(fd[k] / fo[k] - 1.0).max() < 1e-4, k
+
+
+# ------------------------------------------------------------------ NEACRP A1 rod ejection with TH feedback
+def test_oracle_neacrp_a1_rod_ejection_matches_the_benchmark():
+    """smpl/transient/NEACRP/A1t end to end through the oracle (rod_eject_th: th_iter, KNE1, adjoint,
+    280 time steps of outer_tr + th_trans with XS feedback and exponential transformation).  The
+    reference tree has no output for it; the published NEACRP A1 solutions (PANTHER: peak power
+    126.8 % of nominal at 0.54 s, 19.7 % at 5 s, maximum fuel centreline temperature 679 C; original
+    1993 reference 117.9 % at 0.56 s, 19.6 %, 673 C) bracket the result."""
+    from adpres_b200 import thermal, transient
+    from oracle import Oracle, th as oth
+    p = load_problem("NEACRP_A1t")
+    assert (p.mode, p.bextr, p.fbk["bcon"]["val"]) == ("RODEJECT", 1, 560.53)
+    g = thermal.HostGlue(p, Oracle(p), oth)
+    tr = transient.rod_eject_th(p, g)
+    assert len(tr) == 281 and not any(r[5] for r in tr)
+    pw = np.array([r[3] for r in tr]); tt = np.array([r[1] for r in tr])
+    k = int(pw.argmax())
+    assert 1.15 < pw[k] < 1.30 and 0.52 < tt[k] < 0.58
+    assert 0.190 < pw[-1] < 0.205
+    assert 1.05 < max(r[2] for r in tr) < 1.10                      # ejected rod worth ~1.08 $
+    assert 670.0 < tr[-1][6] - 273.15 < 700.0
+
+
+@pytest.mark.gpu
+def test_gpu_neacrp_a1_rod_ejection_first_steps_device_resident():
+    """The same transient with everything on the device (XS feedback update, %EXTR, time-step glue,
+    outer_tr, uPden, PowTot, reactivity, PowDis -> pline, th_trans) against the oracle with numpy glue.
+    Time steps converged tightly (serc = ferc = 1e-9) so that the exit iteration does not depend on
+    round-off; the prompt-critical excursion multiplies the power by 1e4 over these steps."""
+    from adpres_b200 import capi, thermal, transient
+    from oracle import Oracle, th as oth
+    ps = []
+    for _ in range(2):
+        p = load_problem("NEACRP_A1t")
+        p.serc = p.ferc = 1e-9
+        p.nout = 5000
+        ps.append(p)
+    go = thermal.HostGlue(ps[0], Oracle(ps[0]), oth)
+    gd = thermal.DeviceGlue(ps[1], capi.Solver(ps[1]))
+    nst = 70                                                         # 0.35 s: power from 1e-6 to ~2e-2 of nominal
+    tr_o = transient.rod_eject_th(ps[0], go, max_steps=nst)
+    tr_d = transient.rod_eject_th_device(ps[1], gd, max_steps=nst)
+    assert tr_o[-1][3] > 1e3 * tr_o[0][3]
+    for a, b in zip(tr_d, tr_o):
+        assert a[1] == b[1]
+        assert abs(a[3] / b[3] - 1) < 1e-4, (a, b)                   # north star: transient power within 1e-4
+        assert abs(a[2] - b[2]) < 1e-5, (a, b)
+        assert abs(a[6] / b[6] - 1) < 1e-7, (a, b)
