@@ -29,6 +29,7 @@ DECKS = {
     "NEACRP_A1": "smpl/static/NEACRP/A1", "NEACRP_A2": "smpl/static/NEACRP/A2", "NEACRP_B1": "smpl/static/NEACRP/B1",
     "NEACRP_B2": "smpl/static/NEACRP/B2", "NEACRP_C1": "smpl/static/NEACRP/C1", "NEACRP_C2": "smpl/static/NEACRP/C2",
     "NEACRP_A1t": "smpl/transient/NEACRP/A1t",
+    "MOX_ARO": "smpl/static/MOX/part1_aro_helios", "MOX_ARI": "smpl/static/MOX/part1_ari_helios",
 }
 
 

@@ -150,7 +150,7 @@ def test_iaea3ds_forward_trace_and_keff(mods, golden_trace):
     assert s.trace_extrp[:4] == [5, 10, 15, 20]
 
 
-@pytest.mark.parametrize("deck", ["IAEA2D", "BIBLIS", "KOEBERG", "DVP", "PNM"])
+@pytest.mark.parametrize("deck", ["IAEA2D", "BIBLIS", "KOEBERG", "DVP", "PNM", "MOX_ARO", "MOX_ARI"])
 def test_static_decks_forward(mods, deck):
     p, s, o = _pair(mods, deck)
     rc_s, n_s = s.outer(0)

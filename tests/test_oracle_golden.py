@@ -65,6 +65,21 @@ def test_deck_header_keffs_sanity():
         assert abs(o.state()["Ke"] - ref) < 1.0e-4, (name, o.state()["Ke"], ref)
 
 
+def test_mox_part1_adf_decks_against_the_published_nodal_solution():
+    """smpl/static/MOX/part1_ar{o,i}_helios: the 2-D core of the OECD/NEA PWR MOX/UO2 transient
+    benchmark, 26 compositions, assembly discontinuity factors between 0.23 and 1.38 on every face
+    (the only decks of the reference with realistic ADFs).  External sanity values, not ADPRES
+    output: the benchmark's 2-group nodal solution (PARCS) is k-eff 1.06379 (all rods out) and
+    0.99154 (all rods in); the oracle gives 1.063782 and 0.991535."""
+    for name, ref in (("MOX_ARO", 1.06379), ("MOX_ARI", 0.99154)):
+        p = load_problem(name)
+        assert p.dc.min() < 0.3 and p.dc.max() > 1.25
+        o = Oracle(p)
+        rc, n = o.outer(0)
+        assert rc == 0
+        assert abs(o.state()["Ke"] - ref) < 5.0e-5, (name, o.state()["Ke"], ref)
+
+
 def test_powdis_normalised_and_symmetric(iaea_run, iaea3ds):
     o, _, _ = iaea_run
     rc, pw = o.powdis()
