@@ -32,6 +32,8 @@ def main():
         return transient_main(rank, world, local, uid, dist)
     if deck == "NEACRP_th":
         return th_main(rank, world, local, uid, dist)
+    if deck == "NEACRP_cb":
+        return cb_main(rank, world, local, uid, dist)
     if deck == "IAEA3Ds_z2":                  # 38 planes: uneven slabs at 4 ranks, 2 planes per axial assembly
         p = load_problem("IAEA3Ds").refine(zdiv=[2] * 19)
     else:
@@ -162,6 +164,34 @@ def th_main(rank, world, local, uid, dist):
         assert s.th_trans(xpl * 1.4, 0.05) == 0
         check()
     print(f"RANK {rank}/{world} OK deck=NEACRP_th planes=[{s.k0},{s.k1}) ftem_max={st['ftem'].max():.3f}", flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def cb_main(rank, world, local, uid, dist):
+    """Critical boron search with TH feedback, everything device-resident, on z-slabs: the feedback XS
+    update needs the neighbours' temperatures / densities on the ghost planes, the TH march is a chain,
+    pline comes from the all-reduced PowDis.  Case C2 (half core, full power, partially inserted rods)
+    against the reference's own value and the single-process oracle."""
+    import json
+    import numpy as np
+    from conftest import GOLDEN, load_problem
+    from adpres_b200 import capi, thermal
+    from oracle import Oracle, th as oth
+    gold = json.load(open(os.path.join(GOLDEN, "neacrp_bcon.json")))["ppm"]["C2"]
+    p1, p2 = load_problem("NEACRP_C2"), load_problem("NEACRP_C2")
+    s = capi.Solver(p2, device=local, nranks=world, rank=rank, uid=uid)
+    gd = thermal.DeviceGlue(p2, s)
+    bd, rd = thermal.cbsearcht(gd)
+    assert abs(bd - gold) < 0.1, (bd, gold)
+    go = thermal.HostGlue(p1, Oracle(p1), oth)
+    bo, ro = thermal.cbsearcht(go)
+    assert len(ro) == len(rd) and abs(bo - bd) < 0.02, (bo, bd)
+    fo, fd = go.th_fields(), gd.th_fields()
+    own = s.own
+    for k in fo:
+        assert np.abs(fd[k][own] / fo[k][own] - 1.0).max() < 1e-5, k
+    print(f"RANK {rank}/{world} OK deck=NEACRP_cb planes=[{s.k0},{s.k1}) bcon={bd:.2f}", flush=True)
     dist.barrier()
     dist.destroy_process_group()
 
