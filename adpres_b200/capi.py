@@ -17,6 +17,7 @@ _ip = C.POINTER(C.c_int)
 
 MODE_FORWARD, MODE_ADJOINT, MODE_FIXEDSRC, MODE_TRANSIENT = 0, 1, 2, 3
 STOP_MAXOUTER, STOP_LU_DIAG, STOP_NDMAX, STOP_ZERO_POWER, STOP_STEAM_TABLE = 1, 2, 3, 4, 5
+STOP_XTAB_RANGE, STOP_XTAB_NOROD = 6, 7
 
 TRACE_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int)
 
@@ -25,7 +26,8 @@ SYMBOLS = [
     "adp_create", "adp_destroy", "adp_last_error", "adp_version", "adp_comm_unique_id", "adp_comm_init", "adp_comm_init_env", "adp_slab",
     "adp_set_geometry", "adp_set_xs", "adp_set_control", "adp_matrix_setup", "adp_init_flux", "adp_outer_begin",
     "adp_outer_iter", "adp_nodal_upd", "adp_powdis", "adp_integrate", "adp_set_kinetics", "adp_set_transient",
-    "adp_get_exsrc", "adp_set_material_xs", "adp_set_crod", "adp_xs_update", "adp_set_feedback", "adp_xs_update_th", "adp_get_xs", "adp_save_adjoint", "adp_ipden", "adp_update_omeg", "adp_begin_time_step", "adp_upden", "adp_powtot", "adp_asm_pow", "adp_axi_pow", "adp_asm_flux", "adp_set_th", "adp_set_th_state", "adp_get_th_state", "adp_th_pline",
+    "adp_get_exsrc", "adp_set_material_xs", "adp_set_crod", "adp_xs_update", "adp_set_feedback", "adp_xs_update_th", "adp_get_xs",
+    "adp_set_xtab", "adp_set_crod_map", "adp_xs_update_xtab", "adp_get_dc", "adp_save_adjoint", "adp_ipden", "adp_update_omeg", "adp_begin_time_step", "adp_upden", "adp_powtot", "adp_asm_pow", "adp_axi_pow", "adp_asm_flux", "adp_set_th", "adp_set_th_state", "adp_get_th_state", "adp_th_pline",
     "adp_th_upd", "adp_th_trans",
     "adp_reactivity", "adp_get_state", "adp_set_state", "adp_set_s0", "adp_get_nod", "adp_set_nod_dn", "adp_lxyz_total", "adp_get_exsrc_arrays",
     "adp_get_ndmax", "adp_get_errors", "adp_set_trace", "adp_outer", "adp_outer_ad", "adp_outer_fs", "adp_outer_th", "adp_outer_tr",
@@ -69,6 +71,20 @@ def _i(a):
         return None
     assert a.dtype == np.int32 and a.flags.c_contiguous
     return a.ctypes.data_as(_ip)
+
+
+def pack_xtab(p):
+    """The arguments of adp_set_xtab from the branch tables of a deck (p.xtab, deck.read_xtab_composition):
+    dims (nmat, 4) int32 C-order [= (4, nmat) column-major], trod (nmat), par, xs, rxs (None without rodded sets)."""
+    dims = np.array([[t["nd"], t["nb"], t["nf"], t["nm"]] for t in p.xtab], dtype=np.int32)
+    trod = np.array([t["trod"] for t in p.xtab], dtype=np.int32)
+    par = np.concatenate([np.concatenate([t["pd"], t["pb"], t["pf"], t["pm"]]) for t in p.xtab]).astype(np.float64)
+    xs = np.concatenate([np.ascontiguousarray(t["xs"]).ravel() for t in p.xtab])
+    rxs = None
+    if (trod == 1).any():
+        rxs = np.concatenate([np.ascontiguousarray(t["rxs"] if t["rxs"] is not None else np.zeros_like(t["xs"])).ravel()
+                              for t in p.xtab])
+    return dims, trod, par, xs, rxs
 
 
 class Solver:
@@ -440,6 +456,32 @@ class Solver:
         f = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float64)
         ft, mt, cd, bp = f(ftem), f(mtem), f(cden), f(bpos)
         self._chk(self.L.adp_xs_update_th(self.h, C.c_double(bcon), _d(ft), _d(mt), _d(cd), _d(bp)))
+
+    # ---- XS update on the device (%XTAB branch tables)
+    def set_xtab(self, p=None):
+        """branch tables of the deck (p.xtab, deck.read_xtab_composition) -> device"""
+        p = p or self.p
+        dims, trod, par, xs, rxs = pack_xtab(p)
+        self._chk(self.L.adp_set_xtab(self.h, dims.ctypes.data_as(_ip), trod.ctypes.data_as(_ip), _d(par), _d(xs), _d(rxs)))
+
+    def set_crod_map(self, p=None):
+        p = p or self.p
+        c = p.crod
+        ia, ja, _ = p._node_assembly_maps()
+        fbmap = np.asfortranarray(c["bmap"][np.ix_(ia, ja)].astype(np.int32))          # (nxx, nyy) column-major
+        self._chk(self.L.adp_set_crod_map(self.h, int(c["nb"]), C.c_double(c["pos0"]), C.c_double(c["ssize"]),
+                                          fbmap.ctypes.data_as(_ip)))
+
+    def xs_update_xtab(self, bcon, ftem=None, mtem=None, cden=None, bpos=None):
+        """XStab_updt on the device; returns 0 or ADP_STOP_XTAB_RANGE / ADP_STOP_XTAB_NOROD"""
+        f = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float64)
+        ft, mt, cd, bp = f(ftem), f(mtem), f(cden), f(bpos)
+        return self._chk(self.L.adp_xs_update_xtab(self.h, C.c_double(bcon), _d(ft), _d(mt), _d(cd), _d(bp)))
+
+    def get_dc(self):
+        dc = np.zeros((self.N, self.G, 6), order="F")
+        self._chk(self.L.adp_get_dc(self.h, _d(dc)))
+        return dc
 
     def get_xs(self):
         N, G = self.N, self.G

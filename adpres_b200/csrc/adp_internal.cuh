@@ -171,6 +171,10 @@ struct adp_ctx {
     double *d_ftab[4] = {nullptr, nullptr, nullptr, nullptr};   // feedback tables: bcon, ftem, mtem, cden (layout of d_xtab)
     double fref[4] = {0, 0, 0, 0}, bcon = 0.0;
     bool xs_feedback = false;              // the current adp_xs_update applies the feedback tables
+    // %XTAB branch tables (adp_set_xtab): per-material dims / offsets, branch parameters, (un)rodded value blocks
+    int *d_brmeta = nullptr;               // [nmat][6] nd, nb, nf, nm, trod, offset into d_brpar
+    long long *d_brtoff = nullptr;         // [nmat] offset of the material's block in d_brtab / d_brrtab
+    double *d_brpar = nullptr, *d_brtab = nullptr, *d_brrtab = nullptr;
     double *d_stab = nullptr;              // (ntem, 6) column-major
     double *d_tfm = nullptr;               // [nt+1][NV] radial pin temperatures
     double *d_heatf = nullptr, *d_ent = nullptr, *d_ftem = nullptr, *d_mtem = nullptr, *d_cden = nullptr, *d_frate = nullptr,
@@ -285,6 +289,7 @@ int adp_k_scale_by_slot(adp_ctx *c, double *d_vec, int slot);
 int adp_k_get_exsrc(adp_ctx *c, double ht);
 int adp_k_integrate(adp_ctx *c, const double *d_vec, int slot);
 int adp_k_xs_update(adp_ctx *c);
+int adp_k_xs_update_xtab(adp_ctx *c);
 int adp_th_alloc(adp_ctx *c);            // th.cu: node arrays of the thermal-hydraulic state
 int adp_k_ipden(adp_ctx *c);
 int adp_k_upden(adp_ctx *c, double ht);

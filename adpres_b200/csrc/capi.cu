@@ -5,6 +5,7 @@
 #include <cstdlib>
 
 #include "adp_internal.cuh"
+#include "xtab_node.cuh"
 
 void adp_k_preload_cmfd(adp_ctx *c);
 void adp_k_preload_nodal(adp_ctx *c);
@@ -70,6 +71,16 @@ extern "C" int adp_create(adp_ctx **out, int device)
     return ADP_OK;
 }
 
+static void free_xtab(adp_ctx *c)
+{
+    if (c->d_brmeta) cudaFree(c->d_brmeta);
+    if (c->d_brtoff) cudaFree(c->d_brtoff);
+    if (c->d_brpar) cudaFree(c->d_brpar);
+    if (c->d_brtab) cudaFree(c->d_brtab);
+    if (c->d_brrtab) cudaFree(c->d_brrtab);
+    c->d_brmeta = nullptr; c->d_brtoff = nullptr; c->d_brpar = c->d_brtab = c->d_brrtab = nullptr;
+}
+
 static void free_graphs(adp_ctx *c)
 {
     for (auto &kv : c->graphs) cudaGraphExecDestroy(kv.second);
@@ -98,6 +109,8 @@ extern "C" int adp_destroy(adp_ctx *c)
         double *th[] = {c->d_stab, c->d_tfm, c->d_heatf, c->d_ent, c->d_ftem, c->d_mtem, c->d_cden, c->d_frate, c->d_pline, c->d_nodenf, c->d_chain};
         for (double *q : th) if (q) cudaFree(q);
         for (int f = 0; f < 4; ++f) if (c->d_ftab[f]) cudaFree(c->d_ftab[f]);
+        void *br[] = {c->d_brmeta, c->d_brtoff, c->d_brpar, c->d_brtab, c->d_brrtab};
+        for (void *q : br) if (q) cudaFree(q);
     }
     cudaStreamDestroy(c->stream);
     delete c;
@@ -276,6 +289,7 @@ extern "C" int adp_set_geometry(adp_ctx *c, int nxx, int nyy, int nzz, int nnod,
         c->th_set = c->th_state_set = c->th_pline_set = false;
         for (int f = 0; f < 4; ++f)
             if (c->d_ftab[f]) { cudaFree(c->d_ftab[f]); c->d_ftab[f] = nullptr; }
+        free_xtab(c);
     }
     c->abefgh_valid = false;
     c->geometry_set = true;
@@ -630,16 +644,11 @@ extern "C" int adp_set_material_xs(adp_ctx *c, const double *xsigtr, const doubl
     return upload_tables(c, &c->d_xtab, xsigtr, xsiga, xnuf, xsigf, xsigs);
 }
 
-extern "C" int adp_set_crod(adp_ctx *c, int nb, double pos0, double ssize, const int *fbmap, const double *dsigtr,
-                            const double *dsiga, const double *dnuf, const double *dsigf, const double *dsigs)
+// bank of every plane position, rod length above every plane, core height -- accumulated in the
+// reference's order (mod_io.f90:1274-1277, mod_xsec.f90:252-277)
+static int set_crod_geometry(adp_ctx *c, int nb, double pos0, double ssize, const int *fbmap)
 {
-    if (!c || !fbmap || nb < 1 || !dsigtr || !dsiga || !dnuf || !dsigf || !dsigs) return ADP_ERR_USAGE;
-    ADP_REQUIRE(c, c->geometry_set, "adp_set_crod: geometry not set");
-    CUDA_TRY(c, cudaSetDevice(c->device));
-    TRY(upload_tables(c, &c->d_dtab, dsigtr, dsiga, dnuf, dsigf, dsigs));
     c->nb = nb; c->pos0 = pos0; c->ssize = ssize;
-    // bank of every plane position, rod length above every plane, core height -- accumulated in the
-    // reference's order (mod_io.f90:1274-1277, mod_xsec.f90:252-277)
     std::vector<int> fb(c->np);
     for (int r = 0; r < c->np; ++r) fb[r] = fbmap[(size_t)(c->h_iy[r] - 1) * c->nxx + (c->h_ix[r] - 1)];
     std::vector<double> hz(c->nzz + 2), dumtop(c->nzz);
@@ -655,6 +664,24 @@ extern "C" int adp_set_crod(adp_ctx *c, int nb, double pos0, double ssize, const
     CUDA_TRY(c, cudaMemcpy(c->d_fb, fb.data(), c->np * sizeof(int), cudaMemcpyHostToDevice));
     CUDA_TRY(c, cudaMemcpy(c->d_dumtop, dumtop.data(), c->nzz * sizeof(double), cudaMemcpyHostToDevice));
     return ADP_OK;
+}
+
+extern "C" int adp_set_crod(adp_ctx *c, int nb, double pos0, double ssize, const int *fbmap, const double *dsigtr,
+                            const double *dsiga, const double *dnuf, const double *dsigf, const double *dsigs)
+{
+    if (!c || !fbmap || nb < 1 || !dsigtr || !dsiga || !dnuf || !dsigf || !dsigs) return ADP_ERR_USAGE;
+    ADP_REQUIRE(c, c->geometry_set, "adp_set_crod: geometry not set");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    TRY(upload_tables(c, &c->d_dtab, dsigtr, dsiga, dnuf, dsigf, dsigs));
+    return set_crod_geometry(c, nb, pos0, ssize, fbmap);
+}
+
+extern "C" int adp_set_crod_map(adp_ctx *c, int nb, double pos0, double ssize, const int *fbmap)
+{
+    if (!c || !fbmap || nb < 1) return ADP_ERR_USAGE;
+    ADP_REQUIRE(c, c->geometry_set, "adp_set_crod_map: geometry not set");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    return set_crod_geometry(c, nb, pos0, ssize, fbmap);
 }
 
 extern "C" int adp_xs_update(adp_ctx *c, const double *bpos)
@@ -705,6 +732,85 @@ extern "C" int adp_xs_update_th(adp_ctx *c, double bcon, const double *ftem, con
     const int rc = adp_k_xs_update(c);
     c->xs_feedback = false;
     if (rc) return rc;
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return ADP_OK;
+}
+
+// ---- %XTAB branch tables: XStab_updt on the device ----------------------------------------------
+extern "C" int adp_set_xtab(adp_ctx *c, const int *dims, const int *trod, const double *par, const double *xs,
+                            const double *rxs)
+{
+    if (!c || !dims || !trod || !par || !xs) return ADP_ERR_USAGE;
+    ADP_REQUIRE(c, c->geometry_set, "adp_set_xtab: geometry not set");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    const int nmat = c->nmat;
+    std::vector<int> meta((size_t)nmat * 6);
+    std::vector<long long> toff(nmat);
+    long long npar = 0, ntab = 0;
+    bool any_rod = false;
+    ADP_REQUIRE(c, xtab_pack_meta(nmat, c->ng, dims, trod, meta.data(), toff.data(), &npar, &ntab, &any_rod),
+                "adp_set_xtab: ERROR: MINIMUM NUMBER OF BRANCH IS 1");
+    ADP_REQUIRE(c, !any_rod || rxs, "adp_set_xtab: a material has a rodded set (trod = 1) but rxs is NULL");
+    free_xtab(c);
+    // (no zero-fill: every byte is overwritten by the blocking copies below)
+    TRY(dev_alloc(c, &c->d_brmeta, meta.size(), false)); TRY(dev_alloc(c, &c->d_brtoff, (size_t)nmat, false));
+    TRY(dev_alloc(c, &c->d_brpar, (size_t)npar, false)); TRY(dev_alloc(c, &c->d_brtab, (size_t)ntab, false));
+    if (any_rod) TRY(dev_alloc(c, &c->d_brrtab, (size_t)ntab, false));
+    CUDA_TRY(c, cudaMemcpy(c->d_brmeta, meta.data(), meta.size() * sizeof(int), cudaMemcpyHostToDevice));
+    CUDA_TRY(c, cudaMemcpy(c->d_brtoff, toff.data(), (size_t)nmat * sizeof(long long), cudaMemcpyHostToDevice));
+    CUDA_TRY(c, cudaMemcpy(c->d_brpar, par, (size_t)npar * sizeof(double), cudaMemcpyHostToDevice));
+    CUDA_TRY(c, cudaMemcpy(c->d_brtab, xs, (size_t)ntab * sizeof(double), cudaMemcpyHostToDevice));
+    if (any_rod) CUDA_TRY(c, cudaMemcpy(c->d_brrtab, rxs, (size_t)ntab * sizeof(double), cudaMemcpyHostToDevice));
+    return ADP_OK;
+}
+
+extern "C" int adp_xs_update_xtab(adp_ctx *c, double bcon, const double *ftem, const double *mtem, const double *cden,
+                                  const double *bpos)
+{
+    if (!c) return ADP_ERR_USAGE;
+    ADP_REQUIRE(c, c->d_brtab != nullptr, "adp_xs_update_xtab: call adp_set_xtab first");
+    ADP_REQUIRE(c, c->xs_set, "adp_xs_update_xtab: chi / exsrc come from adp_set_xs (call it once)");
+    ADP_REQUIRE(c, !c->d_fb || bpos, "adp_xs_update_xtab: bank positions missing");
+    ADP_REQUIRE(c, !c->d_fb || c->d_brrtab, "adp_xs_update_xtab: control rods but no rodded tables");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    TRY(adp_th_alloc(c));
+    const double *host[3] = {ftem, mtem, cden};
+    double *dev[3] = {c->d_ftem, c->d_mtem, c->d_cden};
+    for (int i = 0; i < 3; ++i) {
+        ADP_REQUIRE(c, host[i] || c->th_state_set, "adp_xs_update_xtab: a feedback parameter is neither passed nor on the device");
+        if (host[i]) TRY(adp_upload_nodes(c, dev[i], host[i], 1));
+    }
+    c->bcon = bcon;
+    if (c->d_fb) CUDA_TRY(c, cudaMemcpyAsync(c->d_bpos, bpos, c->nb * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(c, cudaMemsetAsync(c->d_errflag, 0, sizeof(int), c->stream));
+    TRY(adp_k_xs_update_xtab(c));
+    CUDA_TRY(c, cudaMemcpyAsync(c->h_flags, c->d_errflag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    if (c->nranks > 1) {      // any rank's STOP stops all of them
+        double f = (double)c->h_flags[0];
+        CUDA_TRY(c, cudaMemcpyAsync(c->d_scal + S_TMP1, &f, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        TRY(adp_comm_allreduce_max_nccl(c, c->d_scal + S_TMP1, 1));
+        CUDA_TRY(c, cudaMemcpyAsync(&f, c->d_scal + S_TMP1, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+        c->h_flags[0] = (int)f;
+    }
+    if (c->h_flags[0] == ADP_STOP_XTAB_RANGE) {
+        c->err = "ERROR: A TH PARAMETER OR THE BORON CONCENTRATION IS OUT OF THE RANGE OF THE BRANCH PARAMETER";
+        return ADP_STOP_XTAB_RANGE;
+    }
+    if (c->h_flags[0] == ADP_STOP_XTAB_NOROD) {
+        c->err = "CONTROL ROD BANK COINCIDES WITH A MATERIAL THAT DOES NOT HAVE CONTROL ROD DATA IN XTAB FILE";
+        return ADP_STOP_XTAB_NOROD;
+    }
+    return ADP_OK;
+}
+
+extern "C" int adp_get_dc(adp_ctx *c, double *dc)
+{
+    if (!c || !dc) return ADP_ERR_USAGE;
+    ADP_REQUIRE(c, c->xs_set, "adp_get_dc: cross sections not set");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    TRY(download_nodes(c, dc, c->d_dc, c->ng * 6));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     return ADP_OK;
 }

@@ -16,6 +16,7 @@
 //   k_extrap    (E)  fiss_extrp, Integrate, RelE                           :308-335
 //   k_scalar_*       the handful of scalar statements of the outer loop    :467-485
 #include "adp_internal.cuh"
+#include "xtab_node.cuh"
 
 namespace {
 
@@ -787,6 +788,42 @@ __global__ void __launch_bounds__(ADP_TILE) k_xs_update(Geo G, XsArgs A, int klo
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// XStab_updt for %XTAB decks on the device: brInterp (mod_xsec.f90:520-788) for the unrodded and,
+// under a control rod, the rodded branch tables, the volume-weighted mix of crod_tab_updt
+// (:300-390) and Dsigr_updt (:199-226).  One thread per node; the tables of a material are a
+// (nd, nb, nf, nm, nval) block, nval = 4G + G*G + 6G values packed
+// [sigtr(G), siga(G), nuf(G), sigf(G), sigs(g -> h, g slow), dc(g, face)], a few KB that stay in L1/L2.
+// Every value sees the reference's operations in the reference's order (a + radx * (b - a), moderator
+// temperature first, then fuel temperature, boron, coolant density), so the result is bit-exact.
+// ------------------------------------------------------------------------------------------
+struct XtabArgs {
+    int has_rods;
+    XtabTables T;
+    const int *mat, *fb;
+    const double *bpos, *dumtop;
+    double coreh, pos0, ssize, bcon;
+    const double *ftem, *mtem, *cden;
+    XtabOut O;
+    int *errflag;
+};
+
+__global__ void __launch_bounds__(ADP_TILE) k_xs_update_xtab(Geo G, XtabArgs A, int klo, int npl)
+{
+    FOR_EACH_ROW(G, klo, npl)
+    {
+        const long long idx = node_idx(G, kl, r);
+        const int kg = G.k0 + kl;
+        // rod state of this node: w < 0 not under a rod tip, else the rodded fraction
+        double w = -1.0;
+        const int b = A.has_rods ? A.fb[r] : 0;
+        if (b > 0)
+            w = xt_rod_fraction(A.coreh - A.pos0 - A.bpos[b - 1] * A.ssize, A.dumtop[kg], G.hz[1 + kg], kg == G.nzz - 1);
+        const int rc = xtab_node(A.T, A.mat[idx] - 1, w, b > 0, A.cden[idx], A.bcon, A.ftem[idx], A.mtem[idx], A.O, G.NV, idx);
+        if (rc) atomicExch(A.errflag, rc);
+    }
+}
+
 }  // namespace
 
 // =========================================================================================
@@ -1251,6 +1288,35 @@ int adp_k_xs_update(adp_ctx *c)
     const int klo = -((c->k0 >= ADP_GH) ? ADP_GH : c->k0);
     const int khi = c->nzl + ((c->nzz - c->k1 >= ADP_GH) ? ADP_GH : (c->nzz - c->k1));
     k_xs_update<<<adp_grid(c, k_xs_update, c->geo.tpp * (khi - klo)), ADP_TILE, 0, c->stream>>>(c->geo, A, klo, khi - klo);
+    LAUNCH_CHECK(c);
+    c->abefgh_valid = false;
+    return ADP_OK;
+}
+
+// ---- XStab_updt on the device (%XTAB branch tables) ----------------------------------------------
+int adp_k_xs_update_xtab(adp_ctx *c)
+{
+    XtabArgs A{};
+    A.has_rods = c->d_fb != nullptr;
+    A.T.ng = c->ng; A.T.nval = 4 * c->ng + c->ng * c->ng + 6 * c->ng;
+    A.T.meta = c->d_brmeta; A.T.toff = c->d_brtoff; A.T.par = c->d_brpar; A.T.xs = c->d_brtab; A.T.rxs = c->d_brrtab;
+    A.mat = c->d_mat;
+    if (A.has_rods) {
+        A.fb = c->d_fb; A.bpos = c->d_bpos; A.dumtop = c->d_dumtop;
+        A.coreh = c->coreh; A.pos0 = c->pos0; A.ssize = c->ssize;
+    }
+    A.bcon = c->bcon; A.ftem = c->d_ftem; A.mtem = c->d_mtem; A.cden = c->d_cden;
+    A.O.D = c->d_D; A.O.sigr = c->d_sigr; A.O.nuf = c->d_nuf; A.O.sigf = c->d_sigf; A.O.sigs = c->d_sigs; A.O.dc = c->d_dc;
+    A.errflag = c->d_errflag;
+    if (c->nranks > 1) {   // the ghost planes take the neighbours' temperatures and densities
+        int rc;
+        if ((rc = adp_comm_halo(c, c->d_ftem, ADP_GH))) return rc;
+        if ((rc = adp_comm_halo(c, c->d_mtem, ADP_GH))) return rc;
+        if ((rc = adp_comm_halo(c, c->d_cden, ADP_GH))) return rc;
+    }
+    const int klo = -((c->k0 >= ADP_GH) ? ADP_GH : c->k0);
+    const int khi = c->nzl + ((c->nzz - c->k1 >= ADP_GH) ? ADP_GH : (c->nzz - c->k1));
+    k_xs_update_xtab<<<adp_grid(c, k_xs_update_xtab, c->geo.tpp * (khi - klo)), ADP_TILE, 0, c->stream>>>(c->geo, A, klo, khi - klo);
     LAUNCH_CHECK(c);
     c->abefgh_valid = false;
     return ADP_OK;

@@ -12,6 +12,8 @@ pass.  This module restates only that data preparation (nothing of the hot path)
 * node numbering, ``vdel``, default ``nupd``      -- ``mod_io.f90:1293-1365``
 * ``%ITER`` / ``%KERN`` / ``%THET`` / ``%ESRC`` / ``%ADF`` -- ``mod_io.f90:1522-1689,1369-1517,1732-2097``
 * ``base_updt`` + ``Dsigr_updt``                  -- ``mod_xsec.f90:172-226``
+* ``%XTAB`` branch tables (``inp_xtab``, ``readXS``)  -- ``mod_io.f90:3648-4087``; ``XStab_updt``,
+  ``brInterp``, ``crod_tab_updt``                 -- ``mod_xsec.f90:50-86,300-390,520-788``
 
 All arrays are produced in Fortran (column-major) memory order with the reference's
 1-based node / mesh indices, i.e. bit-for-bit what ``sdata`` would hold.
@@ -43,12 +45,13 @@ _KERN_CODE = {"FDM": KERN_FDM, "PNM": KERN_PNM, "SANM": KERN_SANM}
 
 
 # --------------------------------------------------------------------------- low-level text
-def _strip_comments(text: str) -> List[str]:
-    """``inp_comments`` (mod_io.f90:452-492): drop blank lines and everything after '!'."""
+def _strip_comments(text: str, mark: str = "!") -> List[str]:
+    """``inp_comments`` (mod_io.f90:452-492): drop blank lines and everything after the comment
+    mark ('!' in decks, '*' in %XTAB library files)."""
     out = []
     for raw in text.splitlines():
         line = raw.strip()
-        pos = line.find("!")
+        pos = line.find(mark)
         if pos < 0:
             if line:
                 out.append(line)
@@ -173,6 +176,7 @@ class Problem:
     bextr: int = 0
     fbk: Optional[dict] = None            # %BCON / %CBCS / %FTEM / %MTEM / %CDEN: {name: dict(val, ref, sigtr, siga, nuf, sigf, sigs)}
     ther: Optional[dict] = None           # %THER raw inputs (ppow, pow, tin, cmflow, rf, tg, tc, ppitch, nfpin, ngt, cf)
+    xtab: Optional[list] = None           # %XTAB: per material the branch tables of read_xtab_composition()
     cards: Optional[Dict[str, List[str]]] = None
     # ---- node-wise (filled by build())
     nxx: int = 0
@@ -206,7 +210,7 @@ class Problem:
     _SPEC_FIELDS = ("mode", "ng", "nmat", "nx", "ny", "nz", "xsize", "ysize", "zsize", "xdiv", "ydiv",
                     "zdiv", "zpln", "planars", "bc", "xsigtr", "xsiga", "xnuf", "xsigf", "xsigs", "chi",
                     "nout", "nin", "serc", "ferc", "nac", "nupd", "th_niter", "nth", "kern", "biter",
-                    "sth", "bth", "mdc", "adf_rot", "esrc", "crod", "ejct", "bextr", "ther", "fbk")
+                    "sth", "bth", "mdc", "adf_rot", "esrc", "crod", "ejct", "bextr", "ther", "fbk", "xtab")
 
     def to_spec(self) -> dict:
         """JSON-able problem specification (what the deck says, before node expansion).
@@ -217,7 +221,9 @@ class Problem:
             v = getattr(self, k)
             if k == "nupd" and not self.biter:
                 v = 0
-            if k == "fbk" and v is not None:
+            if k == "xtab" and v is not None:
+                v = [{kk: (vv.tolist() if isinstance(vv, np.ndarray) else vv) for kk, vv in t.items()} for t in v]
+            elif k == "fbk" and v is not None:
                 v = {name: {kk: (vv.tolist() if isinstance(vv, np.ndarray) else vv) for kk, vv in t.items()} for name, t in v.items()}
             elif isinstance(v, dict):
                 v = {kk: (vv.tolist() if isinstance(vv, np.ndarray) else vv) for kk, vv in v.items()}
@@ -245,6 +251,9 @@ class Problem:
         if kw.get("fbk") is not None:
             kw["fbk"] = {name: {kk: (np.array(vv, dtype=np.float64) if isinstance(vv, list) else vv) for kk, vv in t.items()}
                          for name, t in kw["fbk"].items()}
+        if kw.get("xtab") is not None:
+            kw["xtab"] = [{kk: (np.array(vv, dtype=np.float64) if isinstance(vv, list) else vv) for kk, vv in t.items()}
+                          for t in kw["xtab"]]
         return Problem(**kw).build()
 
     # ------------------------------------------------------------------ geometry
@@ -311,15 +320,21 @@ class Problem:
         if self.nupd == 0:
             # nupd = ceiling((nxx+nyy+nzz)/2.5), default REAL arithmetic (mod_io.f90:1363)
             self.nupd = int(math.ceil(float(np.float32(self.nxx + self.nyy + self.nzz) / np.float32(2.5))))
+        if self.xtab is not None:
+            self.chi = np.asfortranarray(np.array([t["chi"] for t in self.xtab], dtype=np.float64))
         self.update_xs()
-        self._build_adf()
+        if self.xtab is None:
+            self._build_adf()          # %XTAB decks: the ADFs come out of the tables (XStab_updt)
         self._build_esrc()
         return self
 
     def update_xs(self, bpos=None, bcon=None, ftem=None, mtem=None, cden=None) -> None:
         """XS_updt (mod_xsec.f90:11-46): base_updt, then bcon_updt / ftem_updt / mtem_updt / cden_updt
         (:396-516) for the feedback cards of the deck, crod_updt(bpos), Dsigr_updt.  A parameter
-        left at None takes the value of its card."""
+        left at None takes the value of its card.  %XTAB decks go through XStab_updt instead."""
+        if self.xtab is not None:
+            self._xstab_updt(bpos, bcon, ftem, mtem, cden)
+            return
         m = self.mat - 1
         N, G = self.nnod, self.ng
         self.sigtr = np.asfortranarray(self.xsigtr[m, :])
@@ -398,6 +413,154 @@ class Problem:
                     blk = a[col]
                     blk[blk < 0.0] = 0.0
                     a[col] = blk
+
+    # ------------------------------------------------------------------ %XTAB branch tables
+    def _br_interp(self, t: dict, rod: int, cden, bcon, ftem, mtem) -> np.ndarray:
+        """brInterp (mod_xsec.f90:520-788) for all nodes of one material at once: the two closest
+        branch points per parameter (up to 20 % -- boron: 100 ppm -- outside the table the end
+        interval extrapolates, further out the reference STOPs), then linear interpolation in the
+        order moderator temperature, fuel temperature, boron, coolant density with the
+        reference's operation order `a + radx * (b - a)`.  Returns (n, nval) packed like t["xs"]."""
+        tab = t["rxs"] if rod else t["xs"]
+        n = len(cden)
+
+        def bracket(x, par, dim, absolute, what):
+            i1 = np.zeros(n, dtype=np.int64)
+            i2 = np.zeros(n, dtype=np.int64)
+            if dim <= 1:
+                return i1, i2
+            x = np.broadcast_to(np.asarray(x, dtype=np.float64), (n,))
+            inside = (x >= par[0]) & (x <= par[dim - 1])
+            found = np.zeros(n, dtype=bool)
+            for s in range(1, dim):                       # DO s = 2, mx ... EXIT at the first hit
+                c = inside & ~found & (x >= par[s - 1]) & (x <= par[s])
+                i1[c], i2[c] = s - 1, s
+                found |= c
+            if absolute:
+                lo = ~inside & (x < par[0]) & ((par[0] - x) < 100.0)
+                hi = ~inside & ~lo & (x > par[dim - 1]) & ((x - par[dim - 1]) < 100.0)
+            else:
+                with np.errstate(divide="ignore", invalid="ignore"):
+                    lo = ~inside & (x < par[0]) & ((par[0] - x) / par[0] < float(np.float32(0.2)))
+                    hi = ~inside & ~lo & (x > par[dim - 1]) & ((x - par[dim - 1]) / par[dim - 1] < float(np.float32(0.2)))
+            i1[lo], i2[lo] = 0, 1
+            i1[hi], i2[hi] = dim - 2, dim - 1
+            bad = ~(inside | lo | hi)
+            if bad.any():
+                raise ValueError(f"ERROR: {what} {x[bad][0]:.3f} IS OUT OF THE RANGE OF THE BRANCH PARAMETER")
+            return i1, i2
+
+        s1, s2 = bracket(cden, t["pd"], t["nd"], False, "COOLANT DENSITY")
+        t1, t2 = bracket(bcon, t["pb"], t["nb"], True, "BORON CONCENTRATION")
+        u1, u2 = bracket(ftem, t["pf"], t["nf"], False, "FUEL TEMPERATURE")
+        v1, v2 = bracket(mtem, t["pm"], t["nm"], False, "MODERATOR TEMPERATURE")
+        xs = [None] * 9
+        corners = ((s1, t1, u1), (s1, t1, u2), (s1, t2, u1), (s1, t2, u2), (s2, t1, u1), (s2, t1, u2), (s2, t2, u1), (s2, t2, u2))
+        if t["nm"] > 1:
+            pm = t["pm"]
+            radx = ((np.asarray(mtem, dtype=np.float64) - pm[v1]) / (pm[v2] - pm[v1]))[:, None]
+            for i, (a, b, c) in enumerate(corners, start=1):
+                xs[i] = tab[a, b, c, v1] + radx * (tab[a, b, c, v2] - tab[a, b, c, v1])
+        else:
+            for i, (a, b, c) in enumerate(corners, start=1):
+                xs[i] = tab[a, b, c, v1]
+        if t["nf"] > 1:
+            pf = t["pf"]
+            radx = ((np.asarray(ftem, dtype=np.float64) - pf[u1]) / (pf[u2] - pf[u1]))[:, None]
+            for i in (1, 3, 5, 7):
+                xs[i] = xs[i] + radx * (xs[i + 1] - xs[i])
+        if t["nb"] > 1:
+            pb = t["pb"]
+            radx = ((np.broadcast_to(np.asarray(bcon, dtype=np.float64), (n,)) - pb[t1]) / (pb[t2] - pb[t1]))[:, None]
+            xs[1] = xs[1] + radx * (xs[3] - xs[1])
+            xs[5] = xs[5] + radx * (xs[7] - xs[5])
+        if t["nd"] > 1:
+            pd = t["pd"]
+            radx = ((np.asarray(cden, dtype=np.float64) - pd[s1]) / (pd[s2] - pd[s1]))[:, None]
+            xs[1] = xs[1] + radx * (xs[5] - xs[1])
+        return xs[1]
+
+    def rod_fractions(self, bpos) -> np.ndarray:
+        """The sweep of crod_updt / crod_tab_updt (mod_xsec.f90:253-279,322-372) reduced to its outcome per
+        node: -1 = not visited (unrodded), 1 = fully rodded, 0 <= w <= 1 = the partially rodded node where
+        the sweep EXITs.  (A rod tip above the core top, rodh < 0, never meets the `partial` test, so the
+        whole column counts as fully rodded -- the reference's behaviour.)"""
+        c = self.crod
+        w = np.full(self.nnod, -1.0)
+        ia, ja, _ = self._node_assembly_maps()
+        fbmap = c["bmap"][np.ix_(ia, ja)]
+        coreh = self.coreh
+        pos = np.full((self.nxx + 1, self.nyy + 1), -1, dtype=np.int64)
+        pos[self.ix[:self.npl], self.iy[:self.npl]] = np.arange(self.npl)
+        for j in range(1, self.nyy + 1):
+            for i in range(1, self.nxx + 1):
+                b = fbmap[i - 1, j - 1]
+                if b <= 0 or pos[i, j] < 0:
+                    continue
+                rodh = coreh - c["pos0"] - bpos[b - 1] * c["ssize"]
+                dum = 0.0
+                for k in range(self.nzz, 0, -1):
+                    n = pos[i, j] + (k - 1) * self.npl
+                    if rodh >= dum and rodh <= dum + self.zdel[k - 1]:
+                        w[n] = (rodh - dum) / self.zdel[k - 1]
+                        break
+                    w[n] = 1.0
+                    dum = dum + self.zdel[k - 1]
+        return w
+
+    def rodded_columns(self) -> np.ndarray:
+        """(nnod) bool: node lies in a column under a control rod bank (fbmap > 0)."""
+        ia, ja, _ = self._node_assembly_maps()
+        fbmap = self.crod["bmap"][np.ix_(ia, ja)]
+        return fbmap[self.ix - 1, self.iy - 1] > 0
+
+    def xtab_defaults(self):
+        """What the XS update sees before the first TH solve: inp_ther sets ftem = 900., cden = 0.711,
+        mtem = 500. (default-REAL literals, mod_io.f90:3103-3105); bcon is the %BCON value if the card
+        is read (RODEJECT only, :294), else rbcon, which XTAB decks never set (0)."""
+        b = (self.fbk or {}).get("bcon")
+        return dict(bcon=0.0 if b is None else b["val"], ftem=900.0, mtem=500.0, cden=float(np.float32(0.711)))
+
+    def _xstab_updt(self, bpos, bcon, ftem, mtem, cden) -> None:
+        """XStab_updt (mod_xsec.f90:50-86): brInterp(unrodded) for every node, crod_tab_updt (:300-390)
+        -- rodded nodes take the rodded table, the partially rodded node the volume-weighted mix, negative
+        values in rodded columns are suppressed --, Dsigr_updt.  The ADFs come out of the tables too."""
+        N, G = self.nnod, self.ng
+        dflt = self.xtab_defaults()
+        bcon = dflt["bcon"] if bcon is None else float(bcon)
+        ftem = np.broadcast_to(np.asarray(dflt["ftem"] if ftem is None else ftem, dtype=np.float64), (N,))
+        mtem = np.broadcast_to(np.asarray(dflt["mtem"] if mtem is None else mtem, dtype=np.float64), (N,))
+        cden = np.broadcast_to(np.asarray(dflt["cden"] if cden is None else cden, dtype=np.float64), (N,))
+        nval = 4 * G + G * G + 6 * G
+        val = np.empty((N, nval))
+        for mn, t in enumerate(self.xtab):
+            sel = np.nonzero(self.mat == mn + 1)[0]
+            if sel.size:
+                val[sel] = self._br_interp(t, 0, cden[sel], bcon, ftem[sel], mtem[sel])
+        if self.crod is not None:
+            w = self.rod_fractions(self.crod["bpos"] if bpos is None else bpos)
+            hit = np.nonzero(w >= 0.0)[0]
+            for mn in np.unique(self.mat[hit]):
+                t = self.xtab[mn - 1]
+                if t["trod"] != 1:
+                    raise ValueError(f"CONTROL ROD BANK COINCIDES WITH MATERIAL NUMBER {mn} THAT DOES NOT HAVE CONTROL ROD DATA IN XTAB FILE")
+                sel = hit[self.mat[hit] == mn]
+                rod = self._br_interp(t, 1, cden[sel], bcon, ftem[sel], mtem[sel])
+                # fully rodded nodes take the rodded set; the partially rodded node the volume-weighted mix
+                # (vfrac == 1 there gives 0 * unrodded + rodded, the same value)
+                vf = w[sel][:, None]
+                val[sel] = np.where(vf == 1.0, rod, (1.0 - vf) * val[sel] + vf * rod)
+            cols = self.rodded_columns()
+            blk = val[cols, G:]                     # siga, nuf, sigf, sigs, dc (not sigtr)
+            blk[blk < 0.0] = 0.0
+            val[cols, G:] = blk
+        self.sigtr = np.asfortranarray(val[:, 0:G])
+        self.siga = np.asfortranarray(val[:, G:2 * G])
+        self.nuf = np.asfortranarray(val[:, 2 * G:3 * G])
+        self.sigf = np.asfortranarray(val[:, 3 * G:4 * G])
+        self.sigs = np.asfortranarray(val[:, 4 * G:4 * G + G * G].reshape(N, G, G))
+        self.dc = np.asfortranarray(val[:, 4 * G + G * G:].reshape(N, G, 6))
+        self.finish_xs()
 
     def finish_xs(self) -> None:
         """Dsigr_updt: D = 1/(3 sigtr); sigr = siga + sum_{h != g} sigs(g -> h), h ascending."""
@@ -530,27 +693,130 @@ class Problem:
         return fasm
 
 
+# --------------------------------------------------------------------------- %XTAB library files
+def _find_xtab_file(name: str, base_dir: str) -> str:
+    """The sample decks carry the absolute paths of the author's machine
+    (/home/imronuke/ADPRES/smpl/xsec/...): if the path does not exist, look for its `smpl/...` tail
+    under the tree the deck itself lives in."""
+    if os.path.exists(name):
+        return os.path.abspath(name)
+    parts = name.replace("\\", "/").split("/")
+    if "smpl" in parts:
+        tail = parts[parts.index("smpl"):]
+        d = os.path.abspath(base_dir)
+        while True:
+            cand = os.path.join(d, *tail)
+            if os.path.exists(cand):
+                return cand
+            if os.path.dirname(d) == d:
+                break
+            d = os.path.dirname(d)
+    cand = os.path.join(base_dir, os.path.basename(name))
+    if os.path.exists(cand):
+        return cand
+    raise FileNotFoundError(f"XTAB File Open Failed: {name}")
+
+
+def read_xtab_composition(lines: List[str], cnum: int, ng: int, fname: str = "") -> dict:
+    """One composition of a %XTAB library (inp_xtab mod_io.f90:3719-3812, readXS :3916-4061).
+    `lines` is the comment-stripped file.  Per branch point (s = coolant density, t = boron,
+    u = fuel temperature, v = moderator temperature) the values are packed as
+    [sigtr(G), siga(G), nuf(G), sigf(G), sigs(G,G) row g -> column h, dc(G,6)]."""
+    r = _Reader(lines, "XTAB " + fname)
+    tadf, trod = r.ints(2)
+    nd, nb, nf, nm = r.ints(4)
+    if min(nd, nb, nf, nm) < 1:
+        raise ValueError("ERROR: MINIMUM NUMBER OF BRANCH IS 1")
+    pars = []
+    for dim, what in ((nd, "COOLANT DENSITY"), (nb, "BORON CONCENTRATION"), (nf, "FUEL TEMPERATURE"), (nm, "MODERATOR TEMPERATURE")):
+        if dim > 1:                                         # branchPar (:3879-3912)
+            par = np.array(r.floats(dim))
+            if (par[:-1] > par[1:]).any():
+                raise ValueError(f"{what} PARAMETER SHALL BE IN ORDER, SMALL to BIG")
+        else:
+            par = np.zeros(1)
+        pars.append(par)
+    if tadf not in (1, 2):
+        raise ValueError("XTAB libraries without ADFs leave dc undefined in the reference; unsupported")
+    nskip = ng * nb * nf * nm
+    per_set = (5 if tadf == 1 else 10) * nskip + ng * nskip          # records of one (un)rodded set
+    r.pos += (cnum - 1) * ((2 if trod == 1 else 1) * per_set + 4)    # skipRead (:3780-3798)
+    if r.pos >= len(lines):
+        raise ValueError(f"END OF FILE REACHED FOR XTAB FILE {fname}")
+    nval = 4 * ng + ng * ng + 6 * ng
+
+    def read_set():
+        a = np.zeros((nd, nb, nf, nm, nval))
+
+        def block(col):
+            for v in range(nm):
+                for u in range(nf):
+                    for t in range(nb):
+                        a[:, t, u, v, col] = r.floats(nd)
+        for kind in range(4):                               # sigtr, siga, nuf, sigf
+            for g in range(ng):
+                block(kind * ng + g)
+        for g in range(ng):
+            for h in range(ng):
+                block(4 * ng + g * ng + h)
+        o = 4 * ng + ng * ng
+        if tadf == 1:
+            for g in range(ng):
+                block(o + g * 6)
+                for k in range(1, 6):
+                    a[..., o + g * 6 + k] = a[..., o + g * 6]
+        else:
+            for g in range(ng):
+                for k in range(6):
+                    block(o + g * 6 + k)
+        return a
+    xs = read_set()
+    rxs = read_set() if trod == 1 else None
+    chi = np.array(r.floats(ng))
+    velo = 1.0 / np.array(r.floats(ng))                     # the library holds inverse velocities
+    lamb = np.array(r.floats(6))
+    ibeta = np.array(r.floats(6))
+    return dict(tadf=tadf, trod=trod, nd=nd, nb=nb, nf=nf, nm=nm, pd=pars[0], pb=pars[1], pf=pars[2], pm=pars[3],
+                xs=xs, rxs=rxs, chi=chi, velo=velo, lamb=lamb, ibeta=ibeta)
+
+
 # --------------------------------------------------------------------------- parsing
 def parse_deck(text: str, base_dir: str = ".") -> Problem:
     cards = _split_cards(_strip_comments(text), base_dir)
     if "MODE" not in cards:
         raise ValueError("CARD %MODE DOES NOT PRESENT")
     mode = cards["MODE"][0].split()[0].upper()
-    if "XSEC" not in cards:
-        raise ValueError("CARD %XSEC DOES NOT PRESENT (XTAB decks are out of scope)")
+    if "XSEC" not in cards and "XTAB" not in cards:
+        raise ValueError("CARD %XSEC OR %XTAB DOES NOT PRESENT")
     if "GEOM" not in cards:
         raise ValueError("CARD %GEOM DOES NOT PRESENT")
 
     # ---- %XSEC (mod_io.f90:683-762); xsigs(mat, g, h) = scattering g -> h
-    r = _Reader(cards["XSEC"], "XSEC")
-    ng, nmat = r.ints(2)
+    xtab = None
+    if "XSEC" in cards:
+        r = _Reader(cards["XSEC"], "XSEC")
+        ng, nmat = r.ints(2)
+    else:
+        # ---- %XTAB (inp_xtab, mod_io.f90:3648-3875): ng, nmat, then per material a library file and
+        # the number of the composition inside it
+        r = _Reader(cards["XTAB"], "XTAB")
+        ng, nmat = r.ints(2)
+        xtab, files = [], {}
+        for i in range(nmat):
+            v = cards["XTAB"][r.pos].split()
+            r.pos += 1
+            path = _find_xtab_file(v[0], base_dir)
+            if path not in files:
+                with open(path) as fh:
+                    files[path] = _strip_comments(fh.read(), mark="*")
+            xtab.append(read_xtab_composition(files[path], int(v[1]), ng, os.path.basename(path)))
     xsigtr = np.zeros((nmat, ng), order="F")
     xsiga = np.zeros((nmat, ng), order="F")
     xnuf = np.zeros((nmat, ng), order="F")
     xsigf = np.zeros((nmat, ng), order="F")
     chi = np.zeros((nmat, ng), order="F")
     xsigs = np.zeros((nmat, ng, ng), order="F")
-    for i in range(nmat):
+    for i in range(nmat if xtab is None else 0):
         for g in range(ng):
             v = r.floats(5 + ng)
             xsigtr[i, g], xsiga[i, g], xnuf[i, g], xsigf[i, g], chi[i, g] = v[:5]
@@ -578,7 +844,7 @@ def parse_deck(text: str, base_dir: str = ".") -> Problem:
     p = Problem(mode=mode, ng=ng, nmat=nmat, nx=nx, ny=ny, nz=nz, xsize=xsize, ysize=ysize,
                 zsize=zsize, xdiv=xdiv, ydiv=ydiv, zdiv=zdiv, zpln=zpln, planars=planars, bc=bc,
                 xsigtr=xsigtr, xsiga=xsiga, xnuf=xnuf, xsigf=xsigf, xsigs=xsigs, chi=chi,
-                cards=cards)
+                cards=cards, xtab=xtab)
 
     if "KERN" in cards:                 # mod_io.f90:1593-1621
         name = cards["KERN"][0].split()[0].upper()
@@ -624,7 +890,7 @@ def parse_deck(text: str, base_dir: str = ".") -> Problem:
             bmap[:, j] = r.ints(nx)
         dsigtr = np.zeros((nmat, ng)); dsiga = np.zeros((nmat, ng)); dnuf = np.zeros((nmat, ng))
         dsigf = np.zeros((nmat, ng)); dsigs = np.zeros((nmat, ng, ng))
-        for i in range(nmat):
+        for i in range(nmat if xtab is None else 0):    # %XTAB decks: the rodded sets are in the library (:2225-2232)
             for g in range(ng):
                 v = r.floats(4 + ng)
                 dsigtr[i, g], dsiga[i, g], dnuf[i, g], dsigf[i, g] = v[:4]

@@ -9,9 +9,9 @@ In the drop-in deployment these loops stay Fortran and call `outer`, `outer_th`,
                                      updated in numpy (deck.Problem.update_xs) and uploaded, PowDis
                                      comes back to the host, th_upd is `th_module.th_upd` (the tests
                                      pass oracle.th)
-    DeviceGlue(p, solver)            solver = capi.Solver: adp_xs_update_th, adp_outer_th,
-                                     adp_th_pline, adp_th_upd -- per TH iteration one boron
-                                     concentration goes up and four scalars come back
+    DeviceGlue(p, solver)            solver = capi.Solver: adp_xs_update_th (adp_xs_update_xtab for
+                                     %XTAB decks), adp_outer_th, adp_th_pline, adp_th_upd -- per TH
+                                     iteration one boron concentration goes up and four scalars come back
 
 Both expose xs_update(bcon), outer(), outer_th(nth), th_step() -> th_err, and state() with Ke,
 ser, fer; the drivers below are written once against that interface.
@@ -40,15 +40,25 @@ def _outer_th(p, solver, nth):
     return solver.outer_th(nth)
 
 
+def _initial_fields(p):
+    """ftem, mtem, cden before the first TH solve: the value of the %FTEM / %MTEM / %CDEN card everywhere
+    (mod_io.f90:2697-2699 etc.); %XTAB decks have no such cards and inp_ther sets 900., 500., 0.711 (:3103-3105)."""
+    n = p.nnod
+    if getattr(p, "xtab", None) is not None:
+        d = p.xtab_defaults()
+        return np.full(n, d["ftem"]), np.full(n, d["mtem"]), np.full(n, d["cden"])
+    return (np.full(n, _card(p, "ftem") if _card(p, "ftem") is not None else 900.0),
+            np.full(n, _card(p, "mtem") if _card(p, "mtem") is not None else 560.0),
+            np.full(n, _card(p, "cden") if _card(p, "cden") is not None else 0.75))
+
+
 class HostGlue:
     def __init__(self, p, solver, th_module):
         self.p, self.s, self.thm = p, solver, th_module
         self.th = p.th_setup() if p.ther is not None else None
         n = p.nnod
         # inp_ftem / inp_mtem / inp_cden: the card's value everywhere (mod_io.f90:2697-2699 etc.)
-        self.ftem = np.full(n, _card(p, "ftem") if _card(p, "ftem") is not None else 900.0)
-        self.mtem = np.full(n, _card(p, "mtem") if _card(p, "mtem") is not None else 560.0)
-        self.cden = np.full(n, _card(p, "cden") if _card(p, "cden") is not None else 0.75)
+        self.ftem, self.mtem, self.cden = _initial_fields(p)
         self.bpos = None if p.crod is None else p.crod["bpos"].astype(np.float64)
         if self.th is not None:
             self.st = th_module.initial_state(p, self.th)
@@ -89,13 +99,17 @@ class DeviceGlue:
         self.th = p.th_setup() if p.ther is not None else None
         n = p.nnod
         self.bpos = None if p.crod is None else p.crod["bpos"].astype(np.float64)
-        solver.set_material_xs(p)
-        if p.crod is not None:
-            solver.set_crod(p)
-        solver.set_feedback(p)
-        ftem = np.full(n, _card(p, "ftem") if _card(p, "ftem") is not None else 900.0)
-        mtem = np.full(n, _card(p, "mtem") if _card(p, "mtem") is not None else 560.0)
-        cden = np.full(n, _card(p, "cden") if _card(p, "cden") is not None else 0.75)
+        self.xtab = getattr(p, "xtab", None) is not None
+        if self.xtab:                       # %XTAB deck: branch tables, the rodded sets are part of them
+            solver.set_xtab(p)
+            if p.crod is not None:
+                solver.set_crod_map(p)
+        else:
+            solver.set_material_xs(p)
+            if p.crod is not None:
+                solver.set_crod(p)
+            solver.set_feedback(p)
+        ftem, mtem, cden = _initial_fields(p)
         if self.th is not None:
             solver.set_th(self.th)
             solver.set_th_state(dict(tfm=np.full((n, self.th["nt"] + 1), 900.0, order="F"), heatf=np.zeros(n), ent=np.zeros(n),
@@ -105,10 +119,12 @@ class DeviceGlue:
             self._first = (ftem, mtem, cden)          # no TH state on the device: pass the card values
 
     def xs_update(self, bcon):
-        if self._first is not None:
-            self.s.xs_update_th(bcon, *self._first, bpos=self.bpos)
+        fields = self._first if self._first is not None else ()
+        if self.xtab:
+            if self.s.xs_update_xtab(bcon, *fields, bpos=self.bpos) > 0:
+                raise StopError(self.s.last_error())
         else:
-            self.s.xs_update_th(bcon, bpos=self.bpos)
+            self.s.xs_update_th(bcon, *fields, bpos=self.bpos)
 
     def outer(self):
         return self.s.outer(0)
@@ -205,4 +221,6 @@ def cbsearcht(g, log=None):
     def evaluate(bcon):
         th_iter(g, bcon, ind=None, log=None)
         return g.state()["Ke"]
-    return _secant(g, g.p.fbk["bcon"]["ref"], evaluate, 30, g.p.serc, g.p.ferc, log)
+    # rbcon: the %CBCS reference; %XTAB decks have no %CBCS card and leave it at its initial 0
+    rbcon = g.p.fbk["bcon"]["ref"] if (g.p.fbk or {}).get("bcon") is not None else 0.0
+    return _secant(g, rbcon, evaluate, 30, g.p.serc, g.p.ferc, log)

@@ -139,6 +139,22 @@ module adpres_b200
       import; type(c_ptr), value :: ctx, ftem, mtem, cden      ! c_null_ptr = the TH state on the device
       real(c_double), value :: bcon; real(c_double), intent(in) :: bpos(*)
     end function
+    ! %XTAB decks: the branch tables of sdata's m(1:nmat) (MBRANCH), packed by the caller -- see include/adpres_b200.h
+    integer(c_int) function adp_set_xtab(ctx, dims, trod, par, xs, rxs) bind(C, name="adp_set_xtab")
+      import; type(c_ptr), value :: ctx, rxs                    ! rxs: c_null_ptr if no material has a rodded set
+      integer(c_int), intent(in) :: dims(4,*), trod(*); real(c_double), intent(in) :: par(*), xs(*)
+    end function
+    integer(c_int) function adp_set_crod_map(ctx, nb, pos0, ssize, fbmap) bind(C, name="adp_set_crod_map")
+      import; type(c_ptr), value :: ctx; integer(c_int), value :: nb; real(c_double), value :: pos0, ssize
+      integer(c_int), intent(in) :: fbmap(*)
+    end function
+    integer(c_int) function adp_xs_update_xtab(ctx, bcon, ftem, mtem, cden, bpos) bind(C, name="adp_xs_update_xtab")
+      import; type(c_ptr), value :: ctx, ftem, mtem, cden      ! c_null_ptr = the TH state on the device
+      real(c_double), value :: bcon; real(c_double), intent(in) :: bpos(*)
+    end function
+    integer(c_int) function adp_get_dc(ctx, dc) bind(C, name="adp_get_dc")
+      import; type(c_ptr), value :: ctx; real(c_double), intent(out) :: dc(*)
+    end function
     integer(c_int) function adp_get_errors(ctx, ser, fer) bind(C, name="adp_get_errors")
       import; type(c_ptr), value :: ctx; real(c_double), intent(out) :: ser, fer
     end function

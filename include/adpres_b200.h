@@ -42,6 +42,8 @@ enum {
     ADP_STOP_NDMAX = 3,      /* "Max. change in nodal coupling coefficient" > 1e3, mod_nodal.f90:131-142 */
     ADP_STOP_ZERO_POWER = 4, /* "TOTAL NODES POWER IS ZERO OR LESS" mod_cmfd.f90:1322-1326 */
     ADP_STOP_STEAM_TABLE = 5, /* "ENTHALPY / MODERATOR TEMP. IS OUT OF THE RANGE ... IN THE STEAM TABLE" mod_th.f90:236-244,293-301 */
+    ADP_STOP_XTAB_RANGE = 6, /* "... IS OUT OF THE RANGE OF THE BRANCH PARAMETER" mod_xsec.f90:569-574,594-599,619-624,644-649 */
+    ADP_STOP_XTAB_NOROD = 7, /* "CONTROL ROD BANK ... COINCIDES WITH MATERIAL ... THAT DOES NOT HAVE CONTROL ROD DATA IN XTAB FILE" mod_xsec.f90:336-343 */
     ADP_ERR_CUDA = -1,
     ADP_ERR_USAGE = -2,
     ADP_ERR_NCCL = -3,
@@ -159,6 +161,28 @@ int adp_set_feedback(adp_ctx *ctx, int which, double ref, const double *dsigtr, 
 int adp_xs_update_th(adp_ctx *ctx, double bcon, const double *ftem, const double *mtem, const double *cden,
                      const double *bpos);
 int adp_get_xs(adp_ctx *ctx, double *D, double *sigr, double *nuf, double *sigf, double *sigs);
+
+/* ---- optional: XStab_updt on the device for %XTAB decks (branch-table cross sections) ---------- */
+/* The tables inp_xtab reads into m(1:nmat) (MBRANCH, mod_data.f90:176-192; mod_io.f90:3648-4061):
+ *   dims (4,nmat) column-major: nd, nb, nf, nm (coolant density, boron, fuel / moderator temperature)
+ *   trod (nmat): 1 = the material has a rodded set
+ *   par: pd(nd), pb(nb), pf(nf), pm(nm) of material 1, then of material 2, ... (a dimension of 1
+ *        contributes one unused value, like branchPar)
+ *   xs, rxs: per material one (nd,nb,nf,nm,nval) block, LAST index fastest, nval = 4 ng + ng*ng + 6 ng
+ *        values per branch point packed [sigtr(ng), siga(ng), nuf(ng), sigf(ng), sigs(g,h) g slow,
+ *        dc(g,face) g slow]; rxs blocks of materials without a rodded set are ignored (rxs may be
+ *        NULL if no material has one).  chi goes through adp_set_xs as usual. */
+int adp_set_xtab(adp_ctx *ctx, const int *dims, const int *trod, const double *par, const double *xs,
+                 const double *rxs);
+/* %CROD of an %XTAB deck: bank map only, the rodded cross sections are in the tables (mod_io.f90:2225-2232) */
+int adp_set_crod_map(adp_ctx *ctx, int nb, double pos0, double ssize, const int *fbmap);
+/* XStab_updt(bcon, ftem, mtem, cden, bpos): brInterp for every node, crod_tab_updt, Dsigr_updt
+ * (mod_xsec.f90:50-86,300-390,520-788) -> D, sigr, nuf, sigf, sigs AND dc on the device.  ftem / mtem /
+ * cden host (nnod) or NULL = the thermal-hydraulic state on the device.  Returns ADP_STOP_XTAB_RANGE /
+ * ADP_STOP_XTAB_NOROD for the reference's two STOPs. */
+int adp_xs_update_xtab(adp_ctx *ctx, double bcon, const double *ftem, const double *mtem, const double *cden,
+                       const double *bpos);
+int adp_get_dc(adp_ctx *ctx, double *dc /* (nnod,ng,6) */);
 
 /* ---- optional: the time-step glue of mod_trans.f90 on the device ------------- */
 /* With these a time step uploads only the new cross sections and reads back scalars.

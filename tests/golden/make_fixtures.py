@@ -8,6 +8,8 @@ that has /root/reference; the GPU box does not).
 * ``iaea3ds_trace.json`` -- the only ADPRES-produced golden numbers in the reference:
   the terminal trace printed in docs/quick-guides.md:161-191 and the k-eff in
   smpl/static/IAEA3Ds:3-4.  Parsed from the docs file, not typed by hand.
+* ``neacrp_bcon.json``, ``mox_bcon.json`` -- critical boron concentrations ADPRES itself found for
+  the static NEACRP decks / MOX part 3, read from the %BCON card of the matching transient decks.
 * ``header_keff.json``   -- the external-reference k-eff values quoted in the deck headers
   (IAEA2D, BIBLIS, KOEBERG): +-few-pcm sanity values, not ADPRES outputs.
 """
@@ -30,6 +32,9 @@ DECKS = {
     "NEACRP_B2": "smpl/static/NEACRP/B2", "NEACRP_C1": "smpl/static/NEACRP/C1", "NEACRP_C2": "smpl/static/NEACRP/C2",
     "NEACRP_A1t": "smpl/transient/NEACRP/A1t",
     "MOX_ARO": "smpl/static/MOX/part1_aro_helios", "MOX_ARI": "smpl/static/MOX/part1_ari_helios",
+    # %XTAB decks: the spec carries the branch tables of the compositions the deck selects
+    "MOX_P2_HELIOS": "smpl/static/MOX/part2_helios", "MOX_P3_HELIOS": "smpl/static/MOX/part3_helios",
+    "MOX_P3_SERPENT": "smpl/static/MOX/part3_serpent",
 }
 
 
@@ -47,6 +52,15 @@ def main():
         bcon[case] = float(lines[i + 1].split()[0])
     with open(os.path.join(HERE, "neacrp_bcon.json"), "w") as fh:
         json.dump({"source": "first number of the %BCON card of smpl/transient/NEACRP/<case>t", "ppm": bcon}, fh)
+    # ---- MOX/UO2 benchmark: part 4 (rod ejection from hot zero power) starts from the critical boron the
+    # reference found for part 3 -- same rule as NEACRP
+    mox = {}
+    for lib in ("helios", "serpent"):
+        lines = open(os.path.join(REF, "smpl/transient/MOX", "part4_" + lib)).read().splitlines()
+        i = next(k for k, ln in enumerate(lines) if ln.strip().upper().startswith("%BCON"))
+        mox["P3_" + lib.upper()] = float(lines[i + 1].split()[0])
+    with open(os.path.join(HERE, "mox_bcon.json"), "w") as fh:
+        json.dump({"source": "first number of the %BCON card of smpl/transient/MOX/part4_<library>", "ppm": mox}, fh)
     # ---- docs trace
     text = open(os.path.join(REF, "docs/quick-guides.md")).read()
     rows = []
