@@ -25,7 +25,7 @@ TRACE_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_doubl
 SYMBOLS = [
     "adp_create", "adp_destroy", "adp_last_error", "adp_version", "adp_comm_unique_id", "adp_comm_init", "adp_comm_init_env", "adp_slab",
     "adp_set_geometry", "adp_set_xs", "adp_set_control", "adp_matrix_setup", "adp_init_flux", "adp_outer_begin",
-    "adp_outer_iter", "adp_nodal_upd", "adp_powdis", "adp_integrate", "adp_set_kinetics", "adp_set_transient",
+    "adp_outer_iter", "adp_nodal_upd", "adp_powdis", "adp_integrate", "adp_set_kinetics", "adp_set_kinetics_xtab", "adp_set_transient",
     "adp_get_exsrc", "adp_set_material_xs", "adp_set_crod", "adp_xs_update", "adp_set_feedback", "adp_xs_update_th", "adp_get_xs",
     "adp_set_xtab", "adp_set_crod_map", "adp_xs_update_xtab", "adp_get_dc", "adp_save_adjoint", "adp_ipden", "adp_update_omeg", "adp_begin_time_step", "adp_upden", "adp_powtot", "adp_asm_pow", "adp_axi_pow", "adp_asm_flux", "adp_set_th", "adp_set_th_state", "adp_get_th_state", "adp_th_pline",
     "adp_th_upd", "adp_th_trans",
@@ -178,6 +178,11 @@ class Solver:
     def set_kinetics(self, ibeta, lamb, velo, tbeta, sth, bth):
         a = [np.ascontiguousarray(x, dtype=np.float64) for x in (ibeta, lamb, velo, tbeta)]
         self._chk(self.L.adp_set_kinetics(self.h, _d(a[0]), _d(a[1]), _d(a[2]), _d(a[3]), C.c_double(sth), C.c_double(bth)))
+
+    def set_kinetics_xtab(self, mibeta, mlamb, mvelo, tbeta, sth, bth):
+        """%XTAB decks: per-material iBeta / lamb (nmat, 6) and velo (nmat, ng), rows = materials"""
+        a = [np.ascontiguousarray(x, dtype=np.float64) for x in (mibeta, mlamb, mvelo, tbeta)]
+        self._chk(self.L.adp_set_kinetics_xtab(self.h, _d(a[0]), _d(a[1]), _d(a[2]), _d(a[3]), C.c_double(sth), C.c_double(bth)))
 
     def set_transient(self, c0=None, ft=None, fst=None, omeg=None, sigrp=None, L=None):
         f = lambda a: None if a is None else np.asfortranarray(a, dtype=np.float64)

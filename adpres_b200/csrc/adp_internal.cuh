@@ -161,6 +161,8 @@ struct adp_ctx {
     double ibeta[ADP_NF] = {0}, lamb[ADP_NF] = {0};
     double sth = 1.0, bth = 0.0;
     bool kinetics_set = false;
+    bool kin_xtab = false;                 // kinetics data per material (adp_set_kinetics_xtab, %XTAB decks)
+    double *d_mkin = nullptr;              // [nmat][6] lamb | [nmat][6] iBeta | [nmat][ng] velo
     // thermal-hydraulic channel solve (th.cu): parameters of %THER and the state the reference keeps in sdata
     struct ThPar {
         double pi = 0, rf = 0, rg = 0, rc = 0, dia = 0, dh = 0, farea = 0, cflow = 0, cf = 0, tin = 0, enti = 0;

@@ -109,7 +109,7 @@ extern "C" int adp_destroy(adp_ctx *c)
         double *th[] = {c->d_stab, c->d_tfm, c->d_heatf, c->d_ent, c->d_ftem, c->d_mtem, c->d_cden, c->d_frate, c->d_pline, c->d_nodenf, c->d_chain};
         for (double *q : th) if (q) cudaFree(q);
         for (int f = 0; f < 4; ++f) if (c->d_ftab[f]) cudaFree(c->d_ftab[f]);
-        void *br[] = {c->d_brmeta, c->d_brtoff, c->d_brpar, c->d_brtab, c->d_brrtab};
+        void *br[] = {c->d_brmeta, c->d_brtoff, c->d_brpar, c->d_brtab, c->d_brrtab, c->d_mkin};
         for (void *q : br) if (q) cudaFree(q);
     }
     cudaStreamDestroy(c->stream);
@@ -290,6 +290,8 @@ extern "C" int adp_set_geometry(adp_ctx *c, int nxx, int nyy, int nzz, int nnod,
         for (int f = 0; f < 4; ++f)
             if (c->d_ftab[f]) { cudaFree(c->d_ftab[f]); c->d_ftab[f] = nullptr; }
         free_xtab(c);
+        if (c->d_mkin) { cudaFree(c->d_mkin); c->d_mkin = nullptr; }
+        c->kin_xtab = false;
     }
     c->abefgh_valid = false;
     c->geometry_set = true;
@@ -583,6 +585,28 @@ extern "C" int adp_set_kinetics(adp_ctx *c, const double *ibeta, const double *l
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     TRY(ensure_transient(c));
     c->kinetics_set = true;
+    c->kin_xtab = false;
+    return ADP_OK;
+}
+
+extern "C" int adp_set_kinetics_xtab(adp_ctx *c, const double *mibeta, const double *mlamb, const double *mvelo,
+                                     const double *tbeta, double sth, double bth)
+{   // %XTAB decks (bxtab = 1): m(mat)%iBeta(6), %lamb(6), %velo(ng) per material; switches get_exsrc, iPden, uPden
+    // and the time-absorption term of adp_begin_time_step to their bxtab = 1 branches
+    if (!c || !mibeta || !mlamb || !mvelo || !tbeta) return ADP_ERR_USAGE;
+    ADP_REQUIRE(c, c->geometry_set, "adp_set_kinetics_xtab: geometry not set");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    const size_t nk = (size_t)ADP_NF * c->nmat, nv = (size_t)c->ng * c->nmat;
+    TRY(dev_alloc(c, &c->d_mkin, 2 * nk + nv, false));
+    CUDA_TRY(c, cudaMemcpyAsync(c->d_mkin, mlamb, nk * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(c, cudaMemcpyAsync(c->d_mkin + nk, mibeta, nk * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(c, cudaMemcpyAsync(c->d_mkin + 2 * nk, mvelo, nv * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(c, cudaMemcpyAsync(c->d_tbeta, tbeta, c->nmat * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    c->sth = sth; c->bth = bth;
+    TRY(ensure_transient(c));
+    c->kinetics_set = true;
+    c->kin_xtab = true;
     return ADP_OK;
 }
 

@@ -17,6 +17,7 @@
 //   k_scalar_*       the handful of scalar statements of the outer loop    :467-485
 #include "adp_internal.cuh"
 #include "xtab_node.cuh"
+#include "kinetics_node.cuh"
 
 namespace {
 
@@ -659,6 +660,47 @@ __global__ void __launch_bounds__(ADP_TILE) k_begin_step(Geo G, StepArgs A)
     }
 }
 
+// ---- the same four with the kinetics data of an %XTAB library: per material, precursors only in fuel
+// (bxtab = 1 branches; per-node code in kinetics_node.cuh)
+__global__ void __launch_bounds__(ADP_TILE) k_get_exsrc_xtab(Geo G, KinTab K, KxExsrc A, const int *__restrict__ mat,
+                                                              const double *__restrict__ nuf)
+{
+    FOR_EACH_ROW(G, 0, G.nzl)
+    {
+        const long long idx = node_idx(G, kl, r);
+        kx_exsrc(K, A, mat[idx] - 1, nuf[(size_t)(K.ng - 1) * G.NV + idx] > 0.0, G.NV, idx);
+    }
+}
+__global__ void __launch_bounds__(ADP_TILE) k_ipden_xtab(Geo G, KinTab K, const int *__restrict__ mat, const double *__restrict__ nuf,
+                                                          const double *__restrict__ fs, double *__restrict__ c0)
+{
+    FOR_EACH_ROW(G, 0, G.nzl)
+    {
+        const long long idx = node_idx(G, kl, r);
+        kx_ipden(K, mat[idx] - 1, nuf[(size_t)(K.ng - 1) * G.NV + idx] > 0.0, fs[idx], c0, G.NV, idx);
+    }
+}
+__global__ void __launch_bounds__(ADP_TILE) k_upden_xtab(Geo G, KinTab K, const int *__restrict__ mat, const double *__restrict__ nuf,
+                                                          double ht, const double *__restrict__ fst, const double *__restrict__ fs,
+                                                          double *__restrict__ c0)
+{
+    FOR_EACH_ROW(G, 0, G.nzl)
+    {
+        const long long idx = node_idx(G, kl, r);
+        kx_upden(K, mat[idx] - 1, nuf[(size_t)(K.ng - 1) * G.NV + idx] > 0.0, ht, fst[idx], fs[idx], c0, G.NV, idx);
+    }
+}
+__global__ void __launch_bounds__(ADP_TILE) k_begin_step_xtab(Geo G, KinTab K, StepArgs A, const int *__restrict__ mat)
+{
+    FOR_EACH_ROW(G, 0, G.nzl)
+    {
+        const long long idx = node_idx(G, kl, r);
+        kx_time_absorption(K, mat[idx] - 1, A.sth, A.ht, A.omeg, A.sigr, A.sigrp, G.NV, idx);
+        for (int g = 0; g < A.ng; ++g) A.ft[(size_t)g * G.NV + idx] = A.f0[g][idx];
+        A.fst[idx] = A.fs[idx];
+    }
+}
+
 // rod_eject (mod_trans.f90:128-134,150-154): omeg = LOG(f0 / ft) / tstep with %EXTR, else 0
 __global__ void __launch_bounds__(ADP_TILE) k_omeg(Geo G, StepArgs A, int bextr)
 {
@@ -1108,16 +1150,34 @@ int adp_k_scale_by_slot(adp_ctx *c, double *d_vec, int slot)
     return ADP_OK;
 }
 
+static KinTab kintab_of(adp_ctx *c)
+{
+    KinTab K;
+    K.ng = c->ng; K.nmat = c->nmat;
+    K.lamb = c->d_mkin; K.ibeta = c->d_mkin + (size_t)ADP_NF * c->nmat; K.velo = c->d_mkin + (size_t)2 * ADP_NF * c->nmat;
+    return K;
+}
+
 int adp_k_get_exsrc(adp_ctx *c, double ht)
 {
-    ExsrcArgs A{};
-    A.ng = c->ng; A.nmat = c->nmat; A.ht = ht; A.sth = c->sth; A.bth = c->bth;
-    for (int i = 0; i < ADP_NF; ++i) { A.lamb[i] = c->lamb[i]; A.ibeta[i] = c->ibeta[i]; }
-    A.c0 = c->d_c0; A.fst = c->d_fst; A.tbeta = c->d_tbeta; A.velo = c->d_velo; A.chi = c->d_chi; A.mat = c->d_mat;
-    A.L = c->d_L; A.sigrp = c->d_sigrp; A.ft = c->d_ft; A.s0 = c->d_s0; A.omeg = c->d_omeg;
-    A.s0_group = c->s0_group - 1;
-    A.exsrc = c->d_exsrc; A.dfis = c->d_dfis;
-    k_get_exsrc<<<adp_grid(c, k_get_exsrc, c->geo.ntiles), ADP_TILE, 0, c->stream>>>(c->geo, A);
+    if (c->kin_xtab) {
+        KxExsrc X{};
+        X.ht = ht; X.sth = c->sth; X.bth = c->bth;
+        X.c0 = c->d_c0; X.fst = c->d_fst; X.tbeta = c->d_tbeta; X.chi = c->d_chi;
+        X.L = c->d_L; X.sigrp = c->d_sigrp; X.ft = c->d_ft; X.s0 = c->d_s0; X.omeg = c->d_omeg;
+        X.s0_group = c->s0_group - 1;
+        X.exsrc = c->d_exsrc; X.dfis = c->d_dfis;
+        k_get_exsrc_xtab<<<adp_grid(c, k_get_exsrc_xtab, c->geo.ntiles), ADP_TILE, 0, c->stream>>>(c->geo, kintab_of(c), X, c->d_mat, c->d_nuf);
+    } else {
+        ExsrcArgs A{};
+        A.ng = c->ng; A.nmat = c->nmat; A.ht = ht; A.sth = c->sth; A.bth = c->bth;
+        for (int i = 0; i < ADP_NF; ++i) { A.lamb[i] = c->lamb[i]; A.ibeta[i] = c->ibeta[i]; }
+        A.c0 = c->d_c0; A.fst = c->d_fst; A.tbeta = c->d_tbeta; A.velo = c->d_velo; A.chi = c->d_chi; A.mat = c->d_mat;
+        A.L = c->d_L; A.sigrp = c->d_sigrp; A.ft = c->d_ft; A.s0 = c->d_s0; A.omeg = c->d_omeg;
+        A.s0_group = c->s0_group - 1;
+        A.exsrc = c->d_exsrc; A.dfis = c->d_dfis;
+        k_get_exsrc<<<adp_grid(c, k_get_exsrc, c->geo.ntiles), ADP_TILE, 0, c->stream>>>(c->geo, A);
+    }
     LAUNCH_CHECK(c);
     if (c->nranks > 1) {
         // the two-node problem across a slab boundary reads dfis (cmode 2) of the neighbour's plane
@@ -1207,12 +1267,24 @@ static KinConst kin_of(adp_ctx *c)
 }
 int adp_k_ipden(adp_ctx *c)
 {
+    if (c->kin_xtab) {
+        k_ipden_xtab<<<adp_grid(c, k_ipden_xtab, c->geo.ntiles), ADP_TILE, 0, c->stream>>>(c->geo, kintab_of(c), c->d_mat, c->d_nuf,
+                                                                                          c->d_fs[c->fcur], c->d_c0);
+        LAUNCH_CHECK(c);
+        return ADP_OK;
+    }
     k_ipden<<<adp_grid(c, k_ipden, c->geo.ntiles), ADP_TILE, 0, c->stream>>>(c->geo, kin_of(c), c->d_fs[c->fcur], c->d_c0);
     LAUNCH_CHECK(c);
     return ADP_OK;
 }
 int adp_k_upden(adp_ctx *c, double ht)
 {
+    if (c->kin_xtab) {
+        k_upden_xtab<<<adp_grid(c, k_upden_xtab, c->geo.ntiles), ADP_TILE, 0, c->stream>>>(c->geo, kintab_of(c), c->d_mat, c->d_nuf, ht,
+                                                                                          c->d_fst, c->d_fs[c->fcur], c->d_c0);
+        LAUNCH_CHECK(c);
+        return ADP_OK;
+    }
     k_upden<<<adp_grid(c, k_upden, c->geo.ntiles), ADP_TILE, 0, c->stream>>>(c->geo, kin_of(c), ht, c->d_fst, c->d_fs[c->fcur], c->d_c0);
     LAUNCH_CHECK(c);
     return ADP_OK;
@@ -1224,7 +1296,10 @@ int adp_k_begin_step(adp_ctx *c, double ht)
     A.sigr = c->d_sigr; A.sigrp = c->d_sigrp; A.ft = c->d_ft;
     for (int g = 0; g < c->ng; ++g) A.f0[g] = f0ptr(c, c->cur[g], g);
     A.fs = c->d_fs[c->fcur]; A.fst = c->d_fst;
-    k_begin_step<<<adp_grid(c, k_begin_step, c->geo.ntiles), ADP_TILE, 0, c->stream>>>(c->geo, A);
+    if (c->kin_xtab)
+        k_begin_step_xtab<<<adp_grid(c, k_begin_step_xtab, c->geo.ntiles), ADP_TILE, 0, c->stream>>>(c->geo, kintab_of(c), A, c->d_mat);
+    else
+        k_begin_step<<<adp_grid(c, k_begin_step, c->geo.ntiles), ADP_TILE, 0, c->stream>>>(c->geo, A);
     LAUNCH_CHECK(c);
     // the nodal kernels read sigr on the neighbour's boundary plane (A..H, B matrix)
     if (c->nranks > 1)

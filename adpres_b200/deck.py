@@ -902,7 +902,10 @@ def parse_deck(text: str, base_dir: str = ".") -> Problem:
         nb = p.crod["nb"]
         fb = np.array([r.floats(3) for _ in range(nb)])
         ttot, tstep1, tdiv, tstep2 = r.floats(4)
-        ibeta = np.array(r.floats(6)); lamb = np.array(r.floats(6)); velo = np.array(r.floats(ng))
+        if xtab is None:
+            ibeta = np.array(r.floats(6)); lamb = np.array(r.floats(6)); velo = np.array(r.floats(ng))
+        else:                            # %XTAB decks: per-material kinetics data come from the library (:2389)
+            ibeta = lamb = velo = None
         p.ejct = dict(fbpos=fb[:, 0].copy(), tmove=fb[:, 1].copy(), bspeed=fb[:, 2].copy(), ttot=ttot, tstep1=tstep1,
                       tdiv=tdiv, tstep2=tstep2, ibeta=ibeta, lamb=lamb, velo=velo)
     if "EXTR" in cards:
@@ -913,11 +916,13 @@ def parse_deck(text: str, base_dir: str = ".") -> Problem:
     for card, key, nval in (("CBCS", "bcon", 1), ("BCON", "bcon", 2), ("FTEM", "ftem", 2), ("MTEM", "mtem", 2), ("CDEN", "cden", 2)):
         if card not in cards:
             continue
+        if xtab is not None and not (card == "BCON" and mode == "RODEJECT"):
+            continue                      # %XTAB decks: only %BCON of a RODEJECT deck is read (mod_io.f90:293-306)
         r = _Reader(cards[card], card)
         v = r.floats(nval)
         tab = dict(val=v[0], ref=v[-1], sigtr=np.zeros((nmat, ng)), siga=np.zeros((nmat, ng)), nuf=np.zeros((nmat, ng)),
                    sigf=np.zeros((nmat, ng)), sigs=np.zeros((nmat, ng, ng)))
-        for i in range(nmat):
+        for i in range(nmat if xtab is None else 0):      # ... and only its two numbers (:2605)
             for g in range(ng):
                 w = r.floats(4 + ng)
                 tab["sigtr"][i, g], tab["siga"][i, g], tab["nuf"][i, g], tab["sigf"][i, g] = w[:4]

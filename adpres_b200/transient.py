@@ -275,6 +275,54 @@ def _move_rods(e, bpos, mdir, ht, t2):
             bpos[b] = min(bpos[b] + ht * bspeed[b], fbpos[b])
 
 
+def _kinetics(p):
+    """Kinetics data of a RODEJECT deck.  %XSEC decks: one set on the %EJCT card.  %XTAB decks
+    (bxtab = 1): one set per material in the library, m(mat)%iBeta / %lamb / %velo.  Returns
+    (xtab?, ibeta, lamb, velo, tbeta): (6,) / (ng,) arrays, or (nmat, 6) / (nmat, ng) for %XTAB;
+    tbeta(nmat) accumulated family by family (mod_trans.f90:235-249)."""
+    if getattr(p, "xtab", None) is None:
+        e = p.ejct
+        tbeta = np.full(p.nmat, 0.0)
+        for jf in range(6):
+            tbeta = tbeta + e["ibeta"][jf]
+        return False, e["ibeta"], e["lamb"], e["velo"], tbeta
+    ibeta = np.array([t["ibeta"] for t in p.xtab])
+    lamb = np.array([t["lamb"] for t in p.xtab])
+    velo = np.array([t["velo"] for t in p.xtab])
+    tbeta = np.zeros(p.nmat)
+    for jf in range(6):
+        tbeta = tbeta + ibeta[:, jf]
+    return True, ibeta, lamb, velo, tbeta
+
+
+def calc_beta(p, af, f0, nuf, ibeta):
+    """calc_beta (mod_trans.f90:692-741): adjoint-weighted core-averaged delayed neutron fraction
+    (%XTAB decks only)."""
+    m = p.mat - 1
+    vdum = np.zeros(p.nnod)
+    for g in range(p.ng):
+        vdum = vdum + nuf[:, g] * f0[:, g]
+    vdum2 = np.zeros(p.nnod)
+    for g in range(p.ng):
+        vdum2 = vdum2 + p.chi[m, g] * vdum * af[:, g]
+    F = _integrate(p, vdum2)
+    ctbeta = 0.0
+    for i in range(6):
+        vdum2 = np.zeros(p.nnod)
+        for g in range(p.ng):
+            vdum2 = vdum2 + p.chi[m, g] * ibeta[m, i] * vdum * af[:, g]
+        ctbeta = ctbeta + _integrate(p, vdum2) / F
+    return ctbeta
+
+
+def _integrate(p, s):
+    """Integrate (mod_cmfd.f90:1120-1139): serial sum of vdel * s"""
+    tot = 0.0
+    for v in (p.vdel * s).tolist():
+        tot = tot + v
+    return tot
+
+
 def rod_eject_th(p, g, max_steps=None, log=None):
     """rod_eject_th + trans_calc(thc = 1) on a thermal.HostGlue `g` (numpy glue; g.s = oracle.Oracle or
     capi.Solver, g.thm = the th module).  Returns rows (step, t, reactivity [$], relative power
@@ -282,13 +330,13 @@ def rod_eject_th(p, g, max_steps=None, log=None):
     from . import thermal
     s, thm, th = g.s, g.thm, g.th
     e, c = p.ejct, p.crod
-    ibeta, lamb, velo = e["ibeta"], e["lamb"], e["velo"]
+    xt, ibeta, lamb, velo, tbeta = _kinetics(p)
     bcon = p.fbk["bcon"]["val"]
     g.bpos = c["bpos"].astype(np.float64).copy()
     mdir = np.where(np.abs(e["fbpos"] - g.bpos) < 1e-5, 0, np.where(e["fbpos"] - g.bpos > 1e-5, 2, 1))
     thermal.th_iter(g, bcon, ind=0)
     ke = s.state()["Ke"]
-    if abs(ke - 1.0) > 1e-5:                                  # KNE1 (mod_trans.f90:483-518)
+    if abs(ke - 1.0) > 1e-5 and not xt:                       # KNE1 (mod_trans.f90:483-518; not for %XTAB decks, :209)
         for it in range(10):
             p.xnuf = p.xnuf / ke
             c["dnuf"] = c["dnuf"] / ke
@@ -303,15 +351,22 @@ def rod_eject_th(p, g, max_steps=None, log=None):
     st = s.state()
     f0, fs0 = st["f0"], st["fs0"]
     tpow1 = powtot(p, f0)
-    c0 = np.asfortranarray((ibeta / lamb)[None, :] * fs0[:, None])
-    tbeta = np.full(p.nmat, 0.0)
-    for jf in range(6):
-        tbeta = tbeta + ibeta[jf]
-    ctbeta = tbeta[0]
+    m = p.mat - 1
+    if xt:                                                    # iPden, bxtab = 1: precursors only where nuf(n, ng) > 0
+        fuel = p.nuf[:, p.ng - 1] > 0.0
+        with np.errstate(divide="ignore", invalid="ignore"):  # the reflector's lamb = 0 never enters (fuel only)
+            c0 = np.asfortranarray(np.where(fuel[:, None], (ibeta / lamb)[m, :] * fs0[:, None], 0.0))
+        ctbeta = calc_beta(p, af, f0, p.nuf, ibeta)
+    else:
+        c0 = np.asfortranarray((ibeta / lamb)[None, :] * fs0[:, None])
+        ctbeta = tbeta[0]
     L = _leakage(p, s, f0)
     rho = reactivity(p, af, p.sigr, f0, fs0, L)
     trace = [(0, 0.0, rho / ctbeta, th["ppow"] * 0.01, 0, False, float(g.st["tfm"][:, 0].max()))]
-    s.set_kinetics(ibeta, lamb, velo, tbeta, p.sth, p.bth)
+    if xt:
+        s.set_kinetics_xtab(ibeta, lamb, velo, tbeta, p.sth, p.bth)
+    else:
+        s.set_kinetics(ibeta, lamb, velo, tbeta, p.sth, p.bth)
     ft = f0
     for step, (_, ht, t2) in enumerate(_time_steps(e), start=1):
         if max_steps is not None and step > max_steps:
@@ -322,7 +377,8 @@ def rod_eject_th(p, g, max_steps=None, log=None):
         sigrp = p.sigr.copy(order="F")
         sigr = p.sigr.copy(order="F")
         for gg in range(p.ng):
-            sigr[:, gg] = sigr[:, gg] + 1.0 / (p.sth * velo[gg] * ht) + omeg[:, gg] / velo[gg]
+            vg = velo[m, gg] if xt else velo[gg]               # m(mat(n))%velo(g) for %XTAB decks (mod_trans.f90:405-411)
+            sigr[:, gg] = sigr[:, gg] + 1.0 / (p.sth * vg * ht) + omeg[:, gg] / vg
         ft, fst = f0.copy(order="F"), fs0.copy()
         _push_xs(s, p, sigr=sigr)
         s.set_transient(c0=c0, ft=ft, fst=fst, omeg=omeg, sigrp=sigrp, L=L)
@@ -331,11 +387,18 @@ def rod_eject_th(p, g, max_steps=None, log=None):
         st = s.state()
         f0, fs0 = st["f0"], st["fs0"]
         for i in range(6):                                    # uPden
-            pxe = np.exp(-lamb[i] * ht)
-            a1 = (1.0 - pxe) / (lamb[i] * ht)
-            a2 = 1.0 - a1
-            a1 = a1 - pxe
-            c0[:, i] = c0[:, i] * pxe + ibeta[i] / lamb[i] * (a1 * fst + a2 * fs0)
+            if xt:
+                fuel = p.nuf[:, p.ng - 1] > 0.0
+                lam, bet = lamb[m, i], ibeta[m, i]
+            else:
+                fuel, lam, bet = slice(None), lamb[i], ibeta[i]
+            with np.errstate(divide="ignore", invalid="ignore"):
+                pxe = np.exp(-lam * ht)
+                a1 = (1.0 - pxe) / (lam * ht)
+                a2 = 1.0 - a1
+                a1 = a1 - pxe
+                new = c0[:, i] * pxe + bet / lam * (a1 * fst + a2 * fs0)
+            c0[fuel, i] = new[fuel]
         tpow2 = powtot(p, f0)
         L = _leakage(p, s, f0)
         rho = reactivity(p, af, sigrp, f0, fs0, L)
@@ -358,13 +421,13 @@ def rod_eject_th_device(p, g, max_steps=None, log=None):
     from . import thermal
     s, th = g.s, g.th
     e, c = p.ejct, p.crod
-    ibeta, lamb, velo = e["ibeta"], e["lamb"], e["velo"]
+    xt, ibeta, lamb, velo, tbeta = _kinetics(p)
     bcon = p.fbk["bcon"]["val"]
     g.bpos = c["bpos"].astype(np.float64).copy()
     mdir = np.where(np.abs(e["fbpos"] - g.bpos) < 1e-5, 0, np.where(e["fbpos"] - g.bpos > 1e-5, 2, 1))
     thermal.th_iter(g, bcon, ind=0)
     ke = s.state()["Ke"]
-    if abs(ke - 1.0) > 1e-5:
+    if abs(ke - 1.0) > 1e-5 and not xt:
         for it in range(10):
             p.xnuf = p.xnuf / ke
             c["dnuf"] = c["dnuf"] / ke
@@ -377,12 +440,16 @@ def rod_eject_th_device(p, g, max_steps=None, log=None):
                 break
     s.outer_ad(0)
     s.save_adjoint()
+    af = s.state()["f0"] if xt else None
     s.outer(0)
-    tbeta = np.full(p.nmat, 0.0)
-    for jf in range(6):
-        tbeta = tbeta + ibeta[jf]
-    ctbeta = tbeta[0]
-    s.set_kinetics(ibeta, lamb, velo, tbeta, p.sth, p.bth)
+    if xt:
+        # calc_beta: a printed, once-per-run quantity (reactivity in $) -- evaluated on the host from the
+        # adjoint and forward flux that come back once
+        ctbeta = calc_beta(p, af, s.state()["f0"], s.get_xs()["nuf"], ibeta)
+        s.set_kinetics_xtab(ibeta, lamb, velo, tbeta, p.sth, p.bth)
+    else:
+        ctbeta = tbeta[0]
+        s.set_kinetics(ibeta, lamb, velo, tbeta, p.sth, p.bth)
     tpow1 = s.powtot()
     s.ipden()
     rho = s.reactivity(0)

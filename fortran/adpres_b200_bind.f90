@@ -71,6 +71,10 @@ module adpres_b200
     integer(c_int) function adp_integrate(ctx, s, res) bind(C, name="adp_integrate")
       import; type(c_ptr), value :: ctx; real(c_double), intent(in) :: s(*); real(c_double), intent(out) :: res
     end function
+    integer(c_int) function adp_set_kinetics_xtab(ctx, mibeta, mlamb, mvelo, tbeta, sth, bth) bind(C, name="adp_set_kinetics_xtab")
+      import; type(c_ptr), value :: ctx; real(c_double), intent(in) :: mibeta(6,*), mlamb(6,*), mvelo(*), tbeta(*)
+      real(c_double), value :: sth, bth
+    end function
     integer(c_int) function adp_set_kinetics(ctx, ibeta, lamb, velo, tbeta, sth, bth) bind(C, name="adp_set_kinetics")
       import; type(c_ptr), value :: ctx
       real(c_double), intent(in) :: ibeta(6), lamb(6), velo(*), tbeta(*); real(c_double), value :: sth, bth

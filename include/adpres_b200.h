@@ -133,12 +133,18 @@ int adp_integrate(adp_ctx *ctx, const double *s, double *result);
 /* kinetics data: iBeta(6), lamb(6), velo(ng), tbeta(nmat), sth, bth (mod_data.f90:120-127) */
 int adp_set_kinetics(adp_ctx *ctx, const double *ibeta, const double *lamb, const double *velo,
                      const double *tbeta, double sth, double bth);
+/* %XTAB decks (bxtab = 1): kinetics data per material -- m(mat)%iBeta(6), %lamb(6), %velo(ng) (mod_data.f90:187-188,
+ * read by inp_xtab mod_io.f90:3800-3812) as (6,nmat), (6,nmat), (ng,nmat) column-major -- and tbeta(nmat).  Selects the
+ * bxtab = 1 branches of get_exsrc (mod_cmfd.f90:898-925), iPden / uPden (mod_trans.f90:574-585,617-629) and of the
+ * time-absorption term in adp_begin_time_step (:405-411): precursors only where nuf(n,ng) > 0. */
+int adp_set_kinetics_xtab(adp_ctx *ctx, const double *mibeta, const double *mlamb, const double *mvelo,
+                          const double *tbeta, double sth, double bth);
 /* state of the previous time level saved by trans_calc (mod_trans.f90:398-416) and the
  * precursors / frequencies / leakage: c0(nnod,6), ft(nnod,ng), fst(nnod), omeg(nnod,ng),
  * sigrp(nnod,ng), L(nnod,ng).  NULL keeps the device copy. */
 int adp_set_transient(adp_ctx *ctx, const double *c0, const double *ft, const double *fst,
                       const double *omeg, const double *sigrp, const double *L);
-/* get_exsrc(ht, exsrc): fills exsrc and dfis on the device (mod_cmfd.f90:872-952, bxtab=0) */
+/* get_exsrc(ht, exsrc): fills exsrc and dfis on the device (mod_cmfd.f90:872-952, both bxtab branches) */
 int adp_get_exsrc(adp_ctx *ctx, double ht);
 
 /* ---- optional: XS_updt on the device for %XSEC (+ %CROD) decks --------------- */

@@ -98,6 +98,12 @@ class Oracle:
                                 _d(np.ascontiguousarray(velo)), _d(np.ascontiguousarray(tbeta)),
                                 C.c_double(sth), C.c_double(bth))
 
+    def set_kinetics_xtab(self, mibeta, mlamb, mvelo, tbeta, sth, bth):
+        """%XTAB decks: per-material iBeta / lamb (nmat, 6) and velo (nmat, ng) -- rows = materials"""
+        self.L.orc_set_kinetics_xtab(self.h, _d(np.ascontiguousarray(mibeta)), _d(np.ascontiguousarray(mlamb)),
+                                     _d(np.ascontiguousarray(mvelo)), _d(np.ascontiguousarray(tbeta)),
+                                     C.c_double(sth), C.c_double(bth))
+
     def set_transient(self, c0=None, ft=None, fst=None, omeg=None, sigrp=None, L=None):
         self.L.orc_set_transient(self.h, _d(c0), _d(ft), _d(fst), _d(omeg), _d(sigrp), _d(L))
 

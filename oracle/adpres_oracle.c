@@ -71,6 +71,9 @@ typedef struct orc {
     int fixedsrc_mode;          /* mode == 'FIXEDSRC' (PowDis) */
     /* ---- sdata: transient */
     double lamb[NF], ibeta[NF], *velo, *tbeta;
+    /* %XTAB decks (bxtab == 1): kinetics data per material, m(mat)%lamb / %iBeta / %velo */
+    int bxtab;
+    double *mlamb, *mibeta, *mvelo;      /* (NF, nmat), (NF, nmat), (ng, nmat) column-major */
     double *c0, *ft, *fst, *omeg, *sigrp, *L, *dfis;
     double sth, bth, ht_cur;
     /* ---- SAVEd first-call flags */
@@ -169,6 +172,7 @@ void orc_destroy(orc *o)
     free(o->xdel); free(o->ydel); free(o->zdel); free(o->vdel);
     free(o->D); free(o->sigr); free(o->nuf); free(o->sigf); free(o->sigs); free(o->chi);
     free(o->dc); free(o->exsrc); free(o->nod); free(o->f0); free(o->fs0); free(o->s0);
+    free(o->mlamb); free(o->mibeta); free(o->mvelo);
     free(o->velo); free(o->tbeta); free(o->c0); free(o->ft); free(o->fst); free(o->omeg);
     free(o->sigrp); free(o->L); free(o->dfis);
     free(o->Bcn); free(o->Bcp); free(o->An); free(o->Bn); free(o->En); free(o->Fn); free(o->Gn);
@@ -675,10 +679,37 @@ int orc_outer_th(orc *o, int maxn, int *niter)
     return outer_body(o, 4, 0, maxn, NULL, niter);
 }
 
-/* get_exsrc, mod_cmfd.f90:872-952 (bxtab == 0 branch; XTAB decks are out of scope) */
+/* get_exsrc, mod_cmfd.f90:872-952: bxtab == 1 branch :898-925, bxtab == 0 branch :926-949 */
+#define MLAMB(m, i) o->mlamb[((m) - 1) * NF + (i) - 1]
+#define MIBETA(m, i) o->mibeta[((m) - 1) * NF + (i) - 1]
+#define MVELO(m, g) o->mvelo[((m) - 1) * G_ + (g) - 1]
 void orc_get_exsrc(orc *o, double ht)
 {
     for (int n = 1; n <= N_; ++n) o->dfis[n - 1] = 0.0;
+    if (o->bxtab) {
+        for (int n = 1; n <= N_; ++n) {
+            double dt = 0.0, dtp = 0.0;
+            int m = MAT(n);
+            for (int i = 1; i <= NF; ++i) {
+                double pxe = exp(-MLAMB(m, i) * ht), a1, a2;
+                if (V2(o->nuf, n, G_) > 0.0) a1 = (1.0 - pxe) / (MLAMB(m, i) * ht);
+                else a1 = 0.0;
+                a2 = 1.0 - a1;
+                a1 = a1 - pxe;
+                o->dfis[n - 1] = o->dfis[n - 1] + MIBETA(m, i) * a2;
+                dt = dt + MLAMB(m, i) * C0(n, i) * pxe + MIBETA(m, i) * a1 * o->fst[n - 1];
+                dtp = dtp + MLAMB(m, i) * C0(n, i);
+            }
+            for (int g = 1; g <= G_; ++g) {
+                double pthet = -V2(o->L, n, g) - V2(o->sigrp, n, g) * V2(o->ft, n, g) + V2(o->s0, n, g) +
+                               (1.0 - o->tbeta[m - 1]) * CHI(m, g) * o->fst[n - 1] + CHI(m, g) * dtp;
+                V2(o->exsrc, n, g) = CHI(m, g) * dt +
+                                     exp(V2(o->omeg, n, g) * ht) * V2(o->ft, n, g) / (o->sth * MVELO(m, g) * ht) +
+                                     o->bth * pthet;
+            }
+        }
+        return;
+    }
     for (int n = 1; n <= N_; ++n) {
         double dt = 0.0, dtp = 0.0;
         for (int i = 1; i <= NF; ++i) {
@@ -1295,9 +1326,19 @@ double orc_powtot(orc *o, const double *fx)
     return tpow;
 }
 
-/* iPden, mod_trans.f90:561-597 (bxtab == 0) */
+/* iPden, mod_trans.f90:561-597 */
 void orc_ipden(orc *o)
 {
+    if (o->bxtab) {
+        for (int n = 1; n <= N_; ++n)
+            for (int j = 1; j <= NF; ++j) {
+                if (V2(o->nuf, n, G_) > 0.0) {      /* if it is fuel */
+                    double blamb = MIBETA(MAT(n), j) / MLAMB(MAT(n), j);
+                    C0(n, j) = blamb * o->fs0[n - 1];
+                } else C0(n, j) = 0.0;
+            }
+        return;
+    }
     for (int n = 1; n <= N_; ++n)
         for (int j = 1; j <= NF; ++j) {
             double blamb = o->ibeta[j - 1] / o->lamb[j - 1];
@@ -1305,9 +1346,22 @@ void orc_ipden(orc *o)
         }
 }
 
-/* uPden, mod_trans.f90:601-644 (bxtab == 0) */
+/* uPden, mod_trans.f90:601-644 */
 void orc_upden(orc *o, double ht)
 {
+    if (o->bxtab) {
+        for (int i = 1; i <= NF; ++i)
+            for (int n = 1; n <= N_; ++n)
+                if (V2(o->nuf, n, G_) > 0.0) {
+                    int m = MAT(n);
+                    double pxe = exp(-MLAMB(m, i) * ht);
+                    double a1 = (1.0 - pxe) / (MLAMB(m, i) * ht);
+                    double a2 = 1.0 - a1;
+                    a1 = a1 - pxe;
+                    C0(n, i) = C0(n, i) * pxe + MIBETA(m, i) / MLAMB(m, i) * (a1 * o->fst[n - 1] + a2 * o->fs0[n - 1]);
+                }
+        return;
+    }
     for (int i = 1; i <= NF; ++i) {
         double pxe = exp(-o->lamb[i - 1] * ht);
         double a1 = (1.0 - pxe) / (o->lamb[i - 1] * ht);
@@ -1347,7 +1401,20 @@ int orc_set_kinetics(orc *o, const double *ibeta, const double *lamb, const doub
 {
     memcpy(o->ibeta, ibeta, NF * sizeof(double)); memcpy(o->lamb, lamb, NF * sizeof(double));
     memcpy(o->velo, velo, G_ * sizeof(double)); memcpy(o->tbeta, tbeta, o->nmat * sizeof(double));
-    o->sth = sth; o->bth = bth;
+    o->sth = sth; o->bth = bth; o->bxtab = 0;
+    return ORC_OK;
+}
+/* %XTAB decks: iBeta, lamb (NF per material) and velo (ng per material) of m(1:nmat), tbeta(nmat) */
+int orc_set_kinetics_xtab(orc *o, const double *mibeta, const double *mlamb, const double *mvelo,
+                          const double *tbeta, double sth, double bth)
+{
+    free(o->mlamb); free(o->mibeta); free(o->mvelo);
+    o->mlamb = dalloc((size_t)NF * o->nmat); o->mibeta = dalloc((size_t)NF * o->nmat); o->mvelo = dalloc((size_t)G_ * o->nmat);
+    memcpy(o->mibeta, mibeta, (size_t)NF * o->nmat * sizeof(double));
+    memcpy(o->mlamb, mlamb, (size_t)NF * o->nmat * sizeof(double));
+    memcpy(o->mvelo, mvelo, (size_t)G_ * o->nmat * sizeof(double));
+    memcpy(o->tbeta, tbeta, o->nmat * sizeof(double));
+    o->sth = sth; o->bth = bth; o->bxtab = 1;
     return ORC_OK;
 }
 /* transient state set by trans_calc before outer_tr (mod_trans.f90:398-416); NULL = keep */

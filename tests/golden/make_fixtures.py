@@ -34,7 +34,7 @@ DECKS = {
     "MOX_ARO": "smpl/static/MOX/part1_aro_helios", "MOX_ARI": "smpl/static/MOX/part1_ari_helios",
     # %XTAB decks: the spec carries the branch tables of the compositions the deck selects
     "MOX_P2_HELIOS": "smpl/static/MOX/part2_helios", "MOX_P3_HELIOS": "smpl/static/MOX/part3_helios",
-    "MOX_P3_SERPENT": "smpl/static/MOX/part3_serpent",
+    "MOX_P3_SERPENT": "smpl/static/MOX/part3_serpent", "MOX_P4_HELIOS": "smpl/transient/MOX/part4_helios",
 }
 
 

@@ -268,6 +268,105 @@ def test_device_node_code_stop_codes(hostlib):
         p.update_xs(p.crod["bpos"], bcon=1000.0, ftem=ftem, mtem=mtem, cden=cden)
 
 
+@pytest.fixture(scope="module")
+def kinlib(tmp_path_factory):
+    gxx = shutil.which("g++")
+    if not gxx:
+        pytest.skip("no g++")
+    out = str(tmp_path_factory.mktemp("hostcheck") / "libkin_host.so")
+    src = os.path.join(ROOT, "tests", "hostcheck", "kinetics_host.cpp")
+    subprocess.run([gxx, "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-Wall", "-Werror", src, "-o", out],
+                   check=True, capture_output=True)
+    return C.CDLL(out)
+
+
+def _kin_state(p, seed=3):
+    """random but physical transient state on the part-3 core: (f0, fs0, c0, ft, fst, omeg, sigrp, L, s0 with one column)"""
+    rng = np.random.default_rng(seed)
+    N, G = p.nnod, p.ng
+    fuel = p.nuf[:, G - 1] > 0
+    f0 = np.asfortranarray(0.5 + rng.random((N, G)))
+    fs0 = np.where(fuel, 0.2 + rng.random(N), 0.0)
+    c0 = np.asfortranarray(np.where(fuel[:, None], rng.random((N, 6)), 0.0))
+    ft = np.asfortranarray(f0 * (1.0 + 0.01 * rng.standard_normal((N, G))))
+    fst = fs0 * (1.0 + 0.01 * rng.standard_normal(N))
+    omeg = np.asfortranarray(5.0 * rng.standard_normal((N, G)))
+    sigrp = np.asfortranarray(p.sigr * (1.0 + 0.01 * rng.random((N, G))))
+    L = np.asfortranarray(0.01 * rng.standard_normal((N, G)))
+    s0 = np.zeros((N, G), order="F")
+    s0[:, G - 1] = 0.05 * rng.random(N)
+    return f0, fs0, c0, ft, fst, omeg, sigrp, L, s0
+
+
+def test_device_kinetics_node_code_against_the_c_oracle(kinlib):
+    """csrc/kinetics_node.cuh (bxtab = 1 branches of iPden, uPden, get_exsrc and the time-absorption term: kinetics
+    data per material from the %XTAB library, precursors only in fuel) compiled with g++ against the C oracle."""
+    from adpres_b200 import transient
+    from adpres_b200.capi import _d, _ip
+    from oracle import Oracle
+    p = load_problem("MOX_P3_HELIOS")
+    N, G = p.nnod, p.ng
+    xt, ibeta, lamb, velo, tbeta = transient._kinetics(p)
+    assert xt and ibeta.shape == (p.nmat, 6) and velo.shape == (p.nmat, G) and np.all(tbeta[:17] > 0.002)
+    sth, ht = 0.7, 0.002
+    bth = (1.0 - sth) / sth
+    f0, fs0, c0, ft, fst, omeg, sigrp, L, s0 = _kin_state(p)
+    o = Oracle(p)
+    o.set_kinetics_xtab(ibeta, lamb, velo, tbeta, sth, bth)
+    mat = np.ascontiguousarray(p.mat.astype(np.int32))
+    kin = (G, p.nmat, _d(np.ascontiguousarray(lamb)), _d(np.ascontiguousarray(ibeta)), _d(np.ascontiguousarray(velo)), C.c_longlong(N),
+           mat.ctypes.data_as(_ip))
+    nuf = np.asfortranarray(p.nuf)
+    fuel = p.nuf[:, G - 1] > 0
+    # iPden
+    o.set_state(f0, fs0, 1.0)
+    o.ipden()
+    c_h = np.full((N, 6), np.nan, order="F")
+    kinlib.kin_host_ipden(*kin, _d(nuf), _d(fs0), _d(c_h))
+    assert np.array_equal(c_h, o.transient()["c0"]) and np.all(c_h[~fuel] == 0.0) and np.all(c_h[fuel] > 0.0)
+    # uPden
+    o.set_transient(c0=c0, ft=ft, fst=fst, omeg=omeg, sigrp=sigrp, L=L)
+    o.upden(ht)
+    c_h = c0.copy(order="F")
+    kinlib.kin_host_upden(*kin, _d(nuf), C.c_double(ht), _d(fst), _d(fs0), _d(c_h))
+    assert np.array_equal(c_h, o.transient()["c0"]) and np.array_equal(c_h[~fuel], c0[~fuel])
+    # get_exsrc (s0: only the column of the last group swept is non-zero)
+    o.set_transient(c0=c0)
+    o.L.orc_set_s0(o.h, _d(s0))
+    o.get_exsrc(ht)
+    t = o.transient()
+    ex_h, df_h = np.zeros((N, G), order="F"), np.zeros(N)
+    kinlib.kin_host_exsrc(*kin, _d(nuf), C.c_double(ht), C.c_double(sth), C.c_double(bth), _d(c0), _d(fst), _d(tbeta),
+                          _d(np.asfortranarray(p.chi)), _d(L), _d(sigrp), _d(ft), _d(np.ascontiguousarray(s0[:, G - 1])), G - 1,
+                          _d(omeg), _d(ex_h), _d(df_h))
+    assert np.array_equal(df_h, t["dfis"]) and np.array_equal(ex_h, t["exsrc"])
+    # the reflector has no delayed neutrons: dfis = 0, and a fuel node sees its own material's data
+    assert np.all(df_h[~fuel] == 0.0) and np.all(df_h[fuel] > 0.0) and len(np.unique(df_h[fuel])) > 5
+    # time-absorption term of trans_calc with m(mat(n))%velo(g)
+    sigr = np.asfortranarray(p.sigr.copy())
+    sp = np.zeros((N, G), order="F")
+    kinlib.kin_host_time_absorption(*kin, C.c_double(sth), C.c_double(ht), _d(omeg), _d(sigr), _d(sp))
+    m = p.mat - 1
+    assert np.array_equal(sp, p.sigr)
+    for g in range(G):
+        assert np.array_equal(sigr[:, g], p.sigr[:, g] + 1.0 / (sth * velo[m, g] * ht) + omeg[:, g] / velo[m, g])
+
+
+def test_oracle_mox_part4_first_steps():
+    """smpl/transient/MOX/part4_helios (rod ejection from hot zero power, %XTAB + %EXTR, 22 616 nodes): steady state,
+    adjoint, core-averaged delayed neutron fraction and the first time steps with the CPU oracle."""
+    from adpres_b200 import thermal, transient
+    from oracle import Oracle, th as oth
+    p = load_problem("MOX_P4_HELIOS")
+    assert (p.mode, p.nnod, p.bextr, p.crod["nb"]) == ("RODEJECT", 22616, 1, 9) and p.ejct["ibeta"] is None
+    g = thermal.HostGlue(p, Oracle(p), oth)
+    tr = transient.rod_eject_th(p, g, max_steps=3)
+    assert abs(g.s.state()["Ke"] - 1.0) < 1e-3                 # critical at the reference's own boron (1341.99 ppm); no KNE1 for %XTAB
+    assert abs(tr[0][2]) < 0.02 and abs(tr[0][3] - 1.0e-6) < 1e-18           # reactivity ~ 0 $, 1e-4 % power
+    assert 0.0 < tr[1][2] < tr[2][2] < tr[3][2] < 0.01           # bank 9 starts to move out: reactivity rises
+    assert tr[3][3] > tr[1][3] > 1.0e-6
+
+
 # ------------------------------------------------------------------ GPU
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", ["MOX_P3_HELIOS", "MOX_P3_SERPENT", "MOX_P2_HELIOS"])
@@ -329,3 +428,24 @@ def test_gpu_mox_part2_search_follows_the_oracle():
     fo, fd = go.th_fields(), gd.th_fields()
     for k in ("ftem", "mtem", "cden"):
         assert np.abs(fo[k] - fd[k]).max() / np.abs(fo[k]).max() < 1e-5, k
+
+
+@pytest.mark.gpu
+def test_gpu_mox_part4_first_steps_device_resident():
+    """MOX part 4 (rod ejection, %XTAB kinetics per material, %EXTR): device-resident time stepping against
+    the oracle-driven run through the first steps of the rod withdrawal"""
+    from adpres_b200 import capi, thermal, transient
+    from oracle import Oracle, th as oth
+    ps = []
+    for _ in range(2):
+        p = load_problem("MOX_P4_HELIOS")
+        p.serc = p.ferc = 1e-9          # converged steps: the exit iteration must not depend on round-off (DESIGN.md 2)
+        p.nout = 5000
+        ps.append(p)
+    to = transient.rod_eject_th(ps[0], thermal.HostGlue(ps[0], Oracle(ps[0]), oth), max_steps=4)
+    td = transient.rod_eject_th_device(ps[1], thermal.DeviceGlue(ps[1], capi.Solver(ps[1])), max_steps=4)
+    assert len(to) == len(td) == 5
+    for a, b in zip(to, td):
+        assert abs(a[2] - b[2]) < 1e-4, (a, b)                       # reactivity [$]
+        assert abs(a[3] / b[3] - 1.0) < 1e-4, (a, b)                 # relative power (north star: 1e-4)
+        assert abs(a[6] / b[6] - 1.0) < 1e-6                         # max fuel centreline temperature
