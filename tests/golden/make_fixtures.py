@@ -32,6 +32,9 @@ DECKS = {
     "NEACRP_B2": "smpl/static/NEACRP/B2", "NEACRP_C1": "smpl/static/NEACRP/C1", "NEACRP_C2": "smpl/static/NEACRP/C2",
     "NEACRP_A1t": "smpl/transient/NEACRP/A1t",
     "MOX_ARO": "smpl/static/MOX/part1_aro_helios", "MOX_ARI": "smpl/static/MOX/part1_ari_helios",
+    "FDM_1D": "smpl/static/FDM-1D", "CBCsearch": "smpl/static/CBCsearch", "MOX_1B_A1": "smpl/static/MOX/Part1b/aroA1",
+    "MOX_1D_E7": "smpl/static/MOX/Part1d/ariE7", "MOX_ARO_SERPENT": "smpl/static/MOX/part1_aro_serpent",
+    "MOX_ARI_SERPENT": "smpl/static/MOX/part1_ari_serpent",
     # %XTAB decks: the spec carries the branch tables of the compositions the deck selects
     "MOX_P2_HELIOS": "smpl/static/MOX/part2_helios", "MOX_P3_HELIOS": "smpl/static/MOX/part3_helios",
     "MOX_P3_SERPENT": "smpl/static/MOX/part3_serpent", "MOX_P4_HELIOS": "smpl/transient/MOX/part4_helios",
