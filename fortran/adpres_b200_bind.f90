@@ -241,4 +241,65 @@ contains
     end do
   end subroutine gpu_pull_results
 
+  !> Optional, %XTAB decks: hand the branch tables m(1:nmat) (MBRANCH / XBRANCH, mod_data.f90:176-192, read by
+  !! inp_xtab) to the device once; afterwards th_iter / trans_calc replace
+  !!     CALL XStab_updt(bcon, ftem, mtem, cden, bpos)                      (mod_th.f90:45-46, mod_trans.f90:393-394)
+  !! by ierr = adp_xs_update_xtab(ctx, bcon, c_null_ptr, c_null_ptr, c_null_ptr, bpos)   ! TH fields already on the device
+  !! Packing: per branch point [sigtr(ng), siga(ng), nuf(ng), sigf(ng), sigs(g,h) g slow, dc(g,face) g slow],
+  !! points ordered (s,t,u,v) with v (moderator temperature) fastest -- see include/adpres_b200.h.
+  subroutine gpu_set_xtab()
+    use sdata, only: ng, nmat, m, nb, pos0, ssize, fbmap
+    use io, only: bcrod
+    integer(c_int) :: ierr
+    integer(c_int), allocatable :: dims(:,:), trod(:)
+    real(c_double), allocatable, target :: par(:), xs(:), rxs(:)
+    integer :: i, s, t, u, v, g, h, k, nval, npar, ntab, ip, it
+    logical :: anyrod
+    call gpu_init()
+    nval = 4*ng + ng*ng + 6*ng
+    allocate(dims(4,nmat), trod(nmat))
+    npar = 0; ntab = 0; anyrod = .false.
+    do i = 1, nmat
+      dims(:,i) = (/ m(i)%nd, m(i)%nb, m(i)%nf, m(i)%nm /)
+      trod(i) = m(i)%trod
+      npar = npar + m(i)%nd + m(i)%nb + m(i)%nf + m(i)%nm
+      ntab = ntab + m(i)%nd * m(i)%nb * m(i)%nf * m(i)%nm * nval
+      if (m(i)%trod == 1) anyrod = .true.
+    end do
+    allocate(par(npar), xs(ntab), rxs(ntab))
+    rxs = 0._c_double
+    ip = 0; it = 0
+    do i = 1, nmat
+      par(ip+1:ip+m(i)%nd) = m(i)%pd(1:m(i)%nd); ip = ip + m(i)%nd
+      par(ip+1:ip+m(i)%nb) = m(i)%pb(1:m(i)%nb); ip = ip + m(i)%nb
+      par(ip+1:ip+m(i)%nf) = m(i)%pf(1:m(i)%nf); ip = ip + m(i)%nf
+      par(ip+1:ip+m(i)%nm) = m(i)%pm(1:m(i)%nm); ip = ip + m(i)%nm
+      do s = 1, m(i)%nd; do t = 1, m(i)%nb; do u = 1, m(i)%nf; do v = 1, m(i)%nm
+        call pack_branch(m(i)%xsec(s,t,u,v), xs(it+1:it+nval))
+        if (m(i)%trod == 1) call pack_branch(m(i)%rxsec(s,t,u,v), rxs(it+1:it+nval))
+        it = it + nval
+      end do; end do; end do; end do
+    end do
+    if (anyrod) then
+      ierr = adp_set_xtab(ctx, dims, trod, par, xs, c_loc(rxs))
+    else
+      ierr = adp_set_xtab(ctx, dims, trod, par, xs, c_null_ptr)
+    end if
+    if (ierr /= 0) stop 'adpres_b200: adp_set_xtab failed'
+    if (bcrod == 1) then
+      ierr = adp_set_crod_map(ctx, nb, pos0, ssize, fbmap)       ! fbmap(nxx,nyy), column-major as the C side expects
+      if (ierr /= 0) stop 'adpres_b200: adp_set_crod_map failed'
+    end if
+  contains
+    subroutine pack_branch(x, a)
+      use sdata, only: XBRANCH
+      type(XBRANCH), intent(in) :: x
+      real(c_double), intent(out) :: a(:)
+      a(1:ng) = x%sigtr; a(ng+1:2*ng) = x%siga; a(2*ng+1:3*ng) = x%nuf; a(3*ng+1:4*ng) = x%sigf
+      k = 4*ng
+      do g = 1, ng; do h = 1, ng; k = k + 1; a(k) = x%sigs(g,h); end do; end do
+      do g = 1, ng; do h = 1, 6;  k = k + 1; a(k) = x%dc(g,h);   end do; end do
+    end subroutine pack_branch
+  end subroutine gpu_set_xtab
+
 end module adpres_b200
