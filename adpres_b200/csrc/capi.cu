@@ -257,6 +257,7 @@ extern "C" int adp_set_geometry(adp_ctx *c, int nxx, int nyy, int nzz, int nnod,
     TRY(dev_alloc(c, &c->d_mat, NV));
     {   // ghost planes outside the core keep material 1 so that table look-ups stay in range
         std::vector<int> ones(NV, 1);
+        CUDA_TRY(c, cudaStreamSynchronize(c->stream));   // dev_alloc's zero fill runs on c->stream, the blocking copy does not
         CUDA_TRY(c, cudaMemcpy(c->d_mat, ones.data(), NV * sizeof(int), cudaMemcpyHostToDevice));
     }
     TRY(upload_nodes_int(c, c->d_mat, mat));
@@ -685,6 +686,7 @@ static int set_crod_geometry(adp_ctx *c, int nb, double pos0, double ssize, cons
     if (!c->d_fb) { TRY(dev_alloc(c, &c->d_fb, c->np)); TRY(dev_alloc(c, &c->d_dumtop, c->nzz)); }
     if (c->d_bpos) { cudaFree(c->d_bpos); c->d_bpos = nullptr; }
     TRY(dev_alloc(c, &c->d_bpos, nb));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));       // dev_alloc's zero fill runs on c->stream, the blocking copies do not
     CUDA_TRY(c, cudaMemcpy(c->d_fb, fb.data(), c->np * sizeof(int), cudaMemcpyHostToDevice));
     CUDA_TRY(c, cudaMemcpy(c->d_dumtop, dumtop.data(), c->nzz * sizeof(double), cudaMemcpyHostToDevice));
     return ADP_OK;
