@@ -174,13 +174,23 @@ contains
   !! sigrp, ft, fst into sdata (src/mod_trans.f90:398-416); c0, omeg, L come from the previous step.
   subroutine outer_tr(ht, maxi)
     use sdata, only: nout, serc, ferc, fer, ser, nupd, Ke, ndmax, kern, exsrc, dfis, c0, ft, fst, omeg, sigrp, L, &
-                     ibeta, lamb, velo, tbeta, sth, bth
+                     ibeta, lamb, velo, tbeta, sth, bth, m, nmat, ng, nf
+    use io, only: bxtab
     real(dp), intent(in)  :: ht
     logical, intent(out)  :: maxi
-    integer :: p
+    integer :: p, i
     integer(c_int) :: ierr
+    real(c_double), allocatable :: mib(:,:), mla(:,:), mve(:,:)
     call gpu_push_inputs()
-    ierr = adp_set_kinetics(ctx, ibeta, lamb, velo, tbeta, sth, bth)
+    if (bxtab == 1) then        ! %XTAB decks: kinetics data per material (get_exsrc, src/mod_cmfd.f90:898-925)
+      allocate(mib(nf,nmat), mla(nf,nmat), mve(ng,nmat))
+      do i = 1, nmat
+        mib(:,i) = m(i)%iBeta; mla(:,i) = m(i)%lamb; mve(:,i) = m(i)%velo
+      end do
+      ierr = adp_set_kinetics_xtab(ctx, mib, mla, mve, tbeta, sth, bth)
+    else
+      ierr = adp_set_kinetics(ctx, ibeta, lamb, velo, tbeta, sth, bth)
+    end if
     ierr = adp_set_transient(ctx, c0, ft, fst, omeg, sigrp, L)
     ierr = adp_matrix_setup(ctx, 1_c_int)
     ierr = adp_get_exsrc(ctx, ht)                                 ! get_exsrc(ht, exsrc) on the device
