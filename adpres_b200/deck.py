@@ -833,6 +833,10 @@ def parse_deck(text: str, base_dir: str = ".") -> Problem:
     # ---- %GEOM part 2 (mod_io.f90:958-1143): planars are listed north (j = ny) first
     npl = r.ints(1)[0]
     zpln = np.array(r.ints(nz), dtype=np.int32)
+    if (zpln > npl).any():               # mod_io.f90:990-1001
+        raise ValueError(f"ERROR: PLANAR {int(zpln.max())} IS GREATER THAN NUMBER OF PLANAR")
+    if (zpln < 1).any():
+        raise ValueError("ERROR: PLANAR SHOULD BE AT LEAST 1")
     planars = np.zeros((npl, nx, ny), dtype=np.int32)
     for k in range(npl):
         for j in range(ny - 1, -1, -1):
