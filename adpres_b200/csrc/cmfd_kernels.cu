@@ -1256,6 +1256,8 @@ void adp_k_preload_cmfd(adp_ctx *c)
     adp_grid(c, k_extrap, 1); adp_grid(c, k_integrate, 1); adp_grid(c, k_fill, 1);
     adp_grid(c, k_scalar, 1); adp_grid(c, k_powdis, 1); adp_grid(c, k_scale, 1); adp_grid(c, k_get_exsrc, 1);
     adp_grid(c, k_xs_update, 1); adp_grid(c, k_ipden, 1); adp_grid(c, k_upden, 1); adp_grid(c, k_begin_step, 1); adp_grid(c, k_reactivity, 1);
+    adp_grid(c, k_xs_update_xtab, 1); adp_grid(c, k_get_exsrc_xtab, 1); adp_grid(c, k_ipden_xtab, 1); adp_grid(c, k_upden_xtab, 1);
+    adp_grid(c, k_begin_step_xtab, 1);
 }
 
 // ---- transient time-step glue -------------------------------------------------------------
