@@ -34,6 +34,8 @@ def main():
         return th_main(rank, world, local, uid, dist)
     if deck == "NEACRP_cb":
         return cb_main(rank, world, local, uid, dist)
+    if deck == "MOX_xtab":
+        return xtab_main(rank, world, local, uid, dist)
     if deck == "IAEA3Ds_z2":                  # 38 planes: uneven slabs at 4 ranks, 2 planes per axial assembly
         p = load_problem("IAEA3Ds").refine(zdiv=[2] * 19)
     else:
@@ -192,6 +194,32 @@ def cb_main(rank, world, local, uid, dist):
     for k in fo:
         assert np.abs(fd[k][own] / fo[k][own] - 1.0).max() < 1e-5, k
     print(f"RANK {rank}/{world} OK deck=NEACRP_cb planes=[{s.k0},{s.k1}) bcon={bd:.2f}", flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def xtab_main(rank, world, local, uid, dist):
+    """MOX part 3 (%XTAB branch tables, rods from the rodded sets, TH feedback) on z-slabs: the table
+    interpolation on the ghost planes takes the neighbours' fuel temperature / coolant density
+    (adp_comm_halo inside adp_xs_update_xtab); a STOP on one rank must come back on all.  Against the
+    reference's own critical boron (1341.99 ppm)."""
+    import json
+    import numpy as np
+    from conftest import GOLDEN, load_problem
+    from adpres_b200 import capi, thermal
+    gold = json.load(open(os.path.join(GOLDEN, "mox_bcon.json")))["ppm"]["P3_HELIOS"]
+    p = load_problem("MOX_P3_HELIOS")
+    s = capi.Solver(p, device=local, nranks=world, rank=rank, uid=uid)
+    gd = thermal.DeviceGlue(p, s)
+    bd, rd = thermal.cbsearcht(gd)
+    assert abs(bd - gold) < 0.02, (bd, gold)
+    # out-of-range coolant density in the TOP plane only: every rank must report the reference's STOP
+    n = p.nnod
+    cden = np.full(n, 0.7)
+    cden[-1] = 0.3
+    rc = s.xs_update_xtab(bd, np.full(n, 900.0), np.full(n, 560.0), cden, p.crod["bpos"].astype(np.float64))
+    assert rc == capi.STOP_XTAB_RANGE, rc
+    print(f"RANK {rank}/{world} OK deck=MOX_xtab planes=[{s.k0},{s.k1}) bcon={bd:.2f}", flush=True)
     dist.barrier()
     dist.destroy_process_group()
 
