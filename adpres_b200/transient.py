@@ -471,7 +471,7 @@ def rod_eject_th_device(p, g, max_steps=None, log=None):
         rc = s.th_trans(None, ht)
         if rc > 0:
             raise thermal.StopError(s.last_error())
-        tmax = float(s.th_state()["tfm"][:, 0].max()) if log or True else 0.0
+        tmax = float(s.th_state()["tfm"][:, 0].max())       # the printed Max. Tf (par_max(tfm(:,1)), mod_trans.f90:452)
         trace.append((step, t2, rho / ctbeta, xppow, n, maxi, tmax))
         if log:
             log(f"{step:4d} {t2:9.4f} {rho / ctbeta:10.4f} {xppow:13.5E}  outers {n}  Tf,max {tmax:.2f}")
