@@ -17,7 +17,7 @@ _ip = C.POINTER(C.c_int)
 
 MODE_FORWARD, MODE_ADJOINT, MODE_FIXEDSRC, MODE_TRANSIENT = 0, 1, 2, 3
 STOP_MAXOUTER, STOP_LU_DIAG, STOP_NDMAX, STOP_ZERO_POWER, STOP_STEAM_TABLE = 1, 2, 3, 4, 5
-STOP_XTAB_RANGE, STOP_XTAB_NOROD = 6, 7
+STOP_XTAB_RANGE, STOP_XTAB_NOROD, STOP_XS_CHECK = 6, 7, 8
 
 TRACE_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int)
 
@@ -445,7 +445,7 @@ class Solver:
 
     def xs_update(self, bpos=None):
         b = None if bpos is None else np.ascontiguousarray(bpos, dtype=np.float64)
-        self._chk(self.L.adp_xs_update(self.h, _d(b)))
+        return self._chk(self.L.adp_xs_update(self.h, _d(b)))           # 0 or STOP_XS_CHECK
 
     def set_feedback(self, p=None):
         """feedback cards of the deck (p.fbk) -> device tables"""
@@ -460,7 +460,7 @@ class Solver:
     def xs_update_th(self, bcon, ftem=None, mtem=None, cden=None, bpos=None):
         f = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float64)
         ft, mt, cd, bp = f(ftem), f(mtem), f(cden), f(bpos)
-        self._chk(self.L.adp_xs_update_th(self.h, C.c_double(bcon), _d(ft), _d(mt), _d(cd), _d(bp)))
+        return self._chk(self.L.adp_xs_update_th(self.h, C.c_double(bcon), _d(ft), _d(mt), _d(cd), _d(bp)))   # 0 or STOP_XS_CHECK
 
     # ---- XS update on the device (%XTAB branch tables)
     def set_xtab(self, p=None):
@@ -478,7 +478,7 @@ class Solver:
                                           fbmap.ctypes.data_as(_ip)))
 
     def xs_update_xtab(self, bcon, ftem=None, mtem=None, cden=None, bpos=None):
-        """XStab_updt on the device; returns 0 or ADP_STOP_XTAB_RANGE / ADP_STOP_XTAB_NOROD"""
+        """XStab_updt on the device; returns 0 or ADP_STOP_XTAB_RANGE / ADP_STOP_XTAB_NOROD / ADP_STOP_XS_CHECK"""
         f = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float64)
         ft, mt, cd, bp = f(ftem), f(mtem), f(cden), f(bpos)
         return self._chk(self.L.adp_xs_update_xtab(self.h, C.c_double(bcon), _d(ft), _d(mt), _d(cd), _d(bp)))

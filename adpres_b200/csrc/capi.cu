@@ -710,6 +710,33 @@ extern "C" int adp_set_crod_map(adp_ctx *c, int nb, double pos0, double ssize, c
     return set_crod_geometry(c, nb, pos0, ssize, fbmap);
 }
 
+// After a device-side XS update: the STOP flag the kernel may have raised, agreed on by all ranks.
+static int xs_update_stop(adp_ctx *c)
+{
+    CUDA_TRY(c, cudaMemcpyAsync(c->h_flags, c->d_errflag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    if (c->nranks > 1) {      // any rank's STOP stops all of them
+        double f = (double)c->h_flags[0];
+        CUDA_TRY(c, cudaMemcpyAsync(c->d_scal + S_TMP1, &f, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        TRY(adp_comm_allreduce_max_nccl(c, c->d_scal + S_TMP1, 1));
+        CUDA_TRY(c, cudaMemcpyAsync(&f, c->d_scal + S_TMP1, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+        c->h_flags[0] = (int)f;
+    }
+    switch (c->h_flags[0]) {
+    case 0: return ADP_OK;
+    case ADP_STOP_XTAB_RANGE:
+        c->err = "ERROR: A TH PARAMETER OR THE BORON CONCENTRATION IS OUT OF THE RANGE OF THE BRANCH PARAMETER";
+        return ADP_STOP_XTAB_RANGE;
+    case ADP_STOP_XTAB_NOROD:
+        c->err = "CONTROL ROD BANK COINCIDES WITH A MATERIAL THAT DOES NOT HAVE CONTROL ROD DATA IN XTAB FILE";
+        return ADP_STOP_XTAB_NOROD;
+    default:
+        c->err = "Negative diffusion coefficient encountered / ERROR IN THE CROSS SECTIONS (removal, nu*fission or scattering XS is negative)";
+        return ADP_STOP_XS_CHECK;
+    }
+}
+
 extern "C" int adp_xs_update(adp_ctx *c, const double *bpos)
 {
     if (!c) return ADP_ERR_USAGE;
@@ -718,9 +745,9 @@ extern "C" int adp_xs_update(adp_ctx *c, const double *bpos)
     ADP_REQUIRE(c, !c->d_fb || bpos, "adp_xs_update: bank positions missing");
     CUDA_TRY(c, cudaSetDevice(c->device));
     if (c->d_fb) CUDA_TRY(c, cudaMemcpyAsync(c->d_bpos, bpos, c->nb * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(c, cudaMemsetAsync(c->d_errflag, 0, sizeof(int), c->stream));
     TRY(adp_k_xs_update(c));
-    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-    return ADP_OK;
+    return xs_update_stop(c);
 }
 
 extern "C" int adp_set_feedback(adp_ctx *c, int which, double ref, const double *dsigtr, const double *dsiga,
@@ -754,12 +781,12 @@ extern "C" int adp_xs_update_th(adp_ctx *c, double bcon, const double *ftem, con
     }
     c->bcon = bcon;
     if (c->d_fb) CUDA_TRY(c, cudaMemcpyAsync(c->d_bpos, bpos, c->nb * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(c, cudaMemsetAsync(c->d_errflag, 0, sizeof(int), c->stream));
     c->xs_feedback = true;
     const int rc = adp_k_xs_update(c);
     c->xs_feedback = false;
     if (rc) return rc;
-    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-    return ADP_OK;
+    return xs_update_stop(c);
 }
 
 // ---- %XTAB branch tables: XStab_updt on the device ----------------------------------------------
@@ -810,25 +837,7 @@ extern "C" int adp_xs_update_xtab(adp_ctx *c, double bcon, const double *ftem, c
     if (c->d_fb) CUDA_TRY(c, cudaMemcpyAsync(c->d_bpos, bpos, c->nb * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     CUDA_TRY(c, cudaMemsetAsync(c->d_errflag, 0, sizeof(int), c->stream));
     TRY(adp_k_xs_update_xtab(c));
-    CUDA_TRY(c, cudaMemcpyAsync(c->h_flags, c->d_errflag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-    if (c->nranks > 1) {      // any rank's STOP stops all of them
-        double f = (double)c->h_flags[0];
-        CUDA_TRY(c, cudaMemcpyAsync(c->d_scal + S_TMP1, &f, sizeof(double), cudaMemcpyHostToDevice, c->stream));
-        TRY(adp_comm_allreduce_max_nccl(c, c->d_scal + S_TMP1, 1));
-        CUDA_TRY(c, cudaMemcpyAsync(&f, c->d_scal + S_TMP1, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-        CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-        c->h_flags[0] = (int)f;
-    }
-    if (c->h_flags[0] == ADP_STOP_XTAB_RANGE) {
-        c->err = "ERROR: A TH PARAMETER OR THE BORON CONCENTRATION IS OUT OF THE RANGE OF THE BRANCH PARAMETER";
-        return ADP_STOP_XTAB_RANGE;
-    }
-    if (c->h_flags[0] == ADP_STOP_XTAB_NOROD) {
-        c->err = "CONTROL ROD BANK COINCIDES WITH A MATERIAL THAT DOES NOT HAVE CONTROL ROD DATA IN XTAB FILE";
-        return ADP_STOP_XTAB_NOROD;
-    }
-    return ADP_OK;
+    return xs_update_stop(c);
 }
 
 extern "C" int adp_get_dc(adp_ctx *c, double *dc)

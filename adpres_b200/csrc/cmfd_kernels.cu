@@ -763,6 +763,7 @@ struct XsArgs {
     const double *ftab[4];
     double fref[4], bcon;
     const double *ftem, *mtem, *cden;
+    int *errflag;                                                // Dsigr_updt / check_xs STOPs (ADP_STOP_XS_CHECK)
 };
 __global__ void __launch_bounds__(ADP_TILE) k_xs_update(Geo G, XsArgs A, int klo, int npl)
 {
@@ -821,11 +822,14 @@ __global__ void __launch_bounds__(ADP_TILE) k_xs_update(Geo G, XsArgs A, int klo
                 if (b > 0 && ss < 0.0) ss = 0.0;
                 A.sigs[((size_t)h * A.ng + g) * NV + idx] = ss;
                 if (h != g) dum = dum + ss;
+                if (ss < 0.0) atomicExch(A.errflag, ADP_STOP_XS_CHECK);     // check_xs: scattering XS is negative
             }
-            A.D[(size_t)g * NV + idx] = 1.0 / (3.0 * sigtr);
-            A.sigr[(size_t)g * NV + idx] = siga + dum;
+            const double Dg = 1.0 / (3.0 * sigtr), sigr = siga + dum;
+            A.D[(size_t)g * NV + idx] = Dg;
+            A.sigr[(size_t)g * NV + idx] = sigr;
             A.nuf[(size_t)g * NV + idx] = nuf;
             A.sigf[(size_t)g * NV + idx] = sigf;
+            if (xs_check_fails(sigtr, Dg, sigr, nuf)) atomicExch(A.errflag, ADP_STOP_XS_CHECK);
         }
     }
 }
@@ -1355,6 +1359,7 @@ int adp_k_xs_update(adp_ctx *c)
     A.D = c->d_D; A.sigr = c->d_sigr; A.nuf = c->d_nuf; A.sigf = c->d_sigf; A.sigs = c->d_sigs;
     for (int f = 0; f < 4; ++f) { A.ftab[f] = c->xs_feedback ? c->d_ftab[f] : nullptr; A.fref[f] = c->fref[f]; }
     A.bcon = c->bcon; A.ftem = c->d_ftem; A.mtem = c->d_mtem; A.cden = c->d_cden;
+    A.errflag = c->d_errflag;
     if (c->xs_feedback && c->nranks > 1) {   // the ghost planes take the neighbours' temperatures and densities
         int rc;
         if (A.ftab[1] && (rc = adp_comm_halo(c, c->d_ftem, ADP_GH))) return rc;

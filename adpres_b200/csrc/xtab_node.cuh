@@ -72,6 +72,14 @@ ADP_HD inline double xt_rod_fraction(double rodh, double dum, double hz, bool to
     return -1.0;
 }
 
+// The STOPs that follow every XS update in the reference: Dsigr_updt's "Negative diffusion coefficient encountered"
+// (sigtr < 1.e-5, mod_xsec.f90:217) and check_xs (:104-127; its scattering test is done where sigs is formed).  The
+// literals are default REAL in the reference.
+ADP_HD inline bool xs_check_fails(double sigtr, double D, double sigr, double nuf)
+{
+    return sigtr < (double)1.e-5f || D < (double)1.e-20f || sigr < 0.0 || nuf < 0.0;
+}
+
 // the two closest branch points (0-based i1, i2); up to 20 % (boron: 100 ppm) outside the table the end
 // interval extrapolates, beyond that the reference STOPs (mod_xsec.f90:556-650)
 ADP_HD inline bool xt_bracket(double x, const double *par, int dim, bool absolute, int &i1, int &i2)
@@ -149,6 +157,7 @@ ADP_HD inline int xtab_node(const XtabTables &T, int m, double w, bool rodded_co
         if (rodded_column && c >= ng && x < 0.0) x = 0.0;
         return x;
     };
+    int rc = ADP_OK;
     for (int g = 0; g < ng; ++g) {
         const double sigtr = val(g), siga = val(ng + g), nuf = val(2 * ng + g), sigf = val(3 * ng + g);
         double dum = 0.0;
@@ -156,13 +165,16 @@ ADP_HD inline int xtab_node(const XtabTables &T, int m, double w, bool rodded_co
             const double ss = val(4 * ng + g * ng + h);                     // sigs(n, g, h): g -> h
             O.sigs[((size_t)h * ng + g) * NV + idx] = ss;
             if (h != g) dum = dum + ss;
+            if (ss < 0.0) rc = ADP_STOP_XS_CHECK;
         }
-        O.D[(size_t)g * NV + idx] = 1.0 / (3.0 * sigtr);
-        O.sigr[(size_t)g * NV + idx] = siga + dum;
+        const double D = 1.0 / (3.0 * sigtr), sigr = siga + dum;
+        O.D[(size_t)g * NV + idx] = D;
+        O.sigr[(size_t)g * NV + idx] = sigr;
         O.nuf[(size_t)g * NV + idx] = nuf;
         O.sigf[(size_t)g * NV + idx] = sigf;
         for (int f = 0; f < 6; ++f)
             O.dc[((size_t)f * ng + g) * NV + idx] = val(4 * ng + ng * ng + g * 6 + f);
+        if (xs_check_fails(sigtr, D, sigr, nuf)) rc = ADP_STOP_XS_CHECK;
     }
-    return ADP_OK;
+    return rc;
 }

@@ -563,9 +563,11 @@ class Problem:
         self.finish_xs()
 
     def finish_xs(self) -> None:
-        """Dsigr_updt: D = 1/(3 sigtr); sigr = siga + sum_{h != g} sigs(g -> h), h ascending."""
+        """Dsigr_updt: D = 1/(3 sigtr); sigr = siga + sum_{h != g} sigs(g -> h), h ascending; then check_xs
+        (mod_xsec.f90:90-168) -- the reference STOPs on a vanishing diffusion coefficient or a negative
+        removal / nu-fission / scattering cross section or fission spectrum."""
         N, G = self.nnod, self.ng
-        if (self.sigtr < 1.0e-5).any():
+        if (self.sigtr < float(np.float32(1.0e-5))).any():
             raise ValueError("Negative diffusion coefficient encountered")
         self.D = np.asfortranarray(1.0 / (3.0 * self.sigtr))
         sigr = np.zeros((N, G), order="F")
@@ -576,6 +578,11 @@ class Problem:
                     dum = dum + self.sigs[:, g, h]
             sigr[:, g] = self.siga[:, g] + dum
         self.sigr = sigr
+        for arr, what in ((self.D < float(np.float32(1.0e-20)), "DIFFUSION COEF. IS CLOSE TO ZERO OR NEGATIVE"),
+                          (self.sigr < 0.0, "REMOVAL XS IS NEGATIVE"), (self.nuf < 0.0, "NU*FISSION XS IS NEGATIVE"),
+                          (self.chi < 0.0, "FISSION SPECTRUM IS NEGATIVE"), (self.sigs < 0.0, "SCATTERING XS IS NEGATIVE")):
+            if arr.any():
+                raise ValueError("ERROR IN THE CROSS SECTIONS: " + what)
 
     # ------------------------------------------------------------------ ADF / ESRC
     def _node_assembly_maps(self):

@@ -120,11 +120,9 @@ class DeviceGlue:
 
     def xs_update(self, bcon):
         fields = self._first if self._first is not None else ()
-        if self.xtab:
-            if self.s.xs_update_xtab(bcon, *fields, bpos=self.bpos) > 0:
-                raise StopError(self.s.last_error())
-        else:
-            self.s.xs_update_th(bcon, *fields, bpos=self.bpos)
+        update = self.s.xs_update_xtab if self.xtab else self.s.xs_update_th
+        if update(bcon, *fields, bpos=self.bpos) > 0:         # the STOPs of brInterp / crod_tab_updt / Dsigr_updt / check_xs
+            raise StopError(self.s.last_error())
 
     def outer(self):
         return self.s.outer(0)

@@ -43,6 +43,9 @@ enum {
     ADP_STOP_ZERO_POWER = 4, /* "TOTAL NODES POWER IS ZERO OR LESS" mod_cmfd.f90:1322-1326 */
     ADP_STOP_STEAM_TABLE = 5, /* "ENTHALPY / MODERATOR TEMP. IS OUT OF THE RANGE ... IN THE STEAM TABLE" mod_th.f90:236-244,293-301 */
     ADP_STOP_XTAB_RANGE = 6, /* "... IS OUT OF THE RANGE OF THE BRANCH PARAMETER" mod_xsec.f90:569-574,594-599,619-624,644-649 */
+    ADP_STOP_XS_CHECK = 8,   /* "Negative diffusion coefficient encountered" (Dsigr_updt, mod_xsec.f90:217) or one of check_xs's
+                                "ERROR IN THE ... CROSS SECTION" STOPs (:104-151): sigtr < 1.e-5, D < 1.e-20, sigr / nuf / sigs < 0
+                                after a device-side XS update */
     ADP_STOP_XTAB_NOROD = 7, /* "CONTROL ROD BANK ... COINCIDES WITH MATERIAL ... THAT DOES NOT HAVE CONTROL ROD DATA IN XTAB FILE" mod_xsec.f90:336-343 */
     ADP_ERR_CUDA = -1,
     ADP_ERR_USAGE = -2,

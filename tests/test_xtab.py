@@ -261,6 +261,20 @@ def test_device_node_code_stop_codes(hostlib):
     assert _host_update(hostlib, p, 2100.0, ftem, mtem, cden, p.crod["bpos"])[0] == capi.STOP_XTAB_RANGE
     bad = cden.copy(); bad[1234] = 0.4
     assert _host_update(hostlib, p, 1000.0, ftem, mtem, bad, p.crod["bpos"])[0] == capi.STOP_XTAB_RANGE
+    # check_xs / Dsigr_updt after the update: a table that extrapolates to a negative nu-fission cross section ...
+    keep = p.xtab[0]["xs"].copy()
+    p.xtab[0]["xs"][:, 2, :, :, 4:6] = -0.5 * np.abs(keep[:, 2, :, :, 4:6])          # nuf at 2000 ppm
+    assert _host_update(hostlib, p, 1900.0, ftem, mtem, cden, p.crod["bpos"])[0] == capi.STOP_XS_CHECK
+    with pytest.raises(ValueError, match="NU\\*FISSION XS IS NEGATIVE"):
+        p.update_xs(p.crod["bpos"], bcon=1900.0, ftem=ftem, mtem=mtem, cden=cden)
+    assert _host_update(hostlib, p, 500.0, ftem, mtem, cden, p.crod["bpos"])[0] == 0
+    # ... or a vanishing transport cross section
+    p.xtab[0]["xs"][...] = keep
+    p.xtab[0]["xs"][..., 0] = 1.0e-6
+    assert _host_update(hostlib, p, 500.0, ftem, mtem, cden, p.crod["bpos"])[0] == capi.STOP_XS_CHECK
+    with pytest.raises(ValueError, match="Negative diffusion coefficient"):
+        p.update_xs(p.crod["bpos"], bcon=500.0, ftem=ftem, mtem=mtem, cden=cden)
+    p.xtab[0]["xs"][...] = keep
     for t in p.xtab:
         t["trod"] = 0
     assert _host_update(hostlib, p, 1000.0, ftem, mtem, cden, p.crod["bpos"])[0] == capi.STOP_XTAB_NOROD
@@ -449,3 +463,20 @@ def test_gpu_mox_part4_first_steps_device_resident():
         assert abs(a[2] - b[2]) < 1e-4, (a, b)                       # reactivity [$]
         assert abs(a[3] / b[3] - 1.0) < 1e-4, (a, b)                 # relative power (north star: 1e-4)
         assert abs(a[6] / b[6] - 1.0) < 1e-6                         # max fuel centreline temperature
+
+
+@pytest.mark.gpu
+def test_gpu_xs_update_reports_the_check_xs_stop():
+    """Dsigr_updt / check_xs follow every XS update in the reference (mod_xsec.f90:41,83,217): a rod increment that
+    cancels the transport cross section must come back as ADP_STOP_XS_CHECK from the %XSEC device path as well."""
+    from adpres_b200 import capi
+    p = load_problem("LMW")
+    s = capi.Solver(p)
+    s.set_material_xs(); s.set_crod()
+    bpos = np.array([100.0, 100.0])
+    assert s.xs_update(bpos) == 0
+    p.crod["dsigtr"] = -p.xsigtr.copy()
+    s.set_crod(p)
+    assert s.xs_update(bpos) == capi.STOP_XS_CHECK and "diffusion coefficient" in s.last_error()
+    with pytest.raises(ValueError, match="Negative diffusion coefficient"):
+        p.update_xs(bpos)
