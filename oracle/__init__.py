@@ -167,7 +167,8 @@ class Oracle:
     def integrate(self, s):
         return self.L.orc_integrate(self.h, _d(np.ascontiguousarray(s)))
 
-    def powdis(self):
+    def powdis(self, fixedsrc=None):
+        """PowDis; `fixedsrc` is accepted for interface parity with capi.Solver.powdis (the oracle knows the mode)"""
         pw = np.empty(self.N)
         rc = self.L.orc_powdis(self.h, _d(pw))
         return rc, pw
