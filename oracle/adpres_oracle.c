@@ -4,7 +4,7 @@
  * A serial, fp64, plain-C restatement of the ADPRES 1.2 eigenvalue hot path:
  *   src/mod_cmfd.f90  (CMFD matrix, BiCGSTAB, sources, outer iterations, PowDis)
  *   src/mod_nodal.f90 (SANM / PNM two-node nodal coupling-coefficient update)
- * plus the few transient helpers of src/mod_trans.f90 that surround outer_tr.
+ * plus the few transient helpers of src/mod_trans.f90 that surround outer_tr (both bxtab branches).
  * Every function cites the reference file:line it follows; loop order, operation
  * order, data structures (ragged matrix rows A(n,g)%elmn, ind(n)%col, AoS nod{df,dn})
  * and the reference's quirks are kept on purpose.
@@ -12,11 +12,17 @@
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
  * legs may load this library.  The CUDA product (adpres_b200/csrc) never does.
  *
- * Parity pin: this oracle reproduces the only ADPRES-produced numbers in the reference
- * repository -- the IAEA3Ds terminal trace of docs/quick-guides.md:161-191 (k-eff
- * 1.029082, 129 outer iterations, first nodal update MAX. CHANGE = 3.16843E-01) -- see
- * tests/test_oracle_golden.py.  Adjoint, fixed-source, ADF, PNM, multigroup > 2 and
- * transient results are NOT pinned by the reference ("parity unpinned" for those).
+ * Parity pins (reference-produced numbers this oracle reproduces):
+ *   1. the IAEA3Ds terminal trace of docs/quick-guides.md:161-191, every printed digit (k-eff
+ *      1.029082, 129 outer iterations, first nodal update MAX. CHANGE = 3.16843E-01) --
+ *      tests/test_oracle_golden.py;
+ *   2. the six NEACRP critical boron concentrations on the %BCON cards of smpl/transient/NEACRP/*t
+ *      (with oracle/th.py and the feedback XS update of the harness) -- tests/test_th.py;
+ *   3. the two MOX/UO2 part-3 critical boron concentrations on the %BCON cards of
+ *      smpl/transient/MOX/part4_* (through the %XTAB branch tables) -- tests/test_xtab.py.
+ * Adjoint, fixed-source, PNM, multigroup > 2 and transient results (outer_tr, get_exsrc incl. its
+ * bxtab = 1 branch, iPden, uPden) are NOT pinned by the reference ("parity unpinned" for those);
+ * they are checked against published benchmark solutions for plausibility only.
  *
  * Build: gcc -O3 -ffp-contract=off (gfortran -O4 on x86-64 without -march does not
  * contract a*b+c into FMA either), see oracle/Makefile.
