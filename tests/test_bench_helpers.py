@@ -1,0 +1,52 @@
+"""bench.py's weak-scaling workload: rank r of N builds only its z-slab of the N-fold axially stacked core
+(SlabProblem) instead of the whole global arrays.  Checked here against the explicitly stacked problem on a
+small base mesh (CPU)."""
+import dataclasses
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, load_problem
+
+
+@pytest.fixture(scope="module")
+def bench():
+    spec = importlib.util.spec_from_file_location("bench", os.path.join(ROOT, "bench.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_slab_problem_equals_the_stacked_core(bench, world):
+    from adpres_b200.slab import slab_planes
+    base = load_problem("IAEA3Ds").refine(xdiv=[1] + [2] * 8, ydiv=[2] * 8 + [1], zdiv=[2] * 19)
+    p0 = load_problem("IAEA3Ds")
+    full = dataclasses.replace(p0, nz=p0.nz * world, zsize=np.tile(p0.zsize, world), zdiv=np.tile(p0.zdiv, world),
+                               zpln=np.tile(p0.zpln, world)).refine(xdiv=[1] + [2] * 8, ydiv=[2] * 8 + [1], zdiv=[2] * 19 * world)
+    assert full.nnod == base.nnod * world and full.nzz == base.nzz * world
+    covered = np.zeros(full.nnod, dtype=int)
+    for rank in range(world):
+        sp = bench.SlabProblem(base, world, rank)
+        assert (sp.nnod, sp.nzz, sp.npl, sp.ng) == (full.nnod, full.nzz, full.npl, full.ng)
+        assert np.array_equal(sp.zdel, full.zdel) and np.array_equal(sp.ix, full.ix) and np.array_equal(sp.iy, full.iy)
+        assert np.array_equal(sp.iz, full.iz)
+        k0, k1 = slab_planes(full.nzz, world, rank)
+        assert (sp.k0, sp.k1) == (k0, k1)
+        rows = sp.rows
+        # own planes plus two ghost planes per side (what the library uploads)
+        assert rows.start == max(0, k0 - 2) * full.npl and rows.stop == min(full.nzz, k1 + 2) * full.npl
+        assert np.array_equal(sp.mat[rows], full.mat[rows])
+        for k in ("D", "sigr", "nuf", "sigf", "exsrc", "sigs", "dc"):
+            assert np.array_equal(getattr(sp, k)[rows], getattr(full, k)[rows]), k
+        covered[k0 * full.npl:k1 * full.npl] += 1
+    assert np.all(covered == 1)                       # the slabs tile the stacked core exactly once
+
+
+def test_load_c2_sample_is_the_bounded_cpu_workload(bench):
+    p = bench.load_c2(sample_planes=19)
+    assert (p.nxx, p.nyy, p.nzz, p.nnod) == (170, 170, 19, 457900)
+    assert np.all(p.xdel == 1.0) and np.all(p.zdel == 20.0)
+    assert bench.CTL["nin"] == 10 and bench.CTL["nupd"] == 50 and bench.SPMV_BYTES_PER_ROW == 72.0
