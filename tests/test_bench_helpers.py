@@ -50,3 +50,18 @@ def test_load_c2_sample_is_the_bounded_cpu_workload(bench):
     assert (p.nxx, p.nyy, p.nzz, p.nnod) == (170, 170, 19, 457900)
     assert np.all(p.xdel == 1.0) and np.all(p.zdel == 20.0)
     assert bench.CTL["nin"] == 10 and bench.CTL["nupd"] == 50 and bench.SPMV_BYTES_PER_ROW == 72.0
+
+
+def test_clock_sampler_parses_nvidia_smi_lines(bench):
+    s = bench.ClockSampler(0)
+    s.proc = type("P", (), {"terminate": lambda self: None, "wait": lambda self, timeout=None: 0, "kill": lambda self: None})()
+    s.lines = ["0, 1965, 1965, 1003.50, Not Active, Not Active, Not Active, Active",
+               "0, 1950, 1965, 998.10, Not Active, Not Active, Not Active, Not Active",
+               "0, [N/A], 1965, 10.0, Not Active, Not Active, Not Active, Not Active",       # unparsable sample: skipped
+               "garbage"]
+    c = s.stop()
+    assert c["sm_mhz"] == 1957.5 and c["sm_max_mhz"] == 1965.0 and c["samples"] == 2 and c["reasons"] == ["sw_power_cap"]
+    s2 = bench.ClockSampler(0)
+    assert s2.stop()["reasons"] == ["nvidia-smi unavailable"]
+    s.lines = ["0, 1300, 1965, 700.0, Active, Active, Not Active, Not Active"]
+    assert s.stop()["reasons"] == ["hw_slowdown", "hw_thermal_slowdown"]
