@@ -55,6 +55,17 @@ def test_device_glue_boron_search(name, gold):
     assert set(f) == {"ftem", "mtem", "cden"} and f["ftem"].shape == (p.nnod,)
 
 
+def test_device_glue_boron_search_without_th():
+    """CBCsearch: no %THER card -> DeviceGlue passes the card values of the TH fields with every update"""
+    from adpres_b200 import thermal
+    from fake_device import FakeDeviceSolver
+    p = load_problem("CBCsearch")
+    g = thermal.DeviceGlue(p, FakeDeviceSolver(p))
+    assert g.th is None and g._first is not None
+    bc, rows = thermal.cbsearch(g)
+    assert abs(bc - 1257.32) < 0.05
+
+
 def test_device_glue_raises_the_reference_stops():
     from adpres_b200 import thermal
     from fake_device import FakeDeviceSolver
