@@ -75,3 +75,15 @@ def test_header_is_plain_c_and_a_c_client_links(tmp_path):
         assert r.returncode == 0 and "cross sections not set" in r.stdout, r.stdout + r.stderr
     else:
         assert r.returncode == 3 and "no CPU fallback" in r.stdout, r.stdout + r.stderr
+
+
+def test_missing_library_fails_loudly(tmp_path):
+    """no silent fallback when the CUDA library has not been built: capi.load() raises"""
+    import subprocess
+    import sys
+    code = ("import sys; sys.path.insert(0, %r)\n"
+            "from adpres_b200 import capi\n"
+            "try:\n    capi.load()\nexcept RuntimeError as e:\n    print('RAISED', e)\n" % ROOT)
+    env = dict(os.environ, ADPRES_B200_LIB=str(tmp_path / "nowhere" / "libadpres_b200.so"))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=120)
+    assert "RAISED" in r.stdout and "no CPU fallback" in r.stdout, r.stdout + r.stderr
