@@ -116,3 +116,35 @@ def test_gpu_critical_boron_search_without_feedback():
     bd, rd = thermal.cbsearch(thermal.DeviceGlue(p2, capi.Solver(p2)))
     assert abs(bo - bd) < 0.05, (bo, bd)
     assert abs(ro[0][2] - rd[0][2]) < 1e-5                                       # k-eff of the first guess (1200.2 ppm)
+
+
+def _lmw_refined(rdiv, zdiv, tol):
+    p = load_problem("LMW").refine(xdiv=[rdiv // 2] + [rdiv] * 5, ydiv=[rdiv // 2] + [rdiv] * 5, zdiv=[zdiv] * 10)
+    p.nin, p.nupd, p.nac, p.nout, p.serc, p.ferc, p.biter = 10, 50, 5, 20000, tol, tol, 1
+    return p
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fixture", ["lmw_refined_mid_oracle.json", "lmw_refined_full_oracle.json"])
+def test_gpu_refined_lmw_transient_against_cpu_oracle_fixture(fixture):
+    """BASELINE configs[4] (LMW rod ejection on a refined mesh) against the CPU oracle's trace, computed once by
+    tools/lmw_refined_oracle.py and committed (mid: 2 cm x 2 cm x 4 cm, 146 250 nodes, 5 min of CPU; full: 1 cm x 1 cm x
+    2 cm, 1.17 M nodes, the size tools/lmw_refined.py times).  Every solve converged to 1e-8 so that the trace does
+    not depend on the exit iteration; device-resident time stepping (XS update, glue, outer_tr on the GPU)."""
+    import json
+    from conftest import GOLDEN
+    from adpres_b200 import capi, transient
+    path = os.path.join(GOLDEN, fixture)
+    if not os.path.exists(path):
+        pytest.skip("fixture not generated")
+    fx = json.load(open(path))
+    p = _lmw_refined(fx["rdiv"], fx["zdiv"], fx["serc"])
+    assert p.nnod == fx["nnod"]
+    s = capi.Solver(p)
+    tr = transient.rod_eject_device_glue(p, s, max_steps=len(fx["trace"]) - 1, device_xs=True)
+    assert len(tr) == len(fx["trace"])
+    for a, b in zip(tr, fx["trace"]):
+        assert abs(a[1] - b[1]) < 1e-12 and not a[5]
+        assert abs(a[3] / b[3] - 1.0) < 1e-5, (a, b)          # relative power (north star: 1e-4)
+        assert abs(a[2] - b[2]) < 1e-5, (a, b)                # reactivity [$]
+    s.close()
