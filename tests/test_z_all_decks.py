@@ -177,3 +177,32 @@ def test_gpu_c3_full_solve_against_cpu_oracle_fixture():
     nzp = ref_pw > 1e-12
     assert np.abs(pw[idx][nzp] / ref_pw[nzp] - 1).max() < 5e-5
     s.close()
+
+
+@pytest.mark.gpu
+def test_gpu_multigroup_adf_mid_size_against_cpu_oracle_fixture():
+    """BASELINE configs[3] at a size where the nodal kernels for many groups matter: 8 groups with ADFs (tests/synth.py) on a
+    5 cm mesh, 73 264 nodes = 586 k unknowns, about 220 000 two-node 16 x 16 systems per nodal update -- against the CPU oracle
+    (tools/c4_mid_oracle.py, 80 s of CPU, committed).  Same number of outer iterations at most, as for configs[2]."""
+    import json
+    import sys
+    from conftest import GOLDEN, ROOT
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from synth import iaea3d_multigroup
+    from adpres_b200 import capi
+    ref = json.load(open(os.path.join(GOLDEN, "c4_mid_oracle_result.json")))
+    p = iaea3d_multigroup(ref["ng"]).refine(xdiv=ref["xdiv"], ydiv=ref["ydiv"], zdiv=ref["zdiv"])
+    assert p.nnod == ref["nnod"]
+    s = capi.Solver(p, nin=ref["nin"], nupd=ref["nupd"], nac=ref["nac"], nout=ref["outers"])
+    rc, n = s.outer(0)
+    assert ref["status"] == 0 and rc in (0, capi.STOP_MAXOUTER), (rc, n)
+    assert abs(s.state()["Ke"] / ref["keff"] - 1.0) < 1e-5
+    rc, pw = s.powdis()
+    asm, asm_ref = p.asm_power(pw), np.array(ref["asm_power"])
+    nz = asm_ref > 0
+    assert np.abs(asm[nz] / asm_ref[nz] - 1).max() < 1e-5
+    idx = np.array(sorted(int(i) for i in ref["power_samples"]))
+    ref_pw = np.array([ref["power_samples"][str(i)] for i in idx])
+    nzp = ref_pw > 1e-12
+    assert np.abs(pw[idx][nzp] / ref_pw[nzp] - 1).max() < 5e-5
+    s.close()
