@@ -36,6 +36,8 @@ def main():
         return cb_main(rank, world, local, uid, dist)
     if deck == "MOX_xtab":
         return xtab_main(rank, world, local, uid, dist)
+    if deck == "C3_fixture":
+        return c3_main(rank, world, local, uid, dist)
     if deck == "IAEA3Ds_z2":                  # 38 planes: uneven slabs at 4 ranks, 2 planes per axial assembly
         p = load_problem("IAEA3Ds").refine(zdiv=[2] * 19)
     else:
@@ -194,6 +196,35 @@ def cb_main(rank, world, local, uid, dist):
     for k in fo:
         assert np.abs(fd[k][own] / fo[k][own] - 1.0).max() < 1e-5, k
     print(f"RANK {rank}/{world} OK deck=NEACRP_cb planes=[{s.k0},{s.k1}) bcon={bd:.2f}", flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def c3_main(rank, world, local, uid, dist):
+    """BASELINE configs[2] -- IAEA-3D at 4 x 4 nodes per assembly, 190 planes, "z-slab over 2/4/8 B200" -- against the
+    committed CPU-oracle solve (tests/golden/c3_oracle_result.json), compared at the oracle's outer count."""
+    import json
+    import numpy as np
+    from conftest import GOLDEN, load_problem
+    from adpres_b200 import capi
+    ref = json.load(open(os.path.join(GOLDEN, "c3_oracle_result.json")))
+    p = load_problem("IAEA3Ds").refine(xdiv=ref["xdiv"], ydiv=ref["ydiv"], zdiv=ref["zdiv"])
+    s = capi.Solver(p, device=local, nranks=world, rank=rank, uid=uid, nout=ref["outers"], serc=0.0, ferc=0.0)
+    rc, n = s.outer(0)
+    assert rc == capi.STOP_MAXOUTER and n == ref["outers"], (rc, n)
+    ke = s.state()["Ke"]
+    assert abs(ke - ref["keff"]) * 1e5 < 1.0, (ke, ref["keff"])
+    _, pw = s.powdis()
+    lo, hi = s.own.start, s.own.stop
+    idx = np.array(sorted(int(i) for i in ref["power_samples"] if lo <= int(i) < hi))
+    ref_pw = np.array([ref["power_samples"][str(i)] for i in idx])
+    nz = ref_pw > 1e-12
+    assert np.abs(pw[idx][nz] / ref_pw[nz] - 1).max() < 5e-5
+    fasm, _, _ = s.asm_pow()                      # all-reduced over the slabs: every rank holds the whole map
+    asm_ref = np.array(ref["asm_power"])
+    nzm = asm_ref > 0
+    assert np.abs(fasm[nzm] / asm_ref[nzm] - 1).max() < 1e-5
+    print(f"RANK {rank}/{world} OK deck=C3_fixture planes=[{s.k0},{s.k1}) keff={ke:.6f}", flush=True)
     dist.barrier()
     dist.destroy_process_group()
 
