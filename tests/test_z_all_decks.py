@@ -143,10 +143,13 @@ def test_gpu_refined_lmw_transient_against_cpu_oracle_fixture(fixture):
     s = capi.Solver(p)
     tr = transient.rod_eject_device_glue(p, s, max_steps=len(fx["trace"]) - 1, device_xs=True)
     assert len(tr) == len(fx["trace"])
+    # steps converged to 1e-8: the trace is independent of the exit iteration (1e-5); the 1 cm mesh cannot be converged
+    # that far with nupd = 50 (see the fixture's "what"), there the north star's 1e-4 applies
+    tol = 1e-5 if fx["serc"] <= 1e-8 else 1e-4
     for a, b in zip(tr, fx["trace"]):
         assert abs(a[1] - b[1]) < 1e-12 and not a[5]
-        assert abs(a[3] / b[3] - 1.0) < 1e-5, (a, b)          # relative power (north star: 1e-4)
-        assert abs(a[2] - b[2]) < 1e-5, (a, b)                # reactivity [$]
+        assert abs(a[3] / b[3] - 1.0) < tol, (a, b)           # relative power (north star: 1e-4)
+        assert abs(a[2] - b[2]) < tol, (a, b)                 # reactivity [$]
     s.close()
 
 
