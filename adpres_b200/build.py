@@ -16,7 +16,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libadpres_b200.so")
 SOURCES = ["cmfd_kernels.cu", "nodal_kernels.cu", "capi.cu", "results.cu", "th.cu", "comm.cu", "host_cmfd.cpp"]
-HEADERS = ["adp_internal.cuh", "xtab_node.cuh", os.path.join("..", "..", "include", "adpres_b200.h")]
+import glob
+# every header of csrc/ is a dependency of every object (edits to any .cuh rebuild the library)
+HEADERS = sorted(os.path.basename(h) for h in glob.glob(os.path.join(CSRC, "*.cuh"))) + \
+          [os.path.join("..", "..", "include", "adpres_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "-Xcompiler", "-ffp-contract=off", "-Xptxas", "-v"]
 

@@ -274,8 +274,8 @@ extern "C" int adp_set_geometry(adp_ctx *c, int nxx, int nyy, int nzz, int nnod,
     TRY(dev_alloc(c, &c->d_chi, Gn * nmat)); TRY(dev_alloc(c, &c->d_S, 3 * Gn * NV));
     TRY(dev_alloc(c, &c->d_tbeta, nmat)); TRY(dev_alloc(c, &c->d_dfis, NV)); TRY(dev_alloc(c, &c->d_velo, ng));
     TRY(dev_alloc(c, &c->d_stage, NV));
-    // D must stay non-zero on ghost planes outside the core (divisions in coup_coef never use
-    // them, but keep every table finite): initialise to 1
+    // ghost planes outside the core stay zero (dev_alloc clears): coup_coef never divides by their D
+    // (boundary branches, mod_cmfd.f90:45-130) and their matrix coefficients are zero
     // buffers allocated on first use are sized by the geometry: drop them, they come back on demand
     {
         double **lazy[] = {&c->d_nd, &c->d_abefgh, &c->d_c0, &c->d_ft, &c->d_fst, &c->d_omeg, &c->d_sigrp, &c->d_L,
@@ -429,15 +429,21 @@ static int launch_outer_iter(adp_ctx *c, int mode, bool extrap)
         CUDA_TRY(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
         int rc = issue_outer_iter(c, mode, extrap);
         cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
-        if (rc) return rc;
-        CUDA_TRY(c, e);
-        cudaGraphExec_t exec = nullptr;
-        CUDA_TRY(c, cudaGraphInstantiate(&exec, graph, 0));
-        cudaGraphDestroy(graph);
-        // capture advanced the host-side bookkeeping once; undo it, the launch below redoes it
-        c->graph_launches[key] = c->launches - l0;
+        // capture advanced the host-side bookkeeping once although nothing ran; undo it on every path
+        // (success: the launch below redoes it; failure: the device buffers have not moved)
+        const long long captured = c->launches - l0;
         c->launches = l0; c->s0_group = s0g; c->fcur = fcur;
         memcpy(c->cur, cur, sizeof(cur));
+        if (rc || e != cudaSuccess) {
+            if (graph) cudaGraphDestroy(graph);
+            if (rc) return rc;
+            CUDA_TRY(c, e);
+        }
+        cudaGraphExec_t exec = nullptr;
+        e = cudaGraphInstantiate(&exec, graph, 0);
+        cudaGraphDestroy(graph);
+        CUDA_TRY(c, e);
+        c->graph_launches[key] = captured;
         it = c->graphs.emplace(key, exec).first;
     }
     CUDA_TRY(c, cudaGraphLaunch(it->second, c->stream));

@@ -5,6 +5,7 @@
 // dependency on it; whichever libnccl.so.2 the process already has loaded (e.g. torch's) wins.
 #include <dlfcn.h>
 #include <time.h>
+#include <sys/stat.h>
 #include <cstdlib>
 #include <cstring>
 
@@ -106,22 +107,40 @@ extern "C" int adp_comm_init_env(adp_ctx *c)
     };
     const int nranks = env_int("ADP_NRANKS", "WORLD_SIZE", 1), rank = env_int("ADP_RANK", "RANK", 0);
     if (nranks <= 1) return adp_comm_init(c, 1, 0, nullptr);
+    // The id file must belong to THIS job: ADP_UID_FILE names it, otherwise the name is derived from the
+    // launcher's job key (MASTER_PORT / ADP_JOB_ID) -- a fixed name in /tmp would pick up the stale file of a
+    // crashed or concurrent job.  Rank 0 removes any old file before it creates the id; the file carries a
+    // 16-byte header (magic + job key) that the readers check.
     const char *path = getenv("ADP_UID_FILE");
-    std::string file = path ? path : "/tmp/adpres_b200.uid";
+    const char *job = getenv("ADP_JOB_ID");
+    if (!job) job = getenv("MASTER_PORT");
+    if (!path && !job) {
+        c->err = "adp_comm_init_env: set ADP_UID_FILE (a path private to this job) or ADP_JOB_ID / MASTER_PORT";
+        return ADP_ERR_USAGE;
+    }
+    std::string file = path ? path : std::string("/tmp/adpres_b200.") + job + ".uid";
+    char hdr[16] = "ADPUID1";
+    strncpy(hdr + 8, job ? job : "", 7);
     char uid[128];
     if (rank == 0) {
+        remove(file.c_str());
         int rc = adp_comm_unique_id(uid);
         if (rc) { c->err = "adp_comm_init_env: cannot create the NCCL unique id"; return rc; }
         std::string tmp = file + ".tmp";
         FILE *f = fopen(tmp.c_str(), "wb");
-        if (!f || fwrite(uid, 1, 128, f) != 128) { c->err = "adp_comm_init_env: cannot write " + tmp; if (f) fclose(f); return ADP_ERR_USAGE; }
+        if (!f || fwrite(hdr, 1, 16, f) != 16 || fwrite(uid, 1, 128, f) != 128) { c->err = "adp_comm_init_env: cannot write " + tmp; if (f) fclose(f); return ADP_ERR_USAGE; }
         fclose(f);
         if (rename(tmp.c_str(), file.c_str()) != 0) { c->err = "adp_comm_init_env: rename failed"; return ADP_ERR_USAGE; }
     } else {
         bool ok = false;
+        const time_t started = time(nullptr);
         for (int tries = 0; tries < 6000 && !ok; ++tries) {
+            struct stat sb;
+            // a file much older than this process is a leftover of another run: rank 0 is about to replace it
+            if (stat(file.c_str(), &sb) != 0 || sb.st_mtime + 60 < started) { struct timespec ts = {0, 10000000}; nanosleep(&ts, nullptr); continue; }
             FILE *f = fopen(file.c_str(), "rb");
-            if (f) { ok = fread(uid, 1, 128, f) == 128; fclose(f); }
+            char h2[16];
+            if (f) { ok = fread(h2, 1, 16, f) == 16 && memcmp(h2, hdr, 16) == 0 && fread(uid, 1, 128, f) == 128; fclose(f); }
             if (!ok) { struct timespec ts = {0, 10000000}; nanosleep(&ts, nullptr); }
         }
         if (!ok) { c->err = "adp_comm_init_env: timed out waiting for " + file; return ADP_ERR_NCCL; }

@@ -96,7 +96,7 @@ def _push_xs(solver, p, **override):
     solver.set_xs(**kw)
 
 
-def rod_eject_device_glue(p, solver, max_steps=None, log=None, device_xs=False):
+def rod_eject_device_glue(p, solver, max_steps=None, log=None, device_xs=False, step_tol=None):
     """The same transient with the time-step glue on the device (adp_save_adjoint, adp_ipden,
     adp_begin_time_step, adp_upden, adp_powtot, adp_reactivity): per step only the new cross
     sections go up and three scalars come back.  With device_xs the cross-section update itself
@@ -137,6 +137,8 @@ def rod_eject_device_glue(p, solver, max_steps=None, log=None, device_xs=False):
         tbeta = tbeta + ibeta[jf]
     ctbeta = tbeta[0]
     solver.set_kinetics(ibeta, lamb, velo, tbeta, p.sth, p.bth)
+    if step_tol is not None:            # harness option: the time steps use their own serc = ferc (fixtures)
+        solver.set_control(serc=step_tol, ferc=step_tol)
     solver.ipden()
     tpow1 = solver.powtot()
     rho = solver.reactivity(0)
@@ -165,7 +167,7 @@ def rod_eject_device_glue(p, solver, max_steps=None, log=None, device_xs=False):
     return trace
 
 
-def rod_eject(p, solver, max_steps=None, log=None):
+def rod_eject(p, solver, max_steps=None, log=None, step_tol=None):
     """rod_eject (mod_trans.f90:17-160) + trans_calc (:332-479), thc = 0.  Returns a list of
     (step, t, reactivity [$], relative power, outer iterations, maxi)."""
     e, c = p.ejct, p.crod
@@ -210,6 +212,8 @@ def rod_eject(p, solver, max_steps=None, log=None):
     rho = reactivity(p, af, p.sigr, f0, fs0, L)
     trace = [(0, 0.0, rho / ctbeta, 1.0, 0, False)]
     solver.set_kinetics(ibeta, lamb, velo, tbeta, p.sth, p.bth)
+    if step_tol is not None:            # harness option: the time steps use their own serc = ferc (fixtures)
+        solver.set_control(serc=step_tol, ferc=step_tol)
 
     steps = [(i, e["tstep1"], i * e["tstep1"]) for i in range(1, int(round(e["tdiv"] / e["tstep1"])) + 1)]
     steps += [(i, e["tstep2"], e["tdiv"] + i * e["tstep2"]) for i in range(1, int(round((e["ttot"] - e["tdiv"]) / e["tstep2"])) + 1)]

@@ -75,8 +75,9 @@ const char *adp_version(void);
  * MPI / a file).  Must be called before adp_set_geometry().  Not calling it = 1 rank. */
 int adp_comm_unique_id(void *uid128);
 int adp_comm_init(adp_ctx *ctx, int nranks, int rank, const void *uid128);
-/* the same from the environment (ADP_NRANKS|WORLD_SIZE, ADP_RANK|RANK, ADP_UID_FILE): what the
- * Fortran driver calls when it is started once per GPU */
+/* the same from the environment (ADP_NRANKS|WORLD_SIZE, ADP_RANK|RANK, and ADP_UID_FILE = a path private
+ * to this job, or ADP_JOB_ID|MASTER_PORT from which /tmp/adpres_b200.<job>.uid is derived; with neither the
+ * call fails with ADP_ERR_USAGE): what the Fortran driver calls when it is started once per GPU */
 int adp_comm_init_env(adp_ctx *ctx);
 /* planes [k0, k1) (0-based) owned by this rank, valid after adp_set_geometry() */
 int adp_slab(const adp_ctx *ctx, int *k0, int *k1);

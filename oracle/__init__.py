@@ -257,6 +257,13 @@ class Oracle:
         m = self.L.orc_trace(self.h, n, _d(ke), _d(ser), _d(fer))
         return ke[:m].copy(), ser[:m].copy(), fer[:m].copy()
 
+    def trace_times(self):
+        """(wall clock, cumulative CMFD cpu time, cumulative nodal cpu time) at the end of every iteration of the last outer*()"""
+        n = 200000
+        w, f, d = np.empty(n), np.empty(n), np.empty(n)
+        m = self.L.orc_trace_times(self.h, n, _d(w), _d(f), _d(d))
+        return w[:m].copy(), f[:m].copy(), d[:m].copy()
+
     def nodal_trace(self):
         n = 4096
         p, im, jm, km = (np.empty(n, dtype=np.int32) for _ in range(4))

@@ -95,6 +95,7 @@ typedef struct orc {
     /* ---- trace (what the reference prints per outer iteration) */
     int ntrace;
     double *tr_ke, *tr_ser, *tr_fer;
+    double *tr_wall, *tr_fdm, *tr_nod; /* per outer iteration: wall clock and the two accumulators at its end (bench.py) */
     int nnodal;               /* nodal updates recorded */
     int *nu_p, *nu_im, *nu_jm, *nu_km;
     double *nu_ndmax;
@@ -160,6 +161,7 @@ orc *orc_create(void)
     o->coup_first = o->matrix_first = o->outer_first = 1;
     o->ndmax = 0.0; /* never initialised by the reference; zero under static storage */
     o->tr_ke = dalloc(MAXTRACE); o->tr_ser = dalloc(MAXTRACE); o->tr_fer = dalloc(MAXTRACE);
+    o->tr_wall = dalloc(MAXTRACE); o->tr_fdm = dalloc(MAXTRACE); o->tr_nod = dalloc(MAXTRACE);
     o->nu_p = ialloc(MAXTRACE); o->nu_im = ialloc(MAXTRACE); o->nu_jm = ialloc(MAXTRACE);
     o->nu_km = ialloc(MAXTRACE); o->nu_ndmax = dalloc(MAXTRACE); o->ex_p = ialloc(MAXTRACE);
     return o;
@@ -186,6 +188,7 @@ void orc_destroy(orc *o)
     free(o->Lm2); free(o->S1); free(o->S2); free(o->S3);
     free(o->a1n); free(o->a2n); free(o->a3n); free(o->a4n); free(o->a1p); free(o->a2p);
     free(o->a3p); free(o->a4p); free(o->Ln1); free(o->Lp1);
+    free(o->tr_wall); free(o->tr_fdm); free(o->tr_nod);
     free(o->tr_ke); free(o->tr_ser); free(o->tr_fer); free(o->nu_p); free(o->nu_im);
     free(o->nu_jm); free(o->nu_km); free(o->nu_ndmax); free(o->ex_p);
     free(o);
@@ -574,7 +577,14 @@ static int nodal_upd(orc *o, int nmode)
 static void trace_reset(orc *o) { o->ntrace = 0; o->nnodal = 0; o->nextrp = 0; }
 static void trace_push(orc *o, double ke, double ser, double fer)
 {
-    if (o->ntrace < MAXTRACE) { int q = o->ntrace++; o->tr_ke[q] = ke; o->tr_ser[q] = ser; o->tr_fer[q] = fer; }
+    if (o->ntrace < MAXTRACE) {
+        int q = o->ntrace++;
+        struct timespec ts;
+        clock_gettime(CLOCK_MONOTONIC, &ts);
+        o->tr_ke[q] = ke; o->tr_ser[q] = ser; o->tr_fer[q] = fer;
+        o->tr_wall[q] = (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+        o->tr_fdm[q] = o->fdm_time; o->tr_nod[q] = o->nod_time;
+    }
 }
 
 /* first-call initialisation shared by outer/outer_fs/outer_th, mod_cmfd.f90:448-454 */
@@ -1530,6 +1540,16 @@ int orc_trace(orc *o, int maxn, double *ke, double *ser, double *fer)
     int n = o->ntrace < maxn ? o->ntrace : maxn;
     memcpy(ke, o->tr_ke, n * sizeof(double)); memcpy(ser, o->tr_ser, n * sizeof(double));
     memcpy(fer, o->tr_fer, n * sizeof(double));
+    return o->ntrace;
+}
+/* timing of the last outer*() call per iteration (test / bench infrastructure, no counterpart in the reference):
+ * wall clock at the end of iteration q and the accumulated "CMFD" / "nodal update" CPU times the reference prints
+ * in its breakdown (ADPRES.f90:55-81), so that a window of iterations of ONE outer() call can be timed */
+int orc_trace_times(orc *o, int maxn, double *wall, double *fdm, double *nod)
+{
+    int n = o->ntrace < maxn ? o->ntrace : maxn;
+    memcpy(wall, o->tr_wall, n * sizeof(double)); memcpy(fdm, o->tr_fdm, n * sizeof(double));
+    memcpy(nod, o->tr_nod, n * sizeof(double));
     return o->ntrace;
 }
 int orc_nodal_trace(orc *o, int maxn, int *p, double *ndmax, int *im, int *jm, int *km)

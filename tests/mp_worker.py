@@ -202,16 +202,18 @@ def cb_main(rank, world, local, uid, dist):
 
 def c3_main(rank, world, local, uid, dist):
     """BASELINE configs[2] -- IAEA-3D at 4 x 4 nodes per assembly, 190 planes, "z-slab over 2/4/8 B200" -- against the
-    committed CPU-oracle solve (tests/golden/c3_oracle_result.json), compared at the oracle's outer count."""
+    committed CPU-oracle solve (tests/golden/c3_oracle_result.json, converged to 1e-8)."""
     import json
     import numpy as np
     from conftest import GOLDEN, load_problem
     from adpres_b200 import capi
     ref = json.load(open(os.path.join(GOLDEN, "c3_oracle_result.json")))
     p = load_problem("IAEA3Ds").refine(xdiv=ref["xdiv"], ydiv=ref["ydiv"], zdiv=ref["zdiv"])
-    s = capi.Solver(p, device=local, nranks=world, rank=rank, uid=uid, nout=ref["outers"], serc=0.0, ferc=0.0)
+    # both sides converged to the fixture's serc = ferc = 1e-8 (see tests/test_z_all_decks.py: at the 1e-5 exit the
+    # iterate still moves by more than the 1e-5 bar)
+    s = capi.Solver(p, device=local, nranks=world, rank=rank, uid=uid, nout=30000, serc=ref["serc"], ferc=ref["serc"])
     rc, n = s.outer(0)
-    assert rc == capi.STOP_MAXOUTER and n == ref["outers"], (rc, n)
+    assert rc == 0 and abs(n - ref["outers"]) <= 0.05 * ref["outers"], (rc, n)
     ke = s.state()["Ke"]
     assert abs(ke - ref["keff"]) * 1e5 < 1.0, (ke, ref["keff"])
     _, pw = s.powdis()
@@ -219,7 +221,7 @@ def c3_main(rank, world, local, uid, dist):
     idx = np.array(sorted(int(i) for i in ref["power_samples"] if lo <= int(i) < hi))
     ref_pw = np.array([ref["power_samples"][str(i)] for i in idx])
     nz = ref_pw > 1e-12
-    assert np.abs(pw[idx][nz] / ref_pw[nz] - 1).max() < 5e-5
+    assert np.abs(pw[idx][nz] / ref_pw[nz] - 1).max() < 1e-5
     fasm, _, _ = s.asm_pow()                      # all-reduced over the slabs: every rank holds the whole map
     asm_ref = np.array(ref["asm_power"])
     nzm = asm_ref > 0

@@ -156,21 +156,23 @@ def test_gpu_refined_lmw_transient_against_cpu_oracle_fixture(fixture):
 @pytest.mark.gpu
 def test_gpu_c3_full_solve_against_cpu_oracle_fixture():
     """BASELINE configs[2] (IAEA-3D at 4 x 4 nodes per assembly, 190 planes: 183 160 nodes) with the reference's default
-    iteration control (nin = 2, nupd = 104) against the CPU oracle's solve (tools/c3_oracle.py, one minute of CPU, committed):
-    k-eff within 1 pcm, assembly power 1e-5; nodal power within 5e-5 -- stopping the oracle itself 20 iterations earlier moves
-    it by 1.2e-5, so that is the resolution of the 1e-5 exit criterion on this mesh."""
+    inner / nodal iteration control (nin = 2, nupd = 104) against the CPU oracle's solve (tools/c3_oracle.py, one minute of
+    CPU, committed): k-eff within 1 pcm, assembly power 1e-5, nodal power 1e-5.
+    Both sides are converged to serc = ferc = 1e-8 (the fixture's "serc").  Round 1 compared at the 1e-5 exit of the oracle,
+    at a fixed outer count; there the iterate still moves by 1.2e-5 per 20 iterations (nin = 2 sweeps are far from converged),
+    so the two summation orders sat 1.4e-5 apart in assembly power -- a property of the unconverged iterate, not of the
+    solution.  Converged, the trajectories contract onto the same solution and the north-star bars apply as they are."""
     import json
     from conftest import GOLDEN
     from adpres_b200 import capi
     ref = json.load(open(os.path.join(GOLDEN, "c3_oracle_result.json")))
     p = load_problem("IAEA3Ds").refine(xdiv=ref["xdiv"], ydiv=ref["ydiv"], zdiv=ref["zdiv"])
     assert (p.nnod, p.nin, p.nupd) == (ref["nnod"], ref["nin"], ref["nupd"])
-    # exactly the oracle's number of outer iterations (1 032, nine nodal updates; serc = ferc = 0 never exits earlier): the
-    # comparison is made at a fixed outer count, so a round-off-induced shift of the exit iteration cannot enter
-    # (SURVEY.md section 7; one iteration moves the nodal power by ~6e-7 here)
-    s = capi.Solver(p, nout=ref["outers"], serc=0.0, ferc=0.0)
+    assert ref["serc"] <= 1e-8 and ref["status"] == 0
+    s = capi.Solver(p, nout=30000, serc=ref["serc"], ferc=ref["serc"])
     rc, n = s.outer(0)
-    assert ref["status"] == 0 and rc == capi.STOP_MAXOUTER and n == ref["outers"], (rc, n)
+    assert rc == 0, (rc, n)
+    assert abs(n - ref["outers"]) <= 0.05 * ref["outers"], (n, ref["outers"])   # same convergence rate (exit iteration +- round-off)
     assert abs(s.state()["Ke"] - ref["keff"]) * 1e5 < 1.0
     rc, pw = s.powdis()
     asm, asm_ref = p.asm_power(pw), np.array(ref["asm_power"])
@@ -179,7 +181,7 @@ def test_gpu_c3_full_solve_against_cpu_oracle_fixture():
     idx = np.array(sorted(int(i) for i in ref["power_samples"]))
     ref_pw = np.array([ref["power_samples"][str(i)] for i in idx])
     nzp = ref_pw > 1e-12
-    assert np.abs(pw[idx][nzp] / ref_pw[nzp] - 1).max() < 5e-5
+    assert np.abs(pw[idx][nzp] / ref_pw[nzp] - 1).max() < 1e-5
     s.close()
 
 
