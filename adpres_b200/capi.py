@@ -23,7 +23,7 @@ TRACE_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_doubl
 
 # every symbol include/adpres_b200.h declares (checked by tests/test_abi.py)
 SYMBOLS = [
-    "adp_create", "adp_destroy", "adp_last_error", "adp_version", "adp_comm_unique_id", "adp_comm_init", "adp_comm_init_env", "adp_slab",
+    "adp_create", "adp_destroy", "adp_last_error", "adp_version", "adp_comm_unique_id", "adp_comm_init", "adp_comm_init_env", "adp_slab", "adp_set_xs_mask", "adp_get_state_mask",
     "adp_set_geometry", "adp_set_xs", "adp_set_control", "adp_matrix_setup", "adp_init_flux", "adp_outer_begin",
     "adp_outer_iter", "adp_nodal_upd", "adp_powdis", "adp_integrate", "adp_set_kinetics", "adp_set_kinetics_xtab", "adp_set_transient",
     "adp_get_exsrc", "adp_set_material_xs", "adp_set_crod", "adp_xs_update", "adp_set_feedback", "adp_xs_update_th", "adp_get_xs",

@@ -51,6 +51,7 @@ enum {
     S_NDMAX,      // max |delta dn|
     S_POW,        // total power
     S_TMP0, S_TMP1,
+    S_FAULT,      // sticky: set to 1 when a peer-memory all-reduce timed out (read back with the scalars at every host sync)
     S_COUNT
 };
 
@@ -90,12 +91,21 @@ enum { PB_RS = 0, PB_V0, PB_V1, PB_R, PB_F0A, PB_F0B, PB_COUNT };
 #define ADP_MAIL_WORDS 8
 #define ADP_MAX_RANKS 8
 struct Mail {
-    double *const *box;               // device table: box[q] = rank q's mailbox (box[rank] is local).  A table in
+    double *const *box = nullptr;     // device table: box[q] = rank q's mailbox (box[rank] is local).  A table in
                                       // global memory, NOT an array inside the kernel parameters: indexing a
                                       // parameter array with a runtime q makes every thread copy it to a stack frame
-    unsigned long long *seq;          // device counter of reductions done on this rank
-    int *errflag;
+    double *mine = nullptr;           // this rank's own mailbox (== box[rank])
+    unsigned long long *seq = nullptr;   // device counter of reductions posted by this rank
+    double *fault = nullptr;          // -> scal[S_FAULT]: sticky timeout flag (never shared with the STOP error flag)
+    long long timeout = 0;            // clock64 ticks a rank waits for its peers before it gives up
     int nranks = 1, rank = 0;
+};
+// what a kernel waits for in its prologue: the `n` sums the preceding kernel posted (n = 0: nothing); they are combined
+// in rank order by every CTA, CTA 0 also stores them to scal[slot[i]] for the kernels that follow
+struct MailWait {
+    Mail m;
+    int n = 0;
+    int slot[2] = {0, 0};
 };
 
 #define FLAG_XM 1
@@ -203,12 +213,16 @@ struct adp_ctx {
     adp_comm *comm = nullptr;
     int nranks = 1, rank = 0;
     double *d_v2 = nullptr;                // second v buffer (iteration parity; see bicg_core)
+    double *d_gather = nullptr;            // staging for one slab of another rank (adp_comm_gather_column)
+    bool gather_results = true;            // node arrays returned to the host are completed with the other ranks' slabs
     bool peer_ok = false;                  // neighbours' vectors are mapped: halos are pushed by the kernels
     double *peer_lo[PB_COUNT] = {nullptr}, *peer_hi[PB_COUNT] = {nullptr};
     int nzl_lo = 0, nzl_hi = 0;            // planes owned by the lower / upper neighbour
     long long NV_lo = 0, NV_hi = 0;
     bool xghost_valid[2][ADP_MAXG] = {{false}};   // ghost planes of f0[which][g] are current
-    bool peer_ar = false;                  // reductions are all-reduced inside the kernels (mailboxes)
+    bool peer_ar = false;                  // reductions are all-reduced over peer-memory mailboxes
+    bool fuse_mail = true;                 // BiCGSTAB: post in the producer's last CTA, wait in the consumer's prologue (no extra kernel)
+    double mail_timeout_s = 30.0;          // ADP_MAIL_TIMEOUT_S
     double *d_mail = nullptr;              // this rank's mailbox
     double *mail_peer[ADP_MAX_RANKS] = {nullptr};
     double **d_mail_table = nullptr;       // device copy of mail_peer[]
@@ -235,6 +249,16 @@ struct adp_ctx {
                          ":" + std::to_string(__LINE__) + ")";                                  \
             return ADP_ERR_CUDA;                                                                \
         }                                                                                       \
+    } while (0)
+
+// after every host synchronisation that brought the device scalars to h_scal: a peer-memory all-reduce that timed
+// out poisons its result with NaN and raises the sticky S_FAULT slot; no call may return ADP_OK after that
+#define ADP_CHECK_FAULT(ctx)                                                                              \
+    do {                                                                                                  \
+        if ((ctx)->h_scal[S_FAULT] != 0.0) {                                                              \
+            (ctx)->err = "peer-memory all-reduce timed out: a rank fell more than ADP_MAIL_TIMEOUT_S behind (results are poisoned with NaN)"; \
+            return ADP_ERR_NCCL;                                                                          \
+        }                                                                                                 \
     } while (0)
 
 #define ADP_REQUIRE(ctx, cond, msg)                 \
@@ -310,6 +334,7 @@ int adp_k_nodal_update(adp_ctx *c, int cmode);
 int adp_k_lxyz_total(adp_ctx *c, double *d_L);
 // comm.cu
 int adp_comm_halo(adp_ctx *c, double *d_vec, int nplanes);            // exchange ghost planes of one vector
+int adp_comm_gather_column(adp_ctx *c, double *h_col, const double *d_owned);   // other ranks' slabs of one host column
 int adp_comm_allreduce_sum(adp_ctx *c, double *d_scal, int count);
 int adp_comm_allreduce_max(adp_ctx *c, double *d_scal, int count);
 int adp_comm_allreduce_min_ll(adp_ctx *c, long long *d_val, int count);
@@ -317,6 +342,8 @@ int adp_comm_allreduce_max_nccl(adp_ctx *c, double *d_scal, int count);
 int adp_comm_allreduce_sum_nccl(adp_ctx *c, double *d_vec, int count);   // any length (not a grid_reduce result)
 void adp_comm_destroy(adp_ctx *c);
 int adp_comm_map_peers(adp_ctx *c);                                     // after the vectors are allocated
+Mail adp_comm_mail(const adp_ctx *c);                                   // mailbox descriptor for kernel parameters
+int adp_comm_drain(adp_ctx *c, int n, int slot0, int slot1);            // wait for a posted reduction outside a fused consumer
 void adp_comm_unmap_peers(adp_ctx *c);
 static inline Push adp_push(const adp_ctx *c, int buf, long long goff_lo = 0, long long goff_hi = 0)
 {

@@ -57,6 +57,8 @@ extern "C" int adp_create(adp_ctx **out, int device)
     cudaDeviceProp prop;
     cudaGetDeviceProperties(&prop, device);
     c->sm_count = prop.multiProcessorCount;
+    if (const char *v = getenv("ADP_MAIL_TIMEOUT_S")) { const double t = atof(v); if (t > 0.0) c->mail_timeout_s = t; }
+    if (getenv("ADP_NO_FUSE_MAIL")) c->fuse_mail = false;
     // persistent grids: a multiple of the SM count (148 on B200) x resident CTAs per SM
     c->grid_blocks = 0;
     if (dev_alloc(c, &c->d_scal, S_COUNT) || dev_alloc(c, &c->d_part, 4 * ADP_MAXPART) || dev_alloc(c, &c->d_ticket, 1) ||
@@ -98,7 +100,7 @@ extern "C" int adp_destroy(adp_ctx *c)
                     c->d_f0[0], c->d_f0[1], c->d_fs[0], c->d_fs[1], c->d_r, c->d_rs, c->d_p, c->d_v, c->d_v2, c->d_s, c->d_t,
                     c->d_s0, c->d_a, c->d_df, c->d_dn, c->d_D, c->d_sigr, c->d_nuf, c->d_sigf, c->d_exsrc, c->d_sigs,
                     c->d_dc, c->d_chi, c->d_S, c->d_c0, c->d_ft, c->d_fst, c->d_omeg, c->d_sigrp, c->d_L, c->d_dfis,
-                    c->d_tbeta, c->d_velo, c->d_af, c->d_xtab, c->d_dtab, c->d_fb, c->d_bpos, c->d_dumtop, c->d_nd, c->d_abefgh, c->d_mail, c->d_arseq, c->d_mail_table, c->d_scal, c->d_part, c->d_ticket, c->d_argidx, c->d_errflag, c->d_stage};
+                    c->d_tbeta, c->d_velo, c->d_af, c->d_xtab, c->d_dtab, c->d_fb, c->d_bpos, c->d_dumtop, c->d_nd, c->d_abefgh, c->d_mail, c->d_arseq, c->d_mail_table, c->d_scal, c->d_part, c->d_ticket, c->d_argidx, c->d_errflag, c->d_stage, c->d_gather};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (c->h_scal) cudaFreeHost(c->h_scal);
     if (c->h_flags) cudaFreeHost(c->h_flags);
@@ -156,10 +158,14 @@ static int upload_nodes_int(adp_ctx *c, int *d, const int *h)
 static int download_nodes(adp_ctx *c, double *h, const double *d, int ncol)
 {
     const size_t cnt = (size_t)c->nzl * c->np;
-    for (int col = 0; col < ncol; ++col)
-        CUDA_TRY(c, cudaMemcpyAsync(h + (size_t)col * c->nnod + (size_t)c->k0 * c->np,
-                                    d + (size_t)col * c->NV + (size_t)ADP_GH * c->np, cnt * sizeof(double),
+    for (int col = 0; col < ncol; ++col) {
+        const double *own = d + (size_t)col * c->NV + (size_t)ADP_GH * c->np;
+        CUDA_TRY(c, cudaMemcpyAsync(h + (size_t)col * c->nnod + (size_t)c->k0 * c->np, own, cnt * sizeof(double),
                                     cudaMemcpyDeviceToHost, c->stream));
+        // several ranks: the rows of the other slabs too (option "gather_results", default on), so that the host
+        // code that consumes whole sdata arrays stays correct on every rank
+        if (c->nranks > 1 && c->gather_results) TRY(adp_comm_gather_column(c, h + (size_t)col * c->nnod, own));
+    }
     return ADP_OK;
 }
 
@@ -281,7 +287,7 @@ extern "C" int adp_set_geometry(adp_ctx *c, int nxx, int nyy, int nzz, int nnod,
         double **lazy[] = {&c->d_nd, &c->d_abefgh, &c->d_c0, &c->d_ft, &c->d_fst, &c->d_omeg, &c->d_sigrp, &c->d_L,
                            &c->d_af, &c->d_xtab, &c->d_dtab, &c->d_bpos, &c->d_dumtop, &c->d_res, &c->d_stab, &c->d_tfm,
                            &c->d_heatf, &c->d_ent, &c->d_ftem, &c->d_mtem, &c->d_cden, &c->d_frate, &c->d_pline, &c->d_nodenf,
-                           &c->d_chain};
+                           &c->d_chain, &c->d_gather};
         for (double **q : lazy)
             if (*q) { cudaFree(*q); *q = nullptr; }
         if (c->d_fb) { cudaFree(c->d_fb); c->d_fb = nullptr; }
@@ -341,6 +347,15 @@ extern "C" int adp_set_xs(adp_ctx *c, const double *D, const double *sigr, const
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     if (D && sigr && nuf && sigf && sigs && chi && dc && exsrc) c->xs_set = true;
     return ADP_OK;
+}
+
+extern "C" int adp_set_xs_mask(adp_ctx *c, int mask, const double *D, const double *sigr, const double *nuf, const double *sigf,
+                               const double *sigs, const double *chi, const double *dc, const double *exsrc)
+{
+    auto sel = [mask](int bit, const double *p) { return (mask >> bit) & 1 ? p : nullptr; };
+    if (!c) return ADP_ERR_USAGE;
+    ADP_REQUIRE(c, c->xs_set || (mask & 0xff) == 0xff, "adp_set_xs_mask: the first upload must carry every array");
+    return adp_set_xs(c, sel(0, D), sel(1, sigr), sel(2, nuf), sel(3, sigf), sel(4, sigs), sel(5, chi), sel(6, dc), sel(7, exsrc));
 }
 
 extern "C" int adp_set_control(adp_ctx *c, int nout, int nin, int nac, int nupd, double serc, double ferc, int kern)
@@ -465,6 +480,7 @@ extern "C" int adp_outer_iter(adp_ctx *c, int mode, int p, double *Ke, double *s
     CUDA_TRY(c, cudaSetDevice(c->device));
     TRY(launch_outer_iter(c, mode, (p % c->nac) == 0));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    ADP_CHECK_FAULT(c);
     if (Ke) *Ke = c->h_scal[S_KE];
     c->last_ser = c->h_scal[S_SER]; c->last_fer = c->h_scal[S_FER];
     if (ser) *ser = c->last_ser;
@@ -500,6 +516,7 @@ extern "C" int adp_nodal_upd(adp_ctx *c, int nmode, double *ndmax, int *im, int 
         TRY(adp_comm_allreduce_max_nccl(c, c->d_scal + S_NDMAX, 1));
         CUDA_TRY(c, cudaMemcpyAsync(c->h_scal, c->d_scal, S_COUNT * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
         CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+        ADP_CHECK_FAULT(c);
         if (c->h_scal[S_TMP0] != c->h_scal[S_NDMAX]) {
             long long big = 0x7fffffffffffffffLL;
             CUDA_TRY(c, cudaMemcpyAsync(c->d_argidx, &big, sizeof(big), cudaMemcpyHostToDevice, c->stream));
@@ -521,6 +538,7 @@ extern "C" int adp_nodal_upd(adp_ctx *c, int nmode, double *ndmax, int *im, int 
     CUDA_TRY(c, cudaMemcpyAsync(c->h_flags, c->d_argidx, sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(c, cudaMemcpyAsync(c->h_flags + 2, c->d_errflag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    ADP_CHECK_FAULT(c);
     c->ndmax = c->h_scal[S_NDMAX];
     if (c->ndmax > 0.0) {
         const long long loc = *(long long *)c->h_flags;
@@ -558,6 +576,7 @@ extern "C" int adp_powdis(adp_ctx *c, double *p, int fixedsrc_mode)
     TRY(adp_k_powdis(c, c->d_stage));
     CUDA_TRY(c, cudaMemcpyAsync(c->h_scal, c->d_scal, S_COUNT * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    ADP_CHECK_FAULT(c);
     if (c->h_scal[S_POW] <= 0.0 && !fixedsrc_mode) { c->err = "ERROR: TOTAL NODES POWER IS ZERO OR LESS"; return ADP_STOP_ZERO_POWER; }
     TRY(adp_k_scale_by_slot(c, c->d_stage, S_POW));
     TRY(download_nodes(c, p, c->d_stage, 1));
@@ -574,6 +593,7 @@ extern "C" int adp_integrate(adp_ctx *c, const double *s, double *result)
     TRY(adp_k_integrate(c, c->d_stage, S_TMP0));
     CUDA_TRY(c, cudaMemcpyAsync(c->h_scal, c->d_scal, S_COUNT * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    ADP_CHECK_FAULT(c);
     *result = c->h_scal[S_TMP0];
     return ADP_OK;
 }
@@ -923,6 +943,7 @@ extern "C" int adp_powtot(adp_ctx *c, double *tpow)
     TRY(adp_k_powdis(c, c->d_stage));
     CUDA_TRY(c, cudaMemcpyAsync(c->h_scal, c->d_scal, S_COUNT * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    ADP_CHECK_FAULT(c);
     *tpow = c->h_scal[S_POW];
     return ADP_OK;
 }
@@ -938,6 +959,7 @@ extern "C" int adp_reactivity(adp_ctx *c, int use_sigrp, double *rho)
     TRY(adp_k_reactivity(c, c->d_af, use_sigrp ? c->d_sigrp : c->d_sigr));
     CUDA_TRY(c, cudaMemcpyAsync(c->h_scal, c->d_scal, S_COUNT * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    ADP_CHECK_FAULT(c);
     const double src = c->h_scal[S_TMP0], rem = c->h_scal[S_TMP1], lea = c->h_scal[S_E2SQ], fde = c->h_scal[S_FINT];
     *rho = (src - lea - rem) / fde;
     return ADP_OK;
@@ -956,16 +978,23 @@ extern "C" int adp_get_state(adp_ctx *c, double *f0, double *fs0, double *s0, do
     if (s0) {
         // TSrc* zero all of s0 and fill only the column of the group being solved
         // (mod_cmfd.f90:1022,1053,1084): after an outer iteration only the last group's column is non-zero
+        const bool whole = c->nranks == 1 || c->gather_results;
         for (int g = 0; g < c->ng; ++g) {
-            double *dst = s0 + (size_t)g * c->nnod + (size_t)c->k0 * c->np;
+            double *dst = s0 + (size_t)g * c->nnod + (whole ? 0 : (size_t)c->k0 * c->np);
             if (g + 1 == c->s0_group) TRY(download_nodes(c, s0 + (size_t)g * c->nnod, c->d_s0, 1));
-            else memset(dst, 0, (size_t)c->nzl * c->np * sizeof(double));
+            else memset(dst, 0, (whole ? (size_t)c->nnod : (size_t)c->nzl * c->np) * sizeof(double));
         }
     }
     CUDA_TRY(c, cudaMemcpyAsync(c->h_scal, c->d_scal, S_COUNT * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    ADP_CHECK_FAULT(c);
     if (Ke) *Ke = c->h_scal[S_KE];
     return ADP_OK;
+}
+
+extern "C" int adp_get_state_mask(adp_ctx *c, int mask, double *f0, double *fs0, double *s0, double *Ke)
+{
+    return adp_get_state(c, (mask & 1) ? f0 : nullptr, (mask & 2) ? fs0 : nullptr, (mask & 4) ? s0 : nullptr, Ke);
 }
 
 extern "C" int adp_set_state(adp_ctx *c, const double *f0, const double *fs0, double Ke)
@@ -1015,19 +1044,21 @@ extern "C" int adp_get_nod(adp_ctx *c, double *df, double *dn)
     if (!c) return ADP_ERR_USAGE;
     ADP_REQUIRE(c, c->matrix_ready, "adp_get_nod: call adp_matrix_setup first");
     CUDA_TRY(c, cudaSetDevice(c->device));
-    const size_t NL = (size_t)c->NL, off = (size_t)c->k0 * c->np;
-    TRY(ensure_host_stage(c, NL));
+    // one global host column at a time through the pinned stage (own rows; with gather_results the other ranks' too),
+    // scattered into the reference's AoS nod(n,g)%df(6) / %dn(6)
+    const bool whole = c->nranks == 1 || c->gather_results;
+    const size_t lo = whole ? 0 : (size_t)c->k0 * c->np, hi = whole ? (size_t)c->nnod : (size_t)c->k1 * c->np;
+    TRY(ensure_host_stage(c, (size_t)c->nnod));
     for (int which = 0; which < 2; ++which) {
         double *dst = which ? dn : df;
         const double *src = which ? c->d_dn : c->d_df;
         if (!dst) continue;
         for (int g = 0; g < c->ng; ++g)
             for (int f = 0; f < 6; ++f) {
-                CUDA_TRY(c, cudaMemcpyAsync(c->h_stage, src + ((size_t)g * 6 + f) * c->NV + (size_t)ADP_GH * c->np,
-                                            NL * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+                TRY(download_nodes(c, c->h_stage, src + ((size_t)g * 6 + f) * c->NV, 1));
                 CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-                double *o = dst + ((size_t)g * c->nnod + off) * 6 + f;
-                for (size_t n = 0; n < NL; ++n) o[n * 6] = c->h_stage[n];
+                double *o = dst + (size_t)g * c->nnod * 6 + f;
+                for (size_t n = lo; n < hi; ++n) o[n * 6] = c->h_stage[n];
             }
     }
     return ADP_OK;
@@ -1147,7 +1178,10 @@ extern "C" int adp_set_option(adp_ctx *c, const char *name, int value)
     if (!c || !name) return ADP_ERR_USAGE;
     if (!strcmp(name, "graphs")) { c->use_graphs = value != 0; free_graphs(c); return ADP_OK; }
     if (!strcmp(name, "peer_push")) { if (!value) c->peer_ok = false; return ADP_OK; }
-    if (!strcmp(name, "peer_allreduce")) { if (!value) c->peer_ar = false; return ADP_OK; }
+    if (!strcmp(name, "peer_allreduce")) { if (!value) c->peer_ar = false; free_graphs(c); return ADP_OK; }
+    if (!strcmp(name, "gather_results")) { c->gather_results = value != 0; return ADP_OK; }
+    if (!strcmp(name, "fuse_mail")) { c->fuse_mail = value != 0; free_graphs(c); return ADP_OK; }
+    if (!strcmp(name, "mail_timeout_s")) { c->mail_timeout_s = value; free_graphs(c); return ADP_OK; }
     if (!strcmp(name, "balance_rounds")) { c->balance_rounds = value != 0; free_graphs(c); return ADP_OK; }
     if (!strcmp(name, "bench_warmup")) { c->bench_warmup = value; return ADP_OK; }
     if (!strcmp(name, "nodal_coop")) { c->nodal_coop = value; free_graphs(c); return ADP_OK; }
@@ -1191,6 +1225,7 @@ extern "C" int adp_outer_steps(adp_ctx *c, int mode, int p_first, int nsteps, do
     CUDA_TRY(c, cudaMemcpyAsync(c->h_scal, c->d_scal, S_COUNT * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(c, cudaMemcpyAsync(c->h_flags + 2, c->d_errflag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    ADP_CHECK_FAULT(c);
     if (Ke) *Ke = c->h_scal[S_KE];
     if (ser) *ser = c->h_scal[S_SER];
     if (fer) *fer = c->h_scal[S_FER];

@@ -18,8 +18,15 @@
 #include "adp_internal.cuh"
 #include "xtab_node.cuh"
 #include "kinetics_node.cuh"
+#include "mail.cuh"
 
 namespace {
+
+// resident CTAs per SM asked of ptxas for P (k_residual) and A (k_update_p): 8 = 32 registers, like every other
+// streaming kernel but k_st (with the boundary-first tile walk and the mailbox prologue they would take 40 / 34)
+#ifndef ADP_LB_PA
+#define ADP_LB_PA 8
+#endif
 
 // ------------------------------------------------------------------------------------------
 // deterministic grid-wide reductions: warp shuffle -> shared memory -> one partial per block
@@ -31,6 +38,8 @@ struct RedOut {
     double *part;        // [4][ADP_MAXPART]
     unsigned int *ticket;
     int slot[4];
+    int post = 0;        // multi-rank: the last CTA posts the (<= 2) sums to every rank's mailbox (mail.cuh)
+    Mail m;
 };
 
 __device__ __forceinline__ double warp_sum(double v)
@@ -103,6 +112,12 @@ __device__ __forceinline__ void grid_reduce(double (&val)[NS + NM], const RedOut
             for (int i = 0; i < NVAL; ++i) ro.scal[ro.slot[i]] = res[i];
             *ro.ticket = 0u;
         }
+        if constexpr (NM == 0 && NS <= 2) {
+            // every CTA's halo stores were fenced at system scope before its ticket: posting now tells the
+            // peers that this rank's partial sums AND its boundary planes have arrived
+            if (ro.post)
+                mail_post(ro.m, NS, __shfl_sync(0xffffffffu, res[0], 0), __shfl_sync(0xffffffffu, res[NS - 1], 0));
+        }
     }
 }
 
@@ -121,29 +136,39 @@ __device__ __forceinline__ long long node_idx(const Geo &G, int kl, int r)
 }
 
 // Boundary planes go straight into the z-neighbours' ghost planes (NVLink peer stores); the
-// all-reduce that ends every such kernel is the barrier that orders them before the reads.
-// The stores are kept OUT of the streaming loop (a possibly-aliasing store there cost the SpMV
-// kernel 10 us, ncu A/B): after its tiles a CTA walks its boundary-plane tiles again, re-reads
-// the values it has just written itself (L1/L2 hits) and forwards them.
-__device__ __forceinline__ void push_tail(const Geo &G, const Push &ps, const double *vec)
+// all-reduce that follows every such kernel is the barrier that orders them before the reads.
+// The tiles of the two boundary planes are walked FIRST, by a copy of the loop body that also
+// stores to the neighbour, and the interior tiles afterwards by a copy without any peer store: the
+// streaming loop stays free of possibly-aliasing stores (an in-loop store cost the SpMV kernel 10 us,
+// ncu A/B) and the NVLink write acknowledgement the system fence at the kernel end waits for has the
+// whole interior sweep to arrive (round 1 pushed after the sweep and every boundary CTA sat out a
+// round trip in the kernel tail: 0.25 ms per step at two ranks).
+//   tile t in [0, nb)        boundary: plane 0 (t < tpp) or plane nzl-1
+//   tile t in [nb, ntiles)   interior planes 1 .. nzl-2
+// grid-stride over this numbering, so the work per CTA stays balanced.
+template <typename FB, typename FI>
+__device__ __forceinline__ void bf_tiles(const Geo &G, FB &&boundary, FI &&interior)
 {
-#ifndef ADP_NO_PUSH
-    if (!ps.lo && !ps.hi) return;
-    bool pushed = false;
-    // boundary-plane tiles are [0, tpp) and [(nzl-1) tpp, nzl tpp): visit only those of this CTA
-    for (int side = 0; side < 2; ++side) {
-        const int kl = side ? G.nzl - 1 : 0;
-        double *dst = side ? ps.hi : ps.lo;
-        if (!dst) continue;
-        const int t0 = kl * G.tpp;
-        int first = t0 + ((int)blockIdx.x - t0 % (int)gridDim.x + (int)gridDim.x) % (int)gridDim.x;   // first tile >= t0 of this CTA
-        for (int tile = first; tile < t0 + G.tpp; tile += gridDim.x) {
-            const int r = (tile - t0) * ADP_TILE + threadIdx.x;
-            if (r < G.np) { dst[r] = vec[node_idx(G, kl, r)]; pushed = true; }
-        }
+    const int nb = (G.nzl >= 2 ? 2 : 1) * G.tpp;
+    int t = blockIdx.x;
+    for (; t < nb; t += gridDim.x) {
+        const int kl = (t >= G.tpp) ? G.nzl - 1 : 0, r = (t % G.tpp) * ADP_TILE + threadIdx.x;
+        if (r < G.np) boundary(kl, r);
     }
-    if (pushed) __threadfence_system();      // only the threads that stored to a neighbour pay for the fence
+    for (; t < G.ntiles; t += gridDim.x) {
+        const int u = t - nb;
+        const int kl = 1 + u / G.tpp, r = (u % G.tpp) * ADP_TILE + threadIdx.x;
+        if (r < G.np) interior(kl, r);
+    }
+}
+__device__ __forceinline__ bool push_row(const Geo &G, const Push &ps, int kl, int r, double val)
+{
+    bool pushed = false;
+#ifndef ADP_NO_PUSH
+    if (ps.lo && kl == 0) { ps.lo[r] = val; pushed = true; }
+    if (ps.hi && kl == G.nzl - 1) { ps.hi[r] = val; pushed = true; }
 #endif
+    return pushed;
 }
 
 // y = A_g x at row idx, terms added in set_ind order (z-,y-,x-,diag,x+,y+,z+) from 0,
@@ -242,13 +267,12 @@ struct SrcArgs {
     const double *b;               // raw mode: right-hand side given explicitly (adp_bicg)
 };
 
-__global__ void __launch_bounds__(ADP_TILE) k_residual(Geo G, SrcArgs A, const double *__restrict__ a,
+__global__ void __launch_bounds__(ADP_TILE, ADP_LB_PA) k_residual(Geo G, SrcArgs A, const double *__restrict__ a,
                                                         const double *__restrict__ x, double *__restrict__ rs, Push ps, RedOut ro)
 {
     double acc[1] = {0.0};
     const double Ke = ro.scal[S_KE];
-    FOR_EACH_ROW(G, 0, G.nzl)
-    {
+    auto row = [&](int kl, int r) -> double {
         const long long idx = node_idx(G, kl, r);
         double bs;
         if (A.b) {
@@ -268,17 +292,22 @@ __global__ void __launch_bounds__(ADP_TILE) k_residual(Geo G, SrcArgs A, const d
         const double res = bs - ax;
         rs[idx] = res;      // r0 = rs = p1: one store serves all three (see bicg_core)
         acc[0] = acc[0] + res * res;
-    }
-    push_tail(G, ps, rs);
+        return res;
+    };
+    bool pushed = false;
+    bf_tiles(G, [&](int kl, int r) { pushed = push_row(G, ps, kl, r, row(kl, r)) || pushed; }, [&](int kl, int r) { row(kl, r); });
+    if (pushed) __threadfence_system();      // only the threads that stored to a neighbour pay for the fence
     grid_reduce<1, 0>(acc, ro);
 }
 
 // A: p = r + beta (p - omega v), beta = (rho/rho_prev)(alpha/omega)   (mod_cmfd.f90:1231-1232)
-__global__ void __launch_bounds__(ADP_TILE) k_update_p(Geo G, const double *__restrict__ scal, int slot_rho, int slot_rho_prev,
+__global__ void __launch_bounds__(ADP_TILE, ADP_LB_PA) k_update_p(Geo G, double *scal, int slot_rho, int slot_rho_prev,
                                                         const double *__restrict__ rv, const double *__restrict__ v,
-                                                        const double *p_in, double *p_out, int klo, int npl)
+                                                        const double *p_in, double *p_out, int klo, int npl, MailWait mw)
 {
-    const double rho = scal[slot_rho], rho_prev = scal[slot_rho_prev];
+    double wv[2];
+    mail_prologue(mw, scal, wv);             // fused multi-rank path: rho = the sum D posted
+    const double rho = mw.n ? wv[0] : scal[slot_rho], rho_prev = scal[slot_rho_prev];
     const double alpha = rho_prev / scal[S_RSV];
     const double omega = scal[S_TS] / scal[S_TT];
     const double beta = (rho / rho_prev) * (alpha / omega);
@@ -291,17 +320,22 @@ __global__ void __launch_bounds__(ADP_TILE) k_update_p(Geo G, const double *__re
 
 // B: v = A p and the partial sums of (rs, v)   (mod_cmfd.f90:1233-1234)
 __global__ void __launch_bounds__(ADP_TILE) k_spmv_dot(Geo G, const double *__restrict__ a, const double *__restrict__ pv,
-                                                        const double *__restrict__ rs, double *__restrict__ v, Push ps, RedOut ro)
+                                                        const double *__restrict__ rs, double *__restrict__ v, Push ps, RedOut ro,
+                                                        MailWait mw)
 {
     double acc[1] = {0.0};
-    FOR_EACH_ROW(G, 0, G.nzl)
-    {
+    double wv[2];
+    mail_prologue(mw, ro.scal, wv);          // first sweep: P's rho (not used here) = the barrier before the ghost planes of p are read
+    auto row = [&](int kl, int r) -> double {
         const long long idx = node_idx(G, kl, r);
         const double y = stencil7(a, G.NV, pv, idx, G.np, G.ypm[r], G.ypp[r]);
         v[idx] = y;
         if (rs) acc[0] = acc[0] + rs[idx] * y;
-    }
-    push_tail(G, ps, v);
+        return y;
+    };
+    bool pushed = false;
+    bf_tiles(G, [&](int kl, int r) { pushed = push_row(G, ps, kl, r, row(kl, r)) || pushed; }, [&](int kl, int r) { row(kl, r); });
+    if (pushed) __threadfence_system();
     if (rs) grid_reduce<1, 0>(acc, ro);
 }
 
@@ -309,10 +343,12 @@ __global__ void __launch_bounds__(ADP_TILE) k_spmv_dot(Geo G, const double *__re
 //    (mod_cmfd.f90:1234-1238).  s is stored for the own row only.
 __global__ void __launch_bounds__(ADP_TILE) k_st(Geo G, const double *__restrict__ a, int slot_rho,
                                                   const double *__restrict__ rv, const double *__restrict__ v,
-                                                  double *__restrict__ s, double *__restrict__ t, RedOut ro)
+                                                  double *__restrict__ s, double *__restrict__ t, RedOut ro, MailWait mw)
 {
     double acc[2] = {0.0, 0.0};
-    const double alpha = ro.scal[slot_rho] / ro.scal[S_RSV];
+    double wv[2];
+    mail_prologue(mw, ro.scal, wv);          // fused multi-rank path: (rs, v) = the sum B posted
+    const double alpha = ro.scal[slot_rho] / (mw.n ? wv[0] : ro.scal[S_RSV]);
     const long long NV = G.NV;
     const int np = G.np;
     FOR_EACH_ROW(G, 0, G.nzl)
@@ -369,24 +405,29 @@ __global__ void __launch_bounds__(ADP_TILE) k_t(Geo G, const double *__restrict_
 __global__ void __launch_bounds__(ADP_TILE) k_update_xr(Geo G, int slot_rho, int last, const double *x_in,
                                                          double *x_out, const double *__restrict__ pv,
                                                          const double *__restrict__ s, const double *__restrict__ t,
-                                                         const double *__restrict__ rs, double *__restrict__ rv, Push ps, RedOut ro)
+                                                         const double *__restrict__ rs, double *__restrict__ rv, Push ps, RedOut ro,
+                                                         MailWait mw)
 {
     double acc[1] = {0.0};
+    double wv[2];
+    mail_prologue(mw, ro.scal, wv);          // fused multi-rank path: (t,t), (t,s) = the sums C posted
     const double alpha = ro.scal[slot_rho] / ro.scal[S_RSV];
-    const double omega = ro.scal[S_TS] / ro.scal[S_TT];
-    FOR_EACH_ROW(G, 0, G.nzl)
-    {
+    const double omega = mw.n ? wv[1] / wv[0] : ro.scal[S_TS] / ro.scal[S_TT];
+    auto row = [&](int kl, int r) -> double {
         const long long idx = node_idx(G, kl, r);
         const double sv = s[idx];
         const double xn = x_in[idx] + alpha * pv[idx] + omega * sv;
         x_out[idx] = xn;
-        if (!last) {
-            const double rn = sv - omega * t[idx];
-            rv[idx] = rn;
-            acc[0] = acc[0] + rs[idx] * rn;
-        }
-    }
-    push_tail(G, ps, last ? x_out : rv);   // the neighbours' copy of r, or (last sweep) of this flux buffer
+        if (last) return xn;
+        const double rn = sv - omega * t[idx];
+        rv[idx] = rn;
+        acc[0] = acc[0] + rs[idx] * rn;
+        return rn;
+    };
+    // pushed: the neighbours' copy of r, or (last sweep) of this flux buffer
+    bool pushed = false;
+    bf_tiles(G, [&](int kl, int r) { pushed = push_row(G, ps, kl, r, row(kl, r)) || pushed; }, [&](int kl, int r) { row(kl, r); });
+    if (pushed) __threadfence_system();
     if (!last) grid_reduce<1, 0>(acc, ro);
 }
 
@@ -991,16 +1032,32 @@ static int bicg_core(adp_ctx *c, const SrcArgs &src, const double *a, const doub
     const int nt = c->geo.ntiles;
     const bool multi = c->nranks > 1;
     const bool peer = multi && c->peer_ok;       // halos are pushed by the producing kernels
+    // fused all-reduce: the producer's last CTA posts its sums to every rank's mailbox, the NEXT kernel waits for all
+    // ranks in its prologue (mail.cuh) -- no reduction kernel between the BiCGSTAB phases
+    const bool fused = peer && c->peer_ar && c->fuse_mail;
     const Push none;
+    const MailWait nowait;
+    const Mail mail = fused ? adp_comm_mail(c) : Mail();
+    auto red = [&](int s0, int s1 = S_TMP1) {
+        RedOut ro = make_red(c, s0, s1);
+        if (fused) { ro.post = 1; ro.m = mail; }
+        return ro;
+    };
+    auto wait = [&](int n, int s0, int s1 = 0) {
+        MailWait w;
+        if (fused) { w.m = mail; w.n = n; w.slot[0] = s0; w.slot[1] = s1; }
+        return w;
+    };
     int rc;
     // ghost planes of x: pushed by the previous bicg's last D kernel, else exchanged here
     if (multi && !(peer && x_ghost_valid) && (rc = adp_comm_halo(c, const_cast<double *>(x_in), 1))) return rc;
     // iteration i uses rho slot S_RHO0 + (i & 1); P produces the one of iteration 1
     k_residual<<<adp_grid(c, k_residual, nt), ADP_TILE, 0, c->stream>>>(c->geo, src, a, x_in, c->d_rs,
-                                                                      peer ? adp_push(c, PB_RS) : none, make_red(c, S_RHO1));
+                                                                      peer ? adp_push(c, PB_RS) : none, red(S_RHO1));
     LAUNCH_CHECK(c);
-    if (multi && (rc = adp_comm_allreduce_sum(c, c->d_scal + S_RHO1, 1))) return rc;
+    if (multi && !fused && (rc = adp_comm_allreduce_sum(c, c->d_scal + S_RHO1, 1))) return rc;
     if (nin <= 0) {
+        if (fused && (rc = adp_comm_drain(c, 1, S_RHO1, 0))) return rc;
         if (x_in != x_out) CUDA_TRY(c, cudaMemcpyAsync(x_out, x_in, sizeof(double) * c->NV, cudaMemcpyDeviceToDevice, c->stream));
         return ADP_OK;
     }
@@ -1020,33 +1077,38 @@ static int bicg_core(adp_ctx *c, const SrcArgs &src, const double *a, const doub
         const double *v_prev = (peer && (i & 1)) ? c->d_v2 : c->d_v;
         const int pb_v = (peer && !(i & 1)) ? PB_V1 : PB_V0;
         if (i > 1) {
+            // waits for the rho D posted at the end of the previous sweep
             k_update_p<<<adp_grid(c, k_update_p, c->geo.tpp * a_npl), ADP_TILE, 0, c->stream>>>(
-                c->geo, c->d_scal, slot, slot_prev, c->d_r, v_prev, (i == 2) ? c->d_rs : c->d_p, c->d_p, a_klo, a_npl);
+                c->geo, c->d_scal, slot, slot_prev, c->d_r, v_prev, (i == 2) ? c->d_rs : c->d_p, c->d_p, a_klo, a_npl, wait(1, slot));
             LAUNCH_CHECK(c);
         }
         if (multi && !peer && (rc = adp_comm_halo(c, p_cur, 1))) return rc;
+        // first sweep: waits for P's rho (the barrier behind P's pushed boundary planes)
         k_spmv_dot<<<adp_grid(c, k_spmv_dot, nt), ADP_TILE, 0, c->stream>>>(c->geo, a, p_cur, c->d_rs, v_cur,
-                                                                          peer ? adp_push(c, pb_v) : none, make_red(c, S_RSV));
+                                                                          peer ? adp_push(c, pb_v) : none, red(S_RSV),
+                                                                          (i == 1) ? wait(1, S_RHO1) : nowait);
         LAUNCH_CHECK(c);
-        if (multi && (rc = adp_comm_allreduce_sum(c, c->d_scal + S_RSV, 1))) return rc;
+        if (multi && !fused && (rc = adp_comm_allreduce_sum(c, c->d_scal + S_RSV, 1))) return rc;
         if ((multi && !peer) || !c->fuse_st) {
+            if (fused && (rc = adp_comm_drain(c, 1, S_RSV, 0))) return rc;
             k_s<<<adp_grid(c, k_s, nt), ADP_TILE, 0, c->stream>>>(c->geo, c->d_scal, slot, r_cur, v_cur, c->d_s);
             LAUNCH_CHECK(c);
-            if (multi && (rc = adp_comm_halo(c, c->d_s, 1))) return rc;
-            k_t<<<adp_grid(c, k_t, nt), ADP_TILE, 0, c->stream>>>(c->geo, a, c->d_s, c->d_t, make_red(c, S_TT, S_TS));
+            if (multi && !peer && (rc = adp_comm_halo(c, c->d_s, 1))) return rc;
+            k_t<<<adp_grid(c, k_t, nt), ADP_TILE, 0, c->stream>>>(c->geo, a, c->d_s, c->d_t, red(S_TT, S_TS));
             LAUNCH_CHECK(c);
         } else {
             // s = r - alpha v on the fly, on ghost planes from the pushed r and v
-            k_st<<<adp_grid(c, k_st, nt), ADP_TILE, 0, c->stream>>>(c->geo, a, slot, r_cur, v_cur, c->d_s, c->d_t, make_red(c, S_TT, S_TS));
+            k_st<<<adp_grid(c, k_st, nt), ADP_TILE, 0, c->stream>>>(c->geo, a, slot, r_cur, v_cur, c->d_s, c->d_t, red(S_TT, S_TS),
+                                                                  wait(1, S_RSV));
             LAUNCH_CHECK(c);
         }
-        if (multi && (rc = adp_comm_allreduce_sum(c, c->d_scal + S_TT, 2))) return rc;
+        if (multi && !fused && (rc = adp_comm_allreduce_sum(c, c->d_scal + S_TT, 2))) return rc;
         const int last = (i == nin) ? 1 : 0;
         k_update_xr<<<adp_grid(c, k_update_xr, nt), ADP_TILE, 0, c->stream>>>(
             c->geo, slot, last, (i == 1) ? x_in : x_out, x_out, p_cur, c->d_s, c->d_t, c->d_rs, c->d_r,
-            peer ? (last ? push_x : adp_push(c, PB_R)) : none, make_red(c, slot_next));
+            peer ? (last ? push_x : adp_push(c, PB_R)) : none, red(slot_next), wait(2, S_TT, S_TS));
         LAUNCH_CHECK(c);
-        if (!last && multi && (rc = adp_comm_allreduce_sum(c, c->d_scal + slot_next, 1))) return rc;
+        if (!last && multi && !fused && (rc = adp_comm_allreduce_sum(c, c->d_scal + slot_next, 1))) return rc;
     }
     return ADP_OK;
 }
@@ -1093,7 +1155,7 @@ int adp_k_spmv(adp_ctx *c, int g, const double *d_x, double *d_v)
 {
     int rc;
     if (c->nranks > 1 && (rc = adp_comm_halo(c, const_cast<double *>(d_x), 1))) return rc;
-    k_spmv_dot<<<adp_grid(c, k_spmv_dot, c->geo.ntiles), ADP_TILE, 0, c->stream>>>(c->geo, a_of(c, g), d_x, nullptr, d_v, Push(), make_red(c, S_TMP1));
+    k_spmv_dot<<<adp_grid(c, k_spmv_dot, c->geo.ntiles), ADP_TILE, 0, c->stream>>>(c->geo, a_of(c, g), d_x, nullptr, d_v, Push(), make_red(c, S_TMP1), MailWait());
     LAUNCH_CHECK(c);
     return ADP_OK;
 }
@@ -1202,20 +1264,20 @@ int adp_k_bench_one(adp_ctx *c, int what, int g)
     const double *a = a_of(c, g);
     switch (what) {
     case 0:
-        k_spmv_dot<<<adp_grid(c, k_spmv_dot, nt), ADP_TILE, 0, c->stream>>>(c->geo, a, c->d_p, c->d_rs, c->d_v, Push(), make_red(c, S_TMP1));
+        k_spmv_dot<<<adp_grid(c, k_spmv_dot, nt), ADP_TILE, 0, c->stream>>>(c->geo, a, c->d_p, c->d_rs, c->d_v, Push(), make_red(c, S_TMP1), MailWait());
         break;
     case 8:
-        k_spmv_dot<<<adp_grid(c, k_spmv_dot, nt), ADP_TILE, 0, c->stream>>>(c->geo, a, c->d_p, nullptr, c->d_v, Push(), make_red(c, S_TMP1));
+        k_spmv_dot<<<adp_grid(c, k_spmv_dot, nt), ADP_TILE, 0, c->stream>>>(c->geo, a, c->d_p, nullptr, c->d_v, Push(), make_red(c, S_TMP1), MailWait());
         break;
     case 1:
-        k_st<<<adp_grid(c, k_st, nt), ADP_TILE, 0, c->stream>>>(c->geo, a, S_RHO1, c->d_r, c->d_v, c->d_s, c->d_t, make_red(c, S_TMP0, S_TMP1));
+        k_st<<<adp_grid(c, k_st, nt), ADP_TILE, 0, c->stream>>>(c->geo, a, S_RHO1, c->d_r, c->d_v, c->d_s, c->d_t, make_red(c, S_TMP0, S_TMP1), MailWait());
         break;
     case 2:
         k_update_xr<<<adp_grid(c, k_update_xr, nt), ADP_TILE, 0, c->stream>>>(c->geo, S_RHO1, 0, c->d_stage, c->d_stage, c->d_p, c->d_s, c->d_t, c->d_rs,
-                                                      c->d_S, Push(), make_red(c, S_TMP1));
+                                                      c->d_S, Push(), make_red(c, S_TMP1), MailWait());
         break;
     case 3:
-        k_update_p<<<adp_grid(c, k_update_p, nt), ADP_TILE, 0, c->stream>>>(c->geo, c->d_scal, S_RHO0, S_RHO1, c->d_r, c->d_v, c->d_p, c->d_S, 0, c->nzl);
+        k_update_p<<<adp_grid(c, k_update_p, nt), ADP_TILE, 0, c->stream>>>(c->geo, c->d_scal, S_RHO0, S_RHO1, c->d_r, c->d_v, c->d_p, c->d_S, 0, c->nzl, MailWait());
         break;
     case 4: {
         SrcArgs S{};

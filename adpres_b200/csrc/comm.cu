@@ -10,6 +10,7 @@
 #include <cstring>
 
 #include "adp_internal.cuh"
+#include "mail.cuh"
 
 namespace {
 typedef struct ncclComm *ncclComm_t;
@@ -25,6 +26,7 @@ struct Nccl {
     int (*CommDestroy)(ncclComm_t) = nullptr;
     int (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     int (*AllGather)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*Broadcast)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     int (*Send)(const void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     int (*Recv)(void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     int (*GroupStart)() = nullptr;
@@ -46,7 +48,7 @@ bool load_nccl(std::string &err)
     *(void **)(&g_nccl.field) = dlsym(g_nccl.h, name);                      \
     if (!g_nccl.field) { err = std::string("NCCL symbol missing: ") + name; return false; }
     SYM(GetUniqueId, "ncclGetUniqueId") SYM(CommInitRank, "ncclCommInitRank") SYM(CommDestroy, "ncclCommDestroy")
-    SYM(AllReduce, "ncclAllReduce") SYM(AllGather, "ncclAllGather") SYM(Send, "ncclSend") SYM(Recv, "ncclRecv") SYM(GroupStart, "ncclGroupStart")
+    SYM(AllReduce, "ncclAllReduce") SYM(AllGather, "ncclAllGather") SYM(Broadcast, "ncclBroadcast") SYM(Send, "ncclSend") SYM(Recv, "ncclRecv") SYM(GroupStart, "ncclGroupStart")
     SYM(GroupEnd, "ncclGroupEnd") SYM(GetErrorString, "ncclGetErrorString")
 #undef SYM
     g_nccl.ok = true;
@@ -286,18 +288,19 @@ int adp_comm_halo(adp_ctx *c, double *v, int n)
     return ADP_OK;
 }
 
-// Scalar all-reduce over peer memory: ONE warp posts this rank's values into row `rank` of slot
-// (seq % ADP_MAIL_SLOTS) of every rank's mailbox (values, system fence, sequence number) and
-// waits until every row of its own mailbox carries that sequence number; rows are combined in
-// rank order (deterministic).  ~2-3 us instead of ~20 us for an 8-byte ncclAllReduce, and like
-// it a barrier: it completes only after every rank's preceding kernel (and its halo pushes) has.
-// A separate tiny kernel on purpose: inlined into the tails of the streaming kernels this code
-// raised their register count and cost k_st / k_residual 10-13 % (A/B measured).
+// Scalar all-reduce over peer memory as a kernel of its own (the reductions of the outer-iteration tail, the
+// transient glue, ...; inside BiCGSTAB the two halves ride in the producing / consuming kernels, mail.cuh).
+// ONE warp posts this rank's values into row `rank` of slot (seq % ADP_MAIL_SLOTS) of every rank's mailbox
+// (values, release at system scope with the sequence number) and waits until every row of its own mailbox carries
+// that sequence number; rows are combined in rank order (deterministic).  Like ncclAllReduce it is a barrier: it
+// completes only after every rank's preceding kernel (and its halo pushes) has.
+// A rank that waits longer than the timeout never combines the stale row: the result becomes NaN and the sticky
+// S_FAULT slot is raised, which every host synchronisation turns into ADP_ERR_NCCL (ADP_CHECK_FAULT).
 template <bool MAX>
 __global__ void k_mail_allreduce(double *vals, int count, Mail m)
 {
-    // one warp; lane q talks to rank q: posts this rank's values into rank q's mailbox and polls
-    // the row rank q writes into this rank's mailbox -- all ranks in parallel, one fence each way
+    // lane q talks to rank q: posts this rank's values into rank q's mailbox and polls
+    // the row rank q writes into this rank's mailbox -- all ranks in parallel
     const int q = threadIdx.x;
     const unsigned long long seq = *m.seq + 1ull;
     const size_t slot = (size_t)(seq % ADP_MAIL_SLOTS) * m.nranks;
@@ -306,15 +309,19 @@ __global__ void k_mail_allreduce(double *vals, int count, Mail m)
     if (q < m.nranks) {
         volatile double *dst = m.box[q] + (slot + m.rank) * ADP_MAIL_WORDS;
         for (int i = 0; i < count; ++i) dst[i] = mine[i];
-        __threadfence_system();
-        *(volatile unsigned long long *)(dst + (ADP_MAIL_WORDS - 1)) = seq;
-        volatile double *src = m.box[m.rank] + (slot + q) * ADP_MAIL_WORDS;
-        volatile unsigned long long *flag = (volatile unsigned long long *)(src + (ADP_MAIL_WORDS - 1));
+        mail_st_release((unsigned long long *)(dst + (ADP_MAIL_WORDS - 1)), seq);
+        const volatile double *src = m.mine + (slot + q) * ADP_MAIL_WORDS;
+        const unsigned long long *flag = (const unsigned long long *)(m.mine + (slot + q) * ADP_MAIL_WORDS + (ADP_MAIL_WORDS - 1));
         const long long t0 = clock64();
-        while (*flag != seq)
-            if (clock64() - t0 > 8000000000LL) { atomicExch(m.errflag, ADP_ERR_NCCL); break; }   // ~4 s: never hang the GPU
-        __threadfence_system();
-        for (int i = 0; i < count; ++i) got[i] = src[i];
+        bool ok = true;
+        while (mail_ld_acquire(flag) != seq)
+            if (clock64() - t0 > m.timeout) { ok = false; break; }
+        if (ok) {
+            for (int i = 0; i < count; ++i) got[i] = src[i];
+        } else {
+            for (int i = 0; i < count; ++i) got[i] = __longlong_as_double(0x7ff8000000000000LL);
+            *(volatile double *)m.fault = 1.0;
+        }
     }
     __syncwarp();
     // combine in rank order on lane 0 (deterministic)
@@ -322,7 +329,7 @@ __global__ void k_mail_allreduce(double *vals, int count, Mail m)
     for (int r = 0; r < m.nranks; ++r)
         for (int i = 0; i < 4; ++i) {
             const double w = __shfl_sync(0xffffffffu, got[i], r);
-            acc[i] = MAX ? fmax(acc[i], w) : acc[i] + w;
+            acc[i] = MAX ? ((w != w) ? w : fmax(acc[i], w)) : acc[i] + w;     // fmax would swallow the NaN of a timed-out row
         }
     if (q == 0) {
         for (int i = 0; i < count; ++i) vals[i] = acc[i];
@@ -330,10 +337,35 @@ __global__ void k_mail_allreduce(double *vals, int count, Mail m)
     }
 }
 
-static int mail_allreduce(adp_ctx *c, double *d, int count, bool is_max)
+// the wait half alone, for a reduction that was posted by a kernel but whose consumer is not a fused one
+__global__ void k_mail_drain(MailWait w, double *scal)
+{
+    __shared__ double out[2];
+    mail_wait(w.m, w.n, out, scal, w.slot[0], w.slot[1], true);
+}
+
+Mail adp_comm_mail(const adp_ctx *c)
 {
     Mail m;
-    m.box = c->d_mail_table; m.seq = c->d_arseq; m.errflag = c->d_errflag; m.nranks = c->nranks; m.rank = c->rank;
+    m.box = c->d_mail_table; m.mine = c->d_mail; m.seq = c->d_arseq; m.fault = c->d_scal + S_FAULT;
+    m.nranks = c->nranks; m.rank = c->rank;
+    m.timeout = (long long)(c->mail_timeout_s * 1.9e9);      // clock64 runs at the SM clock (<= 1.965 GHz)
+    return m;
+}
+
+int adp_comm_drain(adp_ctx *c, int n, int slot0, int slot1)
+{
+    MailWait w;
+    w.m = adp_comm_mail(c); w.n = n; w.slot[0] = slot0; w.slot[1] = slot1;
+    k_mail_drain<<<1, 32, 0, c->stream>>>(w, c->d_scal);
+    c->launches++;
+    if (cudaPeekAtLastError() != cudaSuccess) { c->err = "k_mail_drain launch failed"; return ADP_ERR_CUDA; }
+    return ADP_OK;
+}
+
+static int mail_allreduce(adp_ctx *c, double *d, int count, bool is_max)
+{
+    const Mail m = adp_comm_mail(c);
     if (count > 4) { c->err = "mail_allreduce: at most 4 values"; return ADP_ERR_USAGE; }
     if (is_max) k_mail_allreduce<true><<<1, 32, 0, c->stream>>>(d, count, m);
     else k_mail_allreduce<false><<<1, 32, 0, c->stream>>>(d, count, m);
@@ -370,6 +402,29 @@ int adp_comm_allreduce_max_nccl(adp_ctx *c, double *d, int count)
     NCCL_TRY(c, g_nccl.AllReduce(d, d, count, ncclFloat64, ncclMax, c->comm->comm, c->stream));
     return ADP_OK;
 }
+// Results back to the host on several ranks: the unchanged Fortran drivers (printers, th_upd's axial march,
+// reactivity) read WHOLE sdata arrays, so by default every rank receives every slab -- rank q broadcasts its owned
+// planes of one node column, the others stage them and copy them to the rows of rank q in their global host
+// column.  Rare (once per outer*() call), so plain NCCL; d_owned = this rank's owned planes of the column.
+int adp_comm_gather_column(adp_ctx *c, double *h_col, const double *d_owned)
+{
+    if (c->nranks == 1) return ADP_OK;
+    const int base = c->nzz / c->nranks, rem = c->nzz % c->nranks;
+    const size_t maxcnt = (size_t)(base + (rem ? 1 : 0)) * c->np;
+    if (!c->d_gather) CUDA_TRY(c, cudaMalloc((void **)&c->d_gather, maxcnt * sizeof(double)));
+    for (int q = 0; q < c->nranks; ++q) {
+        const int k0q = q * base + (q < rem ? q : rem), nz = base + (q < rem ? 1 : 0);
+        const size_t cnt = (size_t)nz * c->np;
+        if (q == c->rank) {
+            NCCL_TRY(c, g_nccl.Broadcast(d_owned, const_cast<double *>(d_owned), cnt, ncclFloat64, q, c->comm->comm, c->stream));
+        } else {
+            NCCL_TRY(c, g_nccl.Broadcast(c->d_gather, c->d_gather, cnt, ncclFloat64, q, c->comm->comm, c->stream));
+            CUDA_TRY(c, cudaMemcpyAsync(h_col + (size_t)k0q * c->np, c->d_gather, cnt * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        }
+    }
+    return ADP_OK;
+}
+
 int adp_comm_chain_recv(adp_ctx *c, double *d, int count)
 {
     if (c->nranks == 1 || c->rank == 0) return ADP_OK;

@@ -134,6 +134,7 @@ extern "C" int adp_asm_pow(adp_ctx *c, int nx, int ny, const int *xdiv, const in
     TRY(adp_k_powdis(c, c->d_stage));
     CUDA_TRY(c, cudaMemcpyAsync(c->h_scal, c->d_scal, S_COUNT * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    ADP_CHECK_FAULT(c);
     if (c->h_scal[S_POW] <= 0.0) { c->err = "ERROR: TOTAL NODES POWER IS ZERO OR LESS"; return ADP_STOP_ZERO_POWER; }
     TRY(adp_k_scale_by_slot(c, c->d_stage, S_POW));
     TRY(column_sums(c, c->d_stage, 0));
@@ -171,6 +172,7 @@ extern "C" int adp_axi_pow(adp_ctx *c, int nz, const int *zdiv, double *faxi, in
     TRY(adp_k_powdis(c, c->d_stage));
     CUDA_TRY(c, cudaMemcpyAsync(c->h_scal, c->d_scal, S_COUNT * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    ADP_CHECK_FAULT(c);
     if (c->h_scal[S_POW] <= 0.0) { c->err = "ERROR: TOTAL NODES POWER IS ZERO OR LESS"; return ADP_STOP_ZERO_POWER; }
     TRY(adp_k_scale_by_slot(c, c->d_stage, S_POW));
     CUDA_TRY(c, cudaMemsetAsync(c->d_res, 0, (size_t)c->nzz * sizeof(double), c->stream));

@@ -362,6 +362,7 @@ extern "C" int adp_th_pline(adp_ctx *c, double pw, double ppow, int form, const 
     TRY(adp_k_powdis(c, c->d_stage));
     CUDA_TRY(c, cudaMemcpyAsync(c->h_scal, c->d_scal, S_COUNT * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    ADP_CHECK_FAULT(c);
     if (c->h_scal[S_POW] <= 0.0) { c->err = "ERROR: TOTAL NODES POWER IS ZERO OR LESS"; return ADP_STOP_ZERO_POWER; }
     TRY(adp_k_scale_by_slot(c, c->d_stage, S_POW));
     k_th_pline<<<(c->np + ADP_TILE - 1) / ADP_TILE, ADP_TILE, 0, c->stream>>>(c->geo, c->d_stage, pw, ppow, form, c->d_nodenf,
@@ -406,11 +407,13 @@ static int th_march(adp_ctx *c, const double *xpline, bool trans, double h, doub
         TRY(adp_comm_allreduce_max_nccl(c, c->d_scal + S_TMP1, 1));
         CUDA_TRY(c, cudaMemcpyAsync(c->h_scal, c->d_scal, S_COUNT * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
         CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+        ADP_CHECK_FAULT(c);
         c->h_flags[0] = (int)c->h_scal[S_TMP1];
     } else {
         CUDA_TRY(c, cudaMemcpyAsync(c->h_flags, c->d_errflag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
         CUDA_TRY(c, cudaMemcpyAsync(c->h_scal, c->d_scal, S_COUNT * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
         CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+        ADP_CHECK_FAULT(c);
     }
     if (th_err) *th_err = c->h_scal[S_TMP0];
     if (c->h_flags[0] == ADP_STOP_STEAM_TABLE) {

@@ -8,26 +8,33 @@ iteration control `%ITER . 10 1e-5 1e-5 5 50` (nin = 10, nac = 5, nupd = 50; the
 
 A "step" is one pass of the reference's `do p = 1, nout` loop body (mod_cmfd.f90:465-496):
 G x (TSrc + bicg(nin)), FSrc, l2norm, [fiss_extrp], Integrate, k-eff, RelE, RelEg and, whenever
-mod(p, nupd) == 0, the SANM nodal update + matrix_setup(0).
+mod(p, nupd) == 0, the SANM nodal update + matrix_setup(0).  The K timed steps are the iterations
+p = P0 .. P0+K-1 of a run that starts from flat flux at p = 1, with P0 placed so that the window holds a
+nodal update (window(): K = 20, nupd = 50 -> p = 31..50); iterations 1 .. P0-1 run untimed.  Both arms
+(and the e2e call) time the SAME iterations of the SAME mesh.
 
-  value   device-resident: K steps enqueued back to back (adp_outer_steps), CUDA events on the
+  value   device-resident: the K steps enqueued back to back (adp_outer_steps), CUDA events on the
           library's stream, max over ranks.
   e2e     the same K steps through the drop-in boundary the Fortran driver uses, with HOST
           (pinned) buffers: one outer() call = adp_set_xs (all cross sections H2D) +
           adp_set_state + adp_matrix_setup(1) + K x adp_outer_iter (scalars D2H, exit test on
           the host) + nodal updates + adp_get_state (flux, fission source D2H) + adp_powdis.
           h2d/d2h bytes are the totals of that call divided by K.
-  roofline  the dominant kernel (BiCGSTAB SpMV + dot, k_spmv_dot) timed alone with CUDA events,
-          algorithmic 72 B/row against the measured HBM peak.
+  roofline  every kernel class timed alone with CUDA events against its algorithmic bytes
+          and the measured HBM peak; the dominant one (largest share of the step) is the headline.
   cpu_baseline  the C oracle (oracle/, a line-by-line port of the Fortran; no Fortran compiler
           exists in the image, so oracle/_ref cannot be built) on 1 host core -- the reference
-          is serial -- on a bounded sample (same radial mesh, 19 of the 190 planes).
+          is serial -- on a bounded sample of the same full mesh: ms per outer iteration and ms per
+          nodal update (the reference's two timed regions, ADPRES.f90:55-81).
 
-N > 1 (torchrun): z-slab decomposition, one rank per GPU, weak scaling: N copies of the core
+N > 1 (torchrun): z-slab decomposition, one rank per GPU.  `value` is weak scaling: N copies of the core
 stacked axially (190 planes per rank, same node sizes); halo planes are pushed by the kernels
 over NVLink peer memory, scalar all-reduces go through peer-memory mailboxes (NCCL fallback).
+Two more objects at N > 1: `parity` (BASELINE configs[2] sliced over the N ranks against the committed
+CPU-oracle fixture) and `strong` (C2', 10.07 M nodes, on 1 GPU and sliced over the N GPUs).
 
-`--impl reference` times the reference algorithm on the host CPU (oracle port, 1 thread).
+`--impl reference` times the reference algorithm on the host CPU (oracle port, 1 thread) on the same
+config: the full mesh, one outer() call, the same timed iterations.
 """
 from __future__ import annotations
 
@@ -74,22 +81,26 @@ def load_c2(stack=1, sample_planes=None):
 
 
 class SlabProblem:
-    """Weak-scaling workload for rank `rank` of `world`: `world` copies of the C2 core stacked
-    axially (190*world planes, same 1 cm x 1 cm x 2 cm nodes) == load_c2(stack=world).  The C ABI
-    takes the GLOBAL sdata arrays, but a rank only ever reads its own z-slab (+2 ghost planes) of
+    """Rank `rank`'s view of a problem made of `stack` copies of `base` on top of each other, every plane of `base`
+    split into `zrefine` planes (same cross sections, zdel / zrefine).  With base = load_c2(sample_planes=19) (one plane
+    per axial assembly): zrefine = 10 is the C2 core, stack = world the weak-scaling workload (one core copy per GPU);
+    zrefine = 22, stack = 1 is C2' (170 x 170 x 418 = 10 073 800 nodes), the strong-scaling workload.
+    The C ABI takes the GLOBAL sdata arrays, but a rank only ever reads its own z-slab (+2 ghost planes) of
     them, so the global arrays are allocated uncommitted (np.empty) and only that plane range is
     filled -- host memory per rank stays at the size of the slab instead of growing with N."""
 
-    def __init__(self, base, world, rank):
+    def __init__(self, base, world, rank, stack=None, zrefine=1):
         from adpres_b200.slab import slab_planes
+        stack = world if stack is None else stack
         self.base, self.world = base, world
         for k in ("mode", "ng", "nmat", "nxx", "nyy", "npl", "bc", "xdel", "ydel", "ystag_smin", "ystag_smax",
                   "xstag_smin", "xstag_smax", "chi", "nout", "nin", "serc", "ferc", "nac", "kern"):
             setattr(self, k, getattr(base, k))
-        self.nzz = base.nzz * world
-        self.nnod = base.nnod * world
+        core = base.nzz * zrefine                                  # planes of one core copy
+        self.nzz = core * stack
+        self.nnod = base.npl * self.nzz
         self.nupd = base.nupd
-        self.zdel = np.tile(base.zdel, world)
+        self.zdel = np.tile(np.repeat(base.zdel / np.float64(zrefine), zrefine), stack)
         npl = base.npl
         self.ix = np.tile(base.ix[:npl], self.nzz)
         self.iy = np.tile(base.iy[:npl], self.nzz)
@@ -98,7 +109,7 @@ class SlabProblem:
         self.k0, self.k1 = k0, k1
         ka, kb = max(0, k0 - 2), min(self.nzz, k1 + 2)
         self.rows = slice(ka * npl, kb * npl)                     # global node range this rank touches
-        planes = np.arange(ka, kb) % base.nzz                     # plane of the stack -> plane of the single core
+        planes = (np.arange(ka, kb) % core) // zrefine            # plane of the stack -> plane of `base`
         src = (planes[:, None] * npl + np.arange(npl)[None, :]).reshape(-1)
         self.mat = np.empty(self.nnod, dtype=np.int32)
         self.mat[self.rows] = base.mat[src]
@@ -179,47 +190,100 @@ def cpu_model():
     return "unknown"
 
 
-def run_oracle_sample(steps, warmup, sample_planes=19):
-    """The reference algorithm (oracle port) on one host core: `warmup + steps` passes of the
-    outer loop body on the bounded sample.  Returns (unknowns/s/iter, seconds, description)."""
+def window(K, W, nupd):
+    """First iteration number P0 of the timed steps p = P0 .. P0+K-1.  The reference's loop counts p from 1 and runs the
+    nodal update when mod(p, nupd) == 0 (mod_cmfd.f90:490); with K < nupd a window right after the W warm-up steps would
+    contain none, so it is placed to END on p = nupd (K = 20, nupd = 50: p = 31..50, exactly one nodal update + matrix_setup(0)
+    inside, same for the GPU arm, the e2e call and the CPU arm).  Iterations 1 .. P0-1 run untimed (the last W are the warm-up)."""
+    return W + 1 if K >= nupd - W else nupd - K + 1
+
+
+def updates_in(P0, K, nupd):
+    return sum(1 for q in range(P0, P0 + K) if q % nupd == 0)
+
+
+def workload_config(world, K, W):
+    """`config` of the JSON line -- the SAME dict for the b200 arm and for --impl reference."""
+    nz = 190 * world
+    P0 = window(K, W, CTL["nupd"])
+    return {"workload": "IAEA-3D refined 1cm x 1cm x 2cm (BASELINE configs[1])" + (f", {world} cores stacked axially" if world > 1 else "") +
+                        f": 170x170x{nz} mesh, {24100 * nz} nodes, 2 groups = {48200 * nz} node-groups, SANM kernel; 190 planes per GPU",
+            "nin": CTL["nin"], "nac": CTL["nac"], "nupd": CTL["nupd"], "parallelism": f"z-slab x{world}",
+            "timed_iterations": [P0, P0 + K - 1], "nodal_updates_in_timed_steps": updates_in(P0, K, CTL["nupd"]),
+            "l2": "inputs larger than L2 (each kernel streams >= 290 MB per launch; 126 MB L2)"}
+
+
+def run_oracle_window(P0, K):
+    """The reference algorithm (oracle port, 1 thread -- the reference is serial) on the FULL C2 mesh: ONE outer() call
+    of P0+K-1 iterations (serc = ferc = 0 never exits); the timed steps are its iterations P0 .. P0+K-1, read from the
+    per-iteration time stamps the oracle keeps next to the reference's own two accumulators (CMFD / nodal update,
+    ADPRES.f90:55-81).  Returns a dict."""
     from oracle import Oracle
-    p = load_c2(sample_planes=sample_planes)
-    o = Oracle(p, nout=CTL["nout"], nin=CTL["nin"], nac=CTL["nac"], nupd=CTL["nupd"], serc=0.0, ferc=0.0)
-    o.matrix_setup(1)
-    o.init_flux()
-    # drive the oracle's own outer() for warmup+steps iterations: serc = ferc = 0 never exits
-    o.set_control(nout=warmup, nin=CTL["nin"], nac=CTL["nac"], nupd=CTL["nupd"], serc=0.0, ferc=0.0)
-    if warmup > 0:
-        o.outer(0)
-    o.set_control(nout=steps, nin=CTL["nin"], nac=CTL["nac"], nupd=CTL["nupd"], serc=0.0, ferc=0.0)
-    o.reset_times()
+    p = load_c2()
+    nit = P0 + K - 1
+    o = Oracle(p, nout=nit, nin=CTL["nin"], nac=CTL["nac"], nupd=CTL["nupd"], serc=0.0, ferc=0.0)
     t0 = time.perf_counter()
     o.outer(0)
-    dt = time.perf_counter() - t0
-    fdm, nod = o.times()
-    units = p.nnod * p.ng * steps
-    desc = (f"IAEA-3D 1 cm radial mesh, axial mesh coarsened to {p.nzz} planes ({p.nnod} nodes x {p.ng} groups), "
-            f"{steps} outer iterations after {warmup} warm-up, nin={CTL['nin']} nac={CTL['nac']} nupd={CTL['nupd']}, "
-            f"CMFD {fdm:.2f} s + nodal {nod:.2f} s, {cpu_model()}")
-    return units / dt, dt, desc
+    total = time.perf_counter() - t0
+    wall, fdm, nod = o.trace_times()
+    assert len(wall) == nit, (len(wall), nit)
+    i0, i1 = P0 - 2, nit - 1                      # end of iteration P0-1 .. end of iteration P0+K-1
+    w0 = wall[i0] if i0 >= 0 else wall[0] - (wall[1] - wall[0])
+    f0 = fdm[i0] if i0 >= 0 else 0.0
+    n0 = nod[i0] if i0 >= 0 else 0.0
+    nupd_in = updates_in(P0, K, CTL["nupd"])
+    dt = wall[i1] - w0
+    units = p.nnod * p.ng * K
+    return {"value": units / dt, "seconds": dt, "total_seconds": total, "ms_per_step": 1e3 * dt / K,
+            "cmfd_ms_per_outer": 1e3 * (fdm[i1] - f0) / K,
+            "nodal_ms_per_update": (1e3 * (nod[i1] - n0) / nupd_in) if nupd_in else None,
+            "nodal_updates": nupd_in, "nnod": int(p.nnod), "ng": int(p.ng), "keff_after": o.state()["Ke"],
+            "sample": f"full BASELINE configs[1] mesh ({p.nxx}x{p.nyy}x{p.nzz}, {p.nnod} nodes x {p.ng} groups), one outer() call of "
+                      f"{nit} iterations from flat flux, timed iterations {P0}..{nit} ({nupd_in} nodal update(s) inside), "
+                      f"nin={CTL['nin']} nac={CTL['nac']} nupd={CTL['nupd']}, {cpu_model()}"}
 
 
-def reference_arm(args, rank, emit):
-    """--impl reference: the reference's CPU implementation of the path (oracle port of the
-    Fortran; oracle/_ref cannot be built without a Fortran compiler), all the threads it can
-    use = 1 (the reference is serial)."""
+def run_oracle_sample(n_outer=3):
+    """cpu_baseline of the b200 arm: a bounded sample (about 30 s) of the same workload on the same full mesh -- one
+    warm-up + `n_outer` timed outer iterations and ONE nodal update (nodal_upd: SANM sweep + matrix_setup(0),
+    mod_cmfd.f90:339-383), each timed on its own; combined with the step's mix (one update per nupd iterations)."""
+    from oracle import Oracle
+    p = load_c2()
+    o = Oracle(p, nout=n_outer + 1, nin=CTL["nin"], nac=CTL["nac"], nupd=10 ** 9, serc=0.0, ferc=0.0)
+    o.outer(0)
+    wall, fdm, nod = o.trace_times()
+    cmfd = (wall[-1] - wall[0]) / n_outer
+    t0 = time.perf_counter()
+    rc = o.nodal_upd(1)
+    nodal = time.perf_counter() - t0
+    per_step = cmfd + nodal / CTL["nupd"]
+    return {"value": p.nnod * p.ng / per_step, "unit": UNIT, "cores": 1, "kind": "port",
+            "cmfd_ms_per_outer": 1e3 * cmfd, "nodal_ms_per_update": 1e3 * nodal, "nodal_update_status": int(rc),
+            "seconds": wall[-1] - wall[0] + nodal, "host_cores_available": host_cores(),
+            "sample": f"full BASELINE configs[1] mesh ({p.nnod} nodes x {p.ng} groups): {n_outer} outer iterations after 1 warm-up "
+                      f"+ 1 nodal update, value = unknowns / (cmfd + nodal/nupd), nin={CTL['nin']} nupd={CTL['nupd']}, "
+                      f"C oracle (port of the Fortran; no Fortran compiler in the image), 1 thread, {cpu_model()}"}
+
+
+def reference_arm(args, rank, world, emit):
+    """--impl reference: the reference's CPU implementation of the path (oracle port of the Fortran; oracle/_ref cannot
+    be built without a Fortran compiler), all the threads it can use = 1 (the reference is serial), on the b200 arm's
+    config: same mesh, same %ITER, same timed iterations.  At N > 1 (weak scaling: N stacked cores) rank 0 times ONE of
+    the N core copies -- the bounded sample of that workload; the cost per unknown of the serial code does not depend on N."""
     if rank != 0:
         return
-    val, dt, desc = run_oracle_sample(args.steps, args.warmup)
+    K, W = args.steps, args.warmup
+    P0 = window(K, W, CTL["nupd"])
+    r = run_oracle_window(P0, K)
     line = {
-        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "IAEA-3D refined 1cm x 1cm x 2cm (170x170x190, 4.579M nodes, 2 groups), SANM; "
-                               "CPU arm runs a bounded sample of it", "nin": CTL["nin"], "nac": CTL["nac"], "nupd": CTL["nupd"]},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": "port", "sample": desc},
-        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": world, "steps": K,
+        "warmup": W, "ms_per_step": r["ms_per_step"] * world, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(world, K, W),
+        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": 1, "kind": "port", "sample": r["sample"],
+                         "cmfd_ms_per_outer": r["cmfd_ms_per_outer"], "nodal_ms_per_update": r["nodal_ms_per_update"],
+                         "seconds": r["seconds"], "total_seconds": r["total_seconds"], "host_cores_available": host_cores()},
+        "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "keff_after": r["keff_after"],
     }
     emit(line)
 
@@ -228,6 +292,45 @@ def pinned(a):
     import torch
     t = torch.from_numpy(np.ascontiguousarray(a.ravel(order="K"))).pin_memory()
     return t, t.numpy().reshape(a.shape, order="F" if a.flags.f_contiguous else "C")
+
+
+def ncu_traffic(kernel):
+    """dram read+write bytes per launch of `kernel` from the committed ncu --set full capture, ONLY if that capture was
+    taken from the kernel source that is in the tree now (profiles/ncu_traffic.json records the md5 of csrc/cmfd_kernels.cu;
+    tools/ncu_summary.py writes it).  Otherwise None: a literal would go stale with the next kernel edit."""
+    import hashlib
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        rec = json.load(open(path))
+        md5 = hashlib.md5(open(os.path.join(ROOT, "adpres_b200", "csrc", "cmfd_kernels.cu"), "rb").read()).hexdigest()
+        if rec.get("cmfd_kernels_md5") != md5:
+            return None
+        return rec["kernels"].get(kernel, {}).get("dram_bytes_per_launch")
+    except Exception:
+        return None
+
+
+def c3_parity(world, rank, local_rank, uid, capi):
+    """Multi-GPU parity inside the bench line: BASELINE configs[2] (IAEA-3D, 4 x 4 nodes per assembly, 190 planes,
+    183 160 nodes, reference-default nin = 2) sliced over the N ranks, solved to the fixture's serc = ferc and compared with
+    the committed CPU-oracle result tests/golden/c3_oracle_result.json (the JSON is read; oracle/ is not imported)."""
+    from adpres_b200.deck import Problem
+    ref = json.load(open(os.path.join(ROOT, "tests", "golden", "c3_oracle_result.json")))
+    with open(os.path.join(ROOT, "tests", "golden", "IAEA3Ds.spec.json")) as fh:
+        p = Problem.from_spec(json.load(fh)).refine(xdiv=ref["xdiv"], ydiv=ref["ydiv"], zdiv=ref["zdiv"])
+    s = capi.Solver(p, device=local_rank, nranks=world, rank=rank, uid=uid, nout=30000, serc=ref["serc"], ferc=ref["serc"])
+    t0 = time.perf_counter()
+    rc, n = s.outer(0)
+    dt = time.perf_counter() - t0
+    ke = s.state()["Ke"]
+    fasm, _, _ = s.asm_pow()                      # all-reduced over the slabs: every rank holds the whole map
+    asm_ref = np.array(ref["asm_power"])
+    nz = asm_ref > 0
+    s.close()
+    return {"config": "C3 (BASELINE configs[2]): 34x34x190, 183160 nodes, nin=2 nupd=104, z-slabs over %d GPUs, serc=ferc=%g" % (world, ref["serc"]),
+            "status": int(rc), "outers": int(n), "oracle_outers": int(ref["outers"]), "keff": ke, "keff_pcm": abs(ke - ref["keff"]) * 1e5,
+            "asm_power_rel": float(np.abs(fasm[nz] / asm_ref[nz] - 1).max()), "seconds": dt,
+            "reference": "tests/golden/c3_oracle_result.json (CPU oracle, tools/c3_oracle.py)"}
 
 
 def main():
@@ -239,12 +342,13 @@ def main():
         os.write(real_stdout, (json.dumps(line) + "\n").encode())
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-solve", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="N > 1: skip the C3 parity solve and the C2' strong-scaling leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
 
@@ -252,7 +356,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
-        reference_arm(args, rank, emit)
+        reference_arm(args, rank, world, emit)
         return
 
     import torch
@@ -261,21 +365,32 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the hot path has no CPU fallback")
     torch.cuda.set_device(local_rank)
-    uid = None
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def new_uid():
+        """a fresh NCCL unique id for one more Solver spanning all ranks"""
         buf = (capi.C.c_ubyte * 128)()
         if rank == 0:
             assert capi.load().adp_comm_unique_id(buf) == 0
         t = torch.tensor(list(bytes(buf)), dtype=torch.uint8, device="cuda")
         dist.broadcast(t, 0)
-        uid = bytes(t.cpu().tolist())
+        return bytes(t.cpu().tolist())
+    uid = None
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        uid = new_uid()
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
     # nvidia-smi takes driver locks while it starts up (kernel launches stall for tens of ms):
     # start the sampler now, long before the timed region, and let it reach its steady loop
@@ -283,35 +398,38 @@ def main():
     sampler.start()
 
     # ---------------------------------------------------------------- problem
-    p = load_c2() if world == 1 else SlabProblem(load_c2(), world, rank)
+    base19 = load_c2(sample_planes=19) if world > 1 else None
+    p = load_c2() if world == 1 else SlabProblem(base19, world, rank, stack=world, zrefine=10)
     s = capi.Solver(p, device=local_rank, nranks=world, rank=rank, uid=uid, **CTL)
     units_per_step = p.nnod * p.ng
     N_own = (s.k1 - s.k0) * p.npl
-    s.matrix_setup(1)
-    s.init_flux()
-    s.outer_begin(capi.MODE_FORWARD)
     W, K = args.warmup, args.steps
+    P0 = window(K, W, CTL["nupd"])
+    n_upd = updates_in(P0, K, CTL["nupd"])
+
+    def timed_steps(sv, units):
+        """iterations 1 .. P0-1 untimed (>= W warm-up steps), then K timed steps p = P0 .. P0+K-1 on the device"""
+        sv.matrix_setup(1)
+        sv.init_flux()
+        sv.outer_begin(capi.MODE_FORWARD)
+        sv.outer_steps(capi.MODE_FORWARD, 1, P0 - 1)
+        barrier()
+        l0 = sv.launch_count()
+        sv.timer_start()
+        rc_, ke_, ser_, fer_ = sv.outer_steps(capi.MODE_FORWARD, P0, K)
+        ms_ = sv.timer_stop()
+        barrier()
+        assert rc_ == 0 and np.isfinite(ke_), (rc_, ke_)
+        return max_over_ranks(ms_), sv.launch_count() - l0, ke_
 
     # ---------------------------------------------------------------- value (device resident)
-    s.outer_steps(capi.MODE_FORWARD, 1, W)
     t_wait = time.time()
     while not sampler.lines and time.time() - t_wait < 5.0:
         time.sleep(0.05)
     n_before = len(sampler.lines)
-    barrier()
-    l0 = s.launch_count()
-    s.timer_start()
-    rc, ke, ser, fer = s.outer_steps(capi.MODE_FORWARD, W + 1, K)
-    ms = s.timer_stop()
-    barrier()
-    launches = s.launch_count() - l0
+    ms, launches, ke = timed_steps(s, units_per_step)
     time.sleep(0.12)                       # let the 100 ms sampler take one more reading of the loaded state
     n_after = len(sampler.lines)
-    assert rc == 0 and np.isfinite(ke), (rc, ke)
-    if world > 1:
-        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
     value = units_per_step * K / (ms * 1e-3)
 
     # ---------------------------------------------------------------- e2e (public API, host buffers)
@@ -336,8 +454,13 @@ def main():
         for k in ("D", "sigr", "nuf", "sigf", "sigs", "dc", "exsrc"):
             hx[k] = host_buffer(getattr(p, k))
         hx["chi"] = np.asfortranarray(p.chi)
-        st0 = s.state() if world == 1 else None
+        # the state after iteration P0-1 (the warm-up of this leg), in host buffers
+        s.matrix_setup(1)
+        s.init_flux()
+        s.outer_begin(capi.MODE_FORWARD)
+        s.outer_steps(capi.MODE_FORWARD, 1, P0 - 1)
         if world == 1:
+            st0 = s.state()
             f0_h, fs0_h = host_buffer(st0["f0"]), host_buffer(st0["fs0"])
             ke0 = st0["Ke"]
         else:
@@ -368,26 +491,22 @@ def main():
             s._chk(L.adp_powdis(s.h, d(pw_out), 0))
             return ke_.value
 
-        one_call(W, 1)
+        one_call(max(W, 3), P0 - max(W, 3))       # warm-up of the host path (same state: dn is still zero before p = nupd)
         barrier()
         t0 = time.perf_counter()
         s.timer_start()
-        ke_e2e = one_call(K, W + 1)
+        ke_e2e = one_call(K, P0)
         ms_e2e_dev = s.timer_stop()
         barrier()
-        wall = time.perf_counter() - t0
-        if world > 1:
-            t = torch.tensor([wall], dtype=torch.float64, device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            wall = float(t.item())
+        wall = max_over_ranks(time.perf_counter() - t0)
         nd, G = N_own, p.ng
         h2d = 8 * (nd * (4 * G + G * G + 6 * G + G) + p.nmat * G) + 8 * nd * (G + 1)   # XS + dc + exsrc + chi ; f0, fs0
         d2h = 8 * nd * (G + 1) + 8 * nd + 8 * 18 * K                                     # f0, fs0 ; power ; scalars per step
         e2e = {"value": units_per_step * K / wall, "unit": UNIT, "h2d_bytes_per_step": int(h2d * world / K),
                "d2h_bytes_per_step": int(d2h * world / K), "ms_per_step": 1e3 * wall / K,
-               "device_ms_per_step": ms_e2e_dev / K, "keff_after": ke_e2e,
+               "device_ms_per_step": ms_e2e_dev / K, "keff_after": ke_e2e, "nodal_updates_inside": n_upd,
                "what": "one outer() call through the C ABI with pinned host buffers: adp_set_xs + adp_set_state + "
-                       "adp_matrix_setup + K x adp_outer_iter (+ adp_nodal_upd every nupd) + adp_get_state + adp_powdis"}
+                       "adp_matrix_setup + K x adp_outer_iter (+ adp_nodal_upd when mod(p, nupd) = 0) + adp_get_state + adp_powdis"}
 
     # ---------------------------------------------------------------- roofline of the dominant kernel
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -398,40 +517,43 @@ def main():
     kern = {}
     rows = N_own
     G, nin = p.ng, CTL["nin"]
-    # (name, bench id, algorithmic bytes/row per SURVEY.md 8(d) BiCGSTAB phase table, launches per outer iteration,
-    #  dram bytes per launch from the committed ncu --set full capture profiles/r01_ncu_full.txt at the N = 1 size)
-    table = (("k_st (C: s = r - alpha v on the fly, t = A s, (t,t), (t,s))", 1, 88.0, G * nin, 391.76e6),
-             ("k_spmv_dot (B: v = A p, (rs,v))", 0, 80.0, G * nin, 360.72e6),
-             ("k_spmv (plain v = A p, no dot product)", 8, 72.0, 0, 322.52e6),
-             ("k_update_xr (D: x, r update, rho)", 2, 56.0, G * nin, 226.82e6),
-             ("k_update_p (A: p update)", 3, 32.0, G * (nin - 1), 126.46e6),
-             ("k_residual (P: source + residual)", 4, 8.0 * (7 + 1 + 1 + 2 * (G - 1) + 1 + 1) + 4.0, G, 491.38e6),
-             ("k_fsrc_norms (F: fission source + norms)", 5, 8.0 * (3 * G + 2), 1, 286.86e6))
-    for name, what, bytes_per_row, per_step, traffic in table:
+    # (name, bench id, algorithmic bytes/row per SURVEY.md 8(d) BiCGSTAB phase table, launches per outer iteration)
+    table = (("k_st (C: s = r - alpha v on the fly, t = A s, (t,t), (t,s))", 1, 88.0, G * nin),
+             ("k_spmv_dot (B: v = A p, (rs,v))", 0, 80.0, G * nin),
+             ("k_spmv (plain v = A p, no dot product)", 8, 72.0, 0),
+             ("k_update_xr (D: x, r update, rho)", 2, 56.0, G * nin),
+             ("k_update_p (A: p update)", 3, 32.0, G * (nin - 1)),
+             ("k_residual (P: source + residual)", 4, 8.0 * (7 + 1 + 1 + 2 * (G - 1) + 1 + 1) + 4.0, G),
+             ("k_fsrc_norms (F: fission source + norms)", 5, 8.0 * (3 * G + 2), 1))
+    for name, what, bytes_per_row, per_step in table:
         kms = s.bench_kernel(what, 20)
         kern[name] = {"ms": kms, "alg_bytes_per_row": bytes_per_row, "GBps": rows * bytes_per_row / (kms * 1e-3) / 1e9,
                       "frac": rows * bytes_per_row / (kms * 1e-3) / 1e9 / peak, "launches_per_step": per_step,
                       "ms_per_step": kms * per_step,
-                      "ncu_dram_bytes_per_launch": traffic if (world == 1 and rows == 4579000) else None}
+                      "ncu_dram_bytes_per_launch": ncu_traffic(name.split(" ")[0]) if (world == 1 and rows == 4579000) else None}
     nodal_ms = s.bench_kernel(7, 3)
-    kern["nodal update (source + 3 node-direction + 3 surface launches)"] = {
+    kern["nodal update (source + per-direction two-node kernels)"] = {
         "ms": nodal_ms, "alg_bytes_per_node": 8.0 * (41 * G + G ** 2), "launches_per_step": 1.0 / CTL["nupd"],
-        "GBps": rows * 8.0 * (41 * G + G ** 2) / (nodal_ms * 1e-3) / 1e9, "ms_per_step": nodal_ms / CTL["nupd"]}
-    # the dominant kernel = largest share of the step (agrees with the committed launch list
-    # profiles/r01_launches_summary.txt: k_st 20 %, k_spmv_dot 19 %)
+        "GBps": rows * 8.0 * (41 * G + G ** 2) / (nodal_ms * 1e-3) / 1e9,
+        "frac": rows * 8.0 * (41 * G + G ** 2) / (nodal_ms * 1e-3) / 1e9 / peak, "ms_per_step": nodal_ms / CTL["nupd"]}
+    # the dominant kernel = largest share of the step (agrees with the committed launch list under profiles/)
     dom_name = max((k for k in kern if "alg_bytes_per_row" in kern[k]), key=lambda k: kern[k]["ms_per_step"])
     dom = kern[dom_name]
     roofline = {"bound": "hbm", "kernel": dom_name.split(" ")[0], "achieved": dom["GBps"], "peak": peak, "unit": "GB/s",
-                "frac": dom["frac"], "traffic": dom["ncu_dram_bytes_per_launch"], "traffic_unit": "bytes/launch (ncu dram read+write)",
+                "frac": dom["frac"], "traffic": dom["ncu_dram_bytes_per_launch"],
+                "traffic_unit": "bytes/launch (ncu dram read+write, profiles/ncu_traffic.json; null = no capture of the kernel source in the tree)",
                 "alg_bytes_per_launch": rows * dom["alg_bytes_per_row"], "ms_per_launch": dom["ms"], "peak_source": peak_src,
                 "spmv_on_72B_basis": {"k_spmv_dot": rows * SPMV_BYTES_PER_ROW / (kern["k_spmv_dot (B: v = A p, (rs,v))"]["ms"] * 1e-3) / 1e9 / peak,
                                       "k_spmv": kern["k_spmv (plain v = A p, no dot product)"]["frac"]},
                 "kernels": kern}
-    # whole outer iteration: SURVEY.md 8(d): bicg 8(8+32 nin) + TSrc 8(2(G-1)+4) + tail 8(3G+4)/G per node-group row
+    # whole outer iteration: SURVEY.md 8(d): bicg 8(8+32 nin) + TSrc 8(2(G-1)+4) + tail 8(3G+4)/G per node-group row,
+    # plus the nodal updates inside the timed steps at 8(41G+G^2) per node
     row_bytes = 8.0 * (8 + 32 * CTL["nin"]) + 8.0 * (2 * (p.ng - 1) + 4) + 8.0 * (3 * p.ng + 4) / p.ng
-    step_gbps = (units_per_step / world) * row_bytes / (ms * 1e-3 / K) / 1e9
-    roofline["outer_iteration"] = {"alg_bytes_per_row": row_bytes, "GBps_per_gpu": step_gbps, "frac": step_gbps / peak,
-                                   "note": "includes the nodal updates that fall inside the timed steps"}
+    step_bytes = (units_per_step / world) * row_bytes + n_upd / K * (p.nnod / world) * 8.0 * (41 * G + G ** 2)
+    step_gbps = step_bytes / (ms * 1e-3 / K) / 1e9
+    roofline["outer_iteration"] = {"alg_bytes_per_row": row_bytes, "alg_bytes_per_step_per_gpu": step_bytes, "GBps_per_gpu": step_gbps,
+                                   "frac": step_gbps / peak,
+                                   "note": f"timed iterations {P0}..{P0 + K - 1} contain {n_upd} nodal update(s) + matrix_setup(0)"}
 
     # ---------------------------------------------------------------- seconds to k-eff convergence (N = 1)
     solve = None
@@ -446,29 +568,57 @@ def main():
                  "serc": CTL["serc"], "ferc": CTL["ferc"], "unknowns": units_per_step,
                  "what": "adp_outer(): full eigenvalue solve from flat flux incl. nodal updates, per-iteration exit test on the host"}
         s3.close()
+    clocks = sampler.stop()
+    clocks["samples_during_value_region"] = max(0, n_after - n_before)
+    s.close()
+    del s
+
+    # ---------------------------------------------------------------- N > 1: parity and strong scaling
+    parity = strong = None
+    if world > 1 and not args.no_extras:
+        parity = c3_parity(world, rank, local_rank, new_uid(), capi)
+        # strong scaling: C2' (170 x 170 x 418 = 10 073 800 nodes, BASELINE north star ">= 10 M nodes") on 1 GPU (rank 0
+        # alone, the others wait) and sliced over the N ranks; same %ITER, same timed iterations
+        n1_ms = None
+        if rank == 0:
+            s1 = capi.Solver(SlabProblem(base19, 1, 0, stack=1, zrefine=22), device=local_rank, **CTL)
+            s1.matrix_setup(1); s1.init_flux(); s1.outer_begin(capi.MODE_FORWARD)
+            s1.outer_steps(capi.MODE_FORWARD, 1, P0 - 1)
+            torch.cuda.synchronize()
+            s1.timer_start()
+            rc1, ke1, _, _ = s1.outer_steps(capi.MODE_FORWARD, P0, K)
+            n1_ms = s1.timer_stop() / K
+            assert rc1 == 0 and np.isfinite(ke1)
+            s1.close()
+        n1_ms = max_over_ranks(n1_ms if n1_ms is not None else 0.0)
+        pN = SlabProblem(base19, world, rank, stack=1, zrefine=22)
+        sN = capi.Solver(pN, device=local_rank, nranks=world, rank=rank, uid=new_uid(), **CTL)
+        msN, _, keN = timed_steps(sN, pN.nnod * pN.ng)
+        sN.close()
+        strong = {"config": "C2' IAEA-3D 1cm x 1cm x 0.91cm: 170x170x418 = 10073800 nodes x 2 groups, nin=10 nupd=50, "
+                            f"z-slabs over {world} GPUs ({pN.k1 - pN.k0} planes on rank {rank})",
+                  "ms_per_step": msN / K, "n1_ms_per_step": n1_ms, "speedup_vs_n1": n1_ms / (msN / K),
+                  "unknowns_per_s": pN.nnod * pN.ng * K / (msN * 1e-3), "timed_iterations": [P0, P0 + K - 1], "keff_after": keN,
+                  "limiter": "3 global reductions + 2 halo planes per BiCGSTAB sweep (mod_cmfd.f90:1229-1240): "
+                             f"{(3 * CTL['nin'] + 1) * 2 + 2} barrier points per step, fixed cost independent of the slab size"}
 
     # ---------------------------------------------------------------- CPU baseline (rank 0, N = 1)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, dt, desc = run_oracle_sample(steps=30, warmup=2)
-        cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port", "sample": desc, "seconds": dt,
-               "host_cores_available": host_cores()}
+        cpu = run_oracle_sample()
 
-    clocks = sampler.stop()
-    clocks["samples_during_value_region"] = max(0, n_after - n_before)
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic",
-            "config": {"workload": f"IAEA-3D refined 1cm x 1cm x 2cm" + (f", {world} cores stacked axially" if world > 1 else "") +
-                                   f" ({p.nxx}x{p.nyy}x{p.nzz} mesh, {p.nnod} nodes, {p.ng} groups = {units_per_step} "
-                                   f"node-groups), SANM kernel; {s.k1 - s.k0} planes per GPU",
-                       "nin": CTL["nin"], "nac": CTL["nac"], "nupd": CTL["nupd"], "parallelism": f"z-slab x{world}",
-                       "l2": "inputs larger than L2 (each kernel streams >= 290 MB per launch; 126 MB L2)",
-                       "keff_after_steps": ke},
+            "data": "synthetic", "config": workload_config(world, K, W),
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "solve": solve,
+            "keff_after_steps": ke,
         }
+        if parity is not None:
+            line["parity"] = parity
+        if strong is not None:
+            line["strong"] = strong
         emit(line)
     if world > 1:
         dist.barrier()

@@ -43,6 +43,11 @@ module adpres_b200
       import; type(c_ptr), value :: ctx
       real(c_double), intent(in) :: D(*), sigr(*), nuf(*), sigf(*), sigs(*), chi(*), dc(*), exsrc(*)
     end function
+    !> adp_set_xs reading only the arrays whose bit is set in mask (0 D, 1 sigr, 2 nuf, 3 sigf, 4 sigs, 5 chi, 6 dc, 7 exsrc)
+    integer(c_int) function adp_set_xs_mask(ctx, mask, D, sigr, nuf, sigf, sigs, chi, dc, exsrc) bind(C, name="adp_set_xs_mask")
+      import; type(c_ptr), value :: ctx; integer(c_int), value :: mask
+      real(c_double), intent(in) :: D(*), sigr(*), nuf(*), sigf(*), sigs(*), chi(*), dc(*), exsrc(*)
+    end function
     integer(c_int) function adp_set_control(ctx, nout, nin, nac, nupd, serc, ferc, kern) bind(C, name="adp_set_control")
       import; type(c_ptr), value :: ctx
       integer(c_int), value :: nout, nin, nac, nupd, kern
@@ -91,6 +96,14 @@ module adpres_b200
     end function
     integer(c_int) function adp_get_state(ctx, f0, fs0, s0, Ke) bind(C, name="adp_get_state")
       import; type(c_ptr), value :: ctx; real(c_double), intent(out) :: f0(*), fs0(*), s0(*), Ke
+    end function
+    !> adp_get_state writing only the arrays whose bit is set in mask (0 f0, 1 fs0, 2 s0)
+    integer(c_int) function adp_get_state_mask(ctx, mask, f0, fs0, s0, Ke) bind(C, name="adp_get_state_mask")
+      import; type(c_ptr), value :: ctx; integer(c_int), value :: mask
+      real(c_double), intent(out) :: f0(*), fs0(*), s0(*), Ke
+    end function
+    type(c_ptr) function adp_last_error(ctx) bind(C, name="adp_last_error")
+      import; type(c_ptr), value :: ctx
     end function
     integer(c_int) function adp_set_state(ctx, f0, fs0, Ke) bind(C, name="adp_set_state")
       import; type(c_ptr), value :: ctx; real(c_double), intent(in) :: f0(*), fs0(*); real(c_double), value :: Ke
@@ -200,45 +213,96 @@ contains
     if (c_associated(ctx)) return
     ierr = adp_create(ctx, -1_c_int)      ! device = LOCAL_RANK (one process per GPU), else 0
     if (ierr /= 0) stop 'adpres_b200: no CUDA device (there is no CPU fallback)'
-    ierr = adp_comm_init_env(ctx)
-    if (ierr /= 0) stop 'adpres_b200: multi-GPU initialisation failed'
+    ierr = adp_comm_init_env(ctx)         ! ADP_NRANKS|WORLD_SIZE > 1: needs ADP_UID_FILE or ADP_JOB_ID|MASTER_PORT
+    call gpu_check(ierr, 'adp_comm_init_env')
     allocate(ysmin(nyy), ysmax(nyy), xsmin(nxx), xsmax(nxx))
     do i = 1, nyy; ysmin(i) = ystag(i)%smin; ysmax(i) = ystag(i)%smax; end do
     do i = 1, nxx; xsmin(i) = xstag(i)%smin; xsmax(i) = xstag(i)%smax; end do
     bc = (/ xeast, xwest, ynorth, ysouth, zbott, ztop /)
     ierr = adp_set_geometry(ctx, nxx, nyy, nzz, nnod, ng, nmat, ix, iy, iz, ysmin, ysmax, xsmin, xsmax, &
                             xdel, ydel, zdel, bc, mat)
-    if (ierr /= 0) stop 'adpres_b200: adp_set_geometry failed'
+    call gpu_check(ierr, 'adp_set_geometry')
   end subroutine gpu_init
 
+  !> Every adp_* call returns 0, a positive code for one of the reference's own STOP conditions (handled where it can
+  !! occur) or a negative code for a CUDA / NCCL / usage error.  A negative code is never survivable: the device state is
+  !! undefined, so print the library's message and STOP -- never iterate on stale scalars.
+  subroutine gpu_check(ierr, what)
+    integer(c_int), intent(in) :: ierr
+    character(len=*), intent(in) :: what
+    character(kind=c_char), pointer :: msg(:)
+    type(c_ptr) :: cmsg
+    integer :: i
+    if (ierr >= 0) return
+    write(*,'(A,A,A,I0)') ' adpres_b200: ', what, ' failed, code ', ierr
+    cmsg = adp_last_error(ctx)
+    if (c_associated(cmsg)) then
+      call c_f_pointer(cmsg, msg, (/ 1024 /))
+      do i = 1, 1024
+        if (msg(i) == c_null_char) exit
+        write(*,'(A)',advance='no') msg(i)
+      end do
+      write(*,*)
+    end if
+    stop 'adpres_b200: device error'
+  end subroutine gpu_check
+
   !> Before every outer*(): cross sections as XS_updt left them + the iteration control.
-  subroutine gpu_push_inputs()
+  !! Only what the caller can have changed since the previous outer*() call goes over PCIe:
+  !!   first call            everything
+  !!   later calls           D, sigr, nuf, sigf, sigs (XS_updt / XStab_updt rewrite them: mod_xsec.f90:11-86)
+  !!   dc                    only with %XTAB (XStab_updt takes the ADFs from the tables, mod_xsec.f90:73-75)
+  !!   exsrc                 only in outer_fs (%ESRC); outer_tr computes it on the device (get_exsrc, mod_cmfd.f90:830),
+  !!                         everywhere else it stays zero
+  !!   chi                   never changes after the first call
+  subroutine gpu_push_inputs(with_exsrc)
     use sdata, only: D, sigr, nuf, sigf, sigs, chi, dc, exsrc, nout, nin, nac, nupd, serc, ferc, kern
-    integer(c_int) :: ierr, k
+    use io,    only: bxtab
+    logical, intent(in) :: with_exsrc
+    logical, save :: first = .true.
+    integer(c_int) :: ierr, k, mask
     call gpu_init()
-    ierr = adp_set_xs(ctx, D, sigr, nuf, sigf, sigs, chi, dc, exsrc)
-    if (ierr /= 0) stop 'adpres_b200: adp_set_xs failed'
+    if (first) then
+      mask = 255_c_int
+      first = .false.
+    else
+      mask = 31_c_int                              ! D, sigr, nuf, sigf, sigs
+      if (bxtab == 1) mask = mask + 64_c_int       ! dc
+      if (with_exsrc) mask = mask + 128_c_int      ! exsrc
+    end if
+    ierr = adp_set_xs_mask(ctx, mask, D, sigr, nuf, sigf, sigs, chi, dc, exsrc)
+    call gpu_check(ierr, 'adp_set_xs_mask')
     k = ADP_KERN_SANM
     if (kern == ' FDM') k = ADP_KERN_FDM
     if (kern == ' PNM') k = ADP_KERN_PNM
     ierr = adp_set_control(ctx, nout, nin, nac, nupd, serc, ferc, k)
+    call gpu_check(ierr, 'adp_set_control')
   end subroutine gpu_push_inputs
 
-  !> After an outer*(): results the drivers read from sdata (f0, fs0, s0, Ke, nod%df/dn).
+  !> After an outer*(): results the drivers read from sdata -- f0, fs0, Ke always; nod%df/dn only for the
+  !! rod-ejection drivers, whose `reactivity` calls Lxyz of the (unchanged) nodal module on the host
+  !! (mod_trans.f90:677).  s0 has no reader outside get_exsrc, which runs on the device, and stays there.
+  !! On several ranks the library completes every array with the other ranks' slabs (include/adpres_b200.h), so the
+  !! host code that follows sees whole arrays on every rank.
   subroutine gpu_pull_results()
-    use sdata, only: f0, fs0, s0, Ke, nod, nnod, ng
+    use sdata, only: f0, fs0, s0, Ke, nod, nnod, ng, mode
     integer(c_int) :: ierr
     real(c_double), allocatable :: df(:,:,:), dn(:,:,:)
     integer :: n, g
-    ierr = adp_get_state(ctx, f0, fs0, s0, Ke)
-    allocate(df(6,nnod,ng), dn(6,nnod,ng))
-    ierr = adp_get_nod(ctx, df, dn)
-    do g = 1, ng
-      do n = 1, nnod
-        nod(n,g)%df = df(:,n,g)
-        nod(n,g)%dn = dn(:,n,g)
+    ierr = adp_get_state_mask(ctx, 3_c_int, f0, fs0, s0, Ke)
+    call gpu_check(ierr, 'adp_get_state_mask')
+    if (mode == 'RODEJECT') then
+      allocate(df(6,nnod,ng), dn(6,nnod,ng))
+      ierr = adp_get_nod(ctx, df, dn)
+      call gpu_check(ierr, 'adp_get_nod')
+      do g = 1, ng
+        do n = 1, nnod
+          nod(n,g)%df = df(:,n,g)
+          nod(n,g)%dn = dn(:,n,g)
+        end do
       end do
-    end do
+      deallocate(df, dn)
+    end if
   end subroutine gpu_pull_results
 
   !> Optional, %XTAB decks: hand the branch tables m(1:nmat) (MBRANCH / XBRANCH, mod_data.f90:176-192, read by
@@ -285,10 +349,10 @@ contains
     else
       ierr = adp_set_xtab(ctx, dims, trod, par, xs, c_null_ptr)
     end if
-    if (ierr /= 0) stop 'adpres_b200: adp_set_xtab failed'
+    call gpu_check(ierr, 'adp_set_xtab')
     if (bcrod == 1) then
       ierr = adp_set_crod_map(ctx, nb, pos0, ssize, fbmap)       ! fbmap(nxx,nyy), column-major as the C side expects
-      if (ierr /= 0) stop 'adpres_b200: adp_set_crod_map failed'
+      call gpu_check(ierr, 'adp_set_crod_map')
     end if
   contains
     subroutine pack_branch(x, a)

@@ -22,6 +22,7 @@ contains
     integer(c_int) :: ierr
     st = get_time()
     ierr = adp_nodal_upd(ctx, nmode, ndmax, im, jm, km)   ! ndmax = 0; nodal_update[_pnm]; matrix_setup(0)
+    call gpu_check(ierr, 'adp_nodal_upd')
     if (ierr == 2) then
       write(*,*) 'ERROR IN MATRIX DECOMP: DIAGONAL ELEMENTS CLOSE TO ZERO'
       stop
@@ -55,40 +56,51 @@ contains
     1146 format(2X,'MULTIPLICATION EFFECTIVE (K-EFF) = ', F9.6)
   end subroutine print_keff
 
-  !> common driver of outer / outer_fs / outer_ad: kind 0/1/2
-  subroutine outer_common(kind, popt, label)
+  !> common driver of outer / outer_fs / outer_ad: kind 0/1/2.  `first` is the caller's own SAVEd first-call flag
+  !! (the reference keeps one per procedure: src/mod_cmfd.f90:439,537,626).
+  subroutine outer_common(kind, popt, label, first)
     use sdata, only: ng, nnod, nout, serc, ferc, fer, ser, f0, fs0, s0, nupd, Ke, nac, ndmax, kern, &
                      get_time, fdm_time
     use io,    only: ounit, scr, bther
     integer, intent(in) :: kind, popt
     character(len=*), intent(in) :: label
+    logical, intent(inout) :: first
     integer :: p, mode, nmode
     integer(c_int) :: ierr
-    logical, save :: first = .true.
+    logical :: init
     real(dp) :: st, fn
 
     st = get_time()
-    call gpu_push_inputs()
+    call gpu_push_inputs(kind == 1)                              ! exsrc (%ESRC) only matters to outer_fs
     ierr = adp_matrix_setup(ctx, 1_c_int)                       ! CALL matrix_setup(1)
+    call gpu_check(ierr, 'adp_matrix_setup')
     mode = ADP_MODE_FORWARD; nmode = 1
     if (kind == 1) mode = ADP_MODE_FIXEDSRC
     if (kind == 2) then; mode = ADP_MODE_ADJOINT; nmode = 0; end if
-    if (first .and. .not. (kind == 2 .and. popt <= 0) .and. .not. (kind == 0 .and. bther /= 0)) then
+    ! first-call initialisation: outer `first .and. bther == 0` (:448), outer_fs `first` (:544), outer_ad `first .and. popt > 0` (:635)
+    init = first
+    if (kind == 0) init = first .and. bther == 0
+    if (kind == 2) init = first .and. popt > 0
+    if (init) then
       allocate (f0(nnod,ng), fs0(nnod), s0(nnod,ng))
+      s0 = 0._dp                                                 ! stays on the device (see gpu_pull_results)
       if (kind == 2) then
         ierr = adp_init_flux(ctx, 1_c_int)                      ! Ke = 1; f0 = 1; FSrcAd(fs0)
       else
         ierr = adp_init_flux(ctx, 0_c_int)                      ! Ke = 1; f0 = 1; FSrc(fs0)
       end if
+      call gpu_check(ierr, 'adp_init_flux')
       first = .false.
     end if
     ierr = adp_outer_begin(ctx, mode)                            ! f = Integrate(fs0); e1 = Integrate(errn = 1)
+    call gpu_check(ierr, 'adp_outer_begin')
     fn = get_time()
     fdm_time = fdm_time + (fn-st)
 
     do p = 1, nout
       st = get_time()
       ierr = adp_outer_iter(ctx, mode, p, Ke, ser, fer)          ! src/mod_cmfd.f90:467-487 on the GPU
+      call gpu_check(ierr, 'adp_outer_iter')
       if (MOD(p,nac) == 0 .and. popt > 0) then
         write(ounit,*) '    ...FISSION SOURCE EXTRAPOLATED...'
         if (scr) write(*,*) '    ...FISSION SOURCE EXTRAPOLATED...'
@@ -116,23 +128,26 @@ contains
       write(*,*) '  ADPRES IS STOPING...'
       STOP
     end if
-    call gpu_pull_results()                                       ! f0, fs0, s0, Ke, nod -> sdata
+    call gpu_pull_results()                                       ! f0, fs0, Ke (and nod for RODEJECT) -> sdata
     if (kind /= 1) call print_keff(popt)
   end subroutine outer_common
 
   subroutine outer(popt)          ! src/mod_cmfd.f90:415-509
     integer, optional, intent(in) :: popt
-    call outer_common(0, popt, 'FORWARD')
+    logical, save :: first = .true.
+    call outer_common(0, popt, 'FORWARD', first)
   end subroutine outer
 
   subroutine outer_fs(popt)       ! src/mod_cmfd.f90:513-598
     integer, optional, intent(in) :: popt
-    call outer_common(1, popt, 'FIXED-SOURCE')
+    logical, save :: first = .true.
+    call outer_common(1, popt, 'FIXED-SOURCE', first)
   end subroutine outer_fs
 
   subroutine outer_ad(popt)       ! src/mod_cmfd.f90:602-699
     integer, optional, intent(in) :: popt
-    call outer_common(2, popt, 'ADJOINT')
+    logical, save :: first = .true.
+    call outer_common(2, popt, 'ADJOINT', first)
   end subroutine outer_ad
 
   !> outer_th(maxn), src/mod_cmfd.f90:703-796
@@ -145,17 +160,22 @@ contains
     logical, save :: first = .true.
     logical :: lnupd
     lnupd = .true.
-    call gpu_push_inputs()
+    call gpu_push_inputs(.false.)
     ierr = adp_matrix_setup(ctx, 1_c_int)
+    call gpu_check(ierr, 'adp_matrix_setup')
     if (first) then
       allocate (f0(nnod,ng), fs0(nnod), s0(nnod,ng))
+      s0 = 0._dp
       ierr = adp_init_flux(ctx, 0_c_int)
+      call gpu_check(ierr, 'adp_init_flux')
       first = .false.
     end if
     ierr = adp_outer_begin(ctx, ADP_MODE_FORWARD)
+    call gpu_check(ierr, 'adp_outer_begin')
     if (biter == 0) nupd = int(nth/2)
     do p = 1, maxn
       ierr = adp_outer_iter(ctx, ADP_MODE_FORWARD, p, Ke, ser, fer)
+      call gpu_check(ierr, 'adp_outer_iter')
       if (MOD(p,nupd) == 0 .and. kern /= ' FDM') then
         lnupd = .false.
         call nodal_upd(0, 1)
@@ -181,7 +201,7 @@ contains
     integer :: p, i
     integer(c_int) :: ierr
     real(c_double), allocatable :: mib(:,:), mla(:,:), mve(:,:)
-    call gpu_push_inputs()
+    call gpu_push_inputs(.false.)                                 ! exsrc is computed on the device below
     if (bxtab == 1) then        ! %XTAB decks: kinetics data per material (get_exsrc, src/mod_cmfd.f90:898-925)
       allocate(mib(nf,nmat), mla(nf,nmat), mve(ng,nmat))
       do i = 1, nmat
@@ -191,17 +211,24 @@ contains
     else
       ierr = adp_set_kinetics(ctx, ibeta, lamb, velo, tbeta, sth, bth)
     end if
+    call gpu_check(ierr, 'adp_set_kinetics')
     ierr = adp_set_transient(ctx, c0, ft, fst, omeg, sigrp, L)
+    call gpu_check(ierr, 'adp_set_transient')
     ierr = adp_matrix_setup(ctx, 1_c_int)
+    call gpu_check(ierr, 'adp_matrix_setup')
     ierr = adp_get_exsrc(ctx, ht)                                 ! get_exsrc(ht, exsrc) on the device
+    call gpu_check(ierr, 'adp_get_exsrc')
     ierr = adp_outer_begin(ctx, ADP_MODE_TRANSIENT)
+    call gpu_check(ierr, 'adp_outer_begin')
     do p = 1, nout
       ierr = adp_outer_iter(ctx, ADP_MODE_TRANSIENT, p, Ke, ser, fer)
+      call gpu_check(ierr, 'adp_outer_iter')
       if (MOD(p,nupd) == 0 .and. kern /= ' FDM') call nodal_upd(0, 2)
       if ((ser < serc) .AND. (fer < ferc) .AND. (ndmax < 1.e-2)) exit
     end do
     maxi = (p == nout+1)
-    ierr = adp_get_exsrc_arrays(ctx, exsrc, dfis)
+    ierr = adp_get_exsrc_arrays(ctx, exsrc, dfis)                  ! uPden / the next step's glue read dfis, exsrc
+    call gpu_check(ierr, 'adp_get_exsrc_arrays')
     call gpu_pull_results()
   end subroutine outer_tr
 
@@ -214,6 +241,7 @@ contains
     fs = 0
     if (mode == 'FIXEDSRC') fs = 1
     ierr = adp_powdis(ctx, p, fs)
+    call gpu_check(ierr, 'adp_powdis')
     if (ierr == 4) then
       write(ounit, *) '   ERROR: TOTAL NODES POWER IS ZERO OR LESS'
       write(ounit, *) '   STOP IN subroutine POWDIS'
@@ -227,6 +255,7 @@ contains
     real(dp) :: intg
     integer(c_int) :: ierr
     ierr = adp_integrate(ctx, s, intg)
+    call gpu_check(ierr, 'adp_integrate')
   end function Integrate
 
 end module CMFD

@@ -99,6 +99,15 @@ int adp_set_xs(adp_ctx *ctx, const double *D, const double *sigr, const double *
                const double *chi /* (nmat,ng) */, const double *dc /* (nnod,ng,6) */,
                const double *exsrc /* (nnod,ng) */);
 
+/* The same for callers that cannot pass NULL (Fortran assumed-size dummies): only the arrays whose bit is set in
+ * `mask` are read, the others keep the values on the device.  bit 0 D, 1 sigr, 2 nuf, 3 sigf, 4 sigs, 5 chi, 6 dc,
+ * 7 exsrc.  The shim uses it to upload per outer*() call only what its caller changed: after the first call of a
+ * run dc changes only through XStab_updt (mod_xsec.f90:50-86), exsrc only in outer_fs / on the device in outer_tr
+ * (get_exsrc, mod_cmfd.f90:830), chi never. */
+int adp_set_xs_mask(adp_ctx *ctx, int mask, const double *D, const double *sigr, const double *nuf,
+                    const double *sigf, const double *sigs, const double *chi, const double *dc,
+                    const double *exsrc);
+
 /* %ITER and %KERN values (mod_io.f90:1522-1540; defaults mod_data.f90:78-86) */
 int adp_set_control(adp_ctx *ctx, int nout, int nin, int nac, int nupd, double serc, double ferc,
                     int kern);
@@ -249,8 +258,15 @@ int adp_th_upd(adp_ctx *ctx, const double *xpline, double *th_err);
 int adp_th_trans(adp_ctx *ctx, const double *xpline, double h);
 
 /* ---- state exchange with the Fortran side ----------------------------------------------- */
-/* f0(nnod,ng), fs0(nnod), s0(nnod,ng); NULL = skip.  (drivers read them after outer*) */
+/* f0(nnod,ng), fs0(nnod), s0(nnod,ng); NULL = skip.  (drivers read them after outer*)
+ * On several ranks every node array that comes back to the host (this call, adp_powdis, adp_get_nod, ...) is
+ * completed with the other ranks' slabs, because the unchanged Fortran drivers consume whole sdata arrays on every
+ * rank (th_upd's axial march, reactivity, the printers); adp_set_option(ctx, "gather_results", 0) returns only the
+ * owned slab.  All ranks must make these calls together. */
 int adp_get_state(adp_ctx *ctx, double *f0, double *fs0, double *s0, double *Ke);
+/* the same with a mask instead of NULL pointers: bit 0 f0, 1 fs0, 2 s0 (Fortran callers).  No caller of outer*()
+ * reads s0 -- only get_exsrc does, which runs on the device -- so the shim leaves bit 2 clear. */
+int adp_get_state_mask(adp_ctx *ctx, int mask, double *f0, double *fs0, double *s0, double *Ke);
 /* restart / KNE1 paths: load flux, fission source and k-eff (NULL keeps) */
 int adp_set_state(adp_ctx *ctx, const double *f0, const double *fs0, double Ke);
 /* restart path for s0(nnod,ng): column g (1-based) is loaded, the others are zero, which is the

@@ -23,6 +23,7 @@ def bench():
 def test_slab_problem_equals_the_stacked_core(bench, world):
     from adpres_b200.slab import slab_planes
     base = load_problem("IAEA3Ds").refine(xdiv=[1] + [2] * 8, ydiv=[2] * 8 + [1], zdiv=[2] * 19)
+    base1 = load_problem("IAEA3Ds").refine(xdiv=[1] + [2] * 8, ydiv=[2] * 8 + [1], zdiv=[1] * 19)
     p0 = load_problem("IAEA3Ds")
     full = dataclasses.replace(p0, nz=p0.nz * world, zsize=np.tile(p0.zsize, world), zdiv=np.tile(p0.zdiv, world),
                                zpln=np.tile(p0.zpln, world)).refine(xdiv=[1] + [2] * 8, ydiv=[2] * 8 + [1], zdiv=[2] * 19 * world)
@@ -30,6 +31,13 @@ def test_slab_problem_equals_the_stacked_core(bench, world):
     covered = np.zeros(full.nnod, dtype=int)
     for rank in range(world):
         sp = bench.SlabProblem(base, world, rank)
+        # the same slab from the one-plane-per-assembly base (what bench.py uses: zrefine planes per base plane)
+        sp1 = bench.SlabProblem(base1, world, rank, stack=world, zrefine=2)
+        for k in ("nnod", "nzz", "k0", "k1", "rows"):
+            assert getattr(sp1, k) == getattr(sp, k), k
+        assert np.array_equal(sp1.zdel, sp.zdel) and np.array_equal(sp1.mat[sp.rows], sp.mat[sp.rows])
+        for k in ("D", "sigr", "nuf", "sigf", "exsrc", "sigs", "dc"):
+            assert np.array_equal(getattr(sp1, k)[sp.rows], getattr(sp, k)[sp.rows]), k
         assert (sp.nnod, sp.nzz, sp.npl, sp.ng) == (full.nnod, full.nzz, full.npl, full.ng)
         assert np.array_equal(sp.zdel, full.zdel) and np.array_equal(sp.ix, full.ix) and np.array_equal(sp.iy, full.iy)
         assert np.array_equal(sp.iz, full.iz)
@@ -50,6 +58,20 @@ def test_load_c2_sample_is_the_bounded_cpu_workload(bench):
     assert (p.nxx, p.nyy, p.nzz, p.nnod) == (170, 170, 19, 457900)
     assert np.all(p.xdel == 1.0) and np.all(p.zdel == 20.0)
     assert bench.CTL["nin"] == 10 and bench.CTL["nupd"] == 50 and bench.SPMV_BYTES_PER_ROW == 72.0
+
+
+def test_timed_window_contains_a_nodal_update(bench):
+    # driver call: --steps 20 --warmup 5, nupd = 50 -> timed iterations 31..50, one nodal update inside
+    assert bench.window(20, 5, 50) == 31 and bench.updates_in(31, 20, 50) == 1
+    assert bench.window(200, 5, 50) == 6 and bench.updates_in(6, 200, 50) == 4      # long runs: right after the warm-up
+    assert bench.window(45, 5, 50) == 6 and bench.updates_in(6, 45, 50) == 1
+    for K in (1, 3, 20, 44, 45, 50, 100):
+        for W in (0, 3, 5, 10):
+            P0 = bench.window(K, W, 50)
+            assert P0 >= W + 1 and bench.updates_in(P0, K, 50) >= 1
+    # both arms print the same config dict
+    assert bench.workload_config(1, 20, 5) == bench.workload_config(1, 20, 5)
+    assert bench.workload_config(1, 20, 5)["timed_iterations"] == [31, 50]
 
 
 def test_clock_sampler_parses_nvidia_smi_lines(bench):
