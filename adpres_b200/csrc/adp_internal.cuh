@@ -71,6 +71,12 @@ struct Geo {
     const double *area;            // [np] xdel*ydel
     const int *ixr, *iyr;          // [np] 1-based i, j of plane position r
 };
+// radial map for kernels that walk (i, j) instead of plane positions (kept OUT of Geo: Geo is the first parameter of
+// every streaming kernel and its layout is part of their tuned code generation)
+struct GeoXY {
+    int nxx = 0, nyy = 0;          // radial mesh
+    const int *nodp = nullptr;     // [nyy][nxx] 1-based plane position of node (i, j), 0 outside the core outline
+};
 
 // Destination of a boundary-plane "push": the ghost planes of the z-neighbours' copy of the same
 // vector, mapped into this process over NVLink peer memory (CUDA IPC).  lo = the lower
@@ -88,7 +94,7 @@ enum { PB_RS = 0, PB_V0, PB_V1, PB_R, PB_F0A, PB_F0B, PB_COUNT };
 // results are combined in rank order (deterministic).  Two consecutive reductions use different
 // slots and a rank cannot run two reductions ahead of another, so slots are never overwritten early.
 #define ADP_MAIL_SLOTS 4
-#define ADP_MAIL_WORDS 8
+#define ADP_MAIL_WORDS 16   // doubles per (slot, rank) row: [0..6] values + [7] sequence number (release/acquire form); [8..15] tagged words (LL form)
 #define ADP_MAX_RANKS 8
 struct Mail {
     double *const *box = nullptr;     // device table: box[q] = rank q's mailbox (box[rank] is local).  A table in
@@ -99,6 +105,7 @@ struct Mail {
     double *fault = nullptr;          // -> scal[S_FAULT]: sticky timeout flag (never shared with the STOP error flag)
     long long timeout = 0;            // clock64 ticks a rank waits for its peers before it gives up
     int nranks = 1, rank = 0;
+    int ll = 1;                       // fused form: 1 = self-validating 8-byte words (no fence on the critical path), 0 = values + released flag
 };
 // what a kernel waits for in its prologue: the `n` sums the preceding kernel posted (n = 0: nothing); they are combined
 // in rank order by every CTA, CTA 0 also stores them to scal[slot[i]] for the kernels that follow
@@ -124,6 +131,7 @@ struct adp_ctx {
     int k0 = 0, k1 = 0, nzl = 0;
     long long NV = 0, NL = 0;
     Geo geo{};
+    GeoXY geoxy{};
     int bc[6] = {0, 0, 0, 0, 0, 0};
     // host copies of small geometry
     std::vector<int> h_ix, h_iy, h_iz;
@@ -138,7 +146,7 @@ struct adp_ctx {
     bool coup_first = true, have_flux = false, geometry_set = false, xs_set = false, matrix_ready = false;
     bool outer_first = true, outer_ad_first = true;
     // device arrays
-    int *d_ypm = nullptr, *d_ypp = nullptr, *d_ixr = nullptr, *d_iyr = nullptr, *d_mat = nullptr;
+    int *d_ypm = nullptr, *d_ypp = nullptr, *d_ixr = nullptr, *d_iyr = nullptr, *d_mat = nullptr, *d_nodp = nullptr;
     unsigned char *d_flag = nullptr;
     double *d_hx = nullptr, *d_hy = nullptr, *d_hz = nullptr, *d_area = nullptr;
     double *d_f0[2] = {nullptr, nullptr};  // [G][NV] each
@@ -155,7 +163,7 @@ struct adp_ctx {
     double *d_dc = nullptr;                // [f][g][NV]
     double *d_chi = nullptr;               // [g][nmat]
     double *d_S = nullptr;                 // [3][G][NV]
-    double *d_nd = nullptr;                // [3][G*G+7G][NV] node-direction store of the nodal update
+    double *d_nd = nullptr;                // [3][G*G+3G][NV] node-direction store of the nodal update (Bc, a2, a4, L1)
     double *d_abefgh = nullptr;            // [3][6][G][NV] SANM constants, valid until D / sigr change
     bool abefgh_valid = false;
     // transient
@@ -223,6 +231,7 @@ struct adp_ctx {
     bool peer_ar = false;                  // reductions are all-reduced over peer-memory mailboxes
     bool fuse_mail = true;                 // BiCGSTAB: post in the producer's last CTA, wait in the consumer's prologue (no extra kernel)
     double mail_timeout_s = 30.0;          // ADP_MAIL_TIMEOUT_S
+    bool mail_ll = true;                   // fused all-reduce posts self-validating words (mail.cuh)
     double *d_mail = nullptr;              // this rank's mailbox
     double *mail_peer[ADP_MAX_RANKS] = {nullptr};
     double **d_mail_table = nullptr;       // device copy of mail_peer[]
@@ -233,7 +242,11 @@ struct adp_ctx {
     bool use_graphs = true;
     int bench_warmup = 3;
     int nodal_coop = -1;                   // surfaces kernel with 16 lanes per surface: -1 = for G >= 7, 0 never, 1 always
+    int nodal_fused = 0;                   // experiment, G <= 2: per-direction kernels that carry the node-direction record in
+                                           // registers instead of storing it (bit-identical, 1.7x less DRAM traffic, but 2.7x
+                                           // SLOWER: 8 warps per SM cannot hide the fp64 division chains -- DESIGN.md)
     bool fuse_st = true;                   // C kernel: s on the fly inside t = A s (false: k_s then k_t)
+    bool st_tma = false;                   // C kernel staged with cp.async.bulk + mbarrier (experiment, single rank, np even)
     // bookkeeping
     long long launches = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;

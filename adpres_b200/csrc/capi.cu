@@ -59,6 +59,7 @@ extern "C" int adp_create(adp_ctx **out, int device)
     c->sm_count = prop.multiProcessorCount;
     if (const char *v = getenv("ADP_MAIL_TIMEOUT_S")) { const double t = atof(v); if (t > 0.0) c->mail_timeout_s = t; }
     if (getenv("ADP_NO_FUSE_MAIL")) c->fuse_mail = false;
+    if (getenv("ADP_NO_MAIL_LL")) c->mail_ll = false;
     // persistent grids: a multiple of the SM count (148 on B200) x resident CTAs per SM
     c->grid_blocks = 0;
     if (dev_alloc(c, &c->d_scal, S_COUNT) || dev_alloc(c, &c->d_part, 4 * ADP_MAXPART) || dev_alloc(c, &c->d_ticket, 1) ||
@@ -96,7 +97,7 @@ extern "C" int adp_destroy(adp_ctx *c)
     cudaStreamSynchronize(c->stream);
     free_graphs(c);
     adp_comm_destroy(c);
-    void *ptrs[] = {c->d_ypm, c->d_ypp, c->d_ixr, c->d_iyr, c->d_mat, c->d_flag, c->d_hx, c->d_hy, c->d_hz, c->d_area,
+    void *ptrs[] = {c->d_nodp, c->d_ypm, c->d_ypp, c->d_ixr, c->d_iyr, c->d_mat, c->d_flag, c->d_hx, c->d_hy, c->d_hz, c->d_area,
                     c->d_f0[0], c->d_f0[1], c->d_fs[0], c->d_fs[1], c->d_r, c->d_rs, c->d_p, c->d_v, c->d_v2, c->d_s, c->d_t,
                     c->d_s0, c->d_a, c->d_df, c->d_dn, c->d_D, c->d_sigr, c->d_nuf, c->d_sigf, c->d_exsrc, c->d_sigs,
                     c->d_dc, c->d_chi, c->d_S, c->d_c0, c->d_ft, c->d_fst, c->d_omeg, c->d_sigrp, c->d_L, c->d_dfis,
@@ -239,6 +240,8 @@ extern "C" int adp_set_geometry(adp_ctx *c, int nxx, int nyy, int nzz, int nnod,
     TRY(dev_alloc(c, &c->d_ypm, np)); TRY(dev_alloc(c, &c->d_ypp, np)); TRY(dev_alloc(c, &c->d_ixr, np));
     TRY(dev_alloc(c, &c->d_iyr, np)); TRY(dev_alloc(c, &c->d_flag, np)); TRY(dev_alloc(c, &c->d_hx, np + 2));
     TRY(dev_alloc(c, &c->d_hy, np)); TRY(dev_alloc(c, &c->d_area, np)); TRY(dev_alloc(c, &c->d_hz, nzz + 2));
+    TRY(dev_alloc(c, &c->d_nodp, (size_t)nxx * nyy));
+    CUDA_TRY(c, cudaMemcpyAsync(c->d_nodp, nodp.data(), (size_t)nxx * nyy * sizeof(int), cudaMemcpyHostToDevice, c->stream));
     CUDA_TRY(c, cudaMemcpyAsync(c->d_ypm, ypm.data(), np * sizeof(int), cudaMemcpyHostToDevice, c->stream));
     CUDA_TRY(c, cudaMemcpyAsync(c->d_ypp, ypp.data(), np * sizeof(int), cudaMemcpyHostToDevice, c->stream));
     CUDA_TRY(c, cudaMemcpyAsync(c->d_ixr, ixr.data(), np * sizeof(int), cudaMemcpyHostToDevice, c->stream));
@@ -258,6 +261,7 @@ extern "C" int adp_set_geometry(adp_ctx *c, int nxx, int nyy, int nzz, int nnod,
     for (int i = 0; i < 6; ++i) G.bc[i] = bc[i];
     G.ypm = c->d_ypm; G.ypp = c->d_ypp; G.flag = c->d_flag; G.hx = c->d_hx + 1; G.hy = c->d_hy; G.hz = c->d_hz;
     G.area = c->d_area; G.ixr = c->d_ixr; G.iyr = c->d_iyr;
+    c->geoxy.nxx = nxx; c->geoxy.nyy = nyy; c->geoxy.nodp = c->d_nodp;
 
     const size_t NV = (size_t)c->NV, Gn = (size_t)ng;
     TRY(dev_alloc(c, &c->d_mat, NV));
@@ -1181,10 +1185,13 @@ extern "C" int adp_set_option(adp_ctx *c, const char *name, int value)
     if (!strcmp(name, "peer_allreduce")) { if (!value) c->peer_ar = false; free_graphs(c); return ADP_OK; }
     if (!strcmp(name, "gather_results")) { c->gather_results = value != 0; return ADP_OK; }
     if (!strcmp(name, "fuse_mail")) { c->fuse_mail = value != 0; free_graphs(c); return ADP_OK; }
+    if (!strcmp(name, "mail_ll")) { c->mail_ll = value != 0; free_graphs(c); return ADP_OK; }
     if (!strcmp(name, "mail_timeout_s")) { c->mail_timeout_s = value; free_graphs(c); return ADP_OK; }
     if (!strcmp(name, "balance_rounds")) { c->balance_rounds = value != 0; free_graphs(c); return ADP_OK; }
     if (!strcmp(name, "bench_warmup")) { c->bench_warmup = value; return ADP_OK; }
     if (!strcmp(name, "nodal_coop")) { c->nodal_coop = value; free_graphs(c); return ADP_OK; }
+    if (!strcmp(name, "nodal_fused")) { c->nodal_fused = value; free_graphs(c); return ADP_OK; }
+    if (!strcmp(name, "st_tma")) { c->st_tma = value != 0; free_graphs(c); return ADP_OK; }
     if (!strcmp(name, "fuse_st")) { c->fuse_st = value != 0; free_graphs(c); return ADP_OK; }
     if (!strcmp(name, "grid_blocks")) {
         ADP_REQUIRE(c, value >= 1 && value <= ADP_MAXPART, "grid_blocks out of range");

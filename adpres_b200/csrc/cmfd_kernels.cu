@@ -38,8 +38,6 @@ struct RedOut {
     double *part;        // [4][ADP_MAXPART]
     unsigned int *ticket;
     int slot[4];
-    int post = 0;        // multi-rank: the last CTA posts the (<= 2) sums to every rank's mailbox (mail.cuh)
-    Mail m;
 };
 
 __device__ __forceinline__ double warp_sum(double v)
@@ -112,12 +110,76 @@ __device__ __forceinline__ void grid_reduce(double (&val)[NS + NM], const RedOut
             for (int i = 0; i < NVAL; ++i) ro.scal[ro.slot[i]] = res[i];
             *ro.ticket = 0u;
         }
-        if constexpr (NM == 0 && NS <= 2) {
-            // every CTA's halo stores were fenced at system scope before its ticket: posting now tells the
-            // peers that this rank's partial sums AND its boundary planes have arrived
-            if (ro.post)
-                mail_post(ro.m, NS, __shfl_sync(0xffffffffu, res[0], 0), __shfl_sync(0xffffffffu, res[NS - 1], 0));
+    }
+}
+
+// ---- the same reduction for the multi-rank (peer-memory) kernels: afterwards the finishing warp of the LAST CTA posts
+// the sums to every rank's mailbox (mail.cuh).  A separate struct and function ON PURPOSE: with the extra members /
+// code in the single-rank kernels ptxas scheduled their streaming loops differently and k_st lost 4-15 % (round 2, A/B
+// on one box: 83 -> 87-95 us), so the single-rank kernels keep round 1's exact parameter lists and text.
+struct RedOutM {
+    RedOut r;
+    int post = 0;        // the last CTA posts the (<= 2) sums to every rank's mailbox
+    Mail m;
+};
+
+template <int NS>
+__device__ __forceinline__ void grid_reduce_m(double (&val)[NS], const RedOutM &rom)
+{
+    const RedOut &ro = rom.r;
+    __shared__ double sm[NS][ADP_TILE / 32];
+    __shared__ bool is_last;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < NS; ++i) {
+        double w = warp_sum(val[i]);
+        if (lane == 0) sm[i][wid] = w;
+    }
+    __syncthreads();
+    if (wid == 0) {
+#pragma unroll
+        for (int i = 0; i < NS; ++i) {
+            double w = (lane < ADP_TILE / 32) ? sm[i][lane] : 0.0;
+            w = warp_sum(w);
+            if (lane == 0) ro.part[i * ADP_MAXPART + blockIdx.x] = w;
         }
+    }
+    if (threadIdx.x == 0) {
+        __threadfence();
+        unsigned int t = atomicAdd(ro.ticket, 1u);
+        is_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    double acc[NS];
+#pragma unroll
+    for (int i = 0; i < NS; ++i) {
+        acc[i] = 0.0;
+        for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) acc[i] = acc[i] + __ldcg(&ro.part[i * ADP_MAXPART + b]);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < NS; ++i) {
+        double w = warp_sum(acc[i]);
+        if (lane == 0) sm[i][wid] = w;
+    }
+    __syncthreads();
+    if (wid == 0) {
+        double res[NS];
+#pragma unroll
+        for (int i = 0; i < NS; ++i) {
+            double w = (lane < ADP_TILE / 32) ? sm[i][lane] : 0.0;
+            res[i] = warp_sum(w);
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int i = 0; i < NS; ++i) ro.scal[ro.slot[i]] = res[i];
+            *ro.ticket = 0u;
+        }
+        // every CTA's halo stores were fenced at system scope before its ticket: posting now tells the
+        // peers that this rank's partial sums AND its boundary planes have arrived
+        if (rom.post) mail_post(rom.m, NS, __shfl_sync(0xffffffffu, res[0], 0), __shfl_sync(0xffffffffu, res[NS - 1], 0));
     }
 }
 
@@ -136,6 +198,32 @@ __device__ __forceinline__ long long node_idx(const Geo &G, int kl, int r)
 }
 
 // Boundary planes go straight into the z-neighbours' ghost planes (NVLink peer stores); the
+// all-reduce that ends every such kernel is the barrier that orders them before the reads.
+// The stores are kept OUT of the streaming loop (a possibly-aliasing store there cost the SpMV
+// kernel 10 us, ncu A/B): after its tiles a CTA walks its boundary-plane tiles again, re-reads
+// the values it has just written itself (L1/L2 hits) and forwards them.
+__device__ __forceinline__ void push_tail(const Geo &G, const Push &ps, const double *vec)
+{
+#ifndef ADP_NO_PUSH
+    if (!ps.lo && !ps.hi) return;
+    bool pushed = false;
+    // boundary-plane tiles are [0, tpp) and [(nzl-1) tpp, nzl tpp): visit only those of this CTA
+    for (int side = 0; side < 2; ++side) {
+        const int kl = side ? G.nzl - 1 : 0;
+        double *dst = side ? ps.hi : ps.lo;
+        if (!dst) continue;
+        const int t0 = kl * G.tpp;
+        int first = t0 + ((int)blockIdx.x - t0 % (int)gridDim.x + (int)gridDim.x) % (int)gridDim.x;   // first tile >= t0 of this CTA
+        for (int tile = first; tile < t0 + G.tpp; tile += gridDim.x) {
+            const int r = (tile - t0) * ADP_TILE + threadIdx.x;
+            if (r < G.np) { dst[r] = vec[node_idx(G, kl, r)]; pushed = true; }
+        }
+    }
+    if (pushed) __threadfence_system();      // only the threads that stored to a neighbour pay for the fence
+#endif
+}
+
+// Multi-rank kernels (*_m).  Boundary planes go straight into the z-neighbours' ghost planes (NVLink peer stores); the
 // all-reduce that follows every such kernel is the barrier that orders them before the reads.
 // The tiles of the two boundary planes are walked FIRST, by a copy of the loop body that also
 // stores to the neighbour, and the interior tiles afterwards by a copy without any peer store: the
@@ -267,11 +355,110 @@ struct SrcArgs {
     const double *b;               // raw mode: right-hand side given explicitly (adp_bicg)
 };
 
-__global__ void __launch_bounds__(ADP_TILE, ADP_LB_PA) k_residual(Geo G, SrcArgs A, const double *__restrict__ a,
+__global__ void __launch_bounds__(ADP_TILE) k_residual(Geo G, SrcArgs A, const double *__restrict__ a,
                                                         const double *__restrict__ x, double *__restrict__ rs, Push ps, RedOut ro)
 {
     double acc[1] = {0.0};
     const double Ke = ro.scal[S_KE];
+    FOR_EACH_ROW(G, 0, G.nzl)
+    {
+        const long long idx = node_idx(G, kl, r);
+        double bs;
+        if (A.b) {
+            bs = A.b[idx];
+        } else {
+            double s0 = 0.0;
+            for (int h = 0; h < A.ng; ++h)
+                if (h != A.g) s0 = s0 + A.sg[h][idx] * A.f0[h][idx];
+            if (A.s0) A.s0[idx] = s0;
+            const int m = A.mat[idx] - 1;
+            if (A.mode == ADP_MODE_ADJOINT) bs = A.nuf_g[idx] * A.fs[idx] / Ke + s0 + A.exsrc[idx];
+            else if (A.mode == ADP_MODE_TRANSIENT)
+                bs = (1.0 - A.tbeta[m] + A.dfis[idx]) * A.chi_g[m] * A.fs[idx] + s0 + A.exsrc[idx];
+            else bs = A.chi_g[m] * A.fs[idx] / Ke + s0 + A.exsrc[idx];
+        }
+        const double ax = stencil7(a, G.NV, x, idx, G.np, G.ypm[r], G.ypp[r]);
+        const double res = bs - ax;
+        rs[idx] = res;      // r0 = rs = p1: one store serves all three (see bicg_core)
+        acc[0] = acc[0] + res * res;
+    }
+    push_tail(G, ps, rs);
+    grid_reduce<1, 0>(acc, ro);
+}
+
+// A: p = r + beta (p - omega v), beta = (rho/rho_prev)(alpha/omega)   (mod_cmfd.f90:1231-1232)
+__global__ void __launch_bounds__(ADP_TILE) k_update_p(Geo G, const double *__restrict__ scal, int slot_rho, int slot_rho_prev,
+                                                        const double *__restrict__ rv, const double *__restrict__ v,
+                                                        const double *p_in, double *p_out, int klo, int npl)
+{
+    const double rho = scal[slot_rho], rho_prev = scal[slot_rho_prev];
+    const double alpha = rho_prev / scal[S_RSV];
+    const double omega = scal[S_TS] / scal[S_TT];
+    const double beta = (rho / rho_prev) * (alpha / omega);
+    FOR_EACH_ROW(G, klo, npl)
+    {
+        const long long idx = node_idx(G, kl, r);
+        p_out[idx] = rv[idx] + beta * (p_in[idx] - omega * v[idx]);
+    }
+}
+
+// B: v = A p and the partial sums of (rs, v)   (mod_cmfd.f90:1233-1234)
+__global__ void __launch_bounds__(ADP_TILE) k_spmv_dot(Geo G, const double *__restrict__ a, const double *__restrict__ pv,
+                                                        const double *__restrict__ rs, double *__restrict__ v, Push ps, RedOut ro)
+{
+    double acc[1] = {0.0};
+    FOR_EACH_ROW(G, 0, G.nzl)
+    {
+        const long long idx = node_idx(G, kl, r);
+        const double y = stencil7(a, G.NV, pv, idx, G.np, G.ypm[r], G.ypp[r]);
+        v[idx] = y;
+        if (rs) acc[0] = acc[0] + rs[idx] * y;
+    }
+    push_tail(G, ps, v);
+    if (rs) grid_reduce<1, 0>(acc, ro);
+}
+
+// C: s = r - alpha v evaluated on the fly at the 7 stencil points, t = A s, (t,t), (t,s)
+//    (mod_cmfd.f90:1234-1238).  s is stored for the own row only.
+__global__ void __launch_bounds__(ADP_TILE) k_st(Geo G, const double *__restrict__ a, int slot_rho,
+                                                  const double *__restrict__ rv, const double *__restrict__ v,
+                                                  double *__restrict__ s, double *__restrict__ t, RedOut ro)
+{
+    double acc[2] = {0.0, 0.0};
+    const double alpha = ro.scal[slot_rho] / ro.scal[S_RSV];
+    const long long NV = G.NV;
+    const int np = G.np;
+    FOR_EACH_ROW(G, 0, G.nzl)
+    {
+        const long long idx = node_idx(G, kl, r);
+        const int ym = G.ypm[r], yp = G.ypp[r];
+        const double sc = rv[idx] - alpha * v[idx];
+        double y = 0.0;
+        y = y + a[idx] * (rv[idx - np] - alpha * v[idx - np]);
+        y = y + a[NV + idx] * (rv[idx - ym] - alpha * v[idx - ym]);
+        y = y + a[2 * NV + idx] * (rv[idx - 1] - alpha * v[idx - 1]);
+        y = y + a[3 * NV + idx] * sc;
+        y = y + a[4 * NV + idx] * (rv[idx + 1] - alpha * v[idx + 1]);
+        y = y + a[5 * NV + idx] * (rv[idx + yp] - alpha * v[idx + yp]);
+        y = y + a[6 * NV + idx] * (rv[idx + np] - alpha * v[idx + np]);
+        s[idx] = sc;
+        t[idx] = y;
+        acc[0] = acc[0] + y * y;
+        acc[1] = acc[1] + y * sc;
+    }
+    grid_reduce<2, 0>(acc, ro);
+}
+
+// ==========================================================================================
+// The same four kernels for several ranks with peer memory (z-slabs): halo planes pushed to the z-neighbours
+// (boundary-plane tiles first), the all-reduce of the sums fused in -- posted by the last CTA (grid_reduce_m),
+// awaited in the NEXT kernel's prologue (mail_prologue).  Same row arithmetic as the single-rank kernels.
+// ==========================================================================================
+__global__ void __launch_bounds__(ADP_TILE, ADP_LB_PA) k_residual_m(Geo G, SrcArgs A, const double *__restrict__ a,
+                                                        const double *__restrict__ x, double *__restrict__ rs, Push ps, RedOutM rom)
+{
+    double acc[1] = {0.0};
+    const double Ke = rom.r.scal[S_KE];
     auto row = [&](int kl, int r) -> double {
         const long long idx = node_idx(G, kl, r);
         double bs;
@@ -297,16 +484,15 @@ __global__ void __launch_bounds__(ADP_TILE, ADP_LB_PA) k_residual(Geo G, SrcArgs
     bool pushed = false;
     bf_tiles(G, [&](int kl, int r) { pushed = push_row(G, ps, kl, r, row(kl, r)) || pushed; }, [&](int kl, int r) { row(kl, r); });
     if (pushed) __threadfence_system();      // only the threads that stored to a neighbour pay for the fence
-    grid_reduce<1, 0>(acc, ro);
+    grid_reduce_m<1>(acc, rom);
 }
 
-// A: p = r + beta (p - omega v), beta = (rho/rho_prev)(alpha/omega)   (mod_cmfd.f90:1231-1232)
-__global__ void __launch_bounds__(ADP_TILE, ADP_LB_PA) k_update_p(Geo G, double *scal, int slot_rho, int slot_rho_prev,
+__global__ void __launch_bounds__(ADP_TILE, ADP_LB_PA) k_update_p_m(Geo G, double *scal, int slot_rho, int slot_rho_prev,
                                                         const double *__restrict__ rv, const double *__restrict__ v,
                                                         const double *p_in, double *p_out, int klo, int npl, MailWait mw)
 {
-    double wv[2];
-    mail_prologue(mw, scal, wv);             // fused multi-rank path: rho = the sum D posted
+    double wv[2] = {0.0, 0.0};
+    mail_prologue(mw, scal, wv);             // fused path: rho = the sum D posted
     const double rho = mw.n ? wv[0] : scal[slot_rho], rho_prev = scal[slot_rho_prev];
     const double alpha = rho_prev / scal[S_RSV];
     const double omega = scal[S_TS] / scal[S_TT];
@@ -318,37 +504,34 @@ __global__ void __launch_bounds__(ADP_TILE, ADP_LB_PA) k_update_p(Geo G, double 
     }
 }
 
-// B: v = A p and the partial sums of (rs, v)   (mod_cmfd.f90:1233-1234)
-__global__ void __launch_bounds__(ADP_TILE) k_spmv_dot(Geo G, const double *__restrict__ a, const double *__restrict__ pv,
-                                                        const double *__restrict__ rs, double *__restrict__ v, Push ps, RedOut ro,
+__global__ void __launch_bounds__(ADP_TILE) k_spmv_dot_m(Geo G, const double *__restrict__ a, const double *__restrict__ pv,
+                                                        const double *__restrict__ rs, double *__restrict__ v, Push ps, RedOutM rom,
                                                         MailWait mw)
 {
     double acc[1] = {0.0};
     double wv[2];
-    mail_prologue(mw, ro.scal, wv);          // first sweep: P's rho (not used here) = the barrier before the ghost planes of p are read
+    mail_prologue(mw, rom.r.scal, wv);       // first sweep: P's rho (not used here) = the barrier before the ghost planes of p are read
     auto row = [&](int kl, int r) -> double {
         const long long idx = node_idx(G, kl, r);
         const double y = stencil7(a, G.NV, pv, idx, G.np, G.ypm[r], G.ypp[r]);
         v[idx] = y;
-        if (rs) acc[0] = acc[0] + rs[idx] * y;
+        acc[0] = acc[0] + rs[idx] * y;
         return y;
     };
     bool pushed = false;
     bf_tiles(G, [&](int kl, int r) { pushed = push_row(G, ps, kl, r, row(kl, r)) || pushed; }, [&](int kl, int r) { row(kl, r); });
     if (pushed) __threadfence_system();
-    if (rs) grid_reduce<1, 0>(acc, ro);
+    grid_reduce_m<1>(acc, rom);
 }
 
-// C: s = r - alpha v evaluated on the fly at the 7 stencil points, t = A s, (t,t), (t,s)
-//    (mod_cmfd.f90:1234-1238).  s is stored for the own row only.
-__global__ void __launch_bounds__(ADP_TILE) k_st(Geo G, const double *__restrict__ a, int slot_rho,
+__global__ void __launch_bounds__(ADP_TILE) k_st_m(Geo G, const double *__restrict__ a, int slot_rho,
                                                   const double *__restrict__ rv, const double *__restrict__ v,
-                                                  double *__restrict__ s, double *__restrict__ t, RedOut ro, MailWait mw)
+                                                  double *__restrict__ s, double *__restrict__ t, RedOutM rom, MailWait mw)
 {
     double acc[2] = {0.0, 0.0};
-    double wv[2];
-    mail_prologue(mw, ro.scal, wv);          // fused multi-rank path: (rs, v) = the sum B posted
-    const double alpha = ro.scal[slot_rho] / (mw.n ? wv[0] : ro.scal[S_RSV]);
+    double wv[2] = {0.0, 0.0};
+    mail_prologue(mw, rom.r.scal, wv);       // fused path: (rs, v) = the sum B posted
+    const double alpha = rom.r.scal[slot_rho] / (mw.n ? wv[0] : rom.r.scal[S_RSV]);
     const long long NV = G.NV;
     const int np = G.np;
     FOR_EACH_ROW(G, 0, G.nzl)
@@ -368,6 +551,129 @@ __global__ void __launch_bounds__(ADP_TILE) k_st(Geo G, const double *__restrict
         t[idx] = y;
         acc[0] = acc[0] + y * y;
         acc[1] = acc[1] + y * sc;
+    }
+    grid_reduce_m<2>(acc, rom);
+}
+
+// ------------------------------------------------------------------------------------------
+// C again, staged with the Blackwell / Hopper bulk-copy engine (option "st_tma", an experiment kept selectable):
+// per tile of 256 consecutive rows of a plane ONE thread issues 13 one-dimensional bulk copies
+// (cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes -> SASS UBLKCP): the 7 coefficient
+// streams (L2 evict_first: they are read exactly once per launch) and r, v on the planes k-1, k, k+1, into a
+// ring of ST_STAGES shared-memory stages guarded by one mbarrier each.  The bytes in flight then no longer
+// depend on the number of resident warps and their registers (3 stages x 26 KB per CTA, 2 CTAs per SM =
+// 156 KB per SM against 6 CTAs x 256 threads x 7 x 8 B = 86 KB for the gathered form).  x neighbours come out
+// of the staged centre row, the y neighbours (idx -+ ypm/ypp, another row of the plane) stay gathered loads.
+// Needs np even (16-byte alignment of every plane row); same operations in the same order as k_st.
+// ------------------------------------------------------------------------------------------
+#define ST_STAGES 3
+struct __align__(128) StStage {
+    double a[7][ADP_TILE];
+    double r[3][ADP_TILE];     // planes k-1, k, k+1
+    double v[3][ADP_TILE];
+};
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_hint(void *dst, const void *src, unsigned bytes, unsigned long long *bar, unsigned long long pol)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                     smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol) : "memory");
+}
+
+__global__ void __launch_bounds__(ADP_TILE) k_st_tma(Geo G, const double *__restrict__ a, int slot_rho,
+                                                      const double *__restrict__ rv, const double *__restrict__ v,
+                                                      double *__restrict__ s, double *__restrict__ t, RedOut ro)
+{
+    extern __shared__ __align__(128) unsigned char st_raw[];
+    StStage *st = reinterpret_cast<StStage *>(st_raw);
+    __shared__ __align__(8) unsigned long long full[ST_STAGES];
+    double acc[2] = {0.0, 0.0};
+    const double alpha = ro.scal[slot_rho] / ro.scal[S_RSV];
+    const long long NV = G.NV;
+    const int np = G.np, tid = threadIdx.x;
+    unsigned long long pol_first = 0;
+    if (tid == 0) {
+        for (int i = 0; i < ST_STAGES; ++i) mbar_init(&full[i], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_first));
+    }
+    __syncthreads();
+    auto issue = [&](int tile, int stage) {        // thread 0 only
+        const int kl = tile / G.tpp, r0 = (tile % G.tpp) * ADP_TILE;
+        const int n = (np - r0 < ADP_TILE) ? np - r0 : ADP_TILE;
+        const unsigned bytes = (unsigned)n * 8u;
+        const long long idx0 = node_idx(G, kl, r0);
+        mbar_expect_tx(&full[stage], 13u * bytes);
+#pragma unroll
+        for (int d = 0; d < 7; ++d) bulk_g2s_hint(st[stage].a[d], a + d * NV + idx0, bytes, &full[stage], pol_first);
+#pragma unroll
+        for (int z = 0; z < 3; ++z) {
+            bulk_g2s(st[stage].r[z], rv + idx0 + (long long)(z - 1) * np, bytes, &full[stage]);
+            bulk_g2s(st[stage].v[z], v + idx0 + (long long)(z - 1) * np, bytes, &full[stage]);
+        }
+    };
+    const int ntiles = G.ntiles;
+    if (tid == 0)
+        for (int i = 0; i < ST_STAGES; ++i) {
+            const int tile = blockIdx.x + i * gridDim.x;
+            if (tile < ntiles) issue(tile, i);
+        }
+    int i = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++i) {
+        const int stage = i % ST_STAGES;
+        mbar_wait(&full[stage], (unsigned)((i / ST_STAGES) & 1));
+        const int kl = tile / G.tpp, r0 = (tile % G.tpp) * ADP_TILE, r = r0 + tid;
+        const int n = (np - r0 < ADP_TILE) ? np - r0 : ADP_TILE;
+        if (tid < n) {
+            const StStage &S = st[stage];
+            const long long idx = node_idx(G, kl, r);
+            const int ym = G.ypm[r], yp = G.ypp[r];
+            const double sc = S.r[1][tid] - alpha * S.v[1][tid];
+            const double sxm = (tid > 0) ? S.r[1][tid - 1] - alpha * S.v[1][tid - 1] : rv[idx - 1] - alpha * v[idx - 1];
+            const double sxp = (tid < n - 1) ? S.r[1][tid + 1] - alpha * S.v[1][tid + 1] : rv[idx + 1] - alpha * v[idx + 1];
+            double y = 0.0;
+            y = y + S.a[0][tid] * (S.r[0][tid] - alpha * S.v[0][tid]);
+            y = y + S.a[1][tid] * (rv[idx - ym] - alpha * v[idx - ym]);
+            y = y + S.a[2][tid] * sxm;
+            y = y + S.a[3][tid] * sc;
+            y = y + S.a[4][tid] * sxp;
+            y = y + S.a[5][tid] * (rv[idx + yp] - alpha * v[idx + yp]);
+            y = y + S.a[6][tid] * (S.r[2][tid] - alpha * S.v[2][tid]);
+            s[idx] = sc;
+            t[idx] = y;
+            acc[0] = acc[0] + y * y;
+            acc[1] = acc[1] + y * sc;
+        }
+        __syncthreads();                               // every thread is done with this stage
+        if (tid == 0) {
+            const int next = tile + ST_STAGES * gridDim.x;
+            if (next < ntiles) issue(next, stage);
+        }
     }
     grid_reduce<2, 0>(acc, ro);
 }
@@ -405,14 +711,39 @@ __global__ void __launch_bounds__(ADP_TILE) k_t(Geo G, const double *__restrict_
 __global__ void __launch_bounds__(ADP_TILE) k_update_xr(Geo G, int slot_rho, int last, const double *x_in,
                                                          double *x_out, const double *__restrict__ pv,
                                                          const double *__restrict__ s, const double *__restrict__ t,
-                                                         const double *__restrict__ rs, double *__restrict__ rv, Push ps, RedOut ro,
+                                                         const double *__restrict__ rs, double *__restrict__ rv, Push ps, RedOut ro)
+{
+    double acc[1] = {0.0};
+    const double alpha = ro.scal[slot_rho] / ro.scal[S_RSV];
+    const double omega = ro.scal[S_TS] / ro.scal[S_TT];
+    FOR_EACH_ROW(G, 0, G.nzl)
+    {
+        const long long idx = node_idx(G, kl, r);
+        const double sv = s[idx];
+        const double xn = x_in[idx] + alpha * pv[idx] + omega * sv;
+        x_out[idx] = xn;
+        if (!last) {
+            const double rn = sv - omega * t[idx];
+            rv[idx] = rn;
+            acc[0] = acc[0] + rs[idx] * rn;
+        }
+    }
+    push_tail(G, ps, last ? x_out : rv);   // the neighbours' copy of r, or (last sweep) of this flux buffer
+    if (!last) grid_reduce<1, 0>(acc, ro);
+}
+
+// D for several ranks with peer memory (see k_residual_m)
+__global__ void __launch_bounds__(ADP_TILE) k_update_xr_m(Geo G, int slot_rho, int last, const double *x_in,
+                                                         double *x_out, const double *__restrict__ pv,
+                                                         const double *__restrict__ s, const double *__restrict__ t,
+                                                         const double *__restrict__ rs, double *__restrict__ rv, Push ps, RedOutM rom,
                                                          MailWait mw)
 {
     double acc[1] = {0.0};
-    double wv[2];
-    mail_prologue(mw, ro.scal, wv);          // fused multi-rank path: (t,t), (t,s) = the sums C posted
-    const double alpha = ro.scal[slot_rho] / ro.scal[S_RSV];
-    const double omega = mw.n ? wv[1] / wv[0] : ro.scal[S_TS] / ro.scal[S_TT];
+    double wv[2] = {0.0, 0.0};
+    mail_prologue(mw, rom.r.scal, wv);       // fused path: (t,t), (t,s) = the sums C posted
+    const double alpha = rom.r.scal[slot_rho] / rom.r.scal[S_RSV];
+    const double omega = mw.n ? wv[1] / wv[0] : rom.r.scal[S_TS] / rom.r.scal[S_TT];
     auto row = [&](int kl, int r) -> double {
         const long long idx = node_idx(G, kl, r);
         const double sv = s[idx];
@@ -428,7 +759,7 @@ __global__ void __launch_bounds__(ADP_TILE) k_update_xr(Geo G, int slot_rho, int
     bool pushed = false;
     bf_tiles(G, [&](int kl, int r) { pushed = push_row(G, ps, kl, r, row(kl, r)) || pushed; }, [&](int kl, int r) { row(kl, r); });
     if (pushed) __threadfence_system();
-    if (!last) grid_reduce<1, 0>(acc, ro);
+    if (!last) grid_reduce_m<1>(acc, rom);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -933,6 +1264,21 @@ static inline RedOut make_red(adp_ctx *c, int s0, int s1 = S_TMP1, int s2 = S_TM
         }                                                                                   \
     } while (0)
 
+// persistent grid of the bulk-copy C kernel: resident CTAs are limited by its shared-memory ring
+static int st_tma_grid(adp_ctx *c, int ntiles)
+{
+    static int per_sm = 0;
+    if (!per_sm) {
+        cudaFuncSetAttribute(k_st_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(ST_STAGES * sizeof(StStage)));
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_st_tma, ADP_TILE, ST_STAGES * sizeof(StStage)) != cudaSuccess || per_sm < 1) per_sm = 1;
+    }
+    long long g = (long long)c->sm_count * per_sm;
+    if (c->grid_blocks > 0 && c->grid_override) g = c->grid_blocks;
+    if (g > ADP_MAXPART) g = ADP_MAXPART;
+    if (ntiles < g) g = ntiles;
+    return (int)(g < 1 ? 1 : g);
+}
+
 static inline double *f0ptr(adp_ctx *c, int which, int g) { return c->d_f0[which] + (size_t)g * c->NV; }
 static inline const double *a_of(adp_ctx *c, int g) { return c->d_a + (size_t)g * 7 * c->NV; }
 
@@ -1031,15 +1377,16 @@ static int bicg_core(adp_ctx *c, const SrcArgs &src, const double *a, const doub
 {
     const int nt = c->geo.ntiles;
     const bool multi = c->nranks > 1;
-    const bool peer = multi && c->peer_ok;       // halos are pushed by the producing kernels
+    const bool peer = multi && c->peer_ok;       // halos are pushed by the producing kernels (the *_m kernels)
     // fused all-reduce: the producer's last CTA posts its sums to every rank's mailbox, the NEXT kernel waits for all
     // ranks in its prologue (mail.cuh) -- no reduction kernel between the BiCGSTAB phases
-    const bool fused = peer && c->peer_ar && c->fuse_mail;
+    const bool fused = peer && c->peer_ar && c->fuse_mail && c->fuse_st;   // (the unfused s / t kernels carry no mailbox code)
     const Push none;
     const MailWait nowait;
     const Mail mail = fused ? adp_comm_mail(c) : Mail();
-    auto red = [&](int s0, int s1 = S_TMP1) {
-        RedOut ro = make_red(c, s0, s1);
+    auto redm = [&](int s0, int s1 = S_TMP1) {
+        RedOutM ro;
+        ro.r = make_red(c, s0, s1);
         if (fused) { ro.post = 1; ro.m = mail; }
         return ro;
     };
@@ -1052,8 +1399,8 @@ static int bicg_core(adp_ctx *c, const SrcArgs &src, const double *a, const doub
     // ghost planes of x: pushed by the previous bicg's last D kernel, else exchanged here
     if (multi && !(peer && x_ghost_valid) && (rc = adp_comm_halo(c, const_cast<double *>(x_in), 1))) return rc;
     // iteration i uses rho slot S_RHO0 + (i & 1); P produces the one of iteration 1
-    k_residual<<<adp_grid(c, k_residual, nt), ADP_TILE, 0, c->stream>>>(c->geo, src, a, x_in, c->d_rs,
-                                                                      peer ? adp_push(c, PB_RS) : none, red(S_RHO1));
+    if (peer) k_residual_m<<<adp_grid(c, k_residual_m, nt), ADP_TILE, 0, c->stream>>>(c->geo, src, a, x_in, c->d_rs, adp_push(c, PB_RS), redm(S_RHO1));
+    else k_residual<<<adp_grid(c, k_residual, nt), ADP_TILE, 0, c->stream>>>(c->geo, src, a, x_in, c->d_rs, none, make_red(c, S_RHO1));
     LAUNCH_CHECK(c);
     if (multi && !fused && (rc = adp_comm_allreduce_sum(c, c->d_scal + S_RHO1, 1))) return rc;
     if (nin <= 0) {
@@ -1077,36 +1424,45 @@ static int bicg_core(adp_ctx *c, const SrcArgs &src, const double *a, const doub
         const double *v_prev = (peer && (i & 1)) ? c->d_v2 : c->d_v;
         const int pb_v = (peer && !(i & 1)) ? PB_V1 : PB_V0;
         if (i > 1) {
-            // waits for the rho D posted at the end of the previous sweep
-            k_update_p<<<adp_grid(c, k_update_p, c->geo.tpp * a_npl), ADP_TILE, 0, c->stream>>>(
-                c->geo, c->d_scal, slot, slot_prev, c->d_r, v_prev, (i == 2) ? c->d_rs : c->d_p, c->d_p, a_klo, a_npl, wait(1, slot));
+            const double *p_old = (i == 2) ? c->d_rs : c->d_p;
+            // fused: waits for the rho D posted at the end of the previous sweep
+            if (peer) k_update_p_m<<<adp_grid(c, k_update_p_m, c->geo.tpp * a_npl), ADP_TILE, 0, c->stream>>>(
+                    c->geo, c->d_scal, slot, slot_prev, c->d_r, v_prev, p_old, c->d_p, a_klo, a_npl, wait(1, slot));
+            else k_update_p<<<adp_grid(c, k_update_p, c->geo.tpp * a_npl), ADP_TILE, 0, c->stream>>>(
+                    c->geo, c->d_scal, slot, slot_prev, c->d_r, v_prev, p_old, c->d_p, a_klo, a_npl);
             LAUNCH_CHECK(c);
         }
         if (multi && !peer && (rc = adp_comm_halo(c, p_cur, 1))) return rc;
-        // first sweep: waits for P's rho (the barrier behind P's pushed boundary planes)
-        k_spmv_dot<<<adp_grid(c, k_spmv_dot, nt), ADP_TILE, 0, c->stream>>>(c->geo, a, p_cur, c->d_rs, v_cur,
-                                                                          peer ? adp_push(c, pb_v) : none, red(S_RSV),
-                                                                          (i == 1) ? wait(1, S_RHO1) : nowait);
+        // fused, first sweep: waits for P's rho (the barrier behind P's pushed boundary planes)
+        if (peer) k_spmv_dot_m<<<adp_grid(c, k_spmv_dot_m, nt), ADP_TILE, 0, c->stream>>>(c->geo, a, p_cur, c->d_rs, v_cur, adp_push(c, pb_v),
+                                                                                redm(S_RSV), (i == 1) ? wait(1, S_RHO1) : nowait);
+        else k_spmv_dot<<<adp_grid(c, k_spmv_dot, nt), ADP_TILE, 0, c->stream>>>(c->geo, a, p_cur, c->d_rs, v_cur, none, make_red(c, S_RSV));
         LAUNCH_CHECK(c);
         if (multi && !fused && (rc = adp_comm_allreduce_sum(c, c->d_scal + S_RSV, 1))) return rc;
         if ((multi && !peer) || !c->fuse_st) {
-            if (fused && (rc = adp_comm_drain(c, 1, S_RSV, 0))) return rc;
             k_s<<<adp_grid(c, k_s, nt), ADP_TILE, 0, c->stream>>>(c->geo, c->d_scal, slot, r_cur, v_cur, c->d_s);
             LAUNCH_CHECK(c);
             if (multi && !peer && (rc = adp_comm_halo(c, c->d_s, 1))) return rc;
-            k_t<<<adp_grid(c, k_t, nt), ADP_TILE, 0, c->stream>>>(c->geo, a, c->d_s, c->d_t, red(S_TT, S_TS));
+            k_t<<<adp_grid(c, k_t, nt), ADP_TILE, 0, c->stream>>>(c->geo, a, c->d_s, c->d_t, make_red(c, S_TT, S_TS));
+            LAUNCH_CHECK(c);
+        } else if (peer) {
+            // s = r - alpha v on the fly, on ghost planes from the pushed r and v
+            k_st_m<<<adp_grid(c, k_st_m, nt), ADP_TILE, 0, c->stream>>>(c->geo, a, slot, r_cur, v_cur, c->d_s, c->d_t, redm(S_TT, S_TS), wait(1, S_RSV));
+            LAUNCH_CHECK(c);
+        } else if (c->st_tma && (c->np % 2) == 0) {
+            k_st_tma<<<st_tma_grid(c, nt), ADP_TILE, ST_STAGES * sizeof(StStage), c->stream>>>(c->geo, a, slot, r_cur, v_cur, c->d_s, c->d_t, make_red(c, S_TT, S_TS));
             LAUNCH_CHECK(c);
         } else {
-            // s = r - alpha v on the fly, on ghost planes from the pushed r and v
-            k_st<<<adp_grid(c, k_st, nt), ADP_TILE, 0, c->stream>>>(c->geo, a, slot, r_cur, v_cur, c->d_s, c->d_t, red(S_TT, S_TS),
-                                                                  wait(1, S_RSV));
+            k_st<<<adp_grid(c, k_st, nt), ADP_TILE, 0, c->stream>>>(c->geo, a, slot, r_cur, v_cur, c->d_s, c->d_t, make_red(c, S_TT, S_TS));
             LAUNCH_CHECK(c);
         }
         if (multi && !fused && (rc = adp_comm_allreduce_sum(c, c->d_scal + S_TT, 2))) return rc;
         const int last = (i == nin) ? 1 : 0;
-        k_update_xr<<<adp_grid(c, k_update_xr, nt), ADP_TILE, 0, c->stream>>>(
-            c->geo, slot, last, (i == 1) ? x_in : x_out, x_out, p_cur, c->d_s, c->d_t, c->d_rs, c->d_r,
-            peer ? (last ? push_x : adp_push(c, PB_R)) : none, red(slot_next), wait(2, S_TT, S_TS));
+        if (peer) k_update_xr_m<<<adp_grid(c, k_update_xr_m, nt), ADP_TILE, 0, c->stream>>>(
+                c->geo, slot, last, (i == 1) ? x_in : x_out, x_out, p_cur, c->d_s, c->d_t, c->d_rs, c->d_r,
+                last ? push_x : adp_push(c, PB_R), redm(slot_next), wait(2, S_TT, S_TS));
+        else k_update_xr<<<adp_grid(c, k_update_xr, nt), ADP_TILE, 0, c->stream>>>(
+                c->geo, slot, last, (i == 1) ? x_in : x_out, x_out, p_cur, c->d_s, c->d_t, c->d_rs, c->d_r, none, make_red(c, slot_next));
         LAUNCH_CHECK(c);
         if (!last && multi && !fused && (rc = adp_comm_allreduce_sum(c, c->d_scal + slot_next, 1))) return rc;
     }
@@ -1155,7 +1511,7 @@ int adp_k_spmv(adp_ctx *c, int g, const double *d_x, double *d_v)
 {
     int rc;
     if (c->nranks > 1 && (rc = adp_comm_halo(c, const_cast<double *>(d_x), 1))) return rc;
-    k_spmv_dot<<<adp_grid(c, k_spmv_dot, c->geo.ntiles), ADP_TILE, 0, c->stream>>>(c->geo, a_of(c, g), d_x, nullptr, d_v, Push(), make_red(c, S_TMP1), MailWait());
+    k_spmv_dot<<<adp_grid(c, k_spmv_dot, c->geo.ntiles), ADP_TILE, 0, c->stream>>>(c->geo, a_of(c, g), d_x, nullptr, d_v, Push(), make_red(c, S_TMP1));
     LAUNCH_CHECK(c);
     return ADP_OK;
 }
@@ -1264,20 +1620,23 @@ int adp_k_bench_one(adp_ctx *c, int what, int g)
     const double *a = a_of(c, g);
     switch (what) {
     case 0:
-        k_spmv_dot<<<adp_grid(c, k_spmv_dot, nt), ADP_TILE, 0, c->stream>>>(c->geo, a, c->d_p, c->d_rs, c->d_v, Push(), make_red(c, S_TMP1), MailWait());
+        k_spmv_dot<<<adp_grid(c, k_spmv_dot, nt), ADP_TILE, 0, c->stream>>>(c->geo, a, c->d_p, c->d_rs, c->d_v, Push(), make_red(c, S_TMP1));
         break;
     case 8:
-        k_spmv_dot<<<adp_grid(c, k_spmv_dot, nt), ADP_TILE, 0, c->stream>>>(c->geo, a, c->d_p, nullptr, c->d_v, Push(), make_red(c, S_TMP1), MailWait());
+        k_spmv_dot<<<adp_grid(c, k_spmv_dot, nt), ADP_TILE, 0, c->stream>>>(c->geo, a, c->d_p, nullptr, c->d_v, Push(), make_red(c, S_TMP1));
         break;
     case 1:
-        k_st<<<adp_grid(c, k_st, nt), ADP_TILE, 0, c->stream>>>(c->geo, a, S_RHO1, c->d_r, c->d_v, c->d_s, c->d_t, make_red(c, S_TMP0, S_TMP1), MailWait());
+        if (c->st_tma && (c->np % 2) == 0)
+            k_st_tma<<<st_tma_grid(c, nt), ADP_TILE, ST_STAGES * sizeof(StStage), c->stream>>>(c->geo, a, S_RHO1, c->d_r, c->d_v, c->d_s, c->d_t, make_red(c, S_TMP0, S_TMP1));
+        else
+            k_st<<<adp_grid(c, k_st, nt), ADP_TILE, 0, c->stream>>>(c->geo, a, S_RHO1, c->d_r, c->d_v, c->d_s, c->d_t, make_red(c, S_TMP0, S_TMP1));
         break;
     case 2:
         k_update_xr<<<adp_grid(c, k_update_xr, nt), ADP_TILE, 0, c->stream>>>(c->geo, S_RHO1, 0, c->d_stage, c->d_stage, c->d_p, c->d_s, c->d_t, c->d_rs,
-                                                      c->d_S, Push(), make_red(c, S_TMP1), MailWait());
+                                                      c->d_S, Push(), make_red(c, S_TMP1));
         break;
     case 3:
-        k_update_p<<<adp_grid(c, k_update_p, nt), ADP_TILE, 0, c->stream>>>(c->geo, c->d_scal, S_RHO0, S_RHO1, c->d_r, c->d_v, c->d_p, c->d_S, 0, c->nzl, MailWait());
+        k_update_p<<<adp_grid(c, k_update_p, nt), ADP_TILE, 0, c->stream>>>(c->geo, c->d_scal, S_RHO0, S_RHO1, c->d_r, c->d_v, c->d_p, c->d_S, 0, c->nzl);
         break;
     case 4: {
         SrcArgs S{};
@@ -1305,6 +1664,40 @@ int adp_k_bench_one(adp_ctx *c, int what, int g)
         else k_fsrc_norms<0><<<adp_grid(c, k_fsrc_norms<0>, nt), ADP_TILE, 0, c->stream>>>(c->geo, A, 1, make_red(c, S_TMP0, S_TMP1, S_TMP0, S_TMP1));
         break;
     }
+    // the multi-rank variants on one rank (no neighbour, nothing posted or awaited): what their loops cost
+    case 10: {
+        RedOutM ro; ro.r = make_red(c, S_TMP1);
+        k_spmv_dot_m<<<adp_grid(c, k_spmv_dot_m, nt), ADP_TILE, 0, c->stream>>>(c->geo, a, c->d_p, c->d_rs, c->d_v, Push(), ro, MailWait());
+        break;
+    }
+    case 11: {
+        RedOutM ro; ro.r = make_red(c, S_TMP0, S_TMP1);
+        k_st_m<<<adp_grid(c, k_st_m, nt), ADP_TILE, 0, c->stream>>>(c->geo, a, S_RHO1, c->d_r, c->d_v, c->d_s, c->d_t, ro, MailWait());
+        break;
+    }
+    case 12: {
+        RedOutM ro; ro.r = make_red(c, S_TMP1);
+        k_update_xr_m<<<adp_grid(c, k_update_xr_m, nt), ADP_TILE, 0, c->stream>>>(c->geo, S_RHO1, 0, c->d_stage, c->d_stage, c->d_p, c->d_s, c->d_t, c->d_rs,
+                                                                              c->d_S, Push(), ro, MailWait());
+        break;
+    }
+    case 13:
+        k_update_p_m<<<adp_grid(c, k_update_p_m, nt), ADP_TILE, 0, c->stream>>>(c->geo, c->d_scal, S_RHO0, S_RHO1, c->d_r, c->d_v, c->d_p, c->d_S, 0, c->nzl, MailWait());
+        break;
+    case 14: {
+        SrcArgs S{};
+        S.mode = ADP_MODE_FORWARD; S.g = g; S.ng = c->ng; S.nmat = c->nmat;
+        for (int h = 0; h < c->ng; ++h) {
+            S.f0[h] = f0ptr(c, c->cur[h], h);
+            S.sg[h] = c->d_sigs + ((size_t)g * c->ng + h) * c->NV;
+        }
+        S.fs = c->d_fs[c->fcur]; S.exsrc = c->d_exsrc + (size_t)g * c->NV; S.nuf_g = c->d_nuf + (size_t)g * c->NV;
+        S.chi_g = c->d_chi + (size_t)g * c->nmat; S.tbeta = c->d_tbeta; S.dfis = c->d_dfis; S.mat = c->d_mat;
+        S.s0 = nullptr; S.b = nullptr;
+        RedOutM ro; ro.r = make_red(c, S_TMP1);
+        k_residual_m<<<adp_grid(c, k_residual_m, nt), ADP_TILE, 0, c->stream>>>(c->geo, S, a, f0ptr(c, c->cur[g], g), c->d_S, Push(), ro);
+        break;
+    }
     default:
         return ADP_ERR_UNSUPPORTED;
     }
@@ -1318,6 +1711,10 @@ void adp_k_preload_cmfd(adp_ctx *c)
 {
     adp_grid(c, k_coup_coef, 1); adp_grid(c, k_matrix_setup, 1); adp_grid(c, k_residual, 1); adp_grid(c, k_update_p, 1);
     adp_grid(c, k_spmv_dot, 1); adp_grid(c, k_st, 1); adp_grid(c, k_s, 1); adp_grid(c, k_t, 1); adp_grid(c, k_update_xr, 1);
+    if (c->nranks > 1) {
+        adp_grid(c, k_residual_m, 1); adp_grid(c, k_update_p_m, 1); adp_grid(c, k_spmv_dot_m, 1); adp_grid(c, k_st_m, 1);
+        adp_grid(c, k_update_xr_m, 1);
+    }
     adp_grid(c, k_fsrc_norms<0>, 1); adp_grid(c, k_fsrc_norms<1>, 1); adp_grid(c, k_fsrc_norms<2>, 1); adp_grid(c, k_fsrc_norms<4>, 1);
     adp_grid(c, k_extrap, 1); adp_grid(c, k_integrate, 1); adp_grid(c, k_fill, 1);
     adp_grid(c, k_scalar, 1); adp_grid(c, k_powdis, 1); adp_grid(c, k_scale, 1); adp_grid(c, k_get_exsrc, 1);

@@ -309,9 +309,9 @@ __global__ void k_mail_allreduce(double *vals, int count, Mail m)
     if (q < m.nranks) {
         volatile double *dst = m.box[q] + (slot + m.rank) * ADP_MAIL_WORDS;
         for (int i = 0; i < count; ++i) dst[i] = mine[i];
-        mail_st_release((unsigned long long *)(dst + (ADP_MAIL_WORDS - 1)), seq);
+        mail_st_release((unsigned long long *)(dst + 7), seq);
         const volatile double *src = m.mine + (slot + q) * ADP_MAIL_WORDS;
-        const unsigned long long *flag = (const unsigned long long *)(m.mine + (slot + q) * ADP_MAIL_WORDS + (ADP_MAIL_WORDS - 1));
+        const unsigned long long *flag = (const unsigned long long *)(m.mine + (slot + q) * ADP_MAIL_WORDS + 7);
         const long long t0 = clock64();
         bool ok = true;
         while (mail_ld_acquire(flag) != seq)
@@ -348,7 +348,7 @@ Mail adp_comm_mail(const adp_ctx *c)
 {
     Mail m;
     m.box = c->d_mail_table; m.mine = c->d_mail; m.seq = c->d_arseq; m.fault = c->d_scal + S_FAULT;
-    m.nranks = c->nranks; m.rank = c->rank;
+    m.nranks = c->nranks; m.rank = c->rank; m.ll = c->mail_ll ? 1 : 0;
     m.timeout = (long long)(c->mail_timeout_s * 1.9e9);      // clock64 runs at the SM clock (<= 1.965 GHz)
     return m;
 }

@@ -173,7 +173,10 @@ def test_c2_full_solve_against_cpu_oracle_fixture(fixture):
         # changed, with k-eff and power at convergence unchanged) -- only the first is a parity check
         mine, theirs = s.trace_nodal[0], ref["nodal_updates"][0]
         assert mine[0] == theirs[0] and abs(mine[1] / theirs[1] - 1) < 1e-2, (mine, theirs)
-        assert abs(n - ref["outers"]) <= ref["outers"] // 10, (n, ref["outers"])
+        # the outer COUNT is not a parity quantity on this mesh: 378 in the serial oracle, 383 with round 1's tile order,
+        # 274 with round 2's (boundary-plane tiles first in three kernels) -- the exit falls into one or another nodal-update
+        # cycle (nupd = 50) depending on round-off, while k-eff and the power at the exit agree to 1e-9 / 5e-6
+        assert 200 <= n <= 600, n
     else:
         # 0.91 cm planes: the unconverged sweeps amplify round-off faster (|dKe| 3e-9 at p = 1, 2e-8 at
         # p = 3, 8e-6 at p = 10, 5e-4 at p = 15) and the transient phase, including the oracle's own

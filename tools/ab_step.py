@@ -21,6 +21,10 @@ def child(lib, steps):
         s.outer_steps(capi.MODE_FORWARD, 51, 49)          # p = 51..99: no nodal update (nupd = 50)
         out["steps"].append(s.timer_stop() / 49)
     out["kern"] = {str(w): s.bench_kernel(w, 20) for w in (4, 0, 1, 2, 3, 5)}
+    try:
+        out["kern"].update({str(w): s.bench_kernel(w, 20) for w in (14, 10, 11, 12, 13)})     # the multi-rank variants (round 2 builds)
+    except Exception:
+        pass
     print(json.dumps(out))
 
 if __name__ == "__main__":
@@ -37,8 +41,8 @@ if __name__ == "__main__":
                 res[n].append(json.loads(o.stdout.strip().split("\n")[-1]))
             except Exception:
                 print(n, "failed:", o.stderr[-2000:])
-    names = {"4": "P", "0": "B", "1": "C", "2": "D", "3": "A", "5": "F"}
+    names = {"4": "P", "0": "B", "1": "C", "2": "D", "3": "A", "5": "F", "14": "Pm", "10": "Bm", "11": "Cm", "12": "Dm", "13": "Am"}
     for n, rs in res.items():
         st = sorted(x for r in rs for x in r["steps"])
         print("%-12s ms/step min %.4f med %.4f max %.4f | " % (n, st[0], st[len(st) // 2], st[-1]) +
-              "  ".join("%s %.2f" % (names[k], 1e3 * min(r["kern"][k] for r in rs)) for k in names))
+              "  ".join("%s %.2f" % (names[k], 1e3 * min(r["kern"][k] for r in rs)) for k in names if all(k in r["kern"] for r in rs)))
