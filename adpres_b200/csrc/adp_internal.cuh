@@ -246,6 +246,9 @@ struct adp_ctx {
                                            // registers instead of storing it (bit-identical, 1.7x less DRAM traffic, but 2.7x
                                            // SLOWER: 8 warps per SM cannot hide the fp64 division chains -- DESIGN.md)
     bool fuse_st = true;                   // C kernel: s on the fly inside t = A s (false: k_s then k_t)
+    int spmv_var = 4;                      // formulation of the B kernel (k_spmv_dot), single rank: 0..6 (4: loads grouped, 48 registers)
+    int st_var = 6;                        // formulation of the C kernel (k_st), single rank: 0..7 (6: loads grouped, 64 registers)
+    int st_m_var = 6;                      // the same for the multi-rank C kernel (k_st_m)
     bool st_tma = false;                   // C kernel staged with cp.async.bulk + mbarrier (experiment, single rank, np even)
     // bookkeeping
     long long launches = 0;

@@ -1191,6 +1191,9 @@ extern "C" int adp_set_option(adp_ctx *c, const char *name, int value)
     if (!strcmp(name, "bench_warmup")) { c->bench_warmup = value; return ADP_OK; }
     if (!strcmp(name, "nodal_coop")) { c->nodal_coop = value; free_graphs(c); return ADP_OK; }
     if (!strcmp(name, "nodal_fused")) { c->nodal_fused = value; free_graphs(c); return ADP_OK; }
+    if (!strcmp(name, "spmv_var")) { c->spmv_var = value; free_graphs(c); return ADP_OK; }
+    if (!strcmp(name, "st_var")) { c->st_var = value; free_graphs(c); return ADP_OK; }
+    if (!strcmp(name, "st_m_var")) { c->st_m_var = value; free_graphs(c); return ADP_OK; }
     if (!strcmp(name, "st_tma")) { c->st_tma = value != 0; free_graphs(c); return ADP_OK; }
     if (!strcmp(name, "fuse_st")) { c->fuse_st = value != 0; free_graphs(c); return ADP_OK; }
     if (!strcmp(name, "grid_blocks")) {

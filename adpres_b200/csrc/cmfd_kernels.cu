@@ -192,6 +192,55 @@ __device__ __forceinline__ void grid_reduce_m(double (&val)[NS], const RedOutM &
                  once__ = 1;                                                                        \
              once__ && r < (G_).np; once__ = 0)
 
+// L2 reuse between consecutive kernels (round 2).  Every BiCGSTAB kernel streams 150 - 400 MB through the 126 MB L2 and the
+// next kernel re-reads part of it (C the matrix and v of B, D the s and t of C, A the r and p of D, B the p of A).  Walking
+// all kernels in the same tile order meets the OLDEST lines of the predecessor first -- the ones a cache of this size has
+// already evicted.  With ADP_SWEEP_REV the kernels B and D walk the tiles from the last to the first (A, C, P, F forward), so
+// every kernel starts where its predecessor has just finished and finds the tail of that kernel's traffic in L2.
+// ADP_L2_HINTS marks the streams that are not re-read by the next kernel evict-first (ld/st.global.cs) so that they do
+// not push out the ones that are.  Same values, same operations; only the order of the reduction partials changes.
+#ifndef ADP_SWEEP_REV
+#define ADP_SWEEP_REV 1
+#endif
+#ifndef ADP_L2_HINTS
+#define ADP_L2_HINTS 0
+#endif
+#define FOR_EACH_ROW_REV(G_, KLO, NPL)                                                                  \
+    for (int tile0__ = blockIdx.x; tile0__ < (G_).tpp * (NPL); tile0__ += gridDim.x)                    \
+        for (int tile__ = (G_).tpp * (NPL) - 1 - tile0__, kl = (KLO) + tile__ / (G_).tpp,               \
+                 r = (tile__ % (G_).tpp) * ADP_TILE + threadIdx.x, once__ = 1;                          \
+             once__ && r < (G_).np; once__ = 0)
+#if ADP_SWEEP_REV
+#define FOR_EACH_ROW_BWD FOR_EACH_ROW_REV
+#else
+#define FOR_EACH_ROW_BWD FOR_EACH_ROW
+#endif
+// loads / stores of streams the NEXT kernel does not read again.  ADP_L2_HINTS is a bit mask (A/B, tools/ab_step.py):
+//   1 A: r, p_old, v          2 B: rs          4 C: the 7 coefficient streams, ld.global.nc + evict-first cache policy
+//   8 D: s, t, x_in, rs      16 D: x_out (store)                32 C: the 7 coefficient streams, ld.global.cs
+#define HINT_A 1
+#define HINT_B 2
+#define HINT_C_POL 4
+#define HINT_D_LD 8
+#define HINT_D_ST 16
+#define HINT_C_CS 32
+#define LD_ONCE(bit, p) ((ADP_L2_HINTS & (bit)) ? __ldcs(p) : *(p))
+#define ST_ONCE(bit, p, v) do { if (ADP_L2_HINTS & (bit)) __stcs(p, v); else *(p) = (v); } while (0)
+__device__ __forceinline__ unsigned long long l2_policy_evict_first()
+{
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ double ld_nc_policy(const double *p, unsigned long long pol)
+{
+    double v;
+    asm("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
+    return v;
+}
+// coefficient loads of C
+#define LD_COEF(p) ((ADP_L2_HINTS & HINT_C_POL) ? ld_nc_policy(p, pol_ef) : ((ADP_L2_HINTS & HINT_C_CS) ? __ldcs(p) : *(p)))
+
 __device__ __forceinline__ long long node_idx(const Geo &G, int kl, int r)
 {
     return (long long)(kl + ADP_GH) * G.np + r;
@@ -234,7 +283,7 @@ __device__ __forceinline__ void push_tail(const Geo &G, const Push &ps, const do
 //   tile t in [0, nb)        boundary: plane 0 (t < tpp) or plane nzl-1
 //   tile t in [nb, ntiles)   interior planes 1 .. nzl-2
 // grid-stride over this numbering, so the work per CTA stays balanced.
-template <typename FB, typename FI>
+template <bool REV = false, typename FB, typename FI>
 __device__ __forceinline__ void bf_tiles(const Geo &G, FB &&boundary, FI &&interior)
 {
     const int nb = (G.nzl >= 2 ? 2 : 1) * G.tpp;
@@ -244,7 +293,7 @@ __device__ __forceinline__ void bf_tiles(const Geo &G, FB &&boundary, FI &&inter
         if (r < G.np) boundary(kl, r);
     }
     for (; t < G.ntiles; t += gridDim.x) {
-        const int u = t - nb;
+        const int u = REV ? G.ntiles - 1 - t : t - nb;      // REV: the interior from the top plane down (ADP_SWEEP_REV)
         const int kl = 1 + u / G.tpp, r = (u % G.tpp) * ADP_TILE + threadIdx.x;
         if (r < G.np) interior(kl, r);
     }
@@ -398,21 +447,44 @@ __global__ void __launch_bounds__(ADP_TILE) k_update_p(Geo G, const double *__re
     FOR_EACH_ROW(G, klo, npl)
     {
         const long long idx = node_idx(G, kl, r);
-        p_out[idx] = rv[idx] + beta * (p_in[idx] - omega * v[idx]);
+        p_out[idx] = LD_ONCE(HINT_A, &rv[idx]) + beta * (LD_ONCE(HINT_A, &p_in[idx]) - omega * LD_ONCE(HINT_A, &v[idx]));
     }
 }
 
 // B: v = A p and the partial sums of (rs, v)   (mod_cmfd.f90:1233-1234)
-__global__ void __launch_bounds__(ADP_TILE) k_spmv_dot(Geo G, const double *__restrict__ a, const double *__restrict__ pv,
+// VAR / MINB as for k_st below (option "spmv_var"): 1 = the 7 coefficients and the row's own p loaded first in the source
+template <int VAR, int MINB>
+__global__ void __launch_bounds__(ADP_TILE, MINB) k_spmv_dot(Geo G, const double *__restrict__ a, const double *__restrict__ pv,
                                                         const double *__restrict__ rs, double *__restrict__ v, Push ps, RedOut ro)
 {
     double acc[1] = {0.0};
-    FOR_EACH_ROW(G, 0, G.nzl)
+    FOR_EACH_ROW_BWD(G, 0, G.nzl)
     {
         const long long idx = node_idx(G, kl, r);
-        const double y = stencil7(a, G.NV, pv, idx, G.np, G.ypm[r], G.ypp[r]);
-        v[idx] = y;
-        if (rs) acc[0] = acc[0] + rs[idx] * y;
+        double y;
+        if (VAR == 1) {
+            const long long NV = G.NV;
+            const int np = G.np, ym = G.ypm[r], yp = G.ypp[r];
+            const double a0 = a[idx], a1 = a[NV + idx], a2 = a[2 * NV + idx], a3 = a[3 * NV + idx], a4 = a[4 * NV + idx],
+                         a5 = a[5 * NV + idx], a6 = a[6 * NV + idx];
+            const double pc = pv[idx], rsv = rs ? rs[idx] : 0.0;
+            const double pzm = pv[idx - np], pym = pv[idx - ym], pxm = pv[idx - 1], pxp = pv[idx + 1], pyp = pv[idx + yp],
+                         pzp = pv[idx + np];
+            y = 0.0;
+            y = y + a0 * pzm;
+            y = y + a1 * pym;
+            y = y + a2 * pxm;
+            y = y + a3 * pc;
+            y = y + a4 * pxp;
+            y = y + a5 * pyp;
+            y = y + a6 * pzp;
+            v[idx] = y;
+            if (rs) acc[0] = acc[0] + rsv * y;
+        } else {
+            y = stencil7(a, G.NV, pv, idx, G.np, G.ypm[r], G.ypp[r]);
+            v[idx] = y;
+            if (rs) acc[0] = acc[0] + LD_ONCE(HINT_B, &rs[idx]) * y;
+        }
     }
     push_tail(G, ps, v);
     if (rs) grid_reduce<1, 0>(acc, ro);
@@ -420,7 +492,57 @@ __global__ void __launch_bounds__(ADP_TILE) k_spmv_dot(Geo G, const double *__re
 
 // C: s = r - alpha v evaluated on the fly at the 7 stencil points, t = A s, (t,t), (t,s)
 //    (mod_cmfd.f90:1234-1238).  s is stored for the own row only.
-__global__ void __launch_bounds__(ADP_TILE) k_st(Geo G, const double *__restrict__ a, int slot_rho,
+// The loop body is one basic block of 21 loads; how ptxas orders them decides how many memory round trips a row costs, and
+// the order it picks depends on everything else in the kernel (with the mailbox prologue of the multi-rank form the same
+// source ran 95 us instead of 80: round 2, one box).  VAR selects formulations of the SAME arithmetic (options "st_var" /
+// "st_m_var", A/B with tools/stm_ab.py):  0 round 1's text;  1 row index by mul.wide.s32 (the prologue makes NVVM widen np
+// and multiply in 64 bits);  2 loads grouped in the source: the nine operands that miss to DRAM (7 coefficients, r, v of
+// the row) first, then the neighbours.  MINB = resident CTAs per SM asked of ptxas (0 = unconstrained -> 40 registers, 6 per
+// SM; 5 = 48 registers; 4 = 64 registers: all 21 loads issue before the first use).
+__device__ __forceinline__ long long node_idx_w(int np, int kl, int r)
+{
+    long long w;
+    asm("mul.wide.s32 %0, %1, %2;" : "=l"(w) : "r"(kl + ADP_GH), "r"(np));
+    return w + r;
+}
+#define ST_ROW_BODY(VAR)                                                                                                  \
+    const long long idx = ((VAR) >= 1) ? node_idx_w(np, kl, r) : node_idx(G, kl, r);                                      \
+    const int ym = G.ypm[r], yp = G.ypp[r];                                                                               \
+    double sc, y = 0.0;                                                                                                   \
+    if ((VAR) == 2) {                                                                                                     \
+        const double a0 = LD_COEF(&a[idx]), a1 = LD_COEF(&a[NV + idx]), a2 = LD_COEF(&a[2 * NV + idx]),                   \
+                     a3 = LD_COEF(&a[3 * NV + idx]), a4 = LD_COEF(&a[4 * NV + idx]), a5 = LD_COEF(&a[5 * NV + idx]),      \
+                     a6 = LD_COEF(&a[6 * NV + idx]);                                                                      \
+        const double rc = rv[idx], vc = v[idx];                                                                           \
+        const double rzm = rv[idx - np], vzm = v[idx - np], rym = rv[idx - ym], vym = v[idx - ym], rxm = rv[idx - 1],     \
+                     vxm = v[idx - 1];                                                                                    \
+        sc = rc - alpha * vc;                                                                                             \
+        y = y + a0 * (rzm - alpha * vzm);                                                                                 \
+        y = y + a1 * (rym - alpha * vym);                                                                                 \
+        y = y + a2 * (rxm - alpha * vxm);                                                                                 \
+        y = y + a3 * sc;                                                                                                  \
+        const double rxp = rv[idx + 1], vxp = v[idx + 1], ryp = rv[idx + yp], vyp = v[idx + yp], rzp = rv[idx + np],      \
+                     vzp = v[idx + np];                                                                                   \
+        y = y + a4 * (rxp - alpha * vxp);                                                                                 \
+        y = y + a5 * (ryp - alpha * vyp);                                                                                 \
+        y = y + a6 * (rzp - alpha * vzp);                                                                                 \
+    } else {                                                                                                              \
+        sc = rv[idx] - alpha * v[idx];                                                                                    \
+        y = y + LD_COEF(&a[idx]) * (rv[idx - np] - alpha * v[idx - np]);                                                  \
+        y = y + LD_COEF(&a[NV + idx]) * (rv[idx - ym] - alpha * v[idx - ym]);                                             \
+        y = y + LD_COEF(&a[2 * NV + idx]) * (rv[idx - 1] - alpha * v[idx - 1]);                                           \
+        y = y + LD_COEF(&a[3 * NV + idx]) * sc;                                                                           \
+        y = y + LD_COEF(&a[4 * NV + idx]) * (rv[idx + 1] - alpha * v[idx + 1]);                                           \
+        y = y + LD_COEF(&a[5 * NV + idx]) * (rv[idx + yp] - alpha * v[idx + yp]);                                         \
+        y = y + LD_COEF(&a[6 * NV + idx]) * (rv[idx + np] - alpha * v[idx + np]);                                         \
+    }                                                                                                                     \
+    s[idx] = sc;                                                                                                          \
+    t[idx] = y;                                                                                                           \
+    acc[0] = acc[0] + y * y;                                                                                              \
+    acc[1] = acc[1] + y * sc;
+
+template <int VAR, int MINB>
+__global__ void __launch_bounds__(ADP_TILE, MINB) k_st(Geo G, const double *__restrict__ a, int slot_rho,
                                                   const double *__restrict__ rv, const double *__restrict__ v,
                                                   double *__restrict__ s, double *__restrict__ t, RedOut ro)
 {
@@ -428,23 +550,10 @@ __global__ void __launch_bounds__(ADP_TILE) k_st(Geo G, const double *__restrict
     const double alpha = ro.scal[slot_rho] / ro.scal[S_RSV];
     const long long NV = G.NV;
     const int np = G.np;
+    [[maybe_unused]] const unsigned long long pol_ef = (ADP_L2_HINTS & HINT_C_POL) ? l2_policy_evict_first() : 0ull;
     FOR_EACH_ROW(G, 0, G.nzl)
     {
-        const long long idx = node_idx(G, kl, r);
-        const int ym = G.ypm[r], yp = G.ypp[r];
-        const double sc = rv[idx] - alpha * v[idx];
-        double y = 0.0;
-        y = y + a[idx] * (rv[idx - np] - alpha * v[idx - np]);
-        y = y + a[NV + idx] * (rv[idx - ym] - alpha * v[idx - ym]);
-        y = y + a[2 * NV + idx] * (rv[idx - 1] - alpha * v[idx - 1]);
-        y = y + a[3 * NV + idx] * sc;
-        y = y + a[4 * NV + idx] * (rv[idx + 1] - alpha * v[idx + 1]);
-        y = y + a[5 * NV + idx] * (rv[idx + yp] - alpha * v[idx + yp]);
-        y = y + a[6 * NV + idx] * (rv[idx + np] - alpha * v[idx + np]);
-        s[idx] = sc;
-        t[idx] = y;
-        acc[0] = acc[0] + y * y;
-        acc[1] = acc[1] + y * sc;
+        ST_ROW_BODY(VAR)
     }
     grid_reduce<2, 0>(acc, ro);
 }
@@ -500,7 +609,7 @@ __global__ void __launch_bounds__(ADP_TILE, ADP_LB_PA) k_update_p_m(Geo G, doubl
     FOR_EACH_ROW(G, klo, npl)
     {
         const long long idx = node_idx(G, kl, r);
-        p_out[idx] = rv[idx] + beta * (p_in[idx] - omega * v[idx]);
+        p_out[idx] = LD_ONCE(HINT_A, &rv[idx]) + beta * (LD_ONCE(HINT_A, &p_in[idx]) - omega * LD_ONCE(HINT_A, &v[idx]));
     }
 }
 
@@ -515,16 +624,18 @@ __global__ void __launch_bounds__(ADP_TILE) k_spmv_dot_m(Geo G, const double *__
         const long long idx = node_idx(G, kl, r);
         const double y = stencil7(a, G.NV, pv, idx, G.np, G.ypm[r], G.ypp[r]);
         v[idx] = y;
-        acc[0] = acc[0] + rs[idx] * y;
+        acc[0] = acc[0] + LD_ONCE(HINT_B, &rs[idx]) * y;
         return y;
     };
     bool pushed = false;
-    bf_tiles(G, [&](int kl, int r) { pushed = push_row(G, ps, kl, r, row(kl, r)) || pushed; }, [&](int kl, int r) { row(kl, r); });
+    bf_tiles<ADP_SWEEP_REV != 0>(G, [&](int kl, int r) { pushed = push_row(G, ps, kl, r, row(kl, r)) || pushed; }, [&](int kl, int r) { row(kl, r); });
     if (pushed) __threadfence_system();
     grid_reduce_m<1>(acc, rom);
 }
 
-__global__ void __launch_bounds__(ADP_TILE) k_st_m(Geo G, const double *__restrict__ a, int slot_rho,
+// C for several ranks: (rs, v) arrives through the mailbox in the prologue; formulations as for k_st
+template <int VAR, int MINB>
+__global__ void __launch_bounds__(ADP_TILE, MINB) k_st_m(Geo G, const double *__restrict__ a, int slot_rho,
                                                   const double *__restrict__ rv, const double *__restrict__ v,
                                                   double *__restrict__ s, double *__restrict__ t, RedOutM rom, MailWait mw)
 {
@@ -534,23 +645,10 @@ __global__ void __launch_bounds__(ADP_TILE) k_st_m(Geo G, const double *__restri
     const double alpha = rom.r.scal[slot_rho] / (mw.n ? wv[0] : rom.r.scal[S_RSV]);
     const long long NV = G.NV;
     const int np = G.np;
+    [[maybe_unused]] const unsigned long long pol_ef = (ADP_L2_HINTS & HINT_C_POL) ? l2_policy_evict_first() : 0ull;
     FOR_EACH_ROW(G, 0, G.nzl)
     {
-        const long long idx = node_idx(G, kl, r);
-        const int ym = G.ypm[r], yp = G.ypp[r];
-        const double sc = rv[idx] - alpha * v[idx];
-        double y = 0.0;
-        y = y + a[idx] * (rv[idx - np] - alpha * v[idx - np]);
-        y = y + a[NV + idx] * (rv[idx - ym] - alpha * v[idx - ym]);
-        y = y + a[2 * NV + idx] * (rv[idx - 1] - alpha * v[idx - 1]);
-        y = y + a[3 * NV + idx] * sc;
-        y = y + a[4 * NV + idx] * (rv[idx + 1] - alpha * v[idx + 1]);
-        y = y + a[5 * NV + idx] * (rv[idx + yp] - alpha * v[idx + yp]);
-        y = y + a[6 * NV + idx] * (rv[idx + np] - alpha * v[idx + np]);
-        s[idx] = sc;
-        t[idx] = y;
-        acc[0] = acc[0] + y * y;
-        acc[1] = acc[1] + y * sc;
+        ST_ROW_BODY(VAR)
     }
     grid_reduce_m<2>(acc, rom);
 }
@@ -716,16 +814,17 @@ __global__ void __launch_bounds__(ADP_TILE) k_update_xr(Geo G, int slot_rho, int
     double acc[1] = {0.0};
     const double alpha = ro.scal[slot_rho] / ro.scal[S_RSV];
     const double omega = ro.scal[S_TS] / ro.scal[S_TT];
-    FOR_EACH_ROW(G, 0, G.nzl)
+    FOR_EACH_ROW_BWD(G, 0, G.nzl)
     {
         const long long idx = node_idx(G, kl, r);
-        const double sv = s[idx];
-        const double xn = x_in[idx] + alpha * pv[idx] + omega * sv;
-        x_out[idx] = xn;
-        if (!last) {
-            const double rn = sv - omega * t[idx];
+        const double sv = LD_ONCE(HINT_D_LD, &s[idx]);
+        const double xn = LD_ONCE(HINT_D_LD, &x_in[idx]) + alpha * pv[idx] + omega * sv;
+        if (last) x_out[idx] = xn;         // the flux: read next by P / F
+        else {
+            ST_ONCE(HINT_D_ST, &x_out[idx], xn);       // read again only by the next D
+            const double rn = sv - omega * LD_ONCE(HINT_D_LD, &t[idx]);
             rv[idx] = rn;
-            acc[0] = acc[0] + rs[idx] * rn;
+            acc[0] = acc[0] + LD_ONCE(HINT_D_LD, &rs[idx]) * rn;
         }
     }
     push_tail(G, ps, last ? x_out : rv);   // the neighbours' copy of r, or (last sweep) of this flux buffer
@@ -746,18 +845,18 @@ __global__ void __launch_bounds__(ADP_TILE) k_update_xr_m(Geo G, int slot_rho, i
     const double omega = mw.n ? wv[1] / wv[0] : rom.r.scal[S_TS] / rom.r.scal[S_TT];
     auto row = [&](int kl, int r) -> double {
         const long long idx = node_idx(G, kl, r);
-        const double sv = s[idx];
-        const double xn = x_in[idx] + alpha * pv[idx] + omega * sv;
-        x_out[idx] = xn;
-        if (last) return xn;
-        const double rn = sv - omega * t[idx];
+        const double sv = LD_ONCE(HINT_D_LD, &s[idx]);
+        const double xn = LD_ONCE(HINT_D_LD, &x_in[idx]) + alpha * pv[idx] + omega * sv;
+        if (last) { x_out[idx] = xn; return xn; }      // the flux: read next by P / F
+        ST_ONCE(HINT_D_ST, &x_out[idx], xn);                       // read again only by the next D
+        const double rn = sv - omega * LD_ONCE(HINT_D_LD, &t[idx]);
         rv[idx] = rn;
-        acc[0] = acc[0] + rs[idx] * rn;
+        acc[0] = acc[0] + LD_ONCE(HINT_D_LD, &rs[idx]) * rn;
         return rn;
     };
     // pushed: the neighbours' copy of r, or (last sweep) of this flux buffer
     bool pushed = false;
-    bf_tiles(G, [&](int kl, int r) { pushed = push_row(G, ps, kl, r, row(kl, r)) || pushed; }, [&](int kl, int r) { row(kl, r); });
+    bf_tiles<ADP_SWEEP_REV != 0>(G, [&](int kl, int r) { pushed = push_row(G, ps, kl, r, row(kl, r)) || pushed; }, [&](int kl, int r) { row(kl, r); });
     if (pushed) __threadfence_system();
     if (!last) grid_reduce_m<1>(acc, rom);
 }
@@ -801,6 +900,32 @@ __global__ void __launch_bounds__(ADP_TILE) k_fsrc_norms(Geo G, FsrcArgs A, int 
         const long long idx = node_idx(G, kl, r);
         const int m = A.adjoint ? A.mat[idx] - 1 : 0;
         double fs = 0.0;
+        if (NG > 0) {
+            // every operand of the row loaded before the first use: the old flux and the old fission source sat behind the
+            // data-dependent tests below and cost a second and third memory round trip per row (round 1: 0.53 of the copy
+            // bandwidth, ncu: 42 % DRAM utilisation at 73 % occupancy)
+            double fn[NG > 0 ? NG : 1], fo[NG > 0 ? NG : 1], w[NG > 0 ? NG : 1];
+#pragma unroll
+            for (int g = 0; g < NG; ++g) {
+                fn[g] = A.fnew[g][idx];
+                w[g] = A.adjoint ? A.w[g][m] : A.w[g][idx];
+                fo[g] = A.fold[g][idx];
+            }
+            const double fso = A.fs_old[idx];
+#pragma unroll
+            for (int g = 0; g < NG; ++g) {
+                fs = fs + fn[g] * w[g];
+                if (do_norms && fabs(fn[g]) > 1.e-10) mfer.take(fabs(fn[g] - fo[g]), fabs(fn[g]));
+            }
+            A.fs_new[idx] = fs;
+            if (do_norms) {
+                const double errn = fs - fso;
+                acc[0] = acc[0] + errn * errn;
+                acc[1] = acc[1] + (G.area[r] * G.hz[1 + G.k0 + kl]) * fs;
+                if (fabs(fs) > 1.e-10) mser.take(fabs(errn), fabs(fs));
+            }
+            continue;
+        }
 #pragma unroll
         for (int g = 0; g < ng; ++g) {
             const double fn = A.fnew[g][idx];
@@ -1264,6 +1389,47 @@ static inline RedOut make_red(adp_ctx *c, int s0, int s1 = S_TMP1, int s2 = S_TM
         }                                                                                   \
     } while (0)
 
+// B: the formulation selected by option "spmv_var"
+static void launch_spmv_dot(adp_ctx *c, int nt, const double *a, const double *pv, const double *rs, double *v, const Push &ps, const RedOut &ro)
+{
+#define SPMV_CASE(V, B) k_spmv_dot<V, B><<<adp_grid(c, k_spmv_dot<V, B>, nt), ADP_TILE, 0, c->stream>>>(c->geo, a, pv, rs, v, ps, ro)
+    switch (c->spmv_var) {
+    case 1: SPMV_CASE(1, 0); break;
+    case 2: SPMV_CASE(0, 6); break;
+    case 3: SPMV_CASE(1, 6); break;
+    case 4: SPMV_CASE(1, 5); break;
+    case 5: SPMV_CASE(1, 4); break;
+    case 6: SPMV_CASE(0, 5); break;
+    default: SPMV_CASE(0, 0); break;
+    }
+#undef SPMV_CASE
+}
+// C: the formulation selected by option "st_var" (single rank) / "st_m_var" (several ranks), see k_st
+#define ST_DISPATCH(var, CASE)        \
+    switch (var) {                    \
+    case 1: CASE(1, 0); break;        \
+    case 2: CASE(2, 0); break;        \
+    case 3: CASE(0, 5); break;        \
+    case 4: CASE(1, 5); break;        \
+    case 5: CASE(2, 5); break;        \
+    case 6: CASE(2, 4); break;        \
+    case 7: CASE(0, 4); break;        \
+    default: CASE(0, 0); break;       \
+    }
+static void launch_st(adp_ctx *c, int nt, const double *a, int slot, const double *r_cur, const double *v_cur, const RedOut &ro)
+{
+#define ST_CASE(V, B) k_st<V, B><<<adp_grid(c, k_st<V, B>, nt), ADP_TILE, 0, c->stream>>>(c->geo, a, slot, r_cur, v_cur, c->d_s, c->d_t, ro)
+    ST_DISPATCH(c->st_var, ST_CASE)
+#undef ST_CASE
+}
+static void launch_st_m(adp_ctx *c, int nt, const double *a, int slot, const double *r_cur, const double *v_cur, const RedOutM &ro,
+                        const MailWait &mw)
+{
+#define ST_M_CASE(V, B) k_st_m<V, B><<<adp_grid(c, k_st_m<V, B>, nt), ADP_TILE, 0, c->stream>>>(c->geo, a, slot, r_cur, v_cur, c->d_s, c->d_t, ro, mw)
+    ST_DISPATCH(c->st_m_var, ST_M_CASE)
+#undef ST_M_CASE
+}
+
 // persistent grid of the bulk-copy C kernel: resident CTAs are limited by its shared-memory ring
 static int st_tma_grid(adp_ctx *c, int ntiles)
 {
@@ -1436,7 +1602,7 @@ static int bicg_core(adp_ctx *c, const SrcArgs &src, const double *a, const doub
         // fused, first sweep: waits for P's rho (the barrier behind P's pushed boundary planes)
         if (peer) k_spmv_dot_m<<<adp_grid(c, k_spmv_dot_m, nt), ADP_TILE, 0, c->stream>>>(c->geo, a, p_cur, c->d_rs, v_cur, adp_push(c, pb_v),
                                                                                 redm(S_RSV), (i == 1) ? wait(1, S_RHO1) : nowait);
-        else k_spmv_dot<<<adp_grid(c, k_spmv_dot, nt), ADP_TILE, 0, c->stream>>>(c->geo, a, p_cur, c->d_rs, v_cur, none, make_red(c, S_RSV));
+        else launch_spmv_dot(c, nt, a, p_cur, c->d_rs, v_cur, none, make_red(c, S_RSV));
         LAUNCH_CHECK(c);
         if (multi && !fused && (rc = adp_comm_allreduce_sum(c, c->d_scal + S_RSV, 1))) return rc;
         if ((multi && !peer) || !c->fuse_st) {
@@ -1447,13 +1613,13 @@ static int bicg_core(adp_ctx *c, const SrcArgs &src, const double *a, const doub
             LAUNCH_CHECK(c);
         } else if (peer) {
             // s = r - alpha v on the fly, on ghost planes from the pushed r and v
-            k_st_m<<<adp_grid(c, k_st_m, nt), ADP_TILE, 0, c->stream>>>(c->geo, a, slot, r_cur, v_cur, c->d_s, c->d_t, redm(S_TT, S_TS), wait(1, S_RSV));
+            launch_st_m(c, nt, a, slot, r_cur, v_cur, redm(S_TT, S_TS), wait(1, S_RSV));
             LAUNCH_CHECK(c);
         } else if (c->st_tma && (c->np % 2) == 0) {
             k_st_tma<<<st_tma_grid(c, nt), ADP_TILE, ST_STAGES * sizeof(StStage), c->stream>>>(c->geo, a, slot, r_cur, v_cur, c->d_s, c->d_t, make_red(c, S_TT, S_TS));
             LAUNCH_CHECK(c);
         } else {
-            k_st<<<adp_grid(c, k_st, nt), ADP_TILE, 0, c->stream>>>(c->geo, a, slot, r_cur, v_cur, c->d_s, c->d_t, make_red(c, S_TT, S_TS));
+            launch_st(c, nt, a, slot, r_cur, v_cur, make_red(c, S_TT, S_TS));
             LAUNCH_CHECK(c);
         }
         if (multi && !fused && (rc = adp_comm_allreduce_sum(c, c->d_scal + S_TT, 2))) return rc;
@@ -1511,7 +1677,7 @@ int adp_k_spmv(adp_ctx *c, int g, const double *d_x, double *d_v)
 {
     int rc;
     if (c->nranks > 1 && (rc = adp_comm_halo(c, const_cast<double *>(d_x), 1))) return rc;
-    k_spmv_dot<<<adp_grid(c, k_spmv_dot, c->geo.ntiles), ADP_TILE, 0, c->stream>>>(c->geo, a_of(c, g), d_x, nullptr, d_v, Push(), make_red(c, S_TMP1));
+    launch_spmv_dot(c, c->geo.ntiles, a_of(c, g), d_x, nullptr, d_v, Push(), make_red(c, S_TMP1));
     LAUNCH_CHECK(c);
     return ADP_OK;
 }
@@ -1620,16 +1786,16 @@ int adp_k_bench_one(adp_ctx *c, int what, int g)
     const double *a = a_of(c, g);
     switch (what) {
     case 0:
-        k_spmv_dot<<<adp_grid(c, k_spmv_dot, nt), ADP_TILE, 0, c->stream>>>(c->geo, a, c->d_p, c->d_rs, c->d_v, Push(), make_red(c, S_TMP1));
+        launch_spmv_dot(c, nt, a, c->d_p, c->d_rs, c->d_v, Push(), make_red(c, S_TMP1));
         break;
     case 8:
-        k_spmv_dot<<<adp_grid(c, k_spmv_dot, nt), ADP_TILE, 0, c->stream>>>(c->geo, a, c->d_p, nullptr, c->d_v, Push(), make_red(c, S_TMP1));
+        launch_spmv_dot(c, nt, a, c->d_p, nullptr, c->d_v, Push(), make_red(c, S_TMP1));
         break;
     case 1:
         if (c->st_tma && (c->np % 2) == 0)
             k_st_tma<<<st_tma_grid(c, nt), ADP_TILE, ST_STAGES * sizeof(StStage), c->stream>>>(c->geo, a, S_RHO1, c->d_r, c->d_v, c->d_s, c->d_t, make_red(c, S_TMP0, S_TMP1));
         else
-            k_st<<<adp_grid(c, k_st, nt), ADP_TILE, 0, c->stream>>>(c->geo, a, S_RHO1, c->d_r, c->d_v, c->d_s, c->d_t, make_red(c, S_TMP0, S_TMP1));
+            launch_st(c, nt, a, S_RHO1, c->d_r, c->d_v, make_red(c, S_TMP0, S_TMP1));
         break;
     case 2:
         k_update_xr<<<adp_grid(c, k_update_xr, nt), ADP_TILE, 0, c->stream>>>(c->geo, S_RHO1, 0, c->d_stage, c->d_stage, c->d_p, c->d_s, c->d_t, c->d_rs,
@@ -1672,7 +1838,7 @@ int adp_k_bench_one(adp_ctx *c, int what, int g)
     }
     case 11: {
         RedOutM ro; ro.r = make_red(c, S_TMP0, S_TMP1);
-        k_st_m<<<adp_grid(c, k_st_m, nt), ADP_TILE, 0, c->stream>>>(c->geo, a, S_RHO1, c->d_r, c->d_v, c->d_s, c->d_t, ro, MailWait());
+        launch_st_m(c, nt, a, S_RHO1, c->d_r, c->d_v, ro, MailWait());
         break;
     }
     case 12: {
@@ -1710,9 +1876,9 @@ int adp_k_bench_one(adp_ctx *c, int what, int g)
 void adp_k_preload_cmfd(adp_ctx *c)
 {
     adp_grid(c, k_coup_coef, 1); adp_grid(c, k_matrix_setup, 1); adp_grid(c, k_residual, 1); adp_grid(c, k_update_p, 1);
-    adp_grid(c, k_spmv_dot, 1); adp_grid(c, k_st, 1); adp_grid(c, k_s, 1); adp_grid(c, k_t, 1); adp_grid(c, k_update_xr, 1);
+    adp_grid(c, k_spmv_dot<0, 0>, 1); adp_grid(c, k_st<0, 0>, 1); adp_grid(c, k_s, 1); adp_grid(c, k_t, 1); adp_grid(c, k_update_xr, 1);
     if (c->nranks > 1) {
-        adp_grid(c, k_residual_m, 1); adp_grid(c, k_update_p_m, 1); adp_grid(c, k_spmv_dot_m, 1); adp_grid(c, k_st_m, 1);
+        adp_grid(c, k_residual_m, 1); adp_grid(c, k_update_p_m, 1); adp_grid(c, k_spmv_dot_m, 1); adp_grid(c, k_st_m<0, 0>, 1);
         adp_grid(c, k_update_xr_m, 1);
     }
     adp_grid(c, k_fsrc_norms<0>, 1); adp_grid(c, k_fsrc_norms<1>, 1); adp_grid(c, k_fsrc_norms<2>, 1); adp_grid(c, k_fsrc_norms<4>, 1);

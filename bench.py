@@ -340,6 +340,14 @@ def main():
 
     def emit(line):
         os.write(real_stdout, (json.dumps(line) + "\n").encode())
+    # a hang must become a traceback on stderr, not a silent driver timeout
+    import faulthandler
+    faulthandler.dump_traceback_later(int(os.environ.get("ADP_BENCH_WATCHDOG_S", "900")), exit=True)
+    t_start = time.time()
+
+    def log(msg):
+        sys.stderr.write("[bench %s +%.1fs] %s\n" % (os.environ.get("RANK", "0"), time.time() - t_start, msg))
+        sys.stderr.flush()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -427,7 +435,9 @@ def main():
     while not sampler.lines and time.time() - t_wait < 5.0:
         time.sleep(0.05)
     n_before = len(sampler.lines)
+    log("value leg")
     ms, launches, ke = timed_steps(s, units_per_step)
+    log("value leg done: %.3f ms/step" % (ms / K))
     time.sleep(0.12)                       # let the 100 ms sampler take one more reading of the loaded state
     n_after = len(sampler.lines)
     value = units_per_step * K / (ms * 1e-3)
@@ -451,6 +461,11 @@ def main():
                 rc_ = cudart.cudaHostRegister(seg.ctypes.data, seg.nbytes, 0)
                 assert int(rc_) == 0, f"cudaHostRegister failed: {rc_}"
             return a
+        if world > 1:
+            # every rank reads back ITS slab (what d2h_bytes_per_step counts).  The library's default on several ranks also
+            # gathers the other slabs into every rank's host arrays (option gather_results, for host code that consumes whole
+            # sdata arrays); that all-gather is not part of the path measured here
+            s.set_option("gather_results", 0)
         for k in ("D", "sigr", "nuf", "sigf", "sigs", "dc", "exsrc"):
             hx[k] = host_buffer(getattr(p, k))
         hx["chi"] = np.asfortranarray(p.chi)
@@ -491,6 +506,7 @@ def main():
             s._chk(L.adp_powdis(s.h, d(pw_out), 0))
             return ke_.value
 
+        log("e2e leg")
         one_call(max(W, 3), P0 - max(W, 3))       # warm-up of the host path (same state: dn is still zero before p = nupd)
         barrier()
         t0 = time.perf_counter()
@@ -506,8 +522,10 @@ def main():
                "d2h_bytes_per_step": int(d2h * world / K), "ms_per_step": 1e3 * wall / K,
                "device_ms_per_step": ms_e2e_dev / K, "keff_after": ke_e2e, "nodal_updates_inside": n_upd,
                "what": "one outer() call through the C ABI with pinned host buffers: adp_set_xs + adp_set_state + "
-                       "adp_matrix_setup + K x adp_outer_iter (+ adp_nodal_upd when mod(p, nupd) = 0) + adp_get_state + adp_powdis"}
+                       "adp_matrix_setup + K x adp_outer_iter (+ adp_nodal_upd when mod(p, nupd) = 0) + adp_get_state + adp_powdis"
+                       + ("; every rank uploads and reads back its own z-slab (gather_results = 0)" if world > 1 else "")}
 
+    log("kernel timings")
     # ---------------------------------------------------------------- roofline of the dominant kernel
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
@@ -574,14 +592,19 @@ def main():
     del s
 
     # ---------------------------------------------------------------- N > 1: parity and strong scaling
-    parity = strong = None
-    if world > 1 and not args.no_extras:
+    def extras():
+        """C3 parity solve and C2' strong-scaling leg (N > 1); returns (parity, strong)"""
+        log("C3 parity leg")
         parity = c3_parity(world, rank, local_rank, new_uid(), capi)
+        log("strong-scaling leg")
+        # C2' needs more inner iterations than C2: on its 0.91 cm planes nin = 10 is at the edge of the two-node iteration's
+        # stability (tools/c2prime_probe.py), nin = 20 converges smoothly in every summation order
+        CTLS = dict(CTL, nin=20)
         # strong scaling: C2' (170 x 170 x 418 = 10 073 800 nodes, BASELINE north star ">= 10 M nodes") on 1 GPU (rank 0
         # alone, the others wait) and sliced over the N ranks; same %ITER, same timed iterations
         n1_ms = None
         if rank == 0:
-            s1 = capi.Solver(SlabProblem(base19, 1, 0, stack=1, zrefine=22), device=local_rank, **CTL)
+            s1 = capi.Solver(SlabProblem(base19, 1, 0, stack=1, zrefine=22), device=local_rank, **CTLS)
             s1.matrix_setup(1); s1.init_flux(); s1.outer_begin(capi.MODE_FORWARD)
             s1.outer_steps(capi.MODE_FORWARD, 1, P0 - 1)
             torch.cuda.synchronize()
@@ -592,33 +615,60 @@ def main():
             s1.close()
         n1_ms = max_over_ranks(n1_ms if n1_ms is not None else 0.0)
         pN = SlabProblem(base19, world, rank, stack=1, zrefine=22)
-        sN = capi.Solver(pN, device=local_rank, nranks=world, rank=rank, uid=new_uid(), **CTL)
+        sN = capi.Solver(pN, device=local_rank, nranks=world, rank=rank, uid=new_uid(), **CTLS)
+        log("strong-scaling leg: N ranks")
         msN, _, keN = timed_steps(sN, pN.nnod * pN.ng)
+        log("strong-scaling leg done")
         sN.close()
-        strong = {"config": "C2' IAEA-3D 1cm x 1cm x 0.91cm: 170x170x418 = 10073800 nodes x 2 groups, nin=10 nupd=50, "
+        strong = {"config": "C2' IAEA-3D 1cm x 1cm x 0.91cm: 170x170x418 = 10073800 nodes x 2 groups, nin=20 nupd=50, "
                             f"z-slabs over {world} GPUs ({pN.k1 - pN.k0} planes on rank {rank})",
                   "ms_per_step": msN / K, "n1_ms_per_step": n1_ms, "speedup_vs_n1": n1_ms / (msN / K),
                   "unknowns_per_s": pN.nnod * pN.ng * K / (msN * 1e-3), "timed_iterations": [P0, P0 + K - 1], "keff_after": keN,
                   "limiter": "3 global reductions + 2 halo planes per BiCGSTAB sweep (mod_cmfd.f90:1229-1240): "
-                             f"{(3 * CTL['nin'] + 1) * 2 + 2} barrier points per step, fixed cost independent of the slab size"}
+                             f"{(3 * CTLS['nin'] + 1) * 2 + 2} barrier points per step, fixed cost independent of the slab size"}
 
+
+        return parity, strong
     # ---------------------------------------------------------------- CPU baseline (rank 0, N = 1)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = run_oracle_sample()
 
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": workload_config(world, K, W),
+        "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "solve": solve,
+        "keff_after_steps": ke,
+    }
+    if world > 1 and not args.no_extras:
+        # the two extra legs must never cost the bench line: if one of them raises, or hangs (a rank that failed inside a
+        # collective leaves the others waiting), the line goes out without it and says why
+        done = threading.Event()
+
+        def give_up():
+            if not done.is_set():
+                if rank == 0:
+                    line["parity"] = line.get("parity") or {"error": "extra legs timed out"}
+                    emit(line)
+                os._exit(0)
+        watchdog = threading.Timer(float(os.environ.get("ADP_BENCH_EXTRAS_S", "420")), give_up)
+        watchdog.daemon = True
+        watchdog.start()
+        try:
+            parity, strong = extras()
+            line["parity"], line["strong"] = parity, strong
+        except Exception as e:          # noqa: BLE001 -- reported in the line
+            line["parity"] = {"error": "%s: %s" % (type(e).__name__, e)}
+            log("extra legs failed: %r" % (e,))
+            done.set()
+            watchdog.cancel()
+            if rank == 0:
+                emit(line)
+            os._exit(0)                 # the other ranks may sit in a collective of the failed leg
+        done.set()
+        watchdog.cancel()
     if rank == 0:
-        line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "config": workload_config(world, K, W),
-            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "solve": solve,
-            "keff_after_steps": ke,
-        }
-        if parity is not None:
-            line["parity"] = parity
-        if strong is not None:
-            line["strong"] = strong
         emit(line)
     if world > 1:
         dist.barrier()

@@ -156,7 +156,10 @@ def test_c2_full_solve_against_cpu_oracle_fixture(fixture):
     ref = json.load(open(path))
     p = _refined([ref["zdiv"]] * 19)
     assert p.nnod == ref["nnod"]
-    s = capi.Solver(p, nin=10, nac=5, nupd=50, nout=3000)
+    # %ITER of the fixture: nin = 10 on the 2 cm planes; nin = 20 on the 0.91 cm planes of C2' -- there nin = 10 sits on the
+    # edge of the two-node iteration's stability (source-error excursions of 1e4 - 1e7 in every summation order tried, and a
+    # "MAX. CHANGE > 1e3" STOP in one of them: tools/c2prime_probe.py), nin = 15 / 20 converge smoothly in all of them
+    s = capi.Solver(p, nin=ref.get("nin", 10), nac=5, nupd=50, nout=3000)
     s.enable_trace()
     rc, n = s.outer(1)
     assert rc == ref["status"] == 0

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Nodal update time on the C2 mesh for G groups, surfaces kernel per thread vs 16 lanes per surface.
+"""Nodal update time on the C2 mesh for G groups: one thread per item (0), 16 lanes per surface (1), quad kernels (2).
 usage: python tools/nodal_ab.py [ng ...]"""
 import os, sys
 ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
@@ -8,7 +8,9 @@ from adpres_b200 import capi
 from synth import iaea3d_multigroup
 for ng in [int(a) for a in sys.argv[1:]] or [8]:
     p = iaea3d_multigroup(ng).refine(xdiv=[10] + [20] * 8, ydiv=[20] * 8 + [10], zdiv=[10] * 19)
-    for coop in (0, 1):
+    for coop in (0, 1, 2):
+        if coop == 2 and ng < 3:
+            continue
         s = capi.Solver(p, nin=10, nac=5, nupd=50, nout=3000)
         s.set_option("nodal_coop", coop)
         s.matrix_setup(1); s.init_flux(); s.outer_begin(capi.MODE_FORWARD)
