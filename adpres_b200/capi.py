@@ -32,7 +32,7 @@ SYMBOLS = [
     "adp_reactivity", "adp_get_state", "adp_set_state", "adp_set_s0", "adp_get_nod", "adp_set_nod_dn", "adp_lxyz_total", "adp_get_exsrc_arrays",
     "adp_get_ndmax", "adp_get_errors", "adp_set_trace", "adp_outer", "adp_outer_ad", "adp_outer_fs", "adp_outer_th", "adp_outer_tr",
     "adp_sp_matvec", "adp_bicg", "adp_get_matrix", "adp_get_source", "adp_set_option", "adp_launch_count",
-    "adp_bench_kernel", "adp_outer_steps", "adp_timer_start", "adp_timer_stop",
+    "adp_bench_kernel", "adp_profile_report", "adp_outer_steps", "adp_timer_start", "adp_timer_stop",
 ]
 
 _lib = None
@@ -144,6 +144,26 @@ class Solver:
 
     def set_option(self, name, value):
         self._chk(self.L.adp_set_option(self.h, name.encode(), int(value)))
+
+    def reset_nodal(self):
+        """the next matrix_setup(1) zeroes dn again, ndmax = 0 (state before the first coup_coef call of a run)"""
+        self.set_option("reset_nodal", 1)
+
+    def profile_report(self):
+        """[(launch site, launches, total ms)] since set_option("profile", 1); the site is the source line of
+        csrc/cmfd_kernels.cu with the launch (kernel name looked up in the source)"""
+        n = 256
+        lines, counts, ms = (C.c_int * n)(), (C.c_int * n)(), (C.c_double * n)()
+        m = self.L.adp_profile_report(self.h, n, lines, counts, ms)
+        src = open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "cmfd_kernels.cu")).read().split("\n")
+        out = []
+        for q in range(max(m, 0)):
+            ln = lines[q]
+            text = " ".join(x.strip() for x in src[max(0, ln - 4):ln])
+            import re as _re
+            names = _re.findall(r"(k_[a-z_]+|launch_[a-z_]+)", text)
+            out.append(("%s:%d" % (names[-1] if names else "?", ln), counts[q], ms[q]))
+        return out
 
     # ---- inputs
     def set_xs(self, **kw):

@@ -250,6 +250,10 @@ struct adp_ctx {
     int st_var = 6;                        // formulation of the C kernel (k_st), single rank: 0..7 (6: loads grouped, 64 registers)
     int st_m_var = 6;                      // the same for the multi-rank C kernel (k_st_m)
     bool st_tma = false;                   // C kernel staged with cp.async.bulk + mbarrier (experiment, single rank, np even)
+    // per-launch profile (option "profile"): an event after every kernel launch of the CMFD path, tagged with the source line
+    bool prof = false;
+    cudaEvent_t prof_start = nullptr;
+    std::vector<std::pair<int, cudaEvent_t>> prof_ev;
     // bookkeeping
     long long launches = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -314,6 +318,14 @@ static inline int adp_grid(adp_ctx *c, K kernel, int ntiles)
         g = (ntiles + rounds - 1) / rounds;
     }
     return (int)g;
+}
+
+static inline void adp_prof_mark(adp_ctx *c, int line)
+{
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    cudaEventRecord(e, c->stream);
+    c->prof_ev.emplace_back(line, e);
 }
 
 // ---- launch wrappers implemented in the kernel files ---------------------------------------

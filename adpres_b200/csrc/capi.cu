@@ -1180,6 +1180,25 @@ extern "C" int adp_launch_count(const adp_ctx *c, long long *launches)
 extern "C" int adp_set_option(adp_ctx *c, const char *name, int value)
 {
     if (!c || !name) return ADP_ERR_USAGE;
+    if (!strcmp(name, "profile")) {
+        // 1: start a per-launch profile of the CMFD kernels (run without CUDA graphs); read it with adp_profile_report
+        for (auto &pe : c->prof_ev) cudaEventDestroy(pe.second);
+        c->prof_ev.clear();
+        if (c->prof_start) { cudaEventDestroy(c->prof_start); c->prof_start = nullptr; }
+        c->prof = value != 0;
+        if (c->prof) {
+            CUDA_TRY(c, cudaSetDevice(c->device));
+            CUDA_TRY(c, cudaEventCreate(&c->prof_start));
+            CUDA_TRY(c, cudaEventRecord(c->prof_start, c->stream));
+        }
+        return ADP_OK;
+    }
+    if (!strcmp(name, "reset_nodal")) {
+        // back to the state before the first coup_coef call of a run: the next adp_matrix_setup(1) zeroes dn
+        // (mod_cmfd.f90:28-36, first call) and ndmax starts at 0 again (mod_data.f90:199) -- repeated timing passes
+        c->coup_first = true; c->ndmax = 0.0; c->im = c->jm = c->km = 0;
+        return ADP_OK;
+    }
     if (!strcmp(name, "graphs")) { c->use_graphs = value != 0; free_graphs(c); return ADP_OK; }
     if (!strcmp(name, "peer_push")) { if (!value) c->peer_ok = false; return ADP_OK; }
     if (!strcmp(name, "peer_allreduce")) { if (!value) c->peer_ar = false; free_graphs(c); return ADP_OK; }
@@ -1270,6 +1289,30 @@ int adp_k_bench_one(adp_ctx *c, int what, int g);
 // 6 nodal source, 7 whole nodal update (source + 3 surface launches), 9 matrix_setup(0).
 // Launches alternate over the energy groups so that consecutive launches stream different
 // matrices (working set >> L2).  Returns the average device time per launch in ms.
+extern "C" int adp_profile_report(adp_ctx *c, int max, int *lines, int *counts, double *ms)
+{
+    if (!c || !lines || !counts || !ms || max < 1) return -1;
+    if (!c->prof_start || c->prof_ev.empty()) return 0;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    std::map<int, std::pair<int, double>> acc;
+    cudaEvent_t prev = c->prof_start;
+    for (auto &pe : c->prof_ev) {
+        float dt = 0.f;
+        cudaEventElapsedTime(&dt, prev, pe.second);
+        auto &a = acc[pe.first];
+        a.first++; a.second += dt;
+        prev = pe.second;
+    }
+    int n = 0;
+    for (auto &kv : acc) {
+        if (n >= max) break;
+        lines[n] = kv.first; counts[n] = kv.second.first; ms[n] = kv.second.second;
+        ++n;
+    }
+    return n;
+}
+
 extern "C" int adp_bench_kernel(adp_ctx *c, int what, int reps, double *avg_ms)
 {
     if (!c || !avg_ms || reps < 1) return ADP_ERR_USAGE;

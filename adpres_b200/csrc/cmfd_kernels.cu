@@ -284,13 +284,21 @@ __device__ __forceinline__ void push_tail(const Geo &G, const Push &ps, const do
 //   tile t in [nb, ntiles)   interior planes 1 .. nzl-2
 // grid-stride over this numbering, so the work per CTA stays balanced.
 template <bool REV = false, typename FB, typename FI>
-__device__ __forceinline__ void bf_tiles(const Geo &G, FB &&boundary, FI &&interior)
+__device__ __forceinline__ void bf_tiles(const Geo &G, bool &pushed, FB &&boundary, FI &&interior)
 {
     const int nb = (G.nzl >= 2 ? 2 : 1) * G.tpp;
     int t = blockIdx.x;
     for (; t < nb; t += gridDim.x) {
         const int kl = (t >= G.tpp) ? G.nzl - 1 : 0, r = (t % G.tpp) * ADP_TILE + threadIdx.x;
         if (r < G.np) boundary(kl, r);
+    }
+    // ONE system-scope fence per pushing CTA, issued NOW: thread 0, behind a CTA barrier that collects the CTA's peer stores.
+    // Its NVLink round trip then overlaps the interior sweep of the other warps; at the kernel end (round 1, and with a fence
+    // in each of the 256 pushing threads: 48 000 MEMBAR.SC.SYS per kernel) it sat in the tail of B, D and P: +11 us each at two
+    // ranks.  The ticket the CTA takes in grid_reduce_m comes later in thread 0's program order, so the post that follows the
+    // last ticket still tells the peers that the boundary planes have arrived.
+    if ((int)blockIdx.x < nb) {                          // uniform over the CTA
+        if (__syncthreads_or(pushed ? 1 : 0) && threadIdx.x == 0) __threadfence_system();
     }
     for (; t < G.ntiles; t += gridDim.x) {
         const int u = REV ? G.ntiles - 1 - t : t - nb;      // REV: the interior from the top plane down (ADP_SWEEP_REV)
@@ -591,8 +599,7 @@ __global__ void __launch_bounds__(ADP_TILE, ADP_LB_PA) k_residual_m(Geo G, SrcAr
         return res;
     };
     bool pushed = false;
-    bf_tiles(G, [&](int kl, int r) { pushed = push_row(G, ps, kl, r, row(kl, r)) || pushed; }, [&](int kl, int r) { row(kl, r); });
-    if (pushed) __threadfence_system();      // only the threads that stored to a neighbour pay for the fence
+    bf_tiles(G, pushed, [&](int kl, int r) { pushed = push_row(G, ps, kl, r, row(kl, r)) || pushed; }, [&](int kl, int r) { row(kl, r); });
     grid_reduce_m<1>(acc, rom);
 }
 
@@ -628,8 +635,7 @@ __global__ void __launch_bounds__(ADP_TILE) k_spmv_dot_m(Geo G, const double *__
         return y;
     };
     bool pushed = false;
-    bf_tiles<ADP_SWEEP_REV != 0>(G, [&](int kl, int r) { pushed = push_row(G, ps, kl, r, row(kl, r)) || pushed; }, [&](int kl, int r) { row(kl, r); });
-    if (pushed) __threadfence_system();
+    bf_tiles<ADP_SWEEP_REV != 0>(G, pushed, [&](int kl, int r) { pushed = push_row(G, ps, kl, r, row(kl, r)) || pushed; }, [&](int kl, int r) { row(kl, r); });
     grid_reduce_m<1>(acc, rom);
 }
 
@@ -856,9 +862,8 @@ __global__ void __launch_bounds__(ADP_TILE) k_update_xr_m(Geo G, int slot_rho, i
     };
     // pushed: the neighbours' copy of r, or (last sweep) of this flux buffer
     bool pushed = false;
-    bf_tiles<ADP_SWEEP_REV != 0>(G, [&](int kl, int r) { pushed = push_row(G, ps, kl, r, row(kl, r)) || pushed; }, [&](int kl, int r) { row(kl, r); });
-    if (pushed) __threadfence_system();
-    if (!last) grid_reduce_m<1>(acc, rom);
+    bf_tiles<ADP_SWEEP_REV != 0>(G, pushed, [&](int kl, int r) { pushed = push_row(G, ps, kl, r, row(kl, r)) || pushed; }, [&](int kl, int r) { row(kl, r); });
+    if (!last) grid_reduce_m<1>(acc, rom);      // (last sweep: the flux halo is ordered by the next all-reduce)
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1382,6 +1387,7 @@ static inline RedOut make_red(adp_ctx *c, int s0, int s1 = S_TMP1, int s2 = S_TM
 #define LAUNCH_CHECK(c)                                                                     \
     do {                                                                                    \
         (c)->launches++;                                                                    \
+        if ((c)->prof) adp_prof_mark(c, __LINE__);                                          \
         cudaError_t e__ = cudaPeekAtLastError();                                            \
         if (e__ != cudaSuccess) {                                                           \
             (c)->err = std::string("kernel launch: ") + cudaGetErrorString(e__) + " (" + __FILE__ + ":" + std::to_string(__LINE__) + ")"; \

@@ -326,6 +326,11 @@ int adp_launch_count(const adp_ctx *ctx, long long *launches);
  * 5 F fission source + norms; 6 nodal source; 7 whole nodal update; 8 plain SpMV; 9 matrix_setup(0).
  * Runs `reps` launches (alternating over groups), returns the average device ms per launch. */
 int adp_bench_kernel(adp_ctx *ctx, int what, int reps, double *avg_ms);
+/* Measurement aid (no reference counterpart): after adp_set_option(ctx, "profile", 1) every kernel launch of the CMFD path
+ * (mod_cmfd.f90:415-509 outer loop body) is followed by an event; the report sums the time between consecutive events per
+ * launch site (source line of csrc/cmfd_kernels.cu), i.e. kernel + the gap before it -- inside a multi-rank step this
+ * includes the time a kernel waits for its peers.  Use with option "graphs" = 0.  Returns the number of sites (<= max). */
+int adp_profile_report(adp_ctx *ctx, int max, int *lines, int *counts, double *ms);
 /* `nsteps` passes of the outer loop body starting at p_first, nodal update + matrix_setup(0)
  * whenever mod(p,nupd)==0, enqueued back to back with ONE synchronisation at the end (no
  * per-iteration exit test): the device-resident throughput path. */

@@ -39,6 +39,24 @@ for rep in range(3):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ms = float(tt.item())
     res.append(ms)
+# per-launch-site profile of a few steps without CUDA graphs (kernel + the gap / peer wait in front of it)
+if os.environ.get("ADP_MG_PROFILE", "1") != "0":
+    s.set_option("graphs", 0)
+    s.outer_steps(capi.MODE_FORWARD, 51, 4)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    s.set_option("profile", 1)
+    s.timer_start()
+    s.outer_steps(capi.MODE_FORWARD, 51, 10)
+    ms_ng = s.timer_stop() / 10
+    rep = s.profile_report()
+    s.set_option("profile", 0)
+    s.set_option("graphs", 1)
+    if rank == 0:
+        print("PROFILE %s N=%d without graphs, with events: %.4f ms/step" % (kind, world, ms_ng))
+        for name, cnt, ms in sorted(rep, key=lambda x: -x[2]):
+            print("   %-28s %5d launches  %8.2f us each  %7.3f ms/step" % (name, cnt, 1e3 * ms / cnt, ms / 10), flush=True)
 if rank == 0:
     print("MG_STEP %s N=%d fuse=%s peer=%s ms/step %s ke %.9f" % (kind, world, "0" if os.environ.get("ADP_NO_FUSE_MAIL") else "1",
           "0" if os.environ.get("ADP_NO_PEER") else "1", " ".join("%.4f" % x for x in res), ke), flush=True)
