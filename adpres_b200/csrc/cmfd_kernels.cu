@@ -620,18 +620,34 @@ __global__ void __launch_bounds__(ADP_TILE, ADP_LB_PA) k_update_p_m(Geo G, doubl
     }
 }
 
-__global__ void __launch_bounds__(ADP_TILE) k_spmv_dot_m(Geo G, const double *__restrict__ a, const double *__restrict__ pv,
+__global__ void __launch_bounds__(ADP_TILE, 5) k_spmv_dot_m(Geo G, const double *__restrict__ a, const double *__restrict__ pv,
                                                         const double *__restrict__ rs, double *__restrict__ v, Push ps, RedOutM rom,
                                                         MailWait mw)
 {
     double acc[1] = {0.0};
     double wv[2];
     mail_prologue(mw, rom.r.scal, wv);       // first sweep: P's rho (not used here) = the barrier before the ghost planes of p are read
+    const long long NV = G.NV;
+    const int np = G.np;
+    // loads grouped in the source, 48 registers: the formulation of k_spmv_dot<1, 5> (spmv_var 4)
     auto row = [&](int kl, int r) -> double {
         const long long idx = node_idx(G, kl, r);
-        const double y = stencil7(a, G.NV, pv, idx, G.np, G.ypm[r], G.ypp[r]);
+        const int ym = G.ypm[r], yp = G.ypp[r];
+        const double a0 = a[idx], a1 = a[NV + idx], a2 = a[2 * NV + idx], a3 = a[3 * NV + idx], a4 = a[4 * NV + idx],
+                     a5 = a[5 * NV + idx], a6 = a[6 * NV + idx];
+        const double pc = pv[idx], rsv = rs[idx];
+        const double pzm = pv[idx - np], pym = pv[idx - ym], pxm = pv[idx - 1], pxp = pv[idx + 1], pyp = pv[idx + yp],
+                     pzp = pv[idx + np];
+        double y = 0.0;
+        y = y + a0 * pzm;
+        y = y + a1 * pym;
+        y = y + a2 * pxm;
+        y = y + a3 * pc;
+        y = y + a4 * pxp;
+        y = y + a5 * pyp;
+        y = y + a6 * pzp;
         v[idx] = y;
-        acc[0] = acc[0] + LD_ONCE(HINT_B, &rs[idx]) * y;
+        acc[0] = acc[0] + rsv * y;
         return y;
     };
     bool pushed = false;
@@ -905,7 +921,7 @@ __global__ void __launch_bounds__(ADP_TILE) k_fsrc_norms(Geo G, FsrcArgs A, int 
         const long long idx = node_idx(G, kl, r);
         const int m = A.adjoint ? A.mat[idx] - 1 : 0;
         double fs = 0.0;
-        if (NG > 0) {
+        if constexpr (NG > 0) {
             // every operand of the row loaded before the first use: the old flux and the old fission source sat behind the
             // data-dependent tests below and cost a second and third memory round trip per row (round 1: 0.53 of the copy
             // bandwidth, ncu: 42 % DRAM utilisation at 73 % occupancy)
@@ -929,8 +945,7 @@ __global__ void __launch_bounds__(ADP_TILE) k_fsrc_norms(Geo G, FsrcArgs A, int 
                 acc[1] = acc[1] + (G.area[r] * G.hz[1 + G.k0 + kl]) * fs;
                 if (fabs(fs) > 1.e-10) mser.take(fabs(errn), fabs(fs));
             }
-            continue;
-        }
+        } else {
 #pragma unroll
         for (int g = 0; g < ng; ++g) {
             const double fn = A.fnew[g][idx];
@@ -944,6 +959,7 @@ __global__ void __launch_bounds__(ADP_TILE) k_fsrc_norms(Geo G, FsrcArgs A, int 
             acc[0] = acc[0] + errn * errn;
             acc[1] = acc[1] + (G.area[r] * G.hz[1 + G.k0 + kl]) * fs;
             if (fabs(fs) > 1.e-10) mser.take(fabs(errn), fabs(fs));
+        }
         }
     }
     if (do_norms) {
@@ -1496,6 +1512,7 @@ static int launch_fsrc(adp_ctx *c, bool adjoint, bool do_norms, int fs_in, int f
     case 1: k_fsrc_norms<1><<<adp_grid(c, k_fsrc_norms<1>, nt), ADP_TILE, 0, c->stream>>>(c->geo, A, dn, ro); break;
     case 2: k_fsrc_norms<2><<<adp_grid(c, k_fsrc_norms<2>, nt), ADP_TILE, 0, c->stream>>>(c->geo, A, dn, ro); break;
     case 4: k_fsrc_norms<4><<<adp_grid(c, k_fsrc_norms<4>, nt), ADP_TILE, 0, c->stream>>>(c->geo, A, dn, ro); break;
+    case 8: k_fsrc_norms<8><<<adp_grid(c, k_fsrc_norms<8>, nt), ADP_TILE, 0, c->stream>>>(c->geo, A, dn, ro); break;
     default: k_fsrc_norms<0><<<adp_grid(c, k_fsrc_norms<0>, nt), ADP_TILE, 0, c->stream>>>(c->geo, A, dn, ro); break;
     }
     LAUNCH_CHECK(c);
@@ -1887,7 +1904,7 @@ void adp_k_preload_cmfd(adp_ctx *c)
         adp_grid(c, k_residual_m, 1); adp_grid(c, k_update_p_m, 1); adp_grid(c, k_spmv_dot_m, 1); adp_grid(c, k_st_m<0, 0>, 1);
         adp_grid(c, k_update_xr_m, 1);
     }
-    adp_grid(c, k_fsrc_norms<0>, 1); adp_grid(c, k_fsrc_norms<1>, 1); adp_grid(c, k_fsrc_norms<2>, 1); adp_grid(c, k_fsrc_norms<4>, 1);
+    adp_grid(c, k_fsrc_norms<0>, 1); adp_grid(c, k_fsrc_norms<1>, 1); adp_grid(c, k_fsrc_norms<2>, 1); adp_grid(c, k_fsrc_norms<4>, 1); adp_grid(c, k_fsrc_norms<8>, 1);
     adp_grid(c, k_extrap, 1); adp_grid(c, k_integrate, 1); adp_grid(c, k_fill, 1);
     adp_grid(c, k_scalar, 1); adp_grid(c, k_powdis, 1); adp_grid(c, k_scale, 1); adp_grid(c, k_get_exsrc, 1);
     adp_grid(c, k_xs_update, 1); adp_grid(c, k_ipden, 1); adp_grid(c, k_upden, 1); adp_grid(c, k_begin_step, 1); adp_grid(c, k_reactivity, 1);

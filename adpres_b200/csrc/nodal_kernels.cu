@@ -1322,7 +1322,9 @@ __global__ void __launch_bounds__(ADP_TILE, 2) k_nodal_surfaces_coop(Geo G, Noda
 // 16-lane form idles half its lanes (15 ms).  Every element sees LU_solve's operations (mod_nodal.f90:829-897) in
 // the same order: bit-identical results.
 // =======================================================================================
-#define QW 4
+#ifndef QW
+#define QW 4          // lanes per (node, direction) / surface in the quad kernels; -DQW=8 for A/B
+#endif
 __device__ __forceinline__ double shflq(double v, int src) { return __shfl_sync(COOP_FULL, v, src, QW); }
 
 // rows i = sl + QW * s (s = 0 .. RPL-1) of the M x M system in lane sl; rows >= M are padding (all zero on entry)

@@ -214,9 +214,11 @@ def c3_main(rank, world, local, uid, dist):
     p = load_problem("IAEA3Ds").refine(xdiv=ref["xdiv"], ydiv=ref["ydiv"], zdiv=ref["zdiv"])
     # both sides converged to the fixture's serc = ferc = 1e-8 (see tests/test_z_all_decks.py: at the 1e-5 exit the
     # iterate still moves by more than the 1e-5 bar)
-    s = capi.Solver(p, device=local, nranks=world, rank=rank, uid=uid, nout=30000, serc=ref["serc"], ferc=ref["serc"])
+    # nin of the fixture (4): with the deck's default nin = 2 the two-node iteration is only marginally stable on this mesh --
+    # 1 461 ... 2 573 outers and, in one summation order, the reference's own ndmax > 1e3 STOP (tools/order_probe.py)
+    s = capi.Solver(p, device=local, nranks=world, rank=rank, uid=uid, nout=30000, serc=ref["serc"], ferc=ref["serc"], nin=ref["nin"])
     rc, n = s.outer(0)
-    assert rc == 0, (rc, n)      # the outer COUNT to 1e-8 depends on the summation order (1 565 serial, 1 922 on two slabs)
+    assert rc == 0 and abs(n - ref["outers"]) <= 0.1 * ref["outers"], (rc, n, ref["outers"])
     ke = s.state()["Ke"]
     assert abs(ke - ref["keff"]) * 1e5 < 1.0, (ke, ref["keff"])
     _, pw = s.powdis()

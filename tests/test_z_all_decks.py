@@ -175,7 +175,7 @@ def test_refined_lmw_fixture_sensitivity_is_below_the_bar():
 @pytest.mark.gpu
 def test_gpu_c3_full_solve_against_cpu_oracle_fixture():
     """BASELINE configs[2] (IAEA-3D at 4 x 4 nodes per assembly, 190 planes: 183 160 nodes) with the reference's default
-    inner / nodal iteration control (nin = 2, nupd = 104) against the CPU oracle's solve (tools/c3_oracle.py, one minute of
+    nodal-update interval (nupd = 104) and nin = 4 against the CPU oracle's solve (tools/c3_oracle.py, one minute of
     CPU, committed): k-eff within 1 pcm, assembly power 1e-5, nodal power 1e-5.
     Both sides are converged to serc = ferc = 1e-8 (the fixture's "serc").  Round 1 compared at the 1e-5 exit of the oracle,
     at a fixed outer count; there the iterate still moves by 1.2e-5 per 20 iterations (nin = 2 sweeps are far from converged),
@@ -186,13 +186,15 @@ def test_gpu_c3_full_solve_against_cpu_oracle_fixture():
     from adpres_b200 import capi
     ref = json.load(open(os.path.join(GOLDEN, "c3_oracle_result.json")))
     p = load_problem("IAEA3Ds").refine(xdiv=ref["xdiv"], ydiv=ref["ydiv"], zdiv=ref["zdiv"])
-    assert (p.nnod, p.nin, p.nupd) == (ref["nnod"], ref["nin"], ref["nupd"])
+    assert (p.nnod, p.nupd) == (ref["nnod"], ref["nupd"]) and p.nin == 2 and ref["nin"] == 4
     assert ref["serc"] <= 1e-8 and ref["status"] == 0
-    s = capi.Solver(p, nout=30000, serc=ref["serc"], ferc=ref["serc"])
+    # nin = 4, twice the deck's default: with nin = 2 the two-node iteration is only marginally stable on this mesh (5 cm x 5 cm
+    # x 2 cm nodes) -- the same solve takes 1 461 ... 2 573 outers depending on how the partial sums of the dot products are
+    # grouped, with source-error excursions of 1e3 ... 1e5, and one order (NCCL path on two slabs) ran into the reference's own
+    # "MAX. CHANGE > 1e3" STOP; from nin = 4 on all orders converge smoothly in 602 - 617 outers (tools/order_probe.py, round 2)
+    s = capi.Solver(p, nout=30000, serc=ref["serc"], ferc=ref["serc"], nin=ref["nin"])
     rc, n = s.outer(0)
-    assert rc == 0, (rc, n)
-    # (the outer COUNT to 1e-8 is not compared: it depends on the summation order -- 1 565 in the serial oracle, 1 922 on two
-    # z-slabs -- because the tail of the convergence is the nodal-update cycle, not a contraction with a fixed rate)
+    assert rc == 0 and abs(n - ref["outers"]) <= 0.1 * ref["outers"], (rc, n, ref["outers"])
     assert abs(s.state()["Ke"] - ref["keff"]) * 1e5 < 1.0
     rc, pw = s.powdis()
     asm, asm_ref = p.asm_power(pw), np.array(ref["asm_power"])
