@@ -313,8 +313,18 @@ int adp_get_matrix(adp_ctx *ctx, double *a);
 /* get_source (mod_nodal.f90:1009-1043): S1,S2,S3 (nnod,ng) for cmode */
 int adp_get_source(adp_ctx *ctx, int cmode, double *S1, double *S2, double *S3);
 
-/* runtime options: "graphs" 0/1 (CUDA-graph replay of an outer iteration, default 1),
- * "grid_blocks" n (persistent grid size, default 8 x SM count) */
+/* runtime options (no reference counterpart; every default is the measured best):
+ *   "graphs" 0/1            CUDA-graph replay of an outer iteration (default 1)
+ *   "grid_blocks" n         persistent grid size (default: SM count x resident CTAs of each kernel); also another grouping
+ *                           of the partial sums of the global reductions (tools/order_probe.py)
+ *   "gather_results" 0/1    several ranks: complete node arrays returned to the host with the other ranks' slabs (default 1)
+ *   "peer_push", "peer_allreduce", "fuse_mail", "mail_ll", "mail_timeout_s"   multi-rank data plane (csrc/comm.cu, mail.cuh)
+ *   "st_var", "st_m_var", "spmv_var", "st_tma", "fuse_st", "balance_rounds"   formulations of the BiCGSTAB kernels kept for A/B
+ *   "nodal_coop" -1/0/1/2   nodal kernels: automatic / one thread per item / 16 lanes per surface / quad kernels
+ *   "nodal_fused" 0/1       fused per-direction nodal kernels for G <= 2 (experiment, slower)
+ *   "reset_nodal" 1         back to the state before the first coup_coef call: the next adp_matrix_setup(1) zeroes dn
+ *   "profile" 0/1           per-launch-site events, read with adp_profile_report
+ *   "bench_warmup" n        untimed launches in front of adp_bench_kernel's timed ones */
 int adp_set_option(adp_ctx *ctx, const char *name, int value);
 
 /* ---- measurement ------------------------------------------------------------------------ */
@@ -323,7 +333,8 @@ int adp_set_option(adp_ctx *ctx, const char *name, int value);
 int adp_launch_count(const adp_ctx *ctx, long long *launches);
 /* device-resident micro-benchmark of one kernel class on the current problem, no host copies:
  * what: 0 B SpMV + (rs,v); 1 C fused s/t; 2 D x,r update; 3 A p update; 4 P source+residual;
- * 5 F fission source + norms; 6 nodal source; 7 whole nodal update; 8 plain SpMV; 9 matrix_setup(0).
+ * 5 F fission source + norms; 6 nodal source; 7 whole nodal update; 8 plain SpMV; 9 matrix_setup(0);
+ * 10..14 the multi-rank forms of B, C, D, A, P launched on this rank alone (no mailbox wait).
  * Runs `reps` launches (alternating over groups), returns the average device ms per launch. */
 int adp_bench_kernel(adp_ctx *ctx, int what, int reps, double *avg_ms);
 /* Measurement aid (no reference counterpart): after adp_set_option(ctx, "profile", 1) every kernel launch of the CMFD path

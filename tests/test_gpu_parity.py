@@ -432,9 +432,9 @@ def test_lxyz_total_on_device(mods):
 @pytest.mark.parametrize("ng,bc,kern", [(2, None, "SANM"), (4, (1, 1, 1, 1, 1, 1), "SANM"), (4, (2, 2, 2, 2, 0, 1), "PNM"),
                                         (6, (0, 2, 1, 2, 2, 0), "SANM"), (8, None, "SANM"), (8, (1, 0, 2, 1, 0, 2), "PNM")])
 def test_cooperative_surfaces_kernel_is_bit_identical(mods, ng, bc, kern):
-    """The surfaces kernel exists twice: one thread per surface (default up to G = 6) and 16 lanes
-    per surface with the rows of the 2G x 2G system spread over the lanes (default from G = 7,
-    where the first spills kilobytes per thread).  Both perform LU_solve's operations element by
+    """The surfaces kernel exists three times: one thread per surface (default up to G = 4), 16 lanes per surface with
+    the rows of the 2G x 2G system spread over the lanes (round 1's form for G >= 7), and the quad kernels of round 2 (four
+    lanes per node-direction / surface, rows dealt cyclically: default from G = 5).  All perform LU_solve's operations element by
     element in the reference's order, so coupling coefficients, ndmax (value and location) and
     the following iterates must agree bit for bit -- for every boundary code, both nodal kernels,
     with ADFs."""
@@ -446,17 +446,19 @@ def test_cooperative_surfaces_kernel_is_bit_identical(mods, ng, bc, kern):
     from adpres_b200 import deck as _deck
     p.kern = _deck.KERN_SANM if kern == "SANM" else _deck.KERN_PNM
     out = []
-    for coop in (0, 1):
+    for coop in (0, 1, 2):     # 2: the quad kernels of round 2 (four lanes per node-direction / surface, default from G = 5)
         s = capi.Solver(p, nupd=3, nout=8)
         s.set_option("nodal_coop", coop)
         s.enable_trace()
         rc, n = s.outer(1)
         out.append((rc, n, s.state(), s.nod()[1].copy(), list(s.trace_nodal), s.ndmax))
-    a, b = out
-    assert a[0] == b[0] and a[1] == b[1]
-    assert a[4] == b[4] and len(a[4]) >= 2                      # (p, ndmax, i, j, k) of every update
-    assert np.array_equal(a[3], b[3])
-    assert np.array_equal(a[2]["f0"], b[2]["f0"]) and a[2]["Ke"] == b[2]["Ke"] and a[5] == b[5]
+        s.close()
+    a = out[0]
+    for b in out[1:]:
+        assert a[0] == b[0] and a[1] == b[1]
+        assert a[4] == b[4] and len(a[4]) >= 2                      # (p, ndmax, i, j, k) of every update
+        assert np.array_equal(a[3], b[3])
+        assert np.array_equal(a[2]["f0"], b[2]["f0"]) and a[2]["Ke"] == b[2]["Ke"] and a[5] == b[5]
 
 
 # ------------------------------------------------------------------ fused per-direction kernels (G <= 4)

@@ -192,10 +192,14 @@ def test_gpu_c3_full_solve_against_cpu_oracle_fixture():
     # x 2 cm nodes) -- the same solve takes 1 461 ... 2 573 outers depending on how the partial sums of the dot products are
     # grouped, with source-error excursions of 1e3 ... 1e5, and one order (NCCL path on two slabs) ran into the reference's own
     # "MAX. CHANGE > 1e3" STOP; from nin = 4 on all orders converge smoothly in 602 - 617 outers (tools/order_probe.py, round 2)
-    s = capi.Solver(p, nout=30000, serc=ref["serc"], ferc=ref["serc"], nin=ref["nin"])
+    # run for exactly the oracle's outer count (its 1e-8 exit, 612): the solution still moves by ~1e-5 in power from one
+    # nodal update to the next (nupd = 104), so both sides must have seen the same number of updates
+    s = capi.Solver(p, nout=ref["outers"], serc=0.0, ferc=0.0, nin=ref["nin"])
     rc, n = s.outer(0)
-    assert rc == 0 and abs(n - ref["outers"]) <= 0.1 * ref["outers"], (rc, n, ref["outers"])
-    assert abs(s.state()["Ke"] - ref["keff"]) * 1e5 < 1.0
+    assert rc == capi.STOP_MAXOUTER and n == ref["outers"], (rc, n, ref["outers"])
+    st = s.state()
+    assert st["ser"] < 10 * ref["serc"] and st["fer"] < 10 * ref["serc"]     # and it IS converged there
+    assert abs(st["Ke"] - ref["keff"]) * 1e5 < 1.0
     rc, pw = s.powdis()
     asm, asm_ref = p.asm_power(pw), np.array(ref["asm_power"])
     nz = asm_ref > 0
