@@ -369,6 +369,10 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
+        # the CPU arm runs ~50 outer iterations of the full mesh on one core (3.5 min on the GPU boxes, 11 min in the build
+        # container): its own, longer watchdog
+        faulthandler.cancel_dump_traceback_later()
+        faulthandler.dump_traceback_later(int(os.environ.get("ADP_BENCH_WATCHDOG_S", "3000")), exit=True)
         reference_arm(args, rank, world, emit)
         return
 
