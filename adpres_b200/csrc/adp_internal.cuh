@@ -241,7 +241,8 @@ struct adp_ctx {
     std::map<unsigned long long, long long> graph_launches;   // kernels inside each graph
     bool use_graphs = true;
     int bench_warmup = 3;
-    int nodal_coop = -1;                   // surfaces kernel with 16 lanes per surface: -1 = for G >= 7, 0 never, 1 always
+    int nodal_coop = -1;                   // nodal kernel form: -1 automatic (quad kernels from G = 5), 0 one thread per item,
+                                           // 1 sixteen lanes per surface (round 1's form for G >= 7), 2 quad kernels
     int nodal_fused = 0;                   // experiment, G <= 2: per-direction kernels that carry the node-direction record in
                                            // registers instead of storing it (bit-identical, 1.7x less DRAM traffic, but 2.7x
                                            // SLOWER: 8 warps per SM cannot hide the fp64 division chains -- DESIGN.md)
