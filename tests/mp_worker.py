@@ -38,6 +38,8 @@ def main():
         return xtab_main(rank, world, local, uid, dist)
     if deck == "C3_fixture":
         return c3_main(rank, world, local, uid, dist)
+    if deck == "SYNTH8_adf":
+        return multigroup_main(rank, world, local, uid, dist)
     if deck == "IAEA3Ds_z2":                  # 38 planes: uneven slabs at 4 ranks, 2 planes per axial assembly
         p = load_problem("IAEA3Ds").refine(zdiv=[2] * 19)
     else:
@@ -199,6 +201,64 @@ def cb_main(rank, world, local, uid, dist):
         dev = np.abs(fd[k][own] / fo[k][own] - 1.0).max()
         assert dev < 1e-4, (k, dev)
     print(f"RANK {rank}/{world} OK deck=NEACRP_cb planes=[{s.k0},{s.k1}) bcon={bd:.2f}", flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def multigroup_main(rank, world, local, uid, dist):
+    """BASELINE configs[3] on z-slabs: the synthetic 8-group deck with ADFs (tests/synth.py; 2 planes per axial assembly so that
+    4 and 8 ranks get slabs too) -- SpMV bit exact on the owned rows, one SANM nodal update from an identical state (the quad
+    kernels of round 2 incl. the surface shared by two slabs, computed redundantly on both ranks), and twelve outer iterations
+    with three nodal updates at a fixed count against the single-process oracle."""
+    from adpres_b200 import capi
+    from oracle import Oracle
+    from synth import iaea3d_multigroup
+    p = iaea3d_multigroup(8, zdiv=[2] * 19)
+    ctl = dict(nin=4, nupd=4, nac=1000, nout=12, serc=0.0, ferc=0.0)     # (no source extrapolation: it amplifies round-off)
+    s = capi.Solver(p, device=local, nranks=world, rank=rank, uid=uid, **ctl)
+    o = Oracle(p, **ctl)
+    own = s.own
+    s.matrix_setup(1); o.matrix_setup(1)
+    assert np.array_equal(s.matrix_dia()[:, own, :], o.matrix_dia()[:, own, :])
+    x = np.random.default_rng(3).standard_normal(p.nnod)
+    for g in (1, 4, 8):
+        assert np.array_equal(s.sp_matvec(g, x)[own], o.sp_matvec(g, x)[own]), "spmv halo"
+    # one nodal update from an identical state
+    o.set_control(nout=3, nupd=1000, nin=4, nac=1000, serc=0.0, ferc=0.0); o.outer(0)
+    st = o.state()
+    s.set_state(st["f0"], st["fs0"], st["Ke"])
+    rc_o = o.nodal_upd(1)
+    rc_s, ndmax, loc = s.nodal_upd(1)
+    assert rc_o == 0 and rc_s == 0
+    dn_s, dn_o = s.nod()[1], o.nod()[1]
+    assert np.abs(dn_s[:, own, :] - dn_o[:, own, :]).max() < 1e-9, np.abs(dn_s[:, own, :] - dn_o[:, own, :]).max()
+    assert abs(ndmax - o.ndmax) < 1e-9 * max(1.0, o.ndmax) and tuple(loc) == tuple(o.ndloc()), (ndmax, o.ndmax, loc, o.ndloc())
+    # fixed-count run with three nodal updates
+    import torch
+    del s
+    dist.barrier()
+    buf2 = (capi.C.c_ubyte * 128)()
+    if rank == 0:
+        assert capi.load().adp_comm_unique_id(buf2) == 0
+    t = torch.tensor(list(bytes(buf2)), dtype=torch.uint8, device="cuda")
+    dist.broadcast(t, 0)
+    s = capi.Solver(p, device=local, nranks=world, rank=rank, uid=bytes(t.cpu().tolist()), **ctl)
+    s.enable_trace()
+    o = Oracle(p, **ctl)
+    rc_s, n_s = s.outer(1)          # popt = 1: the nodal-update line is "printed" (traced) as well
+    rc_o, n_o = o.outer(0)
+    assert rc_s == rc_o == capi.STOP_MAXOUTER and n_s == n_o == 12, (rc_s, rc_o, n_s, n_o)
+    ke_s, ke_o = np.array([r[1] for r in s.trace_rows]), o.trace()[0]
+    assert np.abs(ke_s / ke_o - 1).max() < 1e-7, np.abs(ke_s / ke_o - 1).max()
+    nt_s, nt_o = s.trace_nodal, o.nodal_trace()
+    assert len(nt_s) == len(nt_o) == 3
+    for a, b in zip(nt_s, nt_o):
+        assert a[0] == b[0] and tuple(a[2:]) == tuple(b[2:]) and abs(a[1] / b[1] - 1) < 1e-6, (a, b)
+    f_s, f_o = s.state()["f0"], o.state()["f0"]
+    assert np.abs(f_s[own] / f_o[own] - 1).max() < 1e-6
+    dn_s, dn_o = s.nod()[1], o.nod()[1]
+    assert np.abs(dn_s[:, own, :] - dn_o[:, own, :]).max() < 1e-7
+    print(f"RANK {rank}/{world} OK deck=SYNTH8_adf planes=[{s.k0},{s.k1}) keff={ke_s[-1]:.6f}", flush=True)
     dist.barrier()
     dist.destroy_process_group()
 
