@@ -40,6 +40,8 @@ def main():
         return c3_main(rank, world, local, uid, dist)
     if deck == "SYNTH8_adf":
         return multigroup_main(rank, world, local, uid, dist)
+    if deck == "LMW_refined":
+        return lmw_refined_main(rank, world, local, uid, dist)
     if deck == "IAEA3Ds_z2":                  # 38 planes: uneven slabs at 4 ranks, 2 planes per axial assembly
         p = load_problem("IAEA3Ds").refine(zdiv=[2] * 19)
     else:
@@ -134,6 +136,30 @@ def transient_main(rank, world, local, uid, dist):
         assert abs(a[3] / b[3] - 1) < 1e-5, (a, b)
         assert abs(a[2] - b[2]) < 1e-5, (a, b)
     print(f"RANK {rank}/{world} OK deck=LMW_tr planes=[{s.k0},{s.k1}) power={tr_d[-1][3]:.6f}", flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def lmw_refined_main(rank, world, local, uid, dist):
+    """BASELINE configs[4] on z-slabs: the LMW rod ejection refined to 2 cm x 2 cm x 4 cm (146 250 nodes, nin = 10, nupd = 50),
+    every solve converged to 1e-8, device-resident time stepping, against the committed CPU-oracle trace
+    (tests/golden/lmw_refined_mid_oracle.json, tools/lmw_refined_oracle.py)."""
+    import json
+    from conftest import GOLDEN, load_problem
+    from adpres_b200 import capi, transient
+    fx = json.load(open(os.path.join(GOLDEN, "lmw_refined_mid_oracle.json")))
+    rdiv, zdiv = fx["rdiv"], fx["zdiv"]
+    p = load_problem("LMW").refine(xdiv=[rdiv // 2] + [rdiv] * 5, ydiv=[rdiv // 2] + [rdiv] * 5, zdiv=[zdiv] * 10)
+    p.nin, p.nupd, p.nac, p.nout, p.serc, p.ferc, p.biter = 10, 50, 5, 20000, fx["serc"], fx["serc"], 1
+    assert p.nnod == fx["nnod"]
+    s = capi.Solver(p, device=local, nranks=world, rank=rank, uid=uid)
+    tr = transient.rod_eject_device_glue(p, s, max_steps=len(fx["trace"]) - 1, device_xs=True, step_tol=fx.get("step_tol"))
+    assert len(tr) == len(fx["trace"])
+    for a, b in zip(tr, fx["trace"]):
+        assert abs(a[1] - b[1]) < 1e-12 and not a[5]
+        assert abs(a[3] / b[3] - 1.0) < 1e-5, (a, b)           # relative power (north star: 1e-4)
+        assert abs(a[2] - b[2]) < 1e-4, (a, b)                 # reactivity in dollars
+    print(f"RANK {rank}/{world} OK deck=LMW_refined planes=[{s.k0},{s.k1}) power={tr[-1][3]:.6f}", flush=True)
     dist.barrier()
     dist.destroy_process_group()
 

@@ -23,7 +23,7 @@ def _ngpu():
 WORLD = int(os.environ.get("ADP_TEST_WORLD", "2"))      # 2 by default; 4 / 8 with `gpurun --gpus N`
 
 
-@pytest.mark.parametrize("deck", ["IAEA3Ds", "IAEA3Ds_z2", "LMW_tr", "NEACRP_th", "NEACRP_cb", "MOX_xtab", "C3_fixture", "SYNTH8_adf"])
+@pytest.mark.parametrize("deck", ["IAEA3Ds", "IAEA3Ds_z2", "LMW_tr", "NEACRP_th", "NEACRP_cb", "MOX_xtab", "C3_fixture", "SYNTH8_adf", "LMW_refined"])
 @pytest.mark.parametrize("mode", ["peer", "nccl"])
 def test_slabs_match_oracle(deck, mode):
     """mode peer: halo planes pushed by the kernels over NVLink peer memory + mailbox all-reduce;
