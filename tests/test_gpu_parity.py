@@ -520,3 +520,36 @@ def test_context_reuse_across_decks(mods):
         got = run(s, q)
         assert got[0] == fresh[i][0], (i, got[0], fresh[i][0])
         assert np.array_equal(got[1], fresh[i][1])
+
+
+def test_profile_report_and_reset_nodal(mods):
+    """The two measurement aids of round 2: the per-launch-site profile (option "profile", adp_profile_report) names the
+    BiCGSTAB launch sites with plausible counts, and "reset_nodal" brings a context back to the state before the first
+    coup_coef call (the next matrix_setup(1) zeroes dn, ndmax = 0) so that bench.py can repeat a timed window exactly."""
+    capi, _ = mods
+    p = load_problem("IAEA3Ds")
+    s = capi.Solver(p, nupd=3, nout=1000)
+    s.set_option("graphs", 0)
+    s.matrix_setup(1); s.init_flux(); s.outer_begin(capi.MODE_FORWARD)
+    s.outer_steps(capi.MODE_FORWARD, 1, 2)
+    s.set_option("profile", 1)
+    rc, ke1, _, _ = s.outer_steps(capi.MODE_FORWARD, 3, 4)              # p = 3..6: nodal updates at 3 and 6
+    rep = dict((name.split(":")[0], (cnt, ms)) for name, cnt, ms in s.profile_report())
+    s.set_option("profile", 0)
+    assert rc == 0
+    nin, G = p.nin, p.ng
+    assert rep["launch_st"][0] == 4 * G * nin and rep["launch_spmv_dot"][0] == 4 * G * nin and rep["k_update_xr"][0] == 4 * G * nin
+    assert rep["k_update_p"][0] == 4 * G * (nin - 1) and rep["k_residual"][0] == 4 * G
+    assert all(ms > 0 for _, ms in rep.values())
+    assert np.abs(s.nod()[1]).max() > 0                                  # the updates left dn != 0
+    s.reset_nodal()
+    s.matrix_setup(1)
+    assert np.abs(s.nod()[1]).max() == 0.0 and s.ndmax == 0.0
+    # and the repeated run is the first run
+    s.set_option("graphs", 1)
+    s.init_flux(); s.outer_begin(capi.MODE_FORWARD)
+    rc, ke_a, _, _ = s.outer_steps(capi.MODE_FORWARD, 1, 6)
+    s.reset_nodal(); s.matrix_setup(1); s.init_flux(); s.outer_begin(capi.MODE_FORWARD)
+    rc, ke_b, _, _ = s.outer_steps(capi.MODE_FORWARD, 1, 6)
+    assert ke_a == ke_b == ke1
+    s.close()
