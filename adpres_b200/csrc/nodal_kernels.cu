@@ -23,6 +23,13 @@
 
 namespace {
 
+// resident CTAs per SM asked of ptxas for the G <= 2 node-direction / surfaces kernels (A/B: tools/build_variant.sh -DNODAL_LB_ND=..)
+#ifndef NODAL_LB_ND
+#define NODAL_LB_ND 3
+#endif
+#ifndef NODAL_LB_SF
+#define NODAL_LB_SF 2
+#endif
 #define FOR_EACH_ROW(G_, KLO, NPL)                                                                  \
     for (int tile__ = blockIdx.x; tile__ < (G_).tpp * (NPL); tile__ += gridDim.x)                   \
         for (int kl = (KLO) + tile__ / (G_).tpp, r = (tile__ % (G_).tpp) * ADP_TILE + threadIdx.x, \
@@ -428,7 +435,7 @@ __device__ __forceinline__ void nd_load(NodeDir<NG> &nd, const double *__restric
 
 // one thread per (node, direction): compute and store what the sweep carries for that node
 template <int NG, int KERN>
-__global__ void __launch_bounds__(ADP_TILE, (NG <= 2) ? 3 : 1) k_nodal_nodedir(Geo G, NodalArgs A, int u, int klo, int npl)
+__global__ void __launch_bounds__(ADP_TILE, (NG <= 2) ? NODAL_LB_ND : 1) k_nodal_nodedir(Geo G, NodalArgs A, int u, int klo, int npl)
 {
     bool ok = true;
     FOR_EACH_ROW(G, klo, npl)
@@ -509,7 +516,7 @@ __device__ __forceinline__ void grid_argmax(double v, long long l, const ArgMax 
 // nodal_coup_upd (mod_nodal.f90:282-698).
 // ---------------------------------------------------------------------------------------
 template <int NG, int KERN>
-__global__ void __launch_bounds__(ADP_TILE, (NG <= 2) ? 2 : 1) k_nodal_surfaces(Geo G, NodalArgs A, int u, int klo, int npl, ArgMax am)
+__global__ void __launch_bounds__(ADP_TILE, (NG <= 2) ? NODAL_LB_SF : 1) k_nodal_surfaces(Geo G, NodalArgs A, int u, int klo, int npl, ArgMax am)
 {
     const long long NV = G.NV;
     const double *ndbase = A.nd + (size_t)u * ND_SLOTS(NG) * NV;
