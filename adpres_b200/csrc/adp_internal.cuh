@@ -251,6 +251,14 @@ struct adp_ctx {
     int st_var = 6;                        // formulation of the C kernel (k_st), single rank: 0..7 (6: loads grouped, 64 registers)
     int st_m_var = 6;                      // the same for the multi-rank C kernel (k_st_m)
     bool st_tma = false;                   // C kernel staged with cp.async.bulk + mbarrier (experiment, single rank, np even)
+    // option "lazy_adf": adp_set_xs only remembers the host pointers of dc and sigf -- the two arrays the CMFD iteration never
+    // reads (ADFs: nodal update; sigf: PowDis) -- adp_outer_begin enqueues their upload on a second stream, and the first
+    // consumer makes the main stream wait for it (adp_lazy_sync): 0.5 of the 1.0 GB an outer() call uploads then travels
+    // while the outer iterations run.  The caller keeps both host arrays unchanged until a consumer has returned.
+    bool lazy_adf = false, lazy_pending = false;
+    const double *lazy_dc = nullptr, *lazy_sigf = nullptr;
+    cudaStream_t stream2 = nullptr;
+    cudaEvent_t ev_lazy = nullptr;
     // per-launch profile (option "profile"): an event after every kernel launch of the CMFD path, tagged with the source line
     bool prof = false;
     cudaEvent_t prof_start = nullptr;
@@ -320,6 +328,9 @@ static inline int adp_grid(adp_ctx *c, K kernel, int ntiles)
     }
     return (int)g;
 }
+
+int adp_lazy_enqueue(adp_ctx *c);   // capi.cu: start the deferred uploads (no-op without any)
+int adp_lazy_sync(adp_ctx *c);      // capi.cu: the main stream waits for them; call before any kernel / copy that reads d_dc, d_sigf
 
 static inline void adp_prof_mark(adp_ctx *c, int line)
 {

@@ -95,6 +95,8 @@ extern "C" int adp_destroy(adp_ctx *c)
     if (!c) return ADP_OK;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    if (c->stream2) { cudaStreamSynchronize(c->stream2); cudaStreamDestroy(c->stream2); c->stream2 = nullptr; }
+    if (c->ev_lazy) { cudaEventDestroy(c->ev_lazy); c->ev_lazy = nullptr; }
     free_graphs(c);
     adp_comm_destroy(c);
     void *ptrs[] = {c->d_nodp, c->d_ypm, c->d_ypp, c->d_ixr, c->d_iyr, c->d_mat, c->d_flag, c->d_hx, c->d_hy, c->d_hz, c->d_area,
@@ -183,6 +185,9 @@ extern "C" int adp_set_geometry(adp_ctx *c, int nxx, int nyy, int nzz, int nnod,
     if (!c) return ADP_ERR_USAGE;
     CUDA_TRY(c, cudaSetDevice(c->device));
     adp_comm_unmap_peers(c);
+    // a deferred upload (option "lazy_adf") targets buffers this call re-allocates
+    if (c->stream2) cudaStreamSynchronize(c->stream2);
+    c->lazy_dc = c->lazy_sigf = nullptr; c->lazy_pending = false;
     ADP_REQUIRE(c, ng >= 1 && ng <= ADP_MAXG, "adp_set_geometry: ng must be 1..16");
     ADP_REQUIRE(c, nnod > 0 && nzz > 0 && nnod % nzz == 0, "adp_set_geometry: nnod must be np*nzz (plane-invariant core outline)");
     free_graphs(c);
@@ -326,6 +331,39 @@ static int ensure_transient(adp_ctx *c)
     return ADP_OK;
 }
 
+// ---- option "lazy_adf": deferred upload of dc and sigf (see adp_ctx) ------------------------------------------------
+static int upload_nodes_on(adp_ctx *c, cudaStream_t st, double *d, const double *h, int ncol)
+{
+    const int np = c->np;
+    const int ka = std::max(0, c->k0 - ADP_GH), kb = std::min(c->nzz, c->k1 + ADP_GH);
+    const size_t cnt = (size_t)(kb - ka) * np;
+    for (int col = 0; col < ncol; ++col)
+        CUDA_TRY(c, cudaMemcpyAsync(d + (size_t)col * c->NV + (size_t)(ka - (c->k0 - ADP_GH)) * np,
+                                    h + (size_t)col * c->nnod + (size_t)ka * np, cnt * sizeof(double), cudaMemcpyHostToDevice, st));
+    return ADP_OK;
+}
+int adp_lazy_enqueue(adp_ctx *c)
+{
+    if (!c->lazy_dc && !c->lazy_sigf) return ADP_OK;
+    if (!c->stream2) CUDA_TRY(c, cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+    if (!c->ev_lazy) CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_lazy, cudaEventDisableTiming));
+    if (c->lazy_dc) TRY(upload_nodes_on(c, c->stream2, c->d_dc, c->lazy_dc, c->ng * 6));
+    if (c->lazy_sigf) TRY(upload_nodes_on(c, c->stream2, c->d_sigf, c->lazy_sigf, c->ng));
+    CUDA_TRY(c, cudaEventRecord(c->ev_lazy, c->stream2));
+    c->lazy_dc = c->lazy_sigf = nullptr;
+    c->lazy_pending = true;
+    return ADP_OK;
+}
+int adp_lazy_sync(adp_ctx *c)
+{
+    TRY(adp_lazy_enqueue(c));            // uploads that were never started (no adp_outer_begin in between)
+    if (c->lazy_pending) {
+        CUDA_TRY(c, cudaStreamWaitEvent(c->stream, c->ev_lazy, 0));
+        c->lazy_pending = false;
+    }
+    return ADP_OK;
+}
+
 extern "C" int adp_set_xs(adp_ctx *c, const double *D, const double *sigr, const double *nuf, const double *sigf,
                           const double *sigs, const double *chi, const double *dc, const double *exsrc)
 {
@@ -337,12 +375,16 @@ extern "C" int adp_set_xs(adp_ctx *c, const double *D, const double *sigr, const
     if (sigr) TRY(upload_nodes(c, c->d_sigr, sigr, G, true));
     if (D || sigr) c->abefgh_valid = false;   // the SANM constants A..H depend on sigr/D only
     if (nuf) TRY(upload_nodes(c, c->d_nuf, nuf, G, true));
-    if (sigf) TRY(upload_nodes(c, c->d_sigf, sigf, G, true));
-    if (sigs) TRY(upload_nodes(c, c->d_sigs, sigs, G * G, true));   // host (n,g,h): column g + G*h = device [h][g]
-    if (dc) {
-        // host dc(n,g,f): column g + G*f -> device [f][g]
-        TRY(upload_nodes(c, c->d_dc, dc, G * 6, true));
+    if (c->lazy_adf) {
+        // a deferred upload still in flight must not be overtaken by this one; the new arrays go up from adp_outer_begin
+        TRY(adp_lazy_sync(c));
+        if (sigf) c->lazy_sigf = sigf;
+        if (dc) c->lazy_dc = dc;
+    } else {
+        if (sigf) TRY(upload_nodes(c, c->d_sigf, sigf, G, true));
+        if (dc) TRY(upload_nodes(c, c->d_dc, dc, G * 6, true));      // host dc(n,g,f): column g + G*f -> device [f][g]
     }
+    if (sigs) TRY(upload_nodes(c, c->d_sigs, sigs, G * G, true));   // host (n,g,h): column g + G*h = device [h][g]
     if (exsrc) TRY(upload_nodes(c, c->d_exsrc, exsrc, G, true));
     if (chi) {
         // host chi(nmat, ng) column-major = [g][nmat]
@@ -407,6 +449,7 @@ extern "C" int adp_outer_begin(adp_ctx *c, int mode)
     if (!c) return ADP_ERR_USAGE;
     ADP_REQUIRE(c, c->have_flux && c->matrix_ready, "adp_outer_begin: needs adp_matrix_setup and a flux (adp_init_flux/adp_set_state)");
     CUDA_TRY(c, cudaSetDevice(c->device));
+    TRY(adp_lazy_enqueue(c));            // option "lazy_adf": dc and sigf travel while the outer iterations run
     return adp_k_outer_begin(c, mode);
 }
 
@@ -577,6 +620,7 @@ extern "C" int adp_powdis(adp_ctx *c, double *p, int fixedsrc_mode)
     if (!c || !p) return ADP_ERR_USAGE;
     ADP_REQUIRE(c, c->have_flux, "adp_powdis: no flux");
     CUDA_TRY(c, cudaSetDevice(c->device));
+    TRY(adp_lazy_sync(c));
     TRY(adp_k_powdis(c, c->d_stage));
     CUDA_TRY(c, cudaMemcpyAsync(c->h_scal, c->d_scal, S_COUNT * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
@@ -776,6 +820,7 @@ extern "C" int adp_xs_update(adp_ctx *c, const double *bpos)
     CUDA_TRY(c, cudaSetDevice(c->device));
     if (c->d_fb) CUDA_TRY(c, cudaMemcpyAsync(c->d_bpos, bpos, c->nb * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     CUDA_TRY(c, cudaMemsetAsync(c->d_errflag, 0, sizeof(int), c->stream));
+    TRY(adp_lazy_sync(c));
     TRY(adp_k_xs_update(c));
     return xs_update_stop(c);
 }
@@ -813,6 +858,7 @@ extern "C" int adp_xs_update_th(adp_ctx *c, double bcon, const double *ftem, con
     if (c->d_fb) CUDA_TRY(c, cudaMemcpyAsync(c->d_bpos, bpos, c->nb * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     CUDA_TRY(c, cudaMemsetAsync(c->d_errflag, 0, sizeof(int), c->stream));
     c->xs_feedback = true;
+    TRY(adp_lazy_sync(c));
     const int rc = adp_k_xs_update(c);
     c->xs_feedback = false;
     if (rc) return rc;
@@ -866,6 +912,7 @@ extern "C" int adp_xs_update_xtab(adp_ctx *c, double bcon, const double *ftem, c
     c->bcon = bcon;
     if (c->d_fb) CUDA_TRY(c, cudaMemcpyAsync(c->d_bpos, bpos, c->nb * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     CUDA_TRY(c, cudaMemsetAsync(c->d_errflag, 0, sizeof(int), c->stream));
+    TRY(adp_lazy_sync(c));
     TRY(adp_k_xs_update_xtab(c));
     return xs_update_stop(c);
 }
@@ -875,6 +922,7 @@ extern "C" int adp_get_dc(adp_ctx *c, double *dc)
     if (!c || !dc) return ADP_ERR_USAGE;
     ADP_REQUIRE(c, c->xs_set, "adp_get_dc: cross sections not set");
     CUDA_TRY(c, cudaSetDevice(c->device));
+    TRY(adp_lazy_sync(c));
     TRY(download_nodes(c, dc, c->d_dc, c->ng * 6));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     return ADP_OK;
@@ -888,7 +936,7 @@ extern "C" int adp_get_xs(adp_ctx *c, double *D, double *sigr, double *nuf, doub
     if (D) TRY(download_nodes(c, D, c->d_D, c->ng));
     if (sigr) TRY(download_nodes(c, sigr, c->d_sigr, c->ng));
     if (nuf) TRY(download_nodes(c, nuf, c->d_nuf, c->ng));
-    if (sigf) TRY(download_nodes(c, sigf, c->d_sigf, c->ng));
+    if (sigf) { TRY(adp_lazy_sync(c)); TRY(download_nodes(c, sigf, c->d_sigf, c->ng)); }
     if (sigs) TRY(download_nodes(c, sigs, c->d_sigs, c->ng * c->ng));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     return ADP_OK;
@@ -944,6 +992,7 @@ extern "C" int adp_powtot(adp_ctx *c, double *tpow)
     if (!c || !tpow) return ADP_ERR_USAGE;
     ADP_REQUIRE(c, c->have_flux, "adp_powtot: no flux");
     CUDA_TRY(c, cudaSetDevice(c->device));
+    TRY(adp_lazy_sync(c));
     TRY(adp_k_powdis(c, c->d_stage));
     CUDA_TRY(c, cudaMemcpyAsync(c->h_scal, c->d_scal, S_COUNT * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
@@ -1191,6 +1240,11 @@ extern "C" int adp_set_option(adp_ctx *c, const char *name, int value)
             CUDA_TRY(c, cudaEventCreate(&c->prof_start));
             CUDA_TRY(c, cudaEventRecord(c->prof_start, c->stream));
         }
+        return ADP_OK;
+    }
+    if (!strcmp(name, "lazy_adf")) {
+        if (!value) { const int rc = adp_lazy_sync(c); if (rc) return rc; }
+        c->lazy_adf = value != 0;
         return ADP_OK;
     }
     if (!strcmp(name, "reset_nodal")) {

@@ -1950,7 +1950,9 @@ int adp_k_nodal_update(adp_ctx *c, int cmode)
             return ADP_ERR_CUDA;
         }
     }
-    int rc = adp_k_nodal_source(c, cmode);
+    int rc = adp_lazy_sync(c);            // the ADFs (option "lazy_adf": uploaded behind the outer iterations)
+    if (rc) return rc;
+    rc = adp_k_nodal_source(c, cmode);
     if (rc) return rc;
     NodalArgs A = make_args(c, cmode);
     if (c->nranks > 1) {

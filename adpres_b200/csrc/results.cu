@@ -131,6 +131,7 @@ extern "C" int adp_asm_pow(adp_ctx *c, int nx, int ny, const int *xdiv, const in
     TRY(check_divisions(c, nx, xdiv, c->nxx, "adp_asm_pow (x)"));
     TRY(check_divisions(c, ny, ydiv, c->nyy, "adp_asm_pow (y)"));
     CUDA_TRY(c, cudaSetDevice(c->device));
+    TRY(adp_lazy_sync(c));
     TRY(adp_k_powdis(c, c->d_stage));
     CUDA_TRY(c, cudaMemcpyAsync(c->h_scal, c->d_scal, S_COUNT * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
@@ -169,6 +170,7 @@ extern "C" int adp_axi_pow(adp_ctx *c, int nz, const int *zdiv, double *faxi, in
     TRY(check_divisions(c, nz, zdiv, c->nzz, "adp_axi_pow (z)"));
     CUDA_TRY(c, cudaSetDevice(c->device));
     TRY(ensure_result_buffers(c));
+    TRY(adp_lazy_sync(c));
     TRY(adp_k_powdis(c, c->d_stage));
     CUDA_TRY(c, cudaMemcpyAsync(c->h_scal, c->d_scal, S_COUNT * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));

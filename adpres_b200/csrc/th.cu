@@ -359,6 +359,7 @@ extern "C" int adp_th_pline(adp_ctx *c, double pw, double ppow, int form, const 
     std::vector<double> nf(c->np);
     for (int r = 0; r < c->np; ++r) nf[r] = node_nf[(size_t)(c->h_iy[r] - 1) * c->nxx + (c->h_ix[r] - 1)];
     CUDA_TRY(c, cudaMemcpy(c->d_nodenf, nf.data(), (size_t)c->np * sizeof(double), cudaMemcpyHostToDevice));
+    TRY(adp_lazy_sync(c));
     TRY(adp_k_powdis(c, c->d_stage));
     CUDA_TRY(c, cudaMemcpyAsync(c->h_scal, c->d_scal, S_COUNT * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));

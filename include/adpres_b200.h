@@ -322,6 +322,10 @@ int adp_get_source(adp_ctx *ctx, int cmode, double *S1, double *S2, double *S3);
  *   "st_var", "st_m_var", "spmv_var", "st_tma", "fuse_st", "balance_rounds"   formulations of the BiCGSTAB kernels kept for A/B
  *   "nodal_coop" -1/0/1/2   nodal kernels: automatic / one thread per item / 16 lanes per surface / quad kernels
  *   "nodal_fused" 0/1       fused per-direction nodal kernels for G <= 2 (experiment, slower)
+ *   "lazy_adf" 0/1          adp_set_xs defers the upload of dc and sigf -- the arrays the CMFD iteration never reads -- to
+ *                           adp_outer_begin, on a second stream; the first consumer (nodal update, PowDis, XS update, getters)
+ *                           waits for it.  Both host arrays must stay unchanged until such a consumer has returned
+ *                           (default 0: every array is on the device when adp_set_xs returns)
  *   "reset_nodal" 1         back to the state before the first coup_coef call: the next adp_matrix_setup(1) zeroes dn
  *   "profile" 0/1           per-launch-site events, read with adp_profile_report
  *   "bench_warmup" n        untimed launches in front of adp_bench_kernel's timed ones */

@@ -553,3 +553,33 @@ def test_profile_report_and_reset_nodal(mods):
     rc, ke_b, _, _ = s.outer_steps(capi.MODE_FORWARD, 1, 6)
     assert ke_a == ke_b == ke1
     s.close()
+
+
+def test_lazy_adf_upload_is_transparent(mods):
+    """Option "lazy_adf" (round 2, used by bench.py's e2e leg): adp_set_xs defers the upload of dc and sigf to adp_outer_begin,
+    on a second stream, and the first consumer waits for it.  Same coupling coefficients after the nodal updates (the ADFs
+    are consumed there), same k-eff, same power (sigf) as with every array uploaded up front -- bit for bit; a second
+    adp_set_xs with other ADFs while the first deferred upload may still be pending uses the new ones."""
+    capi, _ = mods
+    from synth import iaea3d_multigroup
+    p = iaea3d_multigroup(4)
+    hx = {k: np.asfortranarray(getattr(p, k), dtype=np.float64) for k in ("D", "sigr", "nuf", "sigf", "sigs", "chi", "dc", "exsrc")}
+    dc2 = np.asfortranarray(1.0 + 0.5 * (hx["dc"] - 1.0))
+    d = capi._d
+    out = []
+    for lazy in (0, 1):
+        s = capi.Solver(p, nupd=2, nout=1000, nin=4)
+        s.set_option("lazy_adf", lazy)
+        res = []
+        for dc in (hx["dc"], dc2):
+            s._chk(s.L.adp_set_xs(s.h, d(hx["D"]), d(hx["sigr"]), d(hx["nuf"]), d(hx["sigf"]), d(hx["sigs"]), d(hx["chi"]), d(dc), d(hx["exsrc"])))
+            s.reset_nodal()
+            s.matrix_setup(1); s.init_flux(); s.outer_begin(capi.MODE_FORWARD)
+            rc, ke, _, _ = s.outer_steps(capi.MODE_FORWARD, 1, 5)          # nodal updates at p = 2, 4
+            assert rc == 0
+            res.append((ke, s.nod()[1].copy(), s.powdis()[1].copy(), s.get_dc().copy()))
+        out.append(res)
+        s.close()
+    for (ka, dna, pwa, dca), (kb, dnb, pwb, dcb) in zip(out[0], out[1]):
+        assert ka == kb and np.array_equal(dna, dnb) and np.array_equal(pwa, pwb) and np.array_equal(dca, dcb)
+    assert not np.array_equal(out[1][0][1], out[1][1][1])                 # the second set of ADFs did change dn
