@@ -87,3 +87,22 @@ def test_clock_sampler_parses_nvidia_smi_lines(bench):
     assert s2.stop()["reasons"] == ["nvidia-smi unavailable"]
     s.lines = ["0, 1300, 1965, 700.0, Active, Active, Not Active, Not Active"]
     assert s.stop()["reasons"] == ["hw_slowdown", "hw_thermal_slowdown"]
+
+
+def test_committed_profile_evidence_is_parseable():
+    """profiles/: the ncu launch list parses with tools/instep_summary.py's reader and names the BiCGSTAB kernels; the traffic
+    file bench.py reads has an entry for every kernel of the roofline table (bench.ncu_traffic returns them only while
+    csrc/cmfd_kernels.cu is the profiled source -- otherwise None, never a stale literal)."""
+    import csv
+    import json
+    import os
+    import bench
+    root = bench.ROOT
+    rows = [r for r in csv.reader(l for l in open(os.path.join(root, "profiles", "r02_launches.csv")) if l.startswith('"'))]
+    names = {r[rows[0].index("Kernel Name")].split("(")[0] for r in rows[1:]}
+    assert any("k_st" in n for n in names) and any("k_spmv_dot" in n for n in names) and any("k_update_xr" in n for n in names)
+    rec = json.load(open(os.path.join(root, "profiles", "ncu_traffic.json")))
+    for k in ("k_st", "k_spmv_dot", "k_spmv", "k_update_xr", "k_update_p", "k_residual", "k_fsrc_norms"):
+        assert rec["kernels"][k]["dram_bytes_per_launch"] > 1e8
+        v = bench.ncu_traffic(k)
+        assert v is None or v == rec["kernels"][k]["dram_bytes_per_launch"]
